@@ -1,0 +1,29 @@
+"""Deterministic stand-in for NNetWrapper.process used by the parity tests:
+a fixed random two-layer net evaluated in float64 on the host and rounded to
+float32, so the engine under test and the oracle are fed bit-identical
+(policy, value) rows for bit-identical observations.  Test infrastructure."""
+import numpy as np
+
+
+class FakeNN:
+    def __init__(self, obs_size, action_size, seed=1234, sharp=3.0):
+        rng = np.random.RandomState(seed)
+        self.w1 = rng.standard_normal((obs_size, 32)) / np.sqrt(obs_size) * 4.0
+        self.wp = rng.standard_normal((32, action_size)) * sharp
+        self.wv = rng.standard_normal((32, 3)) * 1.5
+
+    def __call__(self, obs):
+        x = np.asarray(obs, dtype=np.float64).reshape(len(obs), -1)
+        h = np.tanh(np.stack([r @ self.w1 for r in x]))      # row-wise: independent of batch size
+        lp = np.stack([r @ self.wp for r in h])
+        lv = np.stack([r @ self.wv for r in h])
+        p = np.exp(lp - lp.max(1, keepdims=True)); p /= p.sum(1, keepdims=True)
+        v = np.exp(lv - lv.max(1, keepdims=True)); v /= v.sum(1, keepdims=True)
+        return p.astype(np.float32), v.astype(np.float32)
+
+
+def warmup_outputs(batch, action_size):
+    """SelfPlayAgent warmup constants (SelfPlayAgent.pyx:48-52): float32(1/A), float32(1/3)."""
+    p = np.full((batch, action_size), np.float32(1.0 / action_size), dtype=np.float32)
+    v = np.full((batch, 3), np.float32(1.0 / 3), dtype=np.float32)
+    return p, v
