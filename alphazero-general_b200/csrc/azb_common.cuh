@@ -1,0 +1,168 @@
+// azb_common.cuh -- device-side data layout, RNG streams and the numeric
+// helpers whose rounding must match the reference bit for bit.
+//
+// Layout in HBM (one engine = B game slots, NPG node entries per slot):
+//   node pool, struct-of-arrays, entry index = slot * NPG + local id
+//     n      int32   visit count                      (Node.n,  MCTS.pyx:55)
+//     q      float   running-mean value               (Node.q,  MCTS.pyx:53)
+//     p      float   prior                            (Node.p,  MCTS.pyx:56)
+//     v      float   first-visit value                (Node.v,  MCTS.pyx:54)
+//     child0 int32   local id of the first child; the C children of a node are
+//                    contiguous, in the reference's shuffled list order
+//                    (Node._children, MCTS.pyx:50,76-79)
+//     meta   uint32  action:10 | nchild:8 | e:2 | player:1
+//                    (Node.a, len(_children), Node.e as a code, Node.player)
+//   per-slot state: packed game bitboards, root id, bump allocator, path
+//   buffer, RNG stream, move history, flags.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math_constants.h>
+
+namespace azb {
+
+// ---- node meta word --------------------------------------------------------
+constexpr uint32_t META_ACTION_NONE = 1023u;
+__host__ __device__ __forceinline__ uint32_t meta_pack(uint32_t a, uint32_t nc, uint32_t e, uint32_t pl)
+{
+    return (a & 1023u) | ((nc & 255u) << 10) | ((e & 3u) << 18) | ((pl & 1u) << 20);
+}
+__host__ __device__ __forceinline__ int meta_action(uint32_t m) { return (int)(m & 1023u); }
+__host__ __device__ __forceinline__ int meta_nc(uint32_t m) { return (int)((m >> 10) & 255u); }
+__host__ __device__ __forceinline__ int meta_e(uint32_t m) { return (int)((m >> 18) & 3u); }
+__host__ __device__ __forceinline__ int meta_player(uint32_t m) { return (int)((m >> 20) & 1u); }
+
+// ---- packed game state (32 B) ------------------------------------------------
+struct __align__(16) GState {
+    unsigned long long b0, b1, b2;   // game-specific bitboards
+    int turns;                       // GameState._turns (player = turns & 1 for both games)
+    int flags;                       // game-specific
+};
+
+// device error bits (sticky word in DevView::err)
+enum : uint32_t {
+    ERRB_POOL = 1u, ERRB_ACTION = 2u, ERRB_FP = 4u, ERRB_SAMPLES = 8u, ERRB_NOISE = 16u
+};
+
+// per-slot statistics (one row per slot, reduced on the host)
+struct SlotStats {
+    unsigned long long sims, sum_depth, sum_children, nodes_created, terminal_leaves, moves;
+    int peak_nodes;
+    int pad;
+};
+
+struct Counters {
+    long long games_played;
+    long long results;
+    long long samples_total;   // emitted since reset
+    long long sample_count;    // currently in the ring
+    long long result_count;    // currently in the ring
+};
+
+struct DevView {
+    int B, npg;
+    // node pool
+    int *n; float *q; float *p; float *v; int *child0; uint32_t *meta;
+    // per slot
+    GState *state; int *root; int *alloc; int *path; int *path_len; int *leaf;
+    uint32_t *mt; unsigned long long *ctr;
+    GState *hist_state; float *hist_pi; int *hist_len; int hist_cap;
+    int *next_reset; int *noise_event; int *last_action; int *finished; int *fin_code;
+    long long *emit_off;
+    SlotStats *stats;
+    // NN I/O
+    float *obs; float *policy; float *value;
+    const float *warm_policy; const float *warm_value;
+    // fed root noise
+    const float *noise; int noise_events, noise_stride;
+    // parameters
+    float cpuct, fpu_reduction, noise_frac, root_temp_exp;
+    int add_noise, add_temp, rng_mode, symmetric, reset_threshold;
+    unsigned long long seed; long long gid_base;
+    const float *temp_table; int temp_len;
+    long long quota;
+    // queues
+    float *s_obs; float *s_pi; float *s_z; int *s_slot; long long s_cap;
+    int *r_slot; int *r_turns; uint8_t *r_win; long long r_cap;
+    Counters *counters;
+    uint32_t *err;
+};
+
+// ---- float32 arithmetic with the reference's rounding -------------------------
+// The reference's Cython compiles to scalar C without FMA contraction; every
+// float op rounds once.  (The library is also built with -fmad=false.)
+__device__ __forceinline__ float f_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float f_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float f_div(float a, float b) { return __fdiv_rn(a, b); }
+
+// float32 power as the framework defines it: correctly rounded via a double pow
+// (MCTS.pyx:250 root temperature, :320 probs temperature).
+__device__ __forceinline__ float pow_det(float x, float e)
+{
+    if (e == 1.0f) return x;
+    if (x == 0.0f) return 0.0f;
+    return (float)pow((double)x, (double)e);
+}
+
+// ---- RNG ------------------------------------------------------------------------
+// numpy legacy MT19937, regenerated one word at a time (identical sequence to
+// the batched twist of numpy/random/src/mt19937/mt19937.c).  st[624] = index.
+__device__ inline uint32_t mt_next(uint32_t *st)
+{
+    uint32_t k = st[624];
+    if (k >= 624u) k = 0u;
+    uint32_t k1 = (k + 1u == 624u) ? 0u : k + 1u;
+    uint32_t km = (k + 397u >= 624u) ? k + 397u - 624u : k + 397u;
+    uint32_t y = (st[k] & 0x80000000u) | (st[k1] & 0x7fffffffu);
+    y = st[km] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    st[k] = y;
+    st[624] = k + 1u;
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+
+__host__ __device__ inline void mt_seed(uint32_t seed, uint32_t *st)
+{
+    st[0] = seed;
+    for (int i = 1; i < 624; i++) st[i] = 1812433253u * (st[i - 1] ^ (st[i - 1] >> 30)) + (uint32_t)i;
+    st[624] = 624u;
+}
+
+// random_interval: masked rejection on 32-bit draws (RandomState.shuffle of a list)
+__device__ inline uint32_t mt_interval(uint32_t *st, uint32_t max)
+{
+    if (max == 0u) return 0u;
+    uint32_t mask = max, v;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    do { v = mt_next(st) & mask; } while (v > max);
+    return v;
+}
+
+// Philox4x32-10; word w of stream (seed, gid) = lane w&3 of block w>>2 with
+// counter (block_lo, block_hi, gid_lo, gid_hi) and key (seed_lo, seed_hi).
+__device__ __forceinline__ uint32_t philox_word(unsigned long long seed, unsigned long long gid, unsigned long long w)
+{
+    uint32_t c0 = (uint32_t)(w >> 2), c1 = (uint32_t)(w >> 34), c2 = (uint32_t)gid, c3 = (uint32_t)(gid >> 32);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    uint32_t sel = (uint32_t)w & 3u;
+    return sel == 0u ? c0 : sel == 1u ? c1 : sel == 2u ? c2 : c3;
+}
+
+// 53-bit uniform of numpy's legacy random_sample from two 32-bit words
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b)
+{
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+
+}  // namespace azb
