@@ -1,0 +1,177 @@
+"""Leaf evaluation: the reference's ResNet run through PyTorch/cuDNN.
+
+The north star keeps the leaf evaluation on the reference's own network
+(alphazero/NNetArchitecture.py:69-120) and library kernels; what this module
+adds is the plumbing that lets it overlap with the tree kernels:
+  * ``ResNet``       -- same architecture and state_dict layout as the
+                        reference module, so its checkpoints load unchanged;
+  * ``NNetWrapper``  -- the ``process(batch) -> (pi, v)`` surface of
+                        alphazero/NNetWrapper.py:225-232 (probabilities, not logs);
+  * ``LeafEvaluator``-- a CUDA-graph capture of ``process`` that reads the
+                        engine's observation rows and writes the engine's
+                        policy / value rows in place, on a caller-chosen stream.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+# hyper-parameters the architecture reads from args (Coach.py:103-116)
+DEFAULT_NET_ARGS = dict(num_channels=32, depth=4, value_head_channels=16, policy_head_channels=16,
+                        value_dense_layers=[512, 64], policy_dense_layers=[512, 256])
+# alphazero/envs/connect4/train.py:44-49 and envs/hnefatafl/train_brandubh.py:50-55
+CONNECT4_TRAIN_NET_ARGS = dict(num_channels=128, depth=8, value_head_channels=32, policy_head_channels=32,
+                               value_dense_layers=[1024, 256], policy_dense_layers=[1024])
+BRANDUBH_TRAIN_NET_ARGS = dict(num_channels=64, depth=4, value_head_channels=16, policy_head_channels=16,
+                               value_dense_layers=[1024, 128], policy_dense_layers=[1024])
+
+
+def _conv3x3(cin, cout):
+    return nn.Conv2d(cin, cout, kernel_size=3, stride=1, padding=1, bias=False)
+
+
+def _conv1x1(cin, cout):
+    return nn.Conv2d(cin, cout, kernel_size=1, stride=1, padding=0, bias=False)
+
+
+def _head(sizes):
+    # Linear layers separated by Identity activations (indices 0, 2, 4, ... hold the Linears)
+    layers = []
+    for i in range(len(sizes) - 1):
+        layers += [nn.Linear(sizes[i], sizes[i + 1]), nn.Identity()]
+    return nn.Sequential(*layers)
+
+
+class _PreActBlock(nn.Module):
+    """Pre-activation residual block (NNetArchitecture.py:36-66, no downsample)."""
+
+    def __init__(self, ch):
+        super().__init__()
+        self.bn1 = nn.BatchNorm2d(ch)
+        self.conv1 = _conv3x3(ch, ch)
+        self.bn2 = nn.BatchNorm2d(ch)
+        self.conv2 = _conv3x3(ch, ch)
+
+    def forward(self, x):
+        out = self.conv1(F.relu(self.bn1(x)))
+        out = self.conv2(F.relu(self.bn2(out)))
+        return out + x
+
+
+class ResNet(nn.Module):
+    def __init__(self, observation_size, action_size, value_size=3, num_channels=32, depth=4,
+                 value_head_channels=16, policy_head_channels=16, value_dense_layers=(512, 64),
+                 policy_dense_layers=(512, 256)):
+        super().__init__()
+        self.channels, self.board_x, self.board_y = observation_size
+        self.action_size = action_size
+        cells = self.board_x * self.board_y
+        self.conv1 = _conv3x3(self.channels, num_channels)
+        self.bn1 = nn.BatchNorm2d(num_channels)
+        self.resnet = nn.Sequential(*[_PreActBlock(num_channels) for _ in range(depth)])
+        self.v_conv = _conv1x1(num_channels, value_head_channels)
+        self.v_bn = nn.BatchNorm2d(value_head_channels)
+        self.v_fc = _head([cells * value_head_channels, *value_dense_layers, value_size])
+        self.pi_conv = _conv1x1(num_channels, policy_head_channels)
+        self.pi_bn = nn.BatchNorm2d(policy_head_channels)
+        self.pi_fc = _head([cells * policy_head_channels, *policy_dense_layers, action_size])
+
+    @classmethod
+    def for_game(cls, game_cls, args):
+        keys = ("num_channels", "depth", "value_head_channels", "policy_head_channels",
+                "value_dense_layers", "policy_dense_layers")
+        kw = {k: args[k] for k in keys if k in args}
+        return cls(tuple(game_cls.observation_size()), game_cls.action_size(),
+                   game_cls.num_players() + int(game_cls.has_draw()), **kw)
+
+    def forward(self, s):
+        s = s.view(-1, self.channels, self.board_x, self.board_y)
+        s = F.relu(self.bn1(self.conv1(s)))
+        s = self.resnet(s)
+        v = self.v_fc(torch.flatten(self.v_bn(self.v_conv(s)), 1))
+        pi = self.pi_fc(torch.flatten(self.pi_bn(self.pi_conv(s)), 1))
+        return F.log_softmax(pi, dim=1), F.log_softmax(v, dim=1)
+
+
+class NNetWrapper:
+    """Inference half of alphazero/NNetWrapper.py (process / predict); training
+    stays with the reference wrapper."""
+
+    def __init__(self, game_cls=None, args=None, nnet=None, cuda=None):
+        self.game_cls, self.args = game_cls, args
+        self.nnet = nnet if nnet is not None else ResNet.for_game(game_cls, args)
+        self.cuda = torch.cuda.is_available() if cuda is None else cuda
+        if self.cuda:
+            self.nnet.cuda()
+
+    def process(self, batch):
+        batch = batch.type(torch.FloatTensor) if not batch.is_cuda else batch.float()
+        if self.cuda and not batch.is_cuda:
+            batch = batch.cuda()
+        self.nnet.eval()
+        with torch.no_grad():
+            pi, v = self.nnet(batch)
+            return torch.exp(pi), torch.exp(v)
+
+
+class LeafEvaluator:
+    """process() captured once as a CUDA graph over fixed device buffers.
+
+    ``obs`` / ``policy`` / ``value`` are (row slices of) the engine's NN I/O
+    tensors; replay() enqueues the whole forward as one graph launch on
+    ``stream``, so the tree kernels of another cohort can run beside it.
+    precision: "fp32" (strict, no TF32 -- the parity setting), "tf32" (what the
+    reference gets from PyTorch's cuDNN default) or "bf16" (autocast)."""
+
+    def __init__(self, nnet, obs, policy, value, precision="tf32", use_graph=True, channels_last=False):
+        self.nnet = nnet.eval()
+        self.obs, self.policy, self.value = obs, policy, value
+        self.precision = precision
+        self.channels_last = channels_last
+        if channels_last:
+            self.nnet.to(memory_format=torch.channels_last)
+        self.graph = None
+        self.stream = torch.cuda.Stream(device=obs.device)
+        if use_graph:
+            self._capture()
+
+    def _forward(self):
+        tf32 = self.precision != "fp32"
+        old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32 and self.precision == "bf16"
+        try:
+            with torch.no_grad():
+                x = self.obs
+                if self.channels_last:
+                    x = x.contiguous(memory_format=torch.channels_last)
+                if self.precision == "bf16":
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        lp, lv = self.nnet(x)
+                    lp, lv = lp.float(), lv.float()
+                else:
+                    lp, lv = self.nnet(x)
+                torch.exp(lp, out=self.policy)
+                torch.exp(lv, out=self.value)
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+    def _capture(self):
+        s = self.stream
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._forward()
+        s.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=s):
+            self._forward()
+        s.synchronize()
+
+    def __call__(self, stream=None):
+        """Enqueue one evaluation on ``stream`` (default: the current stream)."""
+        stream = stream or torch.cuda.current_stream()
+        with torch.cuda.stream(stream):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._forward()

@@ -1,0 +1,231 @@
+"""Host-side mirror of the reference's self-play interface on top of the engine.
+
+``SelfPlayAgent`` keeps the constructor and the generateBatch / processBatch /
+playMoves / run methods of alphazero/SelfPlayAgent.pyx:13-202, so
+Coach.generateSelfPlayAgents / processSelfPlayBatches (Coach.py:291-361) drive
+it unchanged: observation batches still travel through ``batch_tensor``, the
+network's answers through ``policy_tensor`` / ``value_tensor`` (host tensors
+-> host<->device copies every simulation), samples through ``output_queue``
+and finished games through ``result_queue``.  It is a thread instead of a
+process: the B games of the agent live on the GPU.
+
+``DeviceSelfPlay`` is the B200-first driver: the NN reads and writes the
+engine's device buffers in place (CUDA-graphed LeafEvaluator), tree kernels
+and network run on separate streams ordered by CUDA events, optionally with
+the games split into two cohorts so the tree work of one overlaps the
+inference of the other.
+"""
+import threading
+import time
+
+import numpy as np
+import torch
+
+from .engine import SelfPlayEngine, default_temp_scaling, temp_table
+
+
+def game_name(game_cls):
+    """DeviceRules registry: which CUDA rule set implements this Game plugin."""
+    mod = getattr(game_cls, "__module__", "") or ""
+    name = getattr(game_cls, "AZB_GAME", None)
+    if name:
+        return name
+    if "connect4" in mod:
+        return "connect4"
+    if "brandubh" in mod:
+        return "brandubh"
+    raise NotImplementedError(f"no device rules for game plugin {game_cls!r} (module {mod})")
+
+
+def _max_turns(game_cls):
+    fn = getattr(game_cls, "max_turns", None)      # brandubh's plugin lacks it -> GameState default None
+    return fn() if fn else None
+
+
+def engine_kwargs_from_args(game_cls, args, num_games, **over):
+    """args (Coach.DEFAULT_ARGS keys) -> SelfPlayEngine keyword arguments."""
+    g = lambda k, d=None: (args[k] if k in args else d)
+    fn = g("temp_scaling_fn", default_temp_scaling)
+    sims = max(int(g("numMCTSSims", 100) or 0), int(g("numFastSims", 0) or 0), int(g("numWarmupSims", 0) or 0), 1)
+    kw = dict(
+        game=game_name(game_cls), num_games=num_games,
+        cpuct=g("cpuct", 1.25), fpu_reduction=g("fpu_reduction", 0.2),
+        root_noise_frac=g("root_noise_frac", 0.1), root_policy_temp=g("root_policy_temp", 1.1),
+        add_root_noise=g("add_root_noise", True), add_root_temp=g("add_root_temp", True),
+        symmetric_samples=g("symmetricSamples", True), mcts_reset_threshold=g("mctsResetThreshold", None),
+        games_per_iteration=g("gamesPerIteration", 0), max_sims_per_move=sims,
+        temps=temp_table(fn, g("startTemp", 1), _max_turns(game_cls)),
+    )
+    kw.update(over)
+    return kw
+
+
+class FinalState:
+    """What result_queue consumers read from the final game state
+    (alphazero/utils.py:43-44 uses .turns)."""
+
+    def __init__(self, turns, winstate):
+        self.turns = int(turns)
+        self._turns = int(turns)
+        self.winstate = winstate
+
+    def win_state(self):
+        return self.winstate
+
+
+class SelfPlayAgent(threading.Thread):
+    def __init__(self, id, game_cls, ready_queue, batch_ready, batch_tensor, policy_tensor, value_tensor,
+                 output_queue, result_queue, complete_count, games_played, stop_event, pause_event, args,
+                 _is_arena=False, _is_warmup=False, engine=None, device=0, rng="philox", seed=None):
+        super().__init__(daemon=True)
+        if _is_arena:
+            raise NotImplementedError("arena mode is served by the reference agent (SURVEY 8f-1)")
+        self.id = id
+        self.game_cls = game_cls
+        self.ready_queue, self.batch_ready = ready_queue, batch_ready
+        self.batch_tensor, self.policy_tensor, self.value_tensor = batch_tensor, policy_tensor, value_tensor
+        self.batch_size = batch_tensor.shape[0]
+        self.output_queue, self.result_queue = output_queue, result_queue
+        self.complete_count, self.games_played = complete_count, games_played
+        self.stop_event, self.pause_event = stop_event, pause_event
+        self.args = args
+        self._is_arena, self._is_warmup = _is_arena, _is_warmup
+        self.fast = False
+        self._rs = np.random.RandomState(seed)       # the worker's own stream: the fast-move coin
+        if engine is None:
+            engine = SelfPlayEngine(**engine_kwargs_from_args(
+                game_cls, args, self.batch_size, device=device, rng=rng,
+                seed=int(self._rs.randint(0, 2 ** 31 - 1)) if seed is None else seed,
+                game_id_base=id * self.batch_size))
+        self.engine = engine
+        if _is_warmup:
+            # SelfPlayAgent.pyx:48-52: policy = 1/A, value = 1/(P+1) (float32)
+            self.engine.policy.copy_(torch.full((engine.A,), 1 / engine.A).expand(engine.B, engine.A))
+            self.engine.value.copy_(torch.full((3,), 1 / 3).expand(engine.B, 3))
+        self._counted = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _check_pause(self):
+        while self.pause_event.is_set():
+            time.sleep(.1)
+
+    def run(self):
+        try:
+            while not self.stop_event.is_set() and self.games_played.value < self.args.gamesPerIteration:
+                self._check_pause()
+                self.fast = self._rs.random_sample() < self.args.probFastSim
+                sims = self.args.numFastSims if self.fast else self.args.numMCTSSims \
+                    if not self._is_warmup else self.args.numWarmupSims
+                if self._is_warmup:
+                    self.engine.warmup_sims(sims)
+                else:
+                    for _ in range(sims):
+                        if self.stop_event.is_set(): break
+                        self.generateBatch()
+                        if self.stop_event.is_set(): break
+                        self.processBatch()
+                if self.stop_event.is_set(): break
+                self.playMoves()
+            with self.complete_count.get_lock():
+                self.complete_count.value += 1
+            self.output_queue.close()
+            self.output_queue.join_thread()
+        except Exception:
+            import traceback
+            print(traceback.format_exc())
+
+    def generateBatch(self):
+        self._check_pause()
+        self.engine.select()
+        if self._is_warmup:
+            return
+        self.batch_tensor.copy_(self.engine.obs)             # device -> caller's (host) tensor
+        if not self.batch_tensor.is_cuda:
+            self.d2h_bytes += self.batch_tensor.numel() * 4
+        self.ready_queue.put(self.id)
+
+    def processBatch(self):
+        if self._is_warmup:
+            self.engine.expand_backup()           # engine policy/value rows hold the warmup constants
+            return
+        self.batch_ready.wait()
+        self.batch_ready.clear()
+        self.engine.policy.copy_(self.policy_tensor, non_blocking=True)
+        self.engine.value.copy_(self.value_tensor, non_blocking=True)
+        if not self.policy_tensor.is_cuda:
+            self.h2d_bytes += (self.policy_tensor.numel() + self.value_tensor.numel()) * 4
+        self.engine.expand_backup()
+
+    def playMoves(self):
+        self._check_pause()
+        self.engine.play_moves(self.fast)
+        self.engine.check_errors()
+        slot, turns, win = self.engine.drain_results()
+        for i in range(len(slot)):
+            self.result_queue.put((FinalState(turns[i], win[i]), win[i].copy(), self.id))
+        if len(slot):
+            obs, pi, z, _ = self.engine.drain_samples()
+            self.d2h_bytes += obs.nbytes + pi.nbytes + z.nbytes
+            for i in range(len(obs)):
+                self.output_queue.put((obs[i], pi[i], z[i]))
+            played = self.engine.games_played()
+            new = played - self._counted
+            self._counted = played
+            if new:
+                with self.games_played.get_lock():
+                    self.games_played.value += new
+
+
+class DeviceSelfPlay:
+    """Device-resident self-play: select -> CUDA-graphed ResNet -> expand/backup
+    per simulation, tree kernels on ``tree_stream`` and the network on
+    ``nn_stream``; with cohorts == 2 the two halves of the games alternate so
+    that tree work of one half overlaps inference of the other."""
+
+    def __init__(self, engine, nnet, cohorts=1, precision="tf32", use_graph=True, channels_last=False):
+        assert cohorts in (1, 2)
+        self.engine = engine
+        self.cohorts = cohorts
+        B = engine.B
+        bounds = [0, B] if cohorts == 1 else [0, B // 2, B]
+        self.ranges = [(bounds[i], bounds[i + 1] - bounds[i]) for i in range(cohorts)]
+        from .nnet import LeafEvaluator
+        self.evals = [LeafEvaluator(nnet, engine.obs[f:f + c], engine.policy[f:f + c], engine.value[f:f + c],
+                                    precision=precision, use_graph=use_graph, channels_last=channels_last)
+                      for f, c in self.ranges]
+        dev = engine.obs.device
+        self.tree_stream = torch.cuda.Stream(device=dev)
+        self.nn_stream = torch.cuda.Stream(device=dev)
+        self.ev_sel = [torch.cuda.Event() for _ in self.ranges]
+        self.ev_nn = [torch.cuda.Event() for _ in self.ranges]
+        self.launches = 0
+
+    def run_round(self, sims, fast=False):
+        """One move-round: ``sims`` simulations for every game, then playMoves.
+        Asynchronous: returns once everything is enqueued on tree_stream."""
+        eng, T, N = self.engine, self.tree_stream, self.nn_stream
+        cur = torch.cuda.current_stream()
+        T.wait_stream(cur)
+        for s in range(sims):
+            for h, (f, c) in enumerate(self.ranges):
+                if s > 0:
+                    T.wait_event(self.ev_nn[h])
+                    eng.expand_backup(f, c, stream=T)
+                eng.select(f, c, stream=T)
+                self.ev_sel[h].record(T)
+                N.wait_event(self.ev_sel[h])
+                self.evals[h](stream=N)
+                self.ev_nn[h].record(N)
+        for h, (f, c) in enumerate(self.ranges):
+            T.wait_event(self.ev_nn[h])
+            eng.expand_backup(f, c, stream=T)
+        eng.play_moves(fast, stream=T)
+        cur.wait_stream(T)
+        self.launches += sims * len(self.ranges) * 2 + 3
+
+    def run_round_warmup(self, sims, fast=False):
+        """Tree-only round (numWarmupSims): one fused kernel + playMoves."""
+        self.engine.warmup_sims(sims)
+        self.engine.play_moves(fast)
+        self.launches += 4

@@ -313,6 +313,39 @@ __device__ __forceinline__ void select_game(const DevView &d, int g, int lane, u
 }
 
 // ------------------------------------------------------------------------------
+// Device Dirichlet(alpha, ..., alpha) for the root noise when no table is fed
+// (MCTS._add_root_noise, MCTS.pyx:197-206: alpha = 10.83 / C).  Child k draws a
+// Gamma(alpha) variate (Marsaglia-Tsang, boosted for alpha < 1) from a private
+// 64-word window of the slot's Philox stream; the variates are normalised by
+// their sum.  Statistically equivalent to numpy's sampler, not bit-equal to it:
+// parity runs feed the vectors instead (azb_set_root_noise).
+// ------------------------------------------------------------------------------
+__device__ inline float gamma_variate(unsigned long long seed, unsigned long long gid, unsigned long long w0, double alpha)
+{
+    unsigned long long w = w0;
+    auto uni = [&]() {   // (0,1)
+        uint32_t a = philox_word(seed, gid, w), b = philox_word(seed, gid, w + 1);
+        w += 2;
+        return (((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) + 0.5) / 9007199254740992.0;
+    };
+    double boost = 1.0, a = alpha;
+    if (a < 1.0) { boost = pow(uni(), 1.0 / a); a += 1.0; }
+    const double dd = a - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
+    double out = dd;
+    for (int it = 0; it < 12; it++) {
+        double u1 = uni(), u2 = uni();
+        double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);      // Box-Muller normal
+        double vv = 1.0 + cc * x;
+        if (vv <= 0.0) continue;
+        vv = vv * vv * vv;
+        double u = uni();
+        out = dd * vv;
+        if (log(u) < 0.5 * x * x + dd - dd * vv + dd * log(vv)) break;
+    }
+    return (float)(out * boost);
+}
+
+// ------------------------------------------------------------------------------
 // MCTS.process_results
 // ------------------------------------------------------------------------------
 template <class G>
@@ -352,17 +385,41 @@ __device__ __forceinline__ void expand_backup_game(const DevView &d, int g, int 
             }
             __syncwarp(gmask);
             const float *nz = nullptr;
+            bool gen = false;
             if (d.add_noise) {
                 int ev = d.noise_event[g];
-                if (d.noise != nullptr && ev < d.noise_events && C <= d.noise_stride)
-                    nz = d.noise + ((size_t)g * d.noise_events + ev) * d.noise_stride;
-                else if (lane == 0) atomicOr(d.err, ERRB_NOISE);
+                if (d.noise != nullptr) {
+                    if (ev < d.noise_events && C <= d.noise_stride)
+                        nz = d.noise + ((size_t)g * d.noise_events + ev) * d.noise_stride;
+                    else if (lane == 0) atomicOr(d.err, ERRB_NOISE);
+                } else gen = true;
             }
             const float keep = __fsub_rn(1.0f, d.noise_frac);
-            for (int k = lane; k < C; k += L) {
-                float pk = sm.vec[meta_action(d.meta[cb + k])];
-                if (nz != nullptr) pk = f_add(f_mul(pk, keep), f_mul(d.noise_frac, nz[k]));
-                d.p[cb + k] = pk;
+            if (gen) {
+                // sample Dirichlet(10.83 / C) on the device; sm.vec2[k] = gamma variate of child k
+                const unsigned long long c0 = d.ctr[g];
+                __syncwarp(gmask);
+                if (lane == 0) d.ctr[g] = c0 + 64ULL * (unsigned long long)C;
+                float part = 0.0f;
+                for (int k = lane; k < C; k += L) {
+                    float gv = gamma_variate(d.seed, (unsigned long long)(d.gid_base + g), c0 + 64ULL * k, 10.83 / (double)C);
+                    sm.key[k] = __float_as_uint(gv);
+                    part += gv;
+                }
+#pragma unroll
+                for (int off = L / 2; off >= 1; off >>= 1) part += __shfl_xor_sync(gmask, part, off, L);
+                __syncwarp(gmask);
+                for (int k = lane; k < C; k += L) {
+                    float pk = sm.vec[meta_action(d.meta[cb + k])];
+                    float nk = __uint_as_float(sm.key[k]) / part;
+                    d.p[cb + k] = f_add(f_mul(pk, keep), f_mul(d.noise_frac, nk));
+                }
+            } else {
+                for (int k = lane; k < C; k += L) {
+                    float pk = sm.vec[meta_action(d.meta[cb + k])];
+                    if (nz != nullptr) pk = f_add(f_mul(pk, keep), f_mul(d.noise_frac, nz[k]));
+                    d.p[cb + k] = pk;
+                }
             }
             __syncwarp(gmask);
             if (lane == 0) d.noise_event[g] += 1;

@@ -1,0 +1,547 @@
+#!/usr/bin/env python
+"""bench.py -- self-play MCTS simulations/sec, 8192 Connect4 games per B200.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A step is one move-round of the hot path for every game of the rank:
+``sims`` x (select -> ResNet leaf evaluation -> expand/backup) + playMoves
+(BASELINE.json configs[1]: Connect4, 8192 concurrent games, 100 sims/move,
+DEFAULT_ARGS net and MCTS hyper-parameters, root noise + temperature on).
+Rank r owns games [r*8192, (r+1)*8192) -- no data-path collective ("weak").
+
+value     device-resident throughput: NN reads/writes the engine buffers in HBM.
+e2e       same metric through the reference-facing SelfPlayAgent surface with
+          HOST batch/policy/value tensors (Coach.processSelfPlayBatches' loop
+          body), host<->device copies and sample drains inside the timed region.
+roofline  k_select (PUCT scan): algorithmic bytes 16*sumD + 12*sumC from the
+          engine's exact counters / CUDA-event time of the select launches.
+cpu_baseline / --impl reference
+          the reference's own Cython SelfPlayAgent processes (oracle/_ref) served
+          by the reference's ResNet as Coach.processSelfPlayBatches does, on
+          this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "alphazero-general_b200"))
+
+METRIC = "self-play MCTS simulations/sec (8192 Connect4 games)"
+UNIT = "sims/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games", type=int, default=8192)
+    ap.add_argument("--sims", type=int, default=100)
+    ap.add_argument("--net", default="default", choices=["default", "connect4_train"])
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--cohorts", type=int, default=2)
+    ap.add_argument("--preroll", type=int, default=48, help="cheap tree-only rounds that de-synchronise the games")
+    ap.add_argument("--tree-only", action="store_true", help="warmup mode (constant NN outputs), one fused kernel per round")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-select-events", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# reference arm: the reference's own SelfPlayAgent processes + NN server loop
+# --------------------------------------------------------------------------
+def run_reference(games, sims, net, steps, warmup, seconds=None, use_cuda=True):
+    """Times the compiled reference (oracle/_ref).  Workers are the reference's
+    mp.Process agents; this process is the NN server exactly as
+    Coach.processSelfPlayBatches (Coach.py:326-361).  One step = one served
+    batch per worker x 8.  Returns a dict or {'unavailable': why}."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import build_ref
+        if not build_ref.built():
+            return {"unavailable": "oracle/_ref not built (run __graft_entry__.build() where /root/reference exists)"}
+    finally:
+        sys.path.pop(0)
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    import numpy as np  # noqa: F401
+    import torch
+    import torch.multiprocessing as mp
+    from queue import Empty
+    from alphazero.SelfPlayAgent import SelfPlayAgent
+    from alphazero.envs.connect4.connect4 import Game
+    from alphazero.NNetArchitecture import ResNet
+    from alphazero.utils import dotdict, default_temp_scaling
+    from azb200 import nnet as aznet
+
+    cores = os.cpu_count() or 2
+    workers = max(1, min(cores - 1, games))
+    pbs = -(-games // workers)
+    netargs = aznet.DEFAULT_NET_ARGS if net == "default" else aznet.CONNECT4_TRAIN_NET_ARGS
+    args = dotdict(dict(
+        startTemp=1, temp_scaling_fn=default_temp_scaling, root_noise_frac=0.1, root_policy_temp=1.1,
+        min_discount=1, fpu_reduction=0.2, cpuct=1.25, _num_players=2, add_root_noise=True, add_root_temp=True,
+        symmetricSamples=True, mctsResetThreshold=None, gamesPerIteration=1 << 40, numMCTSSims=sims,
+        numFastSims=sims, numWarmupSims=sims, probFastSim=0.0, arenaTemp=0.25, process_batch_size=pbs,
+        workers=workers, **netargs))
+    torch.manual_seed(0)
+    model = ResNet(Game, args)
+    stop, pause = mp.Event(), mp.Event()
+    ready, fileq, resq = mp.Queue(), mp.Queue(), mp.Queue()
+    completed, played = mp.Value('i', 0), mp.Value('i', 0)
+    ins, pols, vals, evs, agents = [], [], [], [], []
+    for i in range(workers):
+        ins.append(torch.zeros([pbs, *Game.observation_size()]).share_memory_())
+        pols.append(torch.zeros([pbs, Game.action_size()]).share_memory_())
+        vals.append(torch.zeros([pbs, 3]).share_memory_())
+        evs.append(mp.Event())
+        ag = SelfPlayAgent(i, Game, ready, evs[i], ins[i], pols[i], vals[i], fileq, resq, completed, played,
+                           stop, pause, args)
+        ag.daemon = True
+        agents.append(ag)
+    for ag in agents:      # fork before this process touches CUDA
+        ag.start()
+    cuda = use_cuda and torch.cuda.is_available()
+    if cuda:
+        model.cuda()
+    model.eval()
+
+    def process(batch):   # NNetWrapper.process (NNetWrapper.py:225-232)
+        batch = batch.type(torch.FloatTensor)
+        if cuda:
+            batch = batch.cuda()
+        with torch.no_grad():
+            pi, v = model(batch)
+            return torch.exp(pi), torch.exp(v)
+
+    served = 0
+
+    def serve(n_batches, deadline=None):
+        nonlocal served
+        done = 0
+        while done < n_batches and (deadline is None or time.time() < deadline):
+            try:
+                i = ready.get(timeout=1)
+            except Empty:
+                continue
+            p, v = process(ins[i])
+            pols[i].copy_(p)
+            vals[i].copy_(v)
+            evs[i].set()
+            done += 1
+            served += 1
+            # keep the queues from filling the pipes
+            for q in (fileq, resq):
+                try:
+                    while True:
+                        q.get_nowait()
+                except Empty:
+                    pass
+        return done
+
+    per_step = workers * 8
+    serve(per_step * max(warmup, 1))
+    t0 = time.time()
+    if seconds is not None:
+        n = serve(1 << 60, deadline=t0 + seconds)
+        nsteps = max(1, n // per_step)
+    else:
+        n = serve(per_step * steps)
+        nsteps = steps
+    if cuda:
+        torch.cuda.synchronize()
+    dt = time.time() - t0
+    stop.set()
+    for e in evs:
+        e.set()
+    t_end = time.time() + 20
+    for ag in agents:
+        for q in (ready, fileq, resq):
+            try:
+                while True:
+                    q.get_nowait()
+            except Empty:
+                pass
+        ag.join(timeout=max(0.1, t_end - time.time()))
+        if ag.is_alive():
+            ag.terminate()
+    total_sims = n * pbs
+    return {"value": total_sims / dt, "seconds": dt, "sims": total_sims, "cores": workers + 1, "workers": workers,
+            "process_batch_size": pbs, "steps": nsteps, "nn_device": "cuda" if cuda else "cpu",
+            "sample": f"{n} NN-served batches of {pbs} games ({total_sims} simulations, {dt:.1f} s) by {workers} "
+                      f"reference SelfPlayAgent processes + 1 NN-server process; ResNet on {'cuda' if cuda else 'cpu'}"}
+
+
+def reference_main(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = run_reference(a.games, a.sims, a.net, a.steps, a.warmup)
+    if "unavailable" in r:
+        print(json.dumps({"impl": "reference", "unavailable": r["unavailable"]}))
+        return
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": r["steps"],
+        "warmup": a.warmup, "ms_per_step": 1000.0 * r["seconds"] / r["steps"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"connect4 {a.games} games x {a.sims} sims/move, net={a.net}, reference Cython "
+                               f"SelfPlayAgent x{r['workers']} workers (batch {r['process_batch_size']})"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_main(a)
+        return
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        # before this process initialises CUDA: the reference agents are forked
+        try:
+            r = run_reference(a.games, a.sims, a.net, 0, 1, seconds=a.cpu_seconds)
+            if "unavailable" not in r:
+                cpu_base = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+                            "sample": r["sample"]}
+            else:
+                cpu_base = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": r["unavailable"]}
+        except Exception as ex:   # the baseline must never take the bench down
+            cpu_base = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex!r}"}
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from azb200 import SelfPlayEngine, default_temp_scaling, temp_table
+    from azb200 import nnet as aznet
+    from azb200.selfplay import DeviceSelfPlay, SelfPlayAgent
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    B, sims = a.games, a.sims
+    eng = SelfPlayEngine(
+        game="connect4", num_games=B, device=local, rng="philox", seed=0, game_id_base=rank * B,
+        cpuct=1.25, fpu_reduction=0.2, root_noise_frac=0.1, root_policy_temp=1.1, add_root_noise=True,
+        add_root_temp=True, symmetric_samples=True, games_per_iteration=0, max_sims_per_move=sims,
+        temps=temp_table(default_temp_scaling, 1, 42))
+    torch.manual_seed(0)
+    netargs = aznet.DEFAULT_NET_ARGS if a.net == "default" else aznet.CONNECT4_TRAIN_NET_ARGS
+    model = aznet.ResNet((4, 6, 7), 7, 3, **netargs).to(dev).eval()
+    drv = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision)
+
+    # cheap tree-only pre-roll so the games are spread over all phases (steady state)
+    for _ in range(a.preroll):
+        eng.warmup_sims(8)
+        eng.play_moves(False)
+    torch.cuda.synchronize()
+
+    sel_events = []
+
+    def step():
+        if a.tree_only:
+            drv.run_round_warmup(sims)
+        else:
+            drv.run_round(sims)
+        # keep the sample ring from filling: discard on the device (no host copy)
+        n = eng.sample_count()
+        if n > (eng_cap // 2):
+            clear_samples()
+
+    eng_cap = 8192 * 4 * 42 * 2
+
+    scratch = {}
+
+    def clear_samples():
+        n = eng.sample_count()
+        if n == 0:
+            return
+        if "obs" not in scratch or scratch["obs"].shape[0] < n:
+            scratch["obs"] = torch.empty(n, 4, 6, 7, device=dev)
+            scratch["pi"] = torch.empty(n, 7, device=dev)
+            scratch["z"] = torch.empty(n, 3, device=dev)
+        eng.drain_samples_into(scratch["obs"], scratch["pi"], scratch["z"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    clear_samples()
+    eng.check_errors()
+    st0 = eng.stats()
+    launches0 = drv.launches
+
+    # optional: CUDA events around every select launch (tree stream) for the roofline
+    if not a.no_select_events and not a.tree_only:
+        orig_select = eng.select
+
+        def timed_select(first=0, count=0, stream=None):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            orig_select(first, count, stream=stream)
+            e1.record(stream)
+            sel_events.append((e0, e1))
+        eng.select = timed_select
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(a.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    if not a.no_select_events and not a.tree_only:
+        eng.select = orig_select
+    st1 = eng.stats()
+    eng.check_errors()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    dsims = st1["sims"] - st0["sims"]
+    tot = torch.tensor([dsims], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    total_sims = float(tot.item())
+    value = total_sims / (ms_max / 1000.0)
+
+    # roofline of the PUCT selection kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
+    dD, dC = st1["sum_depth"] - st0["sum_depth"], st1["sum_children"] - st0["sum_children"]
+    alg_bytes = 16.0 * dD + 12.0 * dC
+    roof = None
+    if sel_events:
+        sel_ms = sum(e0.elapsed_time(e1) for e0, e1 in sel_events)
+        nl = len(sel_events)
+        ach = alg_bytes / (sel_ms / 1000.0) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+                "traffic": None, "kernel": "k_select<Connect4>", "launches": nl, "avg_launch_us": 1000.0 * sel_ms / nl,
+                "alg_bytes_per_launch": alg_bytes / nl, "bytes_per_sim": alg_bytes / max(dsims, 1), "peak_source": peak_src,
+                "note": "CUDA-event time of each select launch on the tree stream (NN runs concurrently on another stream)"}
+    elif a.tree_only:
+        ach = alg_bytes / (ms / 1000.0) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+                "traffic": None, "kernel": "k_warmup_sims<Connect4> (select+expand+backup fused)", "launches": a.steps,
+                "avg_launch_us": 1000.0 * ms / a.steps, "alg_bytes_per_launch": alg_bytes / a.steps,
+                "bytes_per_sim": alg_bytes / max(dsims, 1), "peak_source": peak_src}
+    traffic_file = os.path.join(ROOT, "profiles", "select_traffic.json")
+    if roof is not None and os.path.exists(traffic_file):
+        try:
+            roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # e2e: reference-facing SelfPlayAgent surface with host tensors
+    e2e = None
+    if not a.no_e2e and not a.tree_only:
+        e2e = run_e2e(a, eng, model, dev, world)
+
+    if world > 1:
+        gather_ms, gathered = gather_examples(eng, dev, rank, world)
+    else:
+        gather_ms, gathered = None, None
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if a.precision == "fp32" else a.precision, "data": "synthetic",
+            "config": {"workload": f"connect4 {B} games/GPU x {sims} sims/move, DEFAULT_ARGS MCTS (cpuct 1.25, fpu 0.2, "
+                                   f"root noise 0.1 + temp 1.1), net={a.net} ResNet random-init, "
+                                   f"{'tree-only warmup mode' if a.tree_only else 'NN in the loop'}",
+                       "games_per_gpu": B, "sims_per_move": sims, "net": a.net, "nn_precision": a.precision,
+                       "cohorts": a.cohorts, "rng": "philox", "parallelism": f"games x{world} (no data-path collective)",
+                       "l2": "node pool %.1f GB per GPU > 126 MB L2; no flush" % (st1["pool_bytes"] / 1e9),
+                       "preroll_rounds": a.preroll},
+            "clocks": clk, "gpu_launches": drv.launches - launches0,
+            "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e,
+            "tree_stats": {"sims": dsims, "mean_depth": dD / max(dsims, 1), "mean_children_scanned": dC / max(dsims, 1),
+                           "games_finished": st1["results"] - st0["results"], "peak_nodes_per_game": st1["peak_nodes"]},
+        }
+        if gather_ms is not None:
+            line["example_gather"] = {"ms": gather_ms, "samples": gathered}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(a, eng, model, dev, world):
+    """The loop body of Coach.processSelfPlayBatches (Coach.py:337-342) around the
+    reference-shaped SelfPlayAgent with pinned HOST tensors."""
+    import torch
+    import torch.distributed as dist
+    from azb200.nnet import NNetWrapper
+    from azb200.selfplay import SelfPlayAgent
+
+    class _Q:
+        def __init__(self): self.n = 0
+        def put(self, x): self.n += 1
+        def close(self): pass
+        def join_thread(self): pass
+
+    class _Ev:
+        def is_set(self): return False
+        def wait(self): pass
+        def clear(self): pass
+        def set(self): pass
+
+    class _Val:
+        def __init__(self): self.value = 0
+        def get_lock(self): return threading.Lock()
+
+    class _Game:
+        __module__ = "alphazero.envs.connect4.connect4"
+    B = eng.B
+    bt = torch.zeros(B, 4, 6, 7).pin_memory()
+    pt = torch.zeros(B, 7).pin_memory()
+    vt = torch.zeros(B, 3).pin_memory()
+    args = {"gamesPerIteration": 1 << 40, "probFastSim": 0.0, "numMCTSSims": a.sims, "numFastSims": a.sims}
+    ag = SelfPlayAgent(0, _Game, _Q(), _Ev(), bt, pt, vt, _Q(), _Q(), _Val(), _Val(), _Ev(), _Ev(), args, engine=eng)
+    wrap = NNetWrapper(nnet=model, cuda=True)
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = a.precision != "fp32"
+
+    def round_():
+        for _ in range(a.sims):
+            ag.generateBatch()
+            policy, value = wrap.process(bt)
+            pt.copy_(policy)
+            vt.copy_(value)
+            ag.processBatch()
+        ag.playMoves()
+
+    round_()
+    ag.h2d_bytes = ag.d2h_bytes = 0
+    s0 = eng.stats()["sims"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.e2e_steps):
+        round_()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    torch.backends.cudnn.allow_tf32 = old_tf32
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    n = torch.tensor([eng.stats()["sims"] - s0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    obs_b, pv_b = B * 4 * 6 * 7 * 4, B * 10 * 4
+    steps = a.e2e_steps
+    return {"value": float(n.item()) / float(t.item()), "unit": UNIT,
+            # per step: nnet.process uploads the observation batch, processBatch uploads policy/value
+            "h2d_bytes_per_step": a.sims * obs_b + ag.h2d_bytes // steps,
+            # per step: generateBatch downloads observations, the NN answers go to host tensors, samples are drained
+            "d2h_bytes_per_step": a.sims * pv_b + ag.d2h_bytes // steps,
+            "steps": steps, "api": "azb200.selfplay.SelfPlayAgent.generateBatch/processBatch/playMoves + NNetWrapper.process, pinned host tensors"}
+
+
+def gather_examples(eng, dev, rank, world):
+    """BASELINE config 3: NCCL gather of the (s, pi, z) examples to rank 0."""
+    import torch
+    import torch.distributed as dist
+    from azb200.distributed import gather_examples_to_rank0
+    n = eng.sample_count()
+    obs = torch.empty(n, 4, 6, 7, device=dev); pi = torch.empty(n, 7, device=dev); z = torch.empty(n, 3, device=dev)
+    eng.drain_samples_into(obs, pi, z)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = gather_examples_to_rank0(obs, pi, z)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()), (int(out[0].shape[0]) if rank == 0 else None)
+
+
+if __name__ == "__main__":
+    main()
