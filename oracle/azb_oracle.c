@@ -329,6 +329,9 @@ static void find_leaf(orc_agent *ag, slot_t *s)
         ag->ops->win_state(&s->leaf, s->cur->e);
         ag->ops->valid_moves(&s->leaf, valid);
         add_children(ag, s, s->cur, valid);
+        /* children of a terminal leaf are never used; the engine does not
+         * materialise them, so they are left out of the statistic */
+        if (node_terminal(s->cur)) ag->st.nodes_created -= s->cur->nchildren;
     }
     if (node_terminal(s->cur)) ag->st.terminal_leaves++;
 }

@@ -319,7 +319,8 @@ class RefAgent:
         rows = []
 
         def rec(nd, d):
-            rows.append((d, nd.a, nd.n, nd.q, nd.v, nd.p, nd.player, *[int(x) for x in nd.e]))
+            e = [int(x) for x in nd.e] + [0, 0, 0]   # unvisited nodes carry a 2-entry e (MCTS.pyx:62)
+            rows.append((d, nd.a, nd.n, nd.q, nd.v, nd.p, nd.player, *e[:3]))
             for c in nd._children:
                 if len(rows) < max_nodes:
                     rec(c, d + 1)
