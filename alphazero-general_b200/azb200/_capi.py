@@ -24,6 +24,7 @@ class AzbConfig(C.Structure):
         ("rng_mode", C.c_int32), ("add_root_noise", C.c_int32), ("add_root_temp", C.c_int32),
         ("symmetric_samples", C.c_int32), ("mcts_reset_threshold", C.c_int32),
         ("max_sims_per_move", C.c_int32), ("max_nodes_per_game", C.c_int32), ("temp_table_len", C.c_int32),
+        ("lanes_per_game", C.c_int32), ("reserved0", C.c_int32),
         ("games_per_iteration", C.c_int64), ("sample_capacity", C.c_int64), ("game_id_base", C.c_int64),
         ("seed", C.c_uint64),
         ("cpuct", C.c_float), ("fpu_reduction", C.c_float), ("root_noise_frac", C.c_float),

@@ -47,7 +47,7 @@ class SelfPlayEngine:
                  game_id_base=0, cpuct=1.25, fpu_reduction=0.2, root_noise_frac=0.1, root_policy_temp=1.1,
                  add_root_noise=False, add_root_temp=False, symmetric_samples=True,
                  mcts_reset_threshold=None, games_per_iteration=0, max_sims_per_move=100,
-                 max_nodes_per_game=0, sample_capacity=0, temps=None):
+                 max_nodes_per_game=0, sample_capacity=0, temps=None, lanes_per_game=0):
         self.lib = _capi.load()
         self.h = C.c_void_p()
         cfg = AzbConfig()
@@ -61,6 +61,7 @@ class SelfPlayEngine:
         cfg.max_sims_per_move, cfg.max_nodes_per_game = int(max_sims_per_move), int(max_nodes_per_game)
         cfg.games_per_iteration, cfg.sample_capacity = int(games_per_iteration or 0), int(sample_capacity)
         cfg.game_id_base, cfg.seed = int(game_id_base), int(seed)
+        cfg.lanes_per_game = int(lanes_per_game)
         cfg.cpuct, cfg.fpu_reduction = float(cpuct), float(fpu_reduction)
         cfg.root_noise_frac, cfg.root_policy_temp = float(root_noise_frac), float(root_policy_temp)
         if temps is not None:

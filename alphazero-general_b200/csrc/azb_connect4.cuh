@@ -13,7 +13,8 @@
 
 namespace azb {
 
-struct Connect4 {
+template <int LANES_>
+struct Connect4T {
     static constexpr int A = 7;            // Game.action_size()
     static constexpr int H = 6, W = 7;
     static constexpr int OBS_C = 4;
@@ -23,7 +24,7 @@ struct Connect4 {
     static constexpr int MAX_TURNS = 42;   // Game.max_turns()
     static constexpr int MAXD = 44;        // path buffer entries per slot
     static constexpr int NSYM = 2;         // symmetries(): identity, mirror
-    static constexpr int LANES = 8;        // threads cooperating on one game
+    static constexpr int LANES = LANES_;   // threads cooperating on one game (8, 16 or 32)
     static constexpr unsigned long long TOP = 0x0810204081020ULL;  // bits col*7+5
 
     __device__ __forceinline__ static void init(GState &s) { s.b0 = s.b1 = s.b2 = 0ULL; s.turns = 0; s.flags = 0; }
@@ -118,5 +119,6 @@ struct Connect4 {
     }
     __device__ __forceinline__ static int sym_action(int k, int a) { return k == 1 ? (A - 1 - a) : a; }
 };
+using Connect4 = Connect4T<8>;
 
 }  // namespace azb

@@ -57,6 +57,7 @@ struct azb_engine {
     std::vector<float> temp_host;
     float *noise_dev = nullptr;
     long long device_bytes = 0, pool_bytes = 0;
+    int lanes = 8;                  // threads per game (Connect4: 8 / 16 / 32)
     int *scratch_i32 = nullptr;     // B * A ints for introspection
     int8_t *scratch_i8 = nullptr;
 };
@@ -113,10 +114,14 @@ template <class G> static void l_boards(azb_engine *e, cudaStream_t s)
     k_boards<G><<<(e->d.B + 127) / 128, 128, 0, s>>>(e->d, e->scratch_i8);
 }
 
+#define DISPATCH_C4(e, fn, ...) do { \
+        if ((e)->lanes == 32) fn<Connect4T<32>>(__VA_ARGS__); \
+        else if ((e)->lanes == 16) fn<Connect4T<16>>(__VA_ARGS__); \
+        else fn<Connect4T<8>>(__VA_ARGS__); } while (0)
 #ifdef AZB_HAVE_BRANDUBH
-#define DISPATCH(e, fn, ...) do { if ((e)->cfg.game == AZB_GAME_CONNECT4) fn<Connect4>(__VA_ARGS__); else fn<Brandubh>(__VA_ARGS__); } while (0)
+#define DISPATCH(e, fn, ...) do { if ((e)->cfg.game == AZB_GAME_CONNECT4) DISPATCH_C4(e, fn, __VA_ARGS__); else fn<Brandubh>(__VA_ARGS__); } while (0)
 #else
-#define DISPATCH(e, fn, ...) do { fn<Connect4>(__VA_ARGS__); } while (0)
+#define DISPATCH(e, fn, ...) DISPATCH_C4(e, fn, __VA_ARGS__)
 #endif
 
 static int init_slots(azb_engine *e, const uint32_t *mt_seeds_host)
@@ -166,6 +171,12 @@ extern "C" int azb_create(const azb_config *cfg, azb_engine **out)
     e->cfg.temp_table = nullptr;
     e->cfg.mt_seeds = nullptr;
     e->gd = gd;
+    if (cfg->game == AZB_GAME_CONNECT4) {
+        const char *env = getenv("AZB_C4_LANES");
+        int l = cfg->lanes_per_game > 0 ? cfg->lanes_per_game : (env ? atoi(env) : 8);
+        if (l != 8 && l != 16 && l != 32) { delete e; return fail(AZB_ERR_BAD_CONFIG, "lanes_per_game must be 8, 16 or 32"); }
+        e->lanes = l;
+    } else e->lanes = gd.lanes;
     DevView &d = e->d;
     memset(&d, 0, sizeof(d));
     const int B = cfg->num_games;

@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--net", default="default", choices=["default", "connect4_train"])
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--cohorts", type=int, default=2)
+    ap.add_argument("--lanes", type=int, default=0, help="threads per game (0 = library default)")
+    ap.add_argument("--nchw", action="store_true", help="keep the ResNet in NCHW (default: channels_last)")
     ap.add_argument("--preroll", type=int, default=48, help="cheap tree-only rounds that de-synchronise the games")
     ap.add_argument("--tree-only", action="store_true", help="warmup mode (constant NN outputs), one fused kernel per round")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -295,11 +297,11 @@ def main():
         game="connect4", num_games=B, device=local, rng="philox", seed=0, game_id_base=rank * B,
         cpuct=1.25, fpu_reduction=0.2, root_noise_frac=0.1, root_policy_temp=1.1, add_root_noise=True,
         add_root_temp=True, symmetric_samples=True, games_per_iteration=0, max_sims_per_move=sims,
-        temps=temp_table(default_temp_scaling, 1, 42))
+        temps=temp_table(default_temp_scaling, 1, 42), lanes_per_game=a.lanes)
     torch.manual_seed(0)
     netargs = aznet.DEFAULT_NET_ARGS if a.net == "default" else aznet.CONNECT4_TRAIN_NET_ARGS
     model = aznet.ResNet((4, 6, 7), 7, 3, **netargs).to(dev).eval()
-    drv = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision)
+    drv = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision, channels_last=not a.nchw)
 
     # cheap tree-only pre-roll so the games are spread over all phases (steady state)
     for _ in range(a.preroll):
@@ -436,7 +438,7 @@ def main():
                                    f"root noise 0.1 + temp 1.1), net={a.net} ResNet random-init, "
                                    f"{'tree-only warmup mode' if a.tree_only else 'NN in the loop'}",
                        "games_per_gpu": B, "sims_per_move": sims, "net": a.net, "nn_precision": a.precision,
-                       "cohorts": a.cohorts, "rng": "philox", "parallelism": f"games x{world} (no data-path collective)",
+                       "cohorts": a.cohorts, "channels_last": not a.nchw, "lanes_per_game": a.lanes or 8, "rng": "philox", "parallelism": f"games x{world} (no data-path collective)",
                        "l2": "node pool %.1f GB per GPU > 126 MB L2; no flush" % (st1["pool_bytes"] / 1e9),
                        "preroll_rounds": a.preroll},
             "clocks": clk, "gpu_launches": drv.launches - launches0,

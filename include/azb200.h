@@ -67,6 +67,9 @@ typedef struct azb_config {
                                   /* sizes the per-slot node pool when max_nodes_per_game=0*/
     int32_t max_nodes_per_game;   /* node-pool entries per slot (0 = derive)               */
     int32_t temp_table_len;       /* entries of temp_table (0 = constant 1.0)              */
+    int32_t lanes_per_game;       /* threads cooperating on one game: 0 = default, Connect4 */
+                                  /* accepts 8, 16, 32 (tuning knob, results are identical) */
+    int32_t reserved0;
     int64_t games_per_iteration;  /* args.gamesPerIteration (quota of counted games)       */
     int64_t sample_capacity;      /* sample ring entries (0 = derive from the quota)       */
     int64_t game_id_base;         /* global id of slot 0 (multi-GPU: rank * num_games)     */

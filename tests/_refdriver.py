@@ -327,3 +327,7 @@ class RefAgent:
 
         rec(self.agents[slot].mcts[0]._root, 0)
         return np.asarray(rows, dtype=np.float64)
+
+    def stats(self):
+        return {"games_played": int(self.games_played.value), "samples": len(self.sample_order),
+                "results": len(self.result_order)}

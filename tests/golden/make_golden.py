@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Generates the golden traces under tests/golden/ by running the COMPILED
+REFERENCE (oracle/_ref, built by oracle/build_ref.py from /root/reference).
+Run in the build container only:  python tests/golden/make_golden.py
+
+Each .npz holds, for B game slots driven in lock-step through the reference's
+own SelfPlayAgent.generateBatch / processBatch / playMoves:
+  counts  [rounds, B, A]  MCTS.counts before every move
+  actions [rounds, B]     sampled actions
+  turns   [rounds, B]     Game.turns after the move
+  s_obs / s_pi / s_z / s_slot   the output_queue in emission order
+  r_slot / r_turns / r_win      the result_queue
+plus the configuration needed to replay it (seeds, sims, flags, noise table).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import _refdriver  # noqa: E402
+from _fakenn import FakeNN  # noqa: E402
+from _lockstep import run_trace  # noqa: E402
+
+CASES = {
+    # unmodified reference: no root temperature, no noise, warmup constants
+    "c4_warmup_unmodified": dict(game="connect4", B=3, seeds=[11, 12, 13], rounds=50, sims=25, nn=None,
+                                 add_root_temp=False, add_root_noise=False, det_pow=False),
+    # fake NN, root temperature with the deterministic pow, fed Dirichlet noise
+    "c4_nn_temp_noise": dict(game="connect4", B=4, seeds=[21, 22, 23, 24], rounds=45, sims=30, nn=1234,
+                             add_root_temp=True, add_root_noise=True, det_pow=True),
+    # fast moves interleaved, no symmetries, tree reset threshold, quota
+    "c4_nn_fast_quota": dict(game="connect4", B=4, seeds=[31, 32, 33, 34], rounds=200, sims=10, nn=77,
+                             add_root_temp=True, add_root_noise=False, det_pow=True, symmetric=False,
+                             reset_threshold=5, quota=6, fast_pattern=[0, 1, 1, 0, 1]),
+}
+GAME_DIMS = {"connect4": (4 * 6 * 7, 7), "brandubh": (5 * 7 * 7, 588)}
+
+
+def make(name, c):
+    obs_size, A = GAME_DIMS[c["game"]]
+    noise = None
+    if c.get("add_root_noise"):
+        rs = np.random.RandomState(1000 + len(name))
+        noise = rs.dirichlet([10.83 / 7] * 7, size=(c["B"], 24)).astype(np.float32)
+        if A > 7:
+            noise = rs.dirichlet([10.83 / 40] * 96, size=(c["B"], 8)).astype(np.float32)
+    ref = _refdriver.RefAgent(c["game"], c["B"], mt_seeds=c["seeds"], add_root_temp=c["add_root_temp"],
+                              add_root_noise=c.get("add_root_noise", False), det_pow=c["det_pow"], noise=noise,
+                              symmetric_samples=c.get("symmetric", True),
+                              mcts_reset_threshold=c.get("reset_threshold"),
+                              games_per_iteration=c.get("quota", 1 << 40))
+    nn = FakeNN(obs_size, A, seed=c["nn"]) if c["nn"] is not None else None
+    tr = run_trace(ref, nn, c["rounds"], c["sims"], fast_pattern=c.get("fast_pattern"), until_games=c.get("quota"))
+    s_obs, s_pi, s_z, s_slot = ref.samples()
+    r_slot, r_turns, r_win = ref.results()
+    out = dict(counts=np.stack([t["counts"] for t in tr]), actions=np.stack([t["actions"] for t in tr]),
+               turns=np.stack([t["turns"] for t in tr]), s_obs=s_obs.astype(np.float16 if False else np.float32),
+               s_pi=s_pi, s_z=s_z, s_slot=s_slot, r_slot=r_slot, r_turns=r_turns, r_win=r_win,
+               seeds=np.asarray(c["seeds"]), sims=c["sims"], nn_seed=-1 if c["nn"] is None else c["nn"],
+               add_root_temp=c["add_root_temp"], add_root_noise=c.get("add_root_noise", False),
+               symmetric=c.get("symmetric", True), reset_threshold=c.get("reset_threshold") or 0,
+               quota=c.get("quota", 0), fast_pattern=np.asarray(c.get("fast_pattern", [0])),
+               noise=noise if noise is not None else np.zeros((0, 0, 0), np.float32), game=c["game"])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "rounds", len(tr), "samples", len(s_obs), "results", len(r_slot))
+
+
+if __name__ == "__main__":
+    assert _refdriver.available(), "build oracle/_ref first (python oracle/build_ref.py)"
+    only = sys.argv[1:]
+    for name, c in CASES.items():
+        if not only or name in only:
+            make(name, c)

@@ -1,0 +1,37 @@
+"""The C oracle against the compiled reference itself (oracle/_ref), live.
+Skipped where oracle/_ref has not been built (it needs /root/reference)."""
+import numpy as np
+import pytest
+
+import _orc
+import _refdriver
+from _fakenn import FakeNN
+from _lockstep import assert_queues_equal, assert_traces_equal, run_trace
+
+pytestmark = pytest.mark.skipif(not _refdriver.available(), reason="oracle/_ref not built")
+TEMPS = _orc.temp_table(_orc.default_temp_scaling, 1, 42)
+
+
+@pytest.mark.parametrize("mode,root_temp", [("warmup", False), ("nn", False), ("nn", True)])
+def test_connect4_oracle_equals_reference(mode, root_temp):
+    B, seeds = 3, [5, 6, 7]
+    nn = FakeNN(4 * 6 * 7, 7, seed=42) if mode == "nn" else None
+    # root_temp=False runs the UNMODIFIED reference; True needs the deterministic-pow patch
+    ref = _refdriver.RefAgent("connect4", B, mt_seeds=seeds, add_root_temp=root_temp, det_pow=root_temp)
+    orc = _orc.OracleAgent(_orc.GAME_CONNECT4, B, mt_seeds=seeds, add_root_temp=root_temp, temps=TEMPS)
+    assert_traces_equal(run_trace(ref, nn, 48, 16, keep_obs=True), run_trace(orc, nn, 48, 16, keep_obs=True), mode)
+    assert_queues_equal(ref, orc, mode)
+    assert len(ref.results()[0]) > 0
+
+
+def test_connect4_oracle_equals_reference_with_fed_noise_and_reset():
+    B, seeds = 2, [8, 9]
+    noise = np.random.RandomState(3).dirichlet([10.83 / 7] * 7, size=(B, 40)).astype(np.float32)
+    nn = FakeNN(4 * 6 * 7, 7, seed=43)
+    ref = _refdriver.RefAgent("connect4", B, mt_seeds=seeds, add_root_temp=True, add_root_noise=True,
+                              det_pow=True, noise=noise, mcts_reset_threshold=4)
+    orc = _orc.OracleAgent(_orc.GAME_CONNECT4, B, mt_seeds=seeds, add_root_temp=True, add_root_noise=True,
+                           temps=TEMPS, mcts_reset_threshold=4)
+    orc.set_root_noise(noise)
+    assert_traces_equal(run_trace(ref, nn, 40, 12), run_trace(orc, nn, 40, 12), "noise+reset")
+    assert_queues_equal(ref, orc, "noise+reset")
