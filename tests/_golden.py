@@ -36,7 +36,7 @@ def replay(agent, g):
     obs_size, A, _ = DIMS[game]
     if bool(g["add_root_noise"]):
         agent.set_root_noise(g["noise"])
-    nn = FakeNN(obs_size, A, seed=int(g["nn_seed"])) if int(g["nn_seed"]) >= 0 else None
+    nn = FakeNN(obs_size, A, seed=int(g["nn_seed"]), sharp=3.0 if A == 7 else 1.0) if int(g["nn_seed"]) >= 0 else None
     pat = g["fast_pattern"].tolist()
     return run_trace(agent, nn, len(g["counts"]), int(g["sims"]), fast_pattern=pat if any(pat) else None,
                      until_games=int(g["quota"]) or None)

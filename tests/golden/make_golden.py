@@ -34,6 +34,11 @@ CASES = {
     "c4_nn_fast_quota": dict(game="connect4", B=4, seeds=[31, 32, 33, 34], rounds=200, sims=10, nn=77,
                              add_root_temp=True, add_root_noise=False, det_pow=True, symmetric=False,
                              reset_threshold=5, quota=6, fast_pattern=[0, 1, 1, 0, 1]),
+    # brandubh: unmodified reference (warmup constants), 8-fold symmetric samples, draw at 100 plies
+    "tafl_warmup_unmodified": dict(game="brandubh", B=2, seeds=[41, 42], rounds=110, sims=12, nn=None,
+                                   add_root_temp=False, add_root_noise=False, det_pow=False),
+    "tafl_nn_temp_noise": dict(game="brandubh", B=2, seeds=[51, 52], rounds=60, sims=20, nn=99,
+                               add_root_temp=True, add_root_noise=True, det_pow=True),
 }
 GAME_DIMS = {"connect4": (4 * 6 * 7, 7), "brandubh": (5 * 7 * 7, 588)}
 
@@ -51,7 +56,7 @@ def make(name, c):
                               symmetric_samples=c.get("symmetric", True),
                               mcts_reset_threshold=c.get("reset_threshold"),
                               games_per_iteration=c.get("quota", 1 << 40))
-    nn = FakeNN(obs_size, A, seed=c["nn"]) if c["nn"] is not None else None
+    nn = FakeNN(obs_size, A, seed=c["nn"], sharp=3.0 if A == 7 else 1.0) if c["nn"] is not None else None
     tr = run_trace(ref, nn, c["rounds"], c["sims"], fast_pattern=c.get("fast_pattern"), until_games=c.get("quota"))
     s_obs, s_pi, s_z, s_slot = ref.samples()
     r_slot, r_turns, r_win = ref.results()

@@ -109,3 +109,50 @@ def test_tree_dump_matches_oracle_reference_values():
         a = np.asarray(keep)
         assert a.shape == b.shape, (a.shape, b.shape)
         assert np.array_equal(a.astype(np.float32), b.astype(np.float32))
+
+
+TAFL_TEMPS = _orc.temp_table(_orc.default_temp_scaling, 1, None)
+
+
+def _tafl_pair(B, rng, noise=None, **kw):
+    from _engine_agent import EngineAgent
+    okw = {k: v for k, v in kw.items() if k not in ("max_sims_per_move", "max_nodes_per_game")}
+    if rng == "mt19937":
+        seeds = list(range(200, 200 + B))
+        orc = _orc.OracleAgent(_orc.GAME_BRANDUBH, B, rng_mode=_orc.RNG_MT19937, mt_seeds=seeds, **okw)
+        eng = EngineAgent("brandubh", B, rng="mt19937", mt_seeds=seeds, **kw)
+    else:
+        orc = _orc.OracleAgent(_orc.GAME_BRANDUBH, B, rng_mode=_orc.RNG_PHILOX, seed=9, game_id_base=3, **okw)
+        eng = EngineAgent("brandubh", B, rng="philox", seed=9, game_id_base=3, **kw)
+    if noise is not None:
+        orc.set_root_noise(noise)
+        eng.set_root_noise(noise)
+    return orc, eng
+
+
+@pytest.mark.parametrize("rng", ["mt19937", "philox"])
+@pytest.mark.parametrize("mode", ["warmup", "nn"])
+def test_brandubh_selfplay_bit_exact(rng, mode):
+    B, rounds, sims = 6, 120, 16
+    nn = FakeNN(5 * 7 * 7, 588, seed=21, sharp=1.0) if mode == "nn" else None
+    orc, eng = _tafl_pair(B, rng, temps=TAFL_TEMPS, add_root_temp=True, max_sims_per_move=sims)
+    to = run_trace(orc, nn, rounds, sims, keep_obs=True)
+    te = run_trace(eng, nn, rounds, sims, keep_obs=True)
+    assert_traces_equal(to, te, f"tafl {rng}/{mode}")
+    assert_queues_equal(orc, eng, f"tafl {rng}/{mode}")
+    so, se = orc.stats(), eng.stats()
+    for k in ("sims", "sum_depth", "sum_children", "nodes_created", "terminal_leaves", "games_played",
+              "results", "samples", "moves"):
+        assert so[k] == se[k], (k, so[k], se[k])
+    assert so["games_played"] > 0 and so["samples"] > 0
+    assert np.array_equal(orc.boards(), eng.boards())
+
+
+def test_brandubh_root_noise_deep_search():
+    B, rounds, sims = 3, 12, 150
+    noise = np.random.RandomState(8).dirichlet([10.83 / 40] * 96, size=(B, 4)).astype(np.float32)
+    nn = FakeNN(5 * 7 * 7, 588, seed=22, sharp=2.0)
+    orc, eng = _tafl_pair(B, "mt19937", noise=noise, temps=TAFL_TEMPS, add_root_temp=True, add_root_noise=True,
+                          max_sims_per_move=sims)
+    assert_traces_equal(run_trace(orc, nn, rounds, sims), run_trace(eng, nn, rounds, sims), "tafl noise")
+    assert np.array_equal(orc.boards(), eng.boards())

@@ -35,3 +35,14 @@ def test_connect4_oracle_equals_reference_with_fed_noise_and_reset():
     orc.set_root_noise(noise)
     assert_traces_equal(run_trace(ref, nn, 40, 12), run_trace(orc, nn, 40, 12), "noise+reset")
     assert_queues_equal(ref, orc, "noise+reset")
+
+
+@pytest.mark.parametrize("mode,root_temp", [("warmup", False), ("nn", True)])
+def test_brandubh_oracle_equals_reference(mode, root_temp):
+    B, seeds = 2, [3, 4]
+    temps = _orc.temp_table(_orc.default_temp_scaling, 1, None)
+    nn = FakeNN(5 * 7 * 7, 588, seed=5, sharp=1.0) if mode == "nn" else None
+    ref = _refdriver.RefAgent("brandubh", B, mt_seeds=seeds, add_root_temp=root_temp, det_pow=root_temp)
+    orc = _orc.OracleAgent(_orc.GAME_BRANDUBH, B, mt_seeds=seeds, add_root_temp=root_temp, temps=temps)
+    assert_traces_equal(run_trace(ref, nn, 70, 10, keep_obs=True), run_trace(orc, nn, 70, 10, keep_obs=True), mode)
+    assert_queues_equal(ref, orc, mode)
