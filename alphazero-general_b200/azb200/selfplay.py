@@ -129,8 +129,8 @@ class SelfPlayAgent(threading.Thread):
                 self.playMoves()
             with self.complete_count.get_lock():
                 self.complete_count.value += 1
-            self.output_queue.close()
-            self.output_queue.join_thread()
+            # the reference closes its process-local end of output_queue here; a thread shares the
+            # queue object with the consumer, so it is left open
         except Exception:
             import traceback
             print(traceback.format_exc())

@@ -173,8 +173,10 @@ struct Brandubh {
     }
 
     // Game.valid_moves: legal actions of the side to move, ascending, into act[]
-    __device__ __forceinline__ static int list_valid(const GState &s, short *act, int lane, unsigned gmask)
+    __device__ __forceinline__ static int list_valid(const GState &s, short *act, uint32_t &vmask, bool on, int lane)
     {
+        vmask = 0u;
+        if (!on) return 0;                      // one game per warp: uniform
         const unsigned long long occ = s.b0 | s.b1 | s.b2;
         const unsigned long long mine = (s.turns & 1) ? (s.b0 | s.b2) : s.b1;
         const int total = __popcll(mine) * 12;
@@ -200,23 +202,27 @@ struct Brandubh {
                 ok = dest_ok && !(between & occ);
                 action = 12 * sq + mt;
             }
-            const unsigned bal = __ballot_sync(gmask, ok);
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
             if (ok) act[count + __popc(bal & ((1u << lane) - 1u))] = (short)action;
             count += __popc(bal);
         }
-        __syncwarp(gmask);
+        __syncwarp();
         return count;
     }
+    __device__ __forceinline__ static int nth_valid(const short *act, uint32_t vmask, int j) { return (int)act[j]; }
 
     // _add_obs: [code 2, code 1, king, full(player), full(num_turns / 100 as C int division)]
-    __device__ __forceinline__ static float obs_value(const GState &s, int i)
+    __device__ __forceinline__ static void write_obs(const GState &s, float *out, int lane)
     {
-        const int plane = i / CELLS, cell = i - plane * CELLS;
-        if (plane == 0) return (float)((s.b1 >> cell) & 1ULL);
-        if (plane == 1) return (float)((s.b0 >> cell) & 1ULL);
-        if (plane == 2) return (float)((s.b2 >> cell) & 1ULL);
-        if (plane == 3) return (float)(s.turns & 1);
-        return (float)(s.turns / MAX_TURNS);
+        const float pl = (float)(s.turns & 1);
+        const float tn = (float)(s.turns / MAX_TURNS);
+        for (int c = lane; c < CELLS; c += LANES) {
+            out[c] = (float)((s.b1 >> c) & 1ULL);
+            out[CELLS + c] = (float)((s.b0 >> c) & 1ULL);
+            out[2 * CELLS + c] = (float)((s.b2 >> c) & 1ULL);
+            out[3 * CELLS + c] = pl;
+            out[4 * CELLS + c] = tn;
+        }
     }
 
     // np.rot90 (counter-clockwise) `rot` times then optional fliplr: output cell

@@ -2,18 +2,18 @@
 // helpers whose rounding must match the reference bit for bit.
 //
 // Layout in HBM (one engine = B game slots, NPG node entries per slot):
-//   node pool, struct-of-arrays, entry index = slot * NPG + local id
-//     n      int32   visit count                      (Node.n,  MCTS.pyx:55)
-//     q      float   running-mean value               (Node.q,  MCTS.pyx:53)
-//     p      float   prior                            (Node.p,  MCTS.pyx:56)
-//     v      float   first-visit value                (Node.v,  MCTS.pyx:54)
-//     child0 int32   local id of the first child; the C children of a node are
-//                    contiguous, in the reference's shuffled list order
-//                    (Node._children, MCTS.pyx:50,76-79)
-//     meta   uint32  action:10 | nchild:8 | e:2 | player:1
-//                    (Node.a, len(_children), Node.e as a code, Node.player)
-//   per-slot state: packed game bitboards, root id, bump allocator, path
-//   buffer, RNG stream, move history, flags.
+//   node pool, two parallel arrays, entry index = slot * NPG + local id
+//     hot  (16 B)  n int32, q float, p float, child0 int32     -- what the PUCT
+//                  scan reads for every sibling (Node.n/.q/.p, MCTS.pyx:53-56)
+//                  plus the link to the node's own children
+//     cold ( 8 B)  v float, meta uint32 (action:10 | nchild:8 | e:2 | player:1)
+//                  -- read only for the chosen child (Node.v/.a/.e/.player)
+//     The C children of a node are contiguous, in the reference's shuffled
+//     list order (Node._children, MCTS.pyx:50,76-79): one level of the scan is
+//     one coalesced 16*C-byte read.
+//   slot header (64 B, one cache-line half): packed game bitboards + the root's
+//     own fields + allocator, so a simulation starts with a single load.
+//   per slot besides: leaf record, path buffer, RNG stream, move history.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -39,16 +39,33 @@ struct __align__(16) GState {
     int flags;                       // game-specific
 };
 
+// game life-cycle bits kept in GState::flags (game flags use the low byte)
+constexpr int GF_FINISHED = 0x100;   // terminal, waiting for k_finalize / k_emit
+constexpr int GF_DEAD = 0x200;       // finished beyond the games_played quota: no longer stepped
+
+struct __align__(16) NodeHot { int n; float q; float p; int child0; };
+struct __align__(8) NodeCold { float v; uint32_t meta; };
+
+// 64-byte slot header.  While a node is the root its n / v / child0 / meta live
+// here (the pool record of a re-rooted child is copied in by play_moves).
+struct __align__(16) SlotHead {
+    GState st;                                   // 32 B
+    int root; int root_n; float root_v; int root_child0;
+    uint32_t root_meta; int alloc; int pad0; int pad1;
+};
+
+// what select leaves for expand/backup (MCTS._curnode / len(_path))
+struct __align__(16) LeafInfo { int leaf; int depth; int child0; uint32_t meta; };
+
 // device error bits (sticky word in DevView::err)
 enum : uint32_t {
     ERRB_POOL = 1u, ERRB_ACTION = 2u, ERRB_FP = 4u, ERRB_SAMPLES = 8u, ERRB_NOISE = 16u
 };
 
 // per-slot statistics (one row per slot, reduced on the host)
-struct SlotStats {
-    unsigned long long sims, sum_depth, sum_children, nodes_created, terminal_leaves, moves;
-    int peak_nodes;
-    int pad;
+struct __align__(16) SlotStats {
+    unsigned sum_depth, sum_children, nodes_created, terminal_leaves;   // select: one 16-byte RMW
+    unsigned sims, moves; int peak_nodes; int pad;
 };
 
 struct Counters {
@@ -62,12 +79,12 @@ struct Counters {
 struct DevView {
     int B, npg;
     // node pool
-    int *n; float *q; float *p; float *v; int *child0; uint32_t *meta;
+    NodeHot *hot; NodeCold *cold;
     // per slot
-    GState *state; int *root; int *alloc; int *path; int *path_len; int *leaf;
+    SlotHead *head; LeafInfo *leafinfo; int *path;
     uint32_t *mt; unsigned long long *ctr;
     GState *hist_state; float *hist_pi; int *hist_len; int hist_cap;
-    int *next_reset; int *noise_event; int *last_action; int *finished; int *fin_code;
+    int *next_reset; int *noise_event; int *last_action; int *fin_code;
     long long *emit_off;
     SlotStats *stats;
     // NN I/O

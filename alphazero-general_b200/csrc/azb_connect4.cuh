@@ -70,28 +70,32 @@ struct Connect4T {
         return m;
     }
 
-    // valid actions in ascending order into act[]; returns their number.
-    // Called by every lane of the group (redundantly); act is per-group shared memory.
-    __device__ __forceinline__ static int list_valid(const GState &s, short *act, int lane, unsigned gmask)
+    // Game.valid_moves: number of valid columns; vmask gets one bit per valid action
+    __device__ __forceinline__ static int list_valid(const GState &s, short *act, uint32_t &vmask, bool on, int lane)
     {
-        uint32_t m = valid_mask(s);
-        int c = __popc(m);
-        if (lane < W && ((m >> lane) & 1u)) act[__popc(m & ((1u << lane) - 1u))] = (short)lane;
-        __syncwarp(gmask);
-        return c;
+        vmask = valid_mask(s);
+        return __popc(vmask);
+    }
+    // j-th valid action in ascending order
+    __device__ __forceinline__ static int nth_valid(const short *act, uint32_t vmask, int j)
+    {
+        return (int)__fns(vmask, 0, j + 1);
     }
 
     // Game.observation: [cells==+1, cells==-1, full(player), full(float32(turns/42))]
-    // in the reference's row order (row 0 = top).
-    __device__ __forceinline__ static float obs_value(const GState &s, int i)
+    // in the reference's row order (row 0 = top); written by the LANES threads of the group.
+    __device__ __forceinline__ static void write_obs(const GState &s, float *out, int lane)
     {
-        int plane = i / CELLS, cell = i - plane * CELLS;
-        int r = cell / W, c = cell - r * W;
-        int bit = c * 7 + (H - 1 - r);
-        if (plane == 0) return (float)((s.b0 >> bit) & 1ULL);
-        if (plane == 1) return (float)((s.b1 >> bit) & 1ULL);
-        if (plane == 2) return (float)(s.turns & 1);
-        return (float)((double)s.turns / 42.0);
+        const float pl = (float)(s.turns & 1);
+        const float tn = (float)((double)s.turns / 42.0);
+        for (int c = lane; c < CELLS; c += LANES) {
+            const int r = c / W, col = c - r * W;
+            const int bit = col * 7 + (H - 1 - r);
+            out[c] = (float)((s.b0 >> bit) & 1ULL);
+            out[CELLS + c] = (float)((s.b1 >> bit) & 1ULL);
+            out[2 * CELLS + c] = pl;
+            out[3 * CELLS + c] = tn;
+        }
     }
 
     // reference cell code (Board.pieces) of cell i (row-major, row 0 = top)

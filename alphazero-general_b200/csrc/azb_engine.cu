@@ -194,18 +194,18 @@ extern "C" int azb_create(const azb_config *cfg, azb_engine **out)
     const size_t N = (size_t)B * (size_t)npg;
     int rc = 0;
 #define A_(x) do { if (!rc) rc = (x); } while (0)
-    A_(dev_alloc(e, &d.n, N, false)); A_(dev_alloc(e, &d.q, N, false)); A_(dev_alloc(e, &d.p, N, false));
-    A_(dev_alloc(e, &d.v, N, false)); A_(dev_alloc(e, &d.child0, N, false)); A_(dev_alloc(e, &d.meta, N, false));
+    // +128 entries: the speculative sibling-block prefetch may read past a slot's last block
+    A_(dev_alloc(e, &d.hot, N + 128, false)); A_(dev_alloc(e, &d.cold, N + 128, false));
     e->pool_bytes = e->device_bytes;
-    A_(dev_alloc(e, &d.state, B)); A_(dev_alloc(e, &d.root, B)); A_(dev_alloc(e, &d.alloc, B));
-    A_(dev_alloc(e, &d.path, (size_t)B * gd.maxd)); A_(dev_alloc(e, &d.path_len, B)); A_(dev_alloc(e, &d.leaf, B));
+    A_(dev_alloc(e, &d.head, B)); A_(dev_alloc(e, &d.leafinfo, B));
+    A_(dev_alloc(e, &d.path, (size_t)B * gd.maxd));
     if (cfg->rng_mode == AZB_RNG_MT19937) A_(dev_alloc(e, &d.mt, (size_t)B * 625));
     A_(dev_alloc(e, &d.ctr, B));
     d.hist_cap = gd.max_turns;
     A_(dev_alloc(e, &d.hist_state, (size_t)B * d.hist_cap));
     A_(dev_alloc(e, &d.hist_pi, (size_t)B * d.hist_cap * gd.A));
     A_(dev_alloc(e, &d.hist_len, B)); A_(dev_alloc(e, &d.next_reset, B)); A_(dev_alloc(e, &d.noise_event, B));
-    A_(dev_alloc(e, &d.last_action, B)); A_(dev_alloc(e, &d.finished, B)); A_(dev_alloc(e, &d.fin_code, B));
+    A_(dev_alloc(e, &d.last_action, B)); A_(dev_alloc(e, &d.fin_code, B));
     A_(dev_alloc(e, &d.emit_off, B)); A_(dev_alloc(e, &d.stats, B));
     const int obs = gd.obs_c * gd.obs_h * gd.obs_w;
     A_(dev_alloc(e, &d.obs, (size_t)B * obs)); A_(dev_alloc(e, &d.policy, (size_t)B * gd.A));
@@ -462,13 +462,13 @@ extern "C" int azb_game_info(azb_engine *e, int32_t *last_action, int32_t *turns
     cudaStream_t s = (cudaStream_t)stream;
     const int B = e->d.B;
     if (last_action) CK(cudaMemcpyAsync(last_action, e->d.last_action, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, s));
-    std::vector<GState> st;
+    std::vector<SlotHead> hd;
     if (turns) {
-        st.resize(B);
-        CK(cudaMemcpyAsync(st.data(), e->d.state, sizeof(GState) * (size_t)B, cudaMemcpyDeviceToHost, s));
+        hd.resize(B);
+        CK(cudaMemcpyAsync(hd.data(), e->d.head, sizeof(SlotHead) * (size_t)B, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(s));
-    if (turns) for (int i = 0; i < B; i++) turns[i] = st[i].turns;
+    if (turns) for (int i = 0; i < B; i++) turns[i] = hd[i].st.turns;
     return AZB_OK;
 }
 
@@ -490,17 +490,21 @@ extern "C" int azb_tree_dump(azb_engine *e, int32_t slot, double *rows, int64_t 
     if (slot < 0 || slot >= e->d.B) return fail(AZB_ERR_BAD_ARGUMENT, "slot %d", slot);
     cudaStream_t s = (cudaStream_t)stream;
     CK(cudaStreamSynchronize(s));
-    int used = 0, root = 0;
-    CK(cudaMemcpy(&used, e->d.alloc + slot, sizeof(int), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(&root, e->d.root + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    SlotHead hd;
+    CK(cudaMemcpy(&hd, e->d.head + slot, sizeof(SlotHead), cudaMemcpyDeviceToHost));
+    const int used = hd.alloc, root = hd.root;
     const size_t nb = (size_t)slot * (size_t)e->d.npg;
+    std::vector<NodeHot> hot(used); std::vector<NodeCold> cold(used);
+    CK(cudaMemcpy(hot.data(), e->d.hot + nb, sizeof(NodeHot) * used, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cold.data(), e->d.cold + nb, sizeof(NodeCold) * used, cudaMemcpyDeviceToHost));
+    // while a node is the root its live fields are in the slot header
+    hot[root].n = hd.root_n; hot[root].child0 = hd.root_child0; cold[root].v = hd.root_v;
+    cold[root].meta = (cold[root].meta & 1023u) | (hd.root_meta & ~1023u);
+    if (hd.root == 0) { cold[root].meta = hd.root_meta; hot[root].q = 0.0f; hot[root].p = 0.0f; }   // fresh root: no pool record
     std::vector<int> n(used), c0(used); std::vector<float> q(used), p(used), v(used); std::vector<uint32_t> m(used);
-    CK(cudaMemcpy(n.data(), e->d.n + nb, sizeof(int) * used, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(c0.data(), e->d.child0 + nb, sizeof(int) * used, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(q.data(), e->d.q + nb, sizeof(float) * used, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(p.data(), e->d.p + nb, sizeof(float) * used, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(v.data(), e->d.v + nb, sizeof(float) * used, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(m.data(), e->d.meta + nb, sizeof(uint32_t) * used, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < used; i++) {
+        n[i] = hot[i].n; c0[i] = hot[i].child0; q[i] = hot[i].q; p[i] = hot[i].p; v[i] = cold[i].v; m[i] = cold[i].meta;
+    }
     int64_t w = 0;
     std::vector<std::pair<int, int>> stack;   // (node, depth)
     stack.push_back({root, 0});
@@ -530,11 +534,15 @@ extern "C" int azb_stats_get(azb_engine *e, azb_stats *out, void *stream)
     CK(cudaMemcpyAsync(ss.data(), e->d.stats, sizeof(SlotStats) * (size_t)B, cudaMemcpyDeviceToHost, s));
     TRY(read_counters(e, &c, s));
     memset(out, 0, sizeof(*out));
+    std::vector<SlotHead> hd(B);
+    CK(cudaMemcpyAsync(hd.data(), e->d.head, sizeof(SlotHead) * (size_t)B, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     for (int i = 0; i < B; i++) {
         out->sims += (int64_t)ss[i].sims; out->sum_depth += (int64_t)ss[i].sum_depth;
         out->sum_children += (int64_t)ss[i].sum_children; out->nodes_created += (int64_t)ss[i].nodes_created;
         out->terminal_leaves += (int64_t)ss[i].terminal_leaves; out->moves += (int64_t)ss[i].moves;
-        if (ss[i].peak_nodes > out->peak_nodes) out->peak_nodes = ss[i].peak_nodes;
+        const int pk = ss[i].peak_nodes > hd[i].alloc ? ss[i].peak_nodes : hd[i].alloc;
+        if (pk > out->peak_nodes) out->peak_nodes = pk;
     }
     out->games_played = c.games_played; out->results = c.results; out->samples = c.samples_total;
     out->pool_bytes = e->pool_bytes; out->device_bytes = e->device_bytes;

@@ -1,12 +1,16 @@
 // azb_kernels.cuh -- the hot kernels of the batched self-play MCTS engine,
-// templated on the game rules (G = Connect4 | Brandubh).
+// templated on the game rules (G = Connect4T<L> | Brandubh).
 //
 // Work decomposition: G::LANES consecutive threads of a warp (a "group") own
 // one game slot; child k of the node being scanned lives in lane k % LANES, so
-// the N/Q/P loads of a sibling block are coalesced and the argmax is a
-// shuffle reduction.  There is exactly one simulation in flight per game
+// the sibling block (16 B hot records) is one coalesced read and the argmax is
+// a shuffle reduction.  There is exactly one simulation in flight per game
 // (the reference has no virtual loss, SelfPlayAgent.pyx:108-110), so the
 // parallelism is across the B games.
+//
+// Control flow is warp-uniform: the 32/LANES games of a warp step through the
+// same code under per-group predicates, so every collective uses the full
+// mask (segmented by `width`) instead of sub-warp masks.
 //
 //   select_game         MCTS.find_leaf             MCTS.pyx:208-228, :86-104, :76-79
 //   expand_backup_game  MCTS.process_results       MCTS.pyx:230-289, :197-206, :291-295
@@ -18,15 +22,60 @@
 namespace azb {
 
 constexpr int CTA_THREADS = 128;
+constexpr unsigned FULL = 0xffffffffu;
 
 template <class G>
 struct GroupSmem {
     float vec[G::A];        // action-indexed scratch (masked priors / counts)
     float vec2[G::A];       // action-indexed scratch (probabilities)
-    uint32_t key[G::MAXC];  // Philox sort keys
+    uint32_t key[G::MAXC];  // Philox sort keys / gamma variates
     short act[G::MAXC];     // valid actions, ascending
     short order[G::MAXC];   // order[k] = index into act[] of the child at position k
 };
+
+// group-wide helpers (all 32 lanes of the warp must call them)
+template <int L>
+__device__ __forceinline__ unsigned group_ballot(bool p, int sub)
+{
+    const unsigned b = __ballot_sync(FULL, p);
+    if (L == 32) return b;
+    return (b >> (sub * L)) & ((1u << L) - 1u);
+}
+template <int L, class T>
+__device__ __forceinline__ T group_bcast(T v, int src) { return __shfl_sync(FULL, v, src, L); }
+
+__device__ __forceinline__ SlotHead load_head(const SlotHead *p)
+{
+    SlotHead h;
+    const int4 *s = reinterpret_cast<const int4 *>(p);
+    int4 *dst = reinterpret_cast<int4 *>(&h);
+    dst[0] = s[0]; dst[1] = s[1]; dst[2] = s[2]; dst[3] = s[3];
+    return h;
+}
+__device__ __forceinline__ void store_head_tail(SlotHead *p, const SlotHead &h)
+{
+    int4 *dst = reinterpret_cast<int4 *>(p);
+    const int4 *s = reinterpret_cast<const int4 *>(&h);
+    dst[2] = s[2]; dst[3] = s[3];
+}
+__device__ __forceinline__ void store_head(SlotHead *p, const SlotHead &h)
+{
+    int4 *dst = reinterpret_cast<int4 *>(p);
+    const int4 *s = reinterpret_cast<const int4 *>(&h);
+    dst[0] = s[0]; dst[1] = s[1]; dst[2] = s[2]; dst[3] = s[3];
+}
+__device__ __forceinline__ NodeHot load_hot(const NodeHot *p)
+{
+    const int4 v = *reinterpret_cast<const int4 *>(p);
+    NodeHot h; h.n = v.x; h.q = __int_as_float(v.y); h.p = __int_as_float(v.z); h.child0 = v.w;
+    return h;
+}
+__device__ __forceinline__ NodeCold load_cold(const NodeCold *p)
+{
+    const int2 v = *reinterpret_cast<const int2 *>(p);
+    NodeCold c; c.v = __int_as_float(v.x); c.meta = (uint32_t)v.y;
+    return c;
+}
 
 // ------------------------------------------------------------------------------
 // numpy float32 add.reduce (pairwise_sum) over an action-indexed vector in
@@ -34,7 +83,6 @@ struct GroupSmem {
 // ------------------------------------------------------------------------------
 __device__ __forceinline__ float np_leaf_sum(const float *a, int n)
 {
-    // n <= 128: one lane's serial restatement (used for small n)
     if (n < 8) {
         float r = 0.0f;
         for (int i = 0; i < n; i++) r = f_add(r, a[i]);
@@ -61,58 +109,73 @@ __device__ inline float np_sum_serial(const float *a, int n)
     return f_add(np_sum_serial(a, n2), np_sum_serial(a + n2, n - n2));
 }
 
-template <class G>
-__device__ __forceinline__ float np_sum_group(const float *vec, int lane, unsigned gmask)
+// n = 588 (brandubh): the recursion splits into eight leaf blocks
+// [72 x7, 84]; block b, accumulator j is an independent serial chain, so the 64
+// chains run two per lane and are combined in the recursion's order:
+// ((B0+B1)+(B2+B3)) + ((B4+B5)+(B6+B7)).
+__device__ __forceinline__ float np_sum_588_warp(const float *a, int lane)
 {
-    __syncwarp(gmask);
+    float blk[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int b = (lane >> 3) + 4 * h, j = lane & 7;
+        const int off = 72 * b, rows = (b == 7) ? 10 : 9;
+        float r = a[off + j];
+        for (int i = 1; i < rows; i++) r = f_add(r, a[off + 8 * i + j]);
+        // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) within the 8 lanes of the block
+        float t = f_add(r, __shfl_xor_sync(FULL, r, 1));      // lanes j even hold r_j + r_{j+1}
+        float u = f_add(t, __shfl_xor_sync(FULL, t, 2));      // j % 4 == 0: (r_j+r_j+1)+(r_j+2+r_j+3)
+        float w = f_add(u, __shfl_xor_sync(FULL, u, 4));      // j == 0: full block sum
+        if (b == 7) {                                         // tail of the 84-block: 4 serial adds
+            for (int i = 80; i < 84; i++) w = f_add(w, a[off + i]);
+        }
+        blk[h] = w;                                           // valid in lanes with j == 0
+    }
+    // lanes 0, 8, 16, 24 hold B0..B3 (blk[0]) and B4..B7 (blk[1])
+    float s0 = f_add(blk[0], __shfl_xor_sync(FULL, blk[0], 8));    // lane 0: B0+B1, lane 16: B2+B3
+    float s1 = f_add(blk[1], __shfl_xor_sync(FULL, blk[1], 8));    // lane 0: B4+B5, lane 16: B6+B7
+    float t0 = f_add(s0, __shfl_xor_sync(FULL, s0, 16));           // lane 0: (B0+B1)+(B2+B3)
+    float t1 = f_add(s1, __shfl_xor_sync(FULL, s1, 16));           // lane 0: (B4+B5)+(B6+B7)
+    return __shfl_sync(FULL, f_add(t0, t1), 0);
+}
+
+template <class G>
+__device__ __forceinline__ float np_sum_group(const float *vec, int lane)
+{
+    __syncwarp();
     float r;
     if (G::A < 8) {
         r = np_leaf_sum(vec, G::A);          // every lane, broadcast reads
+    } else if (G::A == 588 && G::LANES == 32) {
+        r = np_sum_588_warp(vec, lane);
     } else {
         r = 0.0f;
         if (lane == 0) r = np_sum_serial(vec, G::A);
-        r = __shfl_sync(gmask, r, 0, G::LANES);
+        r = group_bcast<G::LANES>(r, 0);
     }
     return r;
 }
 
 // ------------------------------------------------------------------------------
-// RNG draws of a slot (lane 0 draws, the group gets the value)
-// ------------------------------------------------------------------------------
-template <class G>
-__device__ __forceinline__ void rng_two_words(const DevView &d, int g, int lane, unsigned gmask, uint32_t &a, uint32_t &b)
-{
-    a = b = 0;
-    if (lane == 0) {
-        if (d.rng_mode == 0) {
-            uint32_t *st = d.mt + (size_t)g * 625;
-            a = mt_next(st);
-            b = mt_next(st);
-        } else {
-            unsigned long long c = d.ctr[g];
-            a = philox_word(d.seed, (unsigned long long)(d.gid_base + g), c);
-            b = philox_word(d.seed, (unsigned long long)(d.gid_base + g), c + 1);
-            d.ctr[g] = c + 2;
-        }
-    }
-    a = __shfl_sync(gmask, a, 0, G::LANES);
-    b = __shfl_sync(gmask, b, 0, G::LANES);
-}
-
-// Child order of a freshly expanded node with C children: fills sm.order
-// (order[k] = index into sm.act of the child at list position k).
+// Child order of a freshly expanded node with C children (Node.add_children,
+// MCTS.pyx:76-79).  Lane slot i (child j = lane + i*L of the ascending valid
+// list) receives the list position cpos[i] and the action cact[i] it writes.
 //   MT mode     : numpy legacy list shuffle (reversed Fisher-Yates, masked
-//                 rejection), drawn serially by lane 0.
-//   Philox mode : child j takes key word ctr+j; children are ordered by
-//                 (key, j) -- computed in parallel by rank counting.
-// With store == false only the RNG consumption is replayed (terminal leaves:
-// the reference shuffles their never-used children too, MCTS.pyx:223-226).
-template <class G>
-__device__ __forceinline__ void child_order(const DevView &d, int g, int C, bool store, int lane, unsigned gmask, GroupSmem<G> &sm)
+//                 rejection) drawn serially by lane 0; lane takes position j.
+//   Philox mode : child j takes key word ctr+j; its position is the rank of
+//                 (key, j) -- computed in parallel.
+// `consume` replays the RNG consumption (terminal leaves shuffle their unused
+// children too, MCTS.pyx:223-226); `store` also produces the order.
+// ------------------------------------------------------------------------------
+template <class G, int IT>
+__device__ __forceinline__ void child_order(const DevView &d, int g, int C, bool consume, bool store, int lane,
+                                            GroupSmem<G> &sm, uint32_t valid_mask, int (&cpos)[IT], int (&cact)[IT])
 {
     constexpr int L = G::LANES;
+#pragma unroll
+    for (int i = 0; i < IT; i++) { cpos[i] = lane + i * L; cact[i] = 0; }
     if (d.rng_mode == 0) {
-        if (lane == 0) {
+        if (consume && lane == 0) {
             uint32_t *st = d.mt + (size_t)g * 625;
             if (store) for (int k = 0; k < C; k++) sm.order[k] = (short)k;
             for (int i = C - 1; i >= 1; i--) {
@@ -120,26 +183,58 @@ __device__ __forceinline__ void child_order(const DevView &d, int g, int C, bool
                 if (store) { short t = sm.order[i]; sm.order[i] = sm.order[j]; sm.order[j] = t; }
             }
         }
-    } else {
-        unsigned long long c0 = d.ctr[g];
-        __syncwarp(gmask);
-        if (lane == 0) d.ctr[g] = c0 + (unsigned long long)C;
+        __syncwarp();
         if (store) {
-            for (int j = lane; j < C; j += L)
-                sm.key[j] = philox_word(d.seed, (unsigned long long)(d.gid_base + g), c0 + (unsigned long long)j);
-            __syncwarp(gmask);
-            for (int j = lane; j < C; j += L) {
-                uint32_t kj = sm.key[j];
-                int rank = 0;
-                for (int i = 0; i < C; i++) {
-                    uint32_t ki = sm.key[i];
-                    rank += (ki < kj) || (ki == kj && i < j);
-                }
-                sm.order[rank] = (short)j;
+#pragma unroll
+            for (int i = 0; i < IT; i++) {
+                const int k = lane + i * L;
+                if (k < C) cact[i] = G::nth_valid(sm.act, valid_mask, sm.order[k]);
             }
         }
+    } else {
+        unsigned long long c0 = 0ULL;
+        if (consume) c0 = d.ctr[g];
+        __syncwarp();
+        if (consume && lane == 0) d.ctr[g] = c0 + (unsigned long long)C;
+        uint32_t key[IT];
+#pragma unroll
+        for (int i = 0; i < IT; i++) {
+            const int j = lane + i * L;
+            key[i] = (store && j < C) ? philox_word(d.seed, (unsigned long long)(d.gid_base + g), c0 + (unsigned long long)j) : 0u;
+        }
+        if (IT == 1) {
+            int rank = 0;
+#pragma unroll
+            for (int i = 0; i < G::MAXC; i++) {
+                const uint32_t ki = group_bcast<L>(key[0], i);
+                rank += (i < C) && ((ki < key[0]) || (ki == key[0] && i < lane));
+            }
+            cpos[0] = rank;
+            if (store && lane < C) cact[0] = G::nth_valid(sm.act, valid_mask, lane);
+        } else {
+            if (store) {
+#pragma unroll
+                for (int i = 0; i < IT; i++) { const int j = lane + i * L; if (j < C) sm.key[j] = key[i]; }
+            }
+            __syncwarp();
+            if (store) {
+#pragma unroll
+                for (int i = 0; i < IT; i++) {
+                    const int j = lane + i * L;
+                    if (j < C) {
+                        int rank = 0;
+                        for (int t = 0; t < C; t++) {
+                            const uint32_t kt = sm.key[t];
+                            rank += (kt < key[i]) || (kt == key[i] && t < j);
+                        }
+                        cpos[i] = rank;
+                        cact[i] = G::nth_valid(sm.act, valid_mask, j);
+                    }
+                }
+            }
+            __syncwarp();
+        }
     }
-    __syncwarp(gmask);
 }
 
 // ------------------------------------------------------------------------------
@@ -147,169 +242,197 @@ __device__ __forceinline__ void child_order(const DevView &d, int g, int C, bool
 // (double accumulation in child order, Neumaier-compensated; MCTS.pyx:91).
 // Fast path: when every visited prior is 0 or >= 2^-28 the double partial sums
 // are exact, so an order-free integer reduction gives the identical result.
+// Lanes whose slot is out of range pass n = 0.
 // ------------------------------------------------------------------------------
 template <class G, int IT>
-__device__ __forceinline__ float seen_policy(const int (&kn)[IT], const float (&kp)[IT], int C, int lane, unsigned gmask)
+__device__ __forceinline__ float seen_policy(const NodeHot (&kh)[IT], const bool (&kin)[IT], int C, int lane, int sub)
 {
     constexpr int L = G::LANES;
     bool ok = true;
     unsigned long long acc = 0ULL;
 #pragma unroll
     for (int i = 0; i < IT; i++) {
-        int k = lane + i * L;
-        if (k < C && kn[i] > 0) {
-            float pv = kp[i];
+        if (kin[i] && kh[i].n > 0) {
+            const float pv = kh[i].p;
             ok = ok && ((pv == 0.0f) || (pv >= 3.7252902984619140625e-09f && pv < 2.0f));
             acc += (unsigned long long)(pv * 2251799813685248.0f);   // p * 2^51, exact
         }
     }
-    if (__all_sync(gmask, ok)) {
+    const unsigned bad = group_ballot<L>(!ok, sub);
 #pragma unroll
-        for (int off = L / 2; off >= 1; off >>= 1) acc += __shfl_xor_sync(gmask, acc, off, L);
-        return (float)((double)acc * 4.44089209850062616169452667236328125e-16);   // * 2^-51
-    }
-    // general path: serial compensated sum in child order
-    double f = 0.0, comp = 0.0;
-    for (int k = 0; k < C; k++) {
-        int i = k / L, src = k - i * L;
-        int nn = 0; float pv = 0.0f;
+    for (int off = L / 2; off >= 1; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off, L);
+    float fast = (float)((double)acc * 4.44089209850062616169452667236328125e-16);   // * 2^-51
+    if (__any_sync(FULL, bad != 0u)) {
+        // general path (some group holds a tiny or out-of-range prior): serial compensated sum
+        double f = 0.0, comp = 0.0;
+        for (int k = 0; k < G::MAXC; k++) {
+            const int i = k / L, src = k - i * L;
+            int nn = 0; float pv = 0.0f;
 #pragma unroll
-        for (int ii = 0; ii < IT; ii++) if (ii == i) { nn = kn[ii]; pv = kp[ii]; }
-        nn = __shfl_sync(gmask, nn, src, L);
-        pv = __shfl_sync(gmask, pv, src, L);
-        if (nn > 0) {
-            double x = (double)pv, t = __dadd_rn(f, x);
-            if (fabs(f) >= fabs(x)) comp = __dadd_rn(comp, __dadd_rn(__dsub_rn(f, t), x));
-            else comp = __dadd_rn(comp, __dadd_rn(__dsub_rn(x, t), f));
-            f = t;
+            for (int ii = 0; ii < IT; ii++) if (ii == i) { nn = kin[ii] ? kh[ii].n : 0; pv = kh[ii].p; }
+            nn = __shfl_sync(FULL, nn, src, L);
+            pv = __shfl_sync(FULL, pv, src, L);
+            if (k < C && nn > 0) {
+                const double x = (double)pv, t = __dadd_rn(f, x);
+                if (fabs(f) >= fabs(x)) comp = __dadd_rn(comp, __dadd_rn(__dsub_rn(f, t), x));
+                else comp = __dadd_rn(comp, __dadd_rn(__dsub_rn(x, t), f));
+                f = t;
+            }
         }
+        if (comp != 0.0 && isfinite(comp)) f = __dadd_rn(f, comp);
+        if (bad != 0u) fast = (float)f;
     }
-    if (comp != 0.0 && isfinite(comp)) f = __dadd_rn(f, comp);
-    return (float)f;
+    return fast;
 }
 
 // ------------------------------------------------------------------------------
 // MCTS.find_leaf
 // ------------------------------------------------------------------------------
 template <class G, bool WRITE_OBS>
-__device__ __forceinline__ void select_game(const DevView &d, int g, int lane, unsigned gmask, GroupSmem<G> &sm)
+__device__ __forceinline__ void select_game(const DevView &d, int g, bool active, int lane, int sub, GroupSmem<G> &sm)
 {
     constexpr int L = G::LANES;
     constexpr int IT = (G::MAXC + L - 1) / L;
-    if (d.finished[g] != 0) return;                 // dead slot (finished beyond the quota)
-    GState st = d.state[g];
+    constexpr bool SPEC = (G::MAXC <= L);       // small fan-out: prefetch the next sibling block speculatively
     const size_t nb = (size_t)g * (size_t)d.npg;
+    const bool in_range = active;               // out-of-range groups alias slot `first`: they must not write
+    SlotHead H = load_head(d.head + g);
+    if (H.st.flags & (GF_FINISHED | GF_DEAD)) active = false;
+    GState st = H.st;
     int *path = d.path + (size_t)g * G::MAXD;
-    int cur = d.root[g];
-    int cn = d.n[nb + cur];
-    uint32_t cmeta = d.meta[nb + cur];
-    int cch = d.child0[nb + cur];
-    float cv = d.v[nb + cur];
+    int cur = H.root, cn = H.root_n, cch = H.root_child0;
+    float cv = H.root_v;
+    uint32_t cmeta = H.root_meta;
     int depth = 0, sumc = 0;
+    bool desc = active && cn > 0 && meta_e(cmeta) == 0 && meta_nc(cmeta) > 0;
 
-    while (cn > 0 && meta_e(cmeta) == 0) {
-        const int C = meta_nc(cmeta);
-        if (C == 0 || depth >= G::MAXD - 1) break;  // only after a pool-exhaustion error
-        if (lane == 0) path[depth] = cur;
-        const size_t cb = nb + (size_t)cch;
-        int kn[IT], kc[IT]; float kq[IT], kp[IT], kv[IT]; uint32_t km[IT];
+    NodeHot kh[IT];
+    bool kin[IT];
 #pragma unroll
-        for (int i = 0; i < IT; i++) {
-            int k = lane + i * L;
-            bool in = k < C;
-            kn[i] = in ? d.n[cb + k] : 0;
-            kq[i] = in ? d.q[cb + k] : 0.0f;
-            kp[i] = in ? d.p[cb + k] : 0.0f;
-            kv[i] = in ? d.v[cb + k] : 0.0f;
-            kc[i] = in ? d.child0[cb + k] : -1;
-            km[i] = in ? d.meta[cb + k] : 0u;
-        }
+    for (int i = 0; i < IT; i++) {
+        const int k = lane + i * L;
+        kin[i] = desc && k < meta_nc(cmeta);
+        if (kin[i]) kh[i] = load_hot(d.hot + nb + cch + k);
+        else { kh[i].n = 0; kh[i].q = 0.0f; kh[i].p = 0.0f; kh[i].child0 = -1; }
+    }
+
+    while (__any_sync(FULL, desc)) {
+        const int C = meta_nc(cmeta);
+        if (desc && lane == 0) path[depth] = cur;
         // Node.best_child: fpu value in double, uct in float32, first strict maximum
-        float seen = seen_policy<G, IT>(kn, kp, C, lane, gmask);
-        float fpu = (float)__dsub_rn((double)cv, __dmul_rn((double)d.fpu_reduction, __dsqrt_rn((double)seen)));
-        float sqrt_n = (float)__dsqrt_rn((double)cn);
+        const float seen = seen_policy<G, IT>(kh, kin, C, lane, sub);
+        const float fpu = (float)__dsub_rn((double)cv, __dmul_rn((double)d.fpu_reduction, __dsqrt_rn((double)seen)));
+        const float sqrt_n = __fsqrt_rn((float)cn);      // == (float)sqrt((double)n): double rounding is innocuous for sqrt
         float bu = -CUDART_INF_F; int bk = 0x7fffffff;
 #pragma unroll
         for (int i = 0; i < IT; i++) {
-            int k = lane + i * L;
-            if (k < C) {
-                float t = f_div(f_mul(f_mul(d.cpuct, kp[i]), sqrt_n), (float)(1 + kn[i]));
-                float u = f_add(kn[i] == 0 ? fpu : kq[i], t);
-                if (u > bu) { bu = u; bk = k; }
+            if (kin[i]) {
+                const float t = f_div(f_mul(f_mul(d.cpuct, kh[i].p), sqrt_n), (float)(1 + kh[i].n));
+                const float u = f_add(kh[i].n == 0 ? fpu : kh[i].q, t);
+                if (u > bu) { bu = u; bk = lane + i * L; }
             }
         }
 #pragma unroll
         for (int off = L / 2; off >= 1; off >>= 1) {
-            float ou = __shfl_xor_sync(gmask, bu, off, L);
-            int ok = __shfl_xor_sync(gmask, bk, off, L);
+            const float ou = __shfl_xor_sync(FULL, bu, off, L);
+            const int ok = __shfl_xor_sync(FULL, bk, off, L);
             if (ou > bu || (ou == bu && ok < bk)) { bu = ou; bk = ok; }
         }
-        if (bk == 0x7fffffff) {                      // every uct was NaN
+        if (desc && bk == 0x7fffffff) {               // every uct was NaN
             if (lane == 0) atomicOr(d.err, ERRB_FP);
-            bk = 0;
         }
+        if (bk == 0x7fffffff) bk = 0;
         const int bi = bk / L, src = bk - bi * L;
-        int sn = 0, sc = -1; float sv = 0.0f; uint32_t smeta = 0u;
+        int sn = 0, sc = -1;
 #pragma unroll
-        for (int i = 0; i < IT; i++) if (i == bi) { sn = kn[i]; sc = kc[i]; sv = kv[i]; smeta = km[i]; }
-        cn = __shfl_sync(gmask, sn, src, L);
-        cch = __shfl_sync(gmask, sc, src, L);
-        cv = __shfl_sync(gmask, sv, src, L);
-        cmeta = __shfl_sync(gmask, smeta, src, L);
-        cur = (int)(cb - nb) + bk;
-        G::play(st, meta_action(cmeta));
-        sumc += C;
-        depth++;
-    }
-
-    if (cn == 0) {
-        // first visit: record player and win state, materialise the children
-        const int player = G::player(st);
-        const int e = G::win_code(st);
-        const int C = G::list_valid(st, sm.act, lane, gmask);
-        int nc = 0, base = -1;
-        if (e != 0) {
-            child_order<G>(d, g, C, false, lane, gmask, sm);
-        } else {
-            base = d.alloc[g];
-            __syncwarp(gmask);
-            if (base + C > d.npg) {
-                if (lane == 0) atomicOr(d.err, ERRB_POOL);
-                child_order<G>(d, g, C, false, lane, gmask, sm);
-                base = -1;
+        for (int i = 0; i < IT; i++) if (i == bi) { sn = kh[i].n; sc = kh[i].child0; }
+        const int nn = __shfl_sync(FULL, sn, src, L);
+        const int nch = __shfl_sync(FULL, sc, src, L);
+        const int idx = cch + bk;
+        NodeCold cc; cc.v = 0.0f; cc.meta = 0u;
+        if (desc) cc = load_cold(d.cold + nb + idx);                    // the chosen child's cold half ...
+        NodeHot nh[IT];
+        if constexpr (SPEC) {                                           // ... and, in flight with it, its children
+            const bool pre = desc && nn > 0 && nch >= 0 && lane < G::MAXC;
+            if (pre) nh[0] = load_hot(d.hot + nb + nch + lane);
+            else { nh[0].n = 0; nh[0].q = 0.0f; nh[0].p = 0.0f; nh[0].child0 = -1; }
+        }
+        if (desc) {
+            G::play(st, meta_action(cc.meta));
+            sumc += C;
+            depth++;
+            cur = idx; cn = nn; cch = nch; cv = cc.v; cmeta = cc.meta;
+        }
+        desc = desc && cn > 0 && meta_e(cmeta) == 0 && meta_nc(cmeta) > 0 && depth < G::MAXD - 1;
+#pragma unroll
+        for (int i = 0; i < IT; i++) {
+            const int k = lane + i * L;
+            kin[i] = desc && k < meta_nc(cmeta);
+            if constexpr (SPEC) {
+                kh[i] = nh[i];
             } else {
-                child_order<G>(d, g, C, true, lane, gmask, sm);
-                nc = C;
-                for (int k = lane; k < C; k += L) {
-                    size_t idx = nb + (size_t)(base + k);
-                    d.n[idx] = 0; d.q[idx] = 0.0f; d.p[idx] = 0.0f; d.v[idx] = 0.0f;
-                    d.child0[idx] = -1;
-                    d.meta[idx] = meta_pack((uint32_t)sm.act[sm.order[k]], 0u, 0u, 0u);
-                }
-                if (lane == 0) {
-                    d.alloc[g] = base + C;
-                    SlotStats &ss = d.stats[g];
-                    ss.nodes_created += (unsigned long long)C;
-                    if (base + C > ss.peak_nodes) ss.peak_nodes = base + C;
-                }
+                if (kin[i]) kh[i] = load_hot(d.hot + nb + cch + k);
+                else { kh[i].n = 0; kh[i].q = 0.0f; kh[i].p = 0.0f; kh[i].child0 = -1; }
             }
         }
-        cmeta = meta_pack((uint32_t)meta_action(cmeta), (uint32_t)nc, (uint32_t)e, (uint32_t)player);
-        if (lane == 0) { d.meta[nb + cur] = cmeta; d.child0[nb + cur] = base; }
+    }
+
+    // first visit: record player and win state, materialise the children
+    const bool expd = active && cn == 0;
+    bool head_dirty = false;
+    int nodes_new = 0;
+    if (__any_sync(FULL, expd)) {
+        const int player = G::player(st);
+        const int e = G::win_code(st);
+        uint32_t vmask = 0u;
+        const int C = G::list_valid(st, sm.act, vmask, expd, lane);
+        const bool term = e != 0;
+        int base = -1, nc = 0;
+        bool store = false;
+        if (expd && !term) {
+            base = H.alloc;
+            if (base + C > d.npg) { if (lane == 0) atomicOr(d.err, ERRB_POOL); base = -1; }
+            else { store = true; nc = C; }
+        }
+        int cpos[IT], cact[IT];
+        child_order<G, IT>(d, g, C, expd, store, lane, sm, vmask, cpos, cact);
+        if (store) {
+#pragma unroll
+            for (int i = 0; i < IT; i++) {
+                const int j = lane + i * L;
+                if (j < C) {
+                    const size_t idx = nb + (size_t)(base + cpos[i]);
+                    *reinterpret_cast<int4 *>(d.hot + idx) = make_int4(0, 0, 0, -1);
+                    *reinterpret_cast<int2 *>(d.cold + idx) = make_int2(0, (int)meta_pack((uint32_t)cact[i], 0u, 0u, 0u));
+                }
+            }
+            H.alloc = base + C;
+            nodes_new = C;
+        }
+        if (expd) {
+            cmeta = meta_pack((uint32_t)meta_action(cmeta), (uint32_t)nc, (uint32_t)e, (uint32_t)player);
+            cch = base;
+            if (depth == 0) { H.root_meta = cmeta; H.root_child0 = base; }
+            else if (lane == 0) { d.cold[nb + cur].meta = cmeta; d.hot[nb + cur].child0 = base; }
+            head_dirty = true;
+        }
     }
     if (WRITE_OBS) {
-        float *o = d.obs + (size_t)g * G::OBS;
-        for (int i = lane; i < G::OBS; i += L) o[i] = G::obs_value(st, i);
+        if (active) G::write_obs(st, d.obs + (size_t)g * G::OBS, lane);
     }
-    if (lane == 0) {
-        d.leaf[g] = cur;
-        d.path_len[g] = depth;
-        SlotStats &ss = d.stats[g];
-        ss.sum_depth += (unsigned long long)depth;
-        ss.sum_children += (unsigned long long)sumc;
-        if (meta_e(cmeta) != 0) ss.terminal_leaves += 1ULL;
+    if (lane == 0 && in_range) {
+        LeafInfo li;
+        li.leaf = active ? cur : -1; li.depth = depth; li.child0 = cch; li.meta = cmeta;
+        *reinterpret_cast<int4 *>(d.leafinfo + g) = *reinterpret_cast<const int4 *>(&li);
+        if (active) {
+            if (head_dirty) store_head_tail(d.head + g, H);
+            uint4 *sp = reinterpret_cast<uint4 *>(d.stats + g);
+            uint4 s = *sp;
+            s.x += (unsigned)depth; s.y += (unsigned)sumc; s.z += (unsigned)nodes_new; s.w += (meta_e(cmeta) != 0) ? 1u : 0u;
+            *sp = s;
+        }
     }
-    __syncwarp(gmask);
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------
@@ -320,7 +443,7 @@ __device__ __forceinline__ void select_game(const DevView &d, int g, int lane, u
 // their sum.  Statistically equivalent to numpy's sampler, not bit-equal to it:
 // parity runs feed the vectors instead (azb_set_root_noise).
 // ------------------------------------------------------------------------------
-__device__ inline float gamma_variate(unsigned long long seed, unsigned long long gid, unsigned long long w0, double alpha)
+__device__ __noinline__ float gamma_variate(unsigned long long seed, unsigned long long gid, unsigned long long w0, double alpha)
 {
     unsigned long long w = w0;
     auto uni = [&]() {   // (0,1)
@@ -345,256 +468,327 @@ __device__ inline float gamma_variate(unsigned long long seed, unsigned long lon
     return (float)(out * boost);
 }
 
+// root prior post-processing for child position k with prior pk (MCTS.pyx:247-256)
+template <class G>
+__device__ __forceinline__ float root_noise_mix(const DevView &d, int g, int C, int k, float pk, bool on, float gen_sum,
+                                                float gen_val, const float *nz)
+{
+    const float keep = __fsub_rn(1.0f, d.noise_frac);
+    if (!on) return pk;
+    if (nz != nullptr) return f_add(f_mul(pk, keep), f_mul(d.noise_frac, nz[k]));
+    if (gen_sum > 0.0f) return f_add(f_mul(pk, keep), f_mul(d.noise_frac, gen_val / gen_sum));
+    return pk;
+}
+
 // ------------------------------------------------------------------------------
 // MCTS.process_results
 // ------------------------------------------------------------------------------
 template <class G>
-__device__ __forceinline__ void expand_backup_game(const DevView &d, int g, int lane, unsigned gmask, GroupSmem<G> &sm,
-                                                   const float *pol_row, const float *val_row)
+__device__ __forceinline__ void expand_backup_game(const DevView &d, int g, bool active, int lane, int sub,
+                                                   GroupSmem<G> &sm, const float *pol_row, const float *val_row)
 {
     constexpr int L = G::LANES;
-    if (d.finished[g] != 0) return;
+    constexpr int IT = (G::MAXC + L - 1) / L;
     const size_t nb = (size_t)g * (size_t)d.npg;
-    const int leaf = d.leaf[g], depth = d.path_len[g], root = d.root[g];
-    const uint32_t lmeta = d.meta[nb + leaf];
-    const int e = meta_e(lmeta);
+    const int4 li4 = *reinterpret_cast<const int4 *>(d.leafinfo + g);
+    const int4 hr = reinterpret_cast<const int4 *>(d.head + g)[2];       // root, root_n, root_v, root_child0
+    const int leaf = li4.x, depth = li4.y, base = li4.z;
+    const uint32_t lmeta = (uint32_t)li4.w;
+    const bool on = active && leaf >= 0;
+    const int e = meta_e(lmeta), C = meta_nc(lmeta);
+    const bool term = e != 0;
+    const bool is_root = leaf == hr.x;
     float val0, val1, val2;
-    if (e != 0) {
+    if (term) {
         // value = np.array(self._curnode.e, dtype=np.float32)
         val0 = e == 1 ? 1.0f : 0.0f; val1 = e == 2 ? 1.0f : 0.0f; val2 = e == 3 ? 1.0f : 0.0f;
     } else {
         val0 = val_row[0]; val1 = val_row[1]; val2 = val_row[2];
-        const int C = meta_nc(lmeta);
-        const size_t cb = nb + (size_t)d.child0[nb + leaf];
-        // pi *= valids (valids rebuilt from the children); pi /= np.sum(pi)
-        for (int a = lane; a < G::A; a += L) sm.vec[a] = 0.0f;
-        __syncwarp(gmask);
-        for (int k = lane; k < C; k += L) {
-            int a = meta_action(d.meta[cb + k]);
-            sm.vec[a] = pol_row[a];
+    }
+    const bool ex = on && !term;                       // priors are written
+    const bool rootx = ex && is_root;
+    const size_t cb = nb + (size_t)(base < 0 ? 0 : base);
+    // children's actions (cold halves of the sibling block)
+    int ak[IT];
+    bool kin[IT];
+#pragma unroll
+    for (int i = 0; i < IT; i++) {
+        const int k = lane + i * L;
+        kin[i] = ex && k < C;
+        ak[i] = kin[i] ? meta_action(d.cold[cb + k].meta) : 0;
+    }
+    // fed noise row of this root expansion
+    const float *nz = nullptr;
+    bool gen = false;
+    if (rootx && d.add_noise) {
+        const int ev = d.noise_event[g];
+        if (d.noise != nullptr) {
+            if (ev < d.noise_events && C <= d.noise_stride) nz = d.noise + ((size_t)g * d.noise_events + ev) * d.noise_stride;
+            else if (lane == 0) atomicOr(d.err, ERRB_NOISE);
+        } else gen = true;
+    }
+    float gsum = 0.0f, gval[IT];
+#pragma unroll
+    for (int i = 0; i < IT; i++) gval[i] = 0.0f;
+    if (__any_sync(FULL, gen)) {
+        unsigned long long c0 = 0ULL;
+        if (gen) c0 = d.ctr[g];
+        __syncwarp();
+        if (gen && lane == 0) d.ctr[g] = c0 + 64ULL * (unsigned long long)C;
+#pragma unroll
+        for (int i = 0; i < IT; i++) {
+            const int k = lane + i * L;
+            if (gen && k < C) gval[i] = gamma_variate(d.seed, (unsigned long long)(d.gid_base + g), c0 + 64ULL * k, 10.83 / (double)C);
+            gsum += gval[i];
         }
-        float sum = np_sum_group<G>(sm.vec, lane, gmask);
-        if (!(sum > 0.0f) && lane == 0 && C > 0) atomicOr(d.err, ERRB_FP);
-        for (int a = lane; a < G::A; a += L) sm.vec[a] = f_div(sm.vec[a], sum);
-        if (leaf == root) {
-            if (d.add_temp) {
-                __syncwarp(gmask);
+#pragma unroll
+        for (int off = L / 2; off >= 1; off >>= 1) gsum += __shfl_xor_sync(FULL, gsum, off, L);
+    }
+
+    if (G::A <= L) {
+        // ---- small action space: the action-indexed vector lives in lanes 0..A-1 ----
+        float pa = (ex && lane < G::A) ? pol_row[lane] : 0.0f;
+        unsigned vm = kin[0] ? (1u << ak[0]) : 0u;
+#pragma unroll
+        for (int off = L / 2; off >= 1; off >>= 1) vm |= __shfl_xor_sync(FULL, vm, off, L);
+        pa = ((vm >> lane) & 1u) ? pa : 0.0f;                    // pi *= valids
+        float s = 0.0f;                                          // np.sum, n < 8: serial from 0
+#pragma unroll
+        for (int a = 0; a < G::A; a++) s = f_add(s, group_bcast<L>(pa, a));
+        if (ex && C > 0 && !(s > 0.0f) && lane == 0) atomicOr(d.err, ERRB_FP);
+        float pn = f_div(pa, s);                                 // pi /= np.sum(pi)
+        if (__any_sync(FULL, rootx && d.add_temp)) {
+            float pt = pow_det(pn, d.root_temp_exp);             // pi ** (1 / root_temp)
+            float s2 = 0.0f;
+#pragma unroll
+            for (int a = 0; a < G::A; a++) s2 = f_add(s2, group_bcast<L>(pt, a));
+            pt = f_div(pt, s2);
+            if (rootx && d.add_temp) pn = pt;
+        }
+        float pk = group_bcast<L>(pn, ak[0]);                    // Node.update_policy: c.p = pi[c.a]
+        pk = root_noise_mix<G>(d, g, C, lane, pk, kin[0] && rootx && d.add_noise, gsum, gval[0], nz);
+        if (kin[0]) d.hot[cb + lane].p = pk;
+    } else {
+        // ---- large action space: action-indexed vector in shared memory ----
+        if (__any_sync(FULL, ex)) {
+            for (int a = lane; a < G::A; a += L) sm.vec[a] = 0.0f;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < IT; i++) if (kin[i]) sm.vec[ak[i]] = pol_row[ak[i]];
+            float sum = np_sum_group<G>(sm.vec, lane);
+            if (ex && C > 0 && !(sum > 0.0f) && lane == 0) atomicOr(d.err, ERRB_FP);
+            for (int a = lane; a < G::A; a += L) sm.vec[a] = f_div(sm.vec[a], sum);
+            if (__any_sync(FULL, rootx && d.add_temp)) {
+                __syncwarp();
                 for (int a = lane; a < G::A; a += L) sm.vec[a] = pow_det(sm.vec[a], d.root_temp_exp);
-                float sum2 = np_sum_group<G>(sm.vec, lane, gmask);
+                float sum2 = np_sum_group<G>(sm.vec, lane);
                 for (int a = lane; a < G::A; a += L) sm.vec[a] = f_div(sm.vec[a], sum2);
             }
-            __syncwarp(gmask);
-            const float *nz = nullptr;
-            bool gen = false;
-            if (d.add_noise) {
-                int ev = d.noise_event[g];
-                if (d.noise != nullptr) {
-                    if (ev < d.noise_events && C <= d.noise_stride)
-                        nz = d.noise + ((size_t)g * d.noise_events + ev) * d.noise_stride;
-                    else if (lane == 0) atomicOr(d.err, ERRB_NOISE);
-                } else gen = true;
-            }
-            const float keep = __fsub_rn(1.0f, d.noise_frac);
-            if (gen) {
-                // sample Dirichlet(10.83 / C) on the device; sm.vec2[k] = gamma variate of child k
-                const unsigned long long c0 = d.ctr[g];
-                __syncwarp(gmask);
-                if (lane == 0) d.ctr[g] = c0 + 64ULL * (unsigned long long)C;
-                float part = 0.0f;
-                for (int k = lane; k < C; k += L) {
-                    float gv = gamma_variate(d.seed, (unsigned long long)(d.gid_base + g), c0 + 64ULL * k, 10.83 / (double)C);
-                    sm.key[k] = __float_as_uint(gv);
-                    part += gv;
-                }
+            __syncwarp();
 #pragma unroll
-                for (int off = L / 2; off >= 1; off >>= 1) part += __shfl_xor_sync(gmask, part, off, L);
-                __syncwarp(gmask);
-                for (int k = lane; k < C; k += L) {
-                    float pk = sm.vec[meta_action(d.meta[cb + k])];
-                    float nk = __uint_as_float(sm.key[k]) / part;
-                    d.p[cb + k] = f_add(f_mul(pk, keep), f_mul(d.noise_frac, nk));
-                }
-            } else {
-                for (int k = lane; k < C; k += L) {
-                    float pk = sm.vec[meta_action(d.meta[cb + k])];
-                    if (nz != nullptr) pk = f_add(f_mul(pk, keep), f_mul(d.noise_frac, nz[k]));
-                    d.p[cb + k] = pk;
+            for (int i = 0; i < IT; i++) {
+                const int k = lane + i * L;
+                if (kin[i]) {
+                    float pk = sm.vec[ak[i]];
+                    pk = root_noise_mix<G>(d, g, C, k, pk, rootx && d.add_noise, gsum, gval[i], nz);
+                    d.hot[cb + k].p = pk;
                 }
             }
-            __syncwarp(gmask);
-            if (lane == 0) d.noise_event[g] += 1;
-        } else {
-            __syncwarp(gmask);
-            for (int k = lane; k < C; k += L) d.p[cb + k] = sm.vec[meta_action(d.meta[cb + k])];
+            __syncwarp();
         }
     }
-    // backup along the stored path; level i updates the node entered at step i
+    if (rootx && lane == 0) d.noise_event[g] += 1;
+
+    // backup along the stored path; level i updates the node entered at step i.
+    // player(node at depth t) = (leaf player - depth + t) & 1: turns alternate.
     const int *path = d.path + (size_t)g * G::MAXD;
-    const float share = f_div(val2, 2.0f);            // value[num_players] / num_players
-    for (int i = lane; i < depth; i += L) {
-        const int node = (i == depth - 1) ? leaf : path[i + 1];
-        const int parent = path[i];
-        const int pp = meta_player(d.meta[nb + parent]);
-        const float v = f_add(pp == 0 ? val0 : val1, share);
-        const size_t idx = nb + (size_t)node;
-        const int nn = d.n[idx];
-        const float qq = d.q[idx];
-        d.q[idx] = f_div(f_add(f_mul(qq, (float)nn), f_mul(v, 1.0f)), (float)(nn + 1));
-        if (nn == 0) {
-            const int np_ = (i == depth - 1) ? meta_player(lmeta) : meta_player(d.meta[idx]);
-            d.v[idx] = f_add(np_ == 0 ? val0 : val1, share);
+    const float share = f_div(val2, 2.0f);              // value[num_players] / num_players
+    const int root_player = (meta_player(lmeta) - depth) & 1;
+    if (on) {
+        for (int i = lane; i < depth; i += L) {
+            const int node = (i == depth - 1) ? leaf : path[i + 1];
+            const int pp = (root_player + i) & 1;
+            const float v = f_add(pp == 0 ? val0 : val1, share);
+            NodeHot *hp = d.hot + nb + node;
+            const int2 nq = *reinterpret_cast<const int2 *>(hp);
+            const int nn = nq.x;
+            const float qq = __int_as_float(nq.y);
+            const float qn = f_div(f_add(f_mul(qq, (float)nn), f_mul(v, 1.0f)), (float)(nn + 1));
+            if (nn == 0) d.cold[nb + node].v = f_add(pp == 0 ? val1 : val0, share);   // the node's own player = pp ^ 1
+            *reinterpret_cast<int2 *>(hp) = make_int2(nn + 1, __float_as_int(qn));
         }
-        d.n[idx] = nn + 1;
+        if (lane == 0) {
+            d.head[g].root_n = hr.y + 1;
+            reinterpret_cast<unsigned *>(d.stats + g)[4] += 1u;     // sims
+        }
     }
-    if (lane == 0) {
-        d.n[nb + root] += 1;
-        d.stats[g].sims += 1ULL;
-    }
-    __syncwarp(gmask);
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------
 // MCTS.probs on an action-indexed count vector in shared memory
 // ------------------------------------------------------------------------------
 template <class G>
-__device__ __forceinline__ void probs_group(const DevView &d, const float *counts, float temp, float *out, int lane, unsigned gmask)
+__device__ __forceinline__ void probs_group(const DevView &d, const float *counts, float temp, float *out, bool on, int lane)
 {
     constexpr int L = G::LANES;
-    __syncwarp(gmask);
-    if (temp == 0.0f) {
-        int best = 0;
-        for (int a = 1; a < G::A; a++) if (counts[a] > counts[best]) best = a;   // np.argmax: first maximum
-        for (int a = lane; a < G::A; a += L) out[a] = a == best ? 1.0f : 0.0f;
-        __syncwarp(gmask);
-        return;
-    }
-    float sum = np_sum_group<G>(counts, lane, gmask);
-    if (!(sum > 0.0f) && lane == 0) atomicOr(d.err, ERRB_FP);
-    const float e = (float)(1.0 / (double)temp);
-    for (int a = lane; a < G::A; a += L) out[a] = pow_det(f_div(counts[a], sum), e);
-    float sum2 = np_sum_group<G>(out, lane, gmask);
-    for (int a = lane; a < G::A; a += L) out[a] = f_div(out[a], sum2);
-    __syncwarp(gmask);
+    __syncwarp();
+    // temp == 0: one-hot of np.argmax (first maximum)
+    int best = 0;
+    if (temp == 0.0f) for (int a = 1; a < G::A; a++) if (counts[a] > counts[best]) best = a;
+    const float sum = np_sum_group<G>(counts, lane);
+    if (on && temp != 0.0f && !(sum > 0.0f) && lane == 0) atomicOr(d.err, ERRB_FP);
+    const float e = temp != 0.0f ? (float)(1.0 / (double)temp) : 1.0f;
+    for (int a = lane; a < G::A; a += L) out[a] = temp == 0.0f ? (a == best ? 1.0f : 0.0f) : pow_det(f_div(counts[a], sum), e);
+    const float sum2 = np_sum_group<G>(out, lane);
+    if (temp != 0.0f) for (int a = lane; a < G::A; a += L) out[a] = f_div(out[a], sum2);
+    __syncwarp();
 }
 
-__device__ __forceinline__ void tree_reset(const DevView &d, int g)
+__device__ __forceinline__ void tree_reset(SlotHead &H)
 {
-    const size_t nb = (size_t)g * (size_t)d.npg;
-    d.n[nb] = 0; d.q[nb] = 0.0f; d.p[nb] = 0.0f; d.v[nb] = 0.0f; d.child0[nb] = -1;
-    d.meta[nb] = meta_pack(META_ACTION_NONE, 0u, 0u, 0u);
-    d.root[g] = 0;
-    d.alloc[g] = 1;
-    d.path_len[g] = 0;
-    d.leaf[g] = 0;
+    H.root = 0; H.root_n = 0; H.root_v = 0.0f; H.root_child0 = -1;
+    H.root_meta = meta_pack(META_ACTION_NONE, 0u, 0u, 0u);
+    H.alloc = 1;
 }
 
 // ------------------------------------------------------------------------------
 // SelfPlayAgent.playMoves, the per-game part up to the terminal test
 // ------------------------------------------------------------------------------
 template <class G>
-__device__ __forceinline__ void play_move_game(const DevView &d, int g, int fast, int lane, unsigned gmask, GroupSmem<G> &sm)
+__device__ __forceinline__ void play_move_game(const DevView &d, int g, bool active, int fast, int lane, int sub, GroupSmem<G> &sm)
 {
     constexpr int L = G::LANES;
-    if (d.finished[g] != 0) return;
-    GState st = d.state[g];
+    constexpr int IT = (G::MAXC + L - 1) / L;
     const size_t nb = (size_t)g * (size_t)d.npg;
-    const int root = d.root[g];
-    const uint32_t rmeta = d.meta[nb + root];
-    const int C = meta_nc(rmeta);
-    const size_t cb = nb + (size_t)d.child0[nb + root];
+    SlotHead H = load_head(d.head + g);
+    bool on = active && !(H.st.flags & (GF_FINISHED | GF_DEAD));
+    GState st = H.st;
+    const int C = on ? meta_nc(H.root_meta) : 0;
+    const size_t cb = nb + (size_t)(H.root_child0 < 0 ? 0 : H.root_child0);
     // MCTS.counts
     for (int a = lane; a < G::A; a += L) sm.vec[a] = 0.0f;
-    __syncwarp(gmask);
-    for (int k = lane; k < C; k += L) sm.vec[meta_action(d.meta[cb + k])] = (float)d.n[cb + k];
-    __syncwarp(gmask);
-    int t = st.turns < d.temp_len ? st.turns : d.temp_len - 1;
-    const float temp = d.temp_table[t];
-    probs_group<G>(d, sm.vec, temp, sm.vec2, lane, gmask);
+    __syncwarp();
+    int ka[IT], kn[IT];
+#pragma unroll
+    for (int i = 0; i < IT; i++) {
+        const int k = lane + i * L;
+        ka[i] = -1; kn[i] = 0;
+        if (k < C) {
+            ka[i] = meta_action(d.cold[cb + k].meta);
+            kn[i] = d.hot[cb + k].n;
+            sm.vec[ka[i]] = (float)kn[i];
+        }
+    }
+    __syncwarp();
+    const int t = st.turns < d.temp_len ? st.turns : d.temp_len - 1;
+    const float temp = d.temp_table[t < 0 ? 0 : t];
+    probs_group<G>(d, sm.vec, temp, sm.vec2, on, lane);
     // np.random.choice(A, p=policy): cdf in double, one 53-bit uniform, searchsorted 'right'
-    uint32_t wa, wb;
-    rng_two_words<G>(d, g, lane, gmask, wa, wb);
-    int action = 0;
-    if (lane == 0) {
+    uint32_t wa = 0, wb = 0;
+    if (on && lane == 0) {
+        if (d.rng_mode == 0) {
+            uint32_t *ms = d.mt + (size_t)g * 625;
+            wa = mt_next(ms); wb = mt_next(ms);
+        } else {
+            const unsigned long long c = d.ctr[g];
+            wa = philox_word(d.seed, (unsigned long long)(d.gid_base + g), c);
+            wb = philox_word(d.seed, (unsigned long long)(d.gid_base + g), c + 1);
+            d.ctr[g] = c + 2;
+        }
+    }
+    int action = G::A;
+    if (on && lane == 0) {
         const double u = u53(wa, wb);
         double last = 0.0;
         for (int a = 0; a < G::A; a++) last = __dadd_rn(last, (double)sm.vec2[a]);
         double acc = 0.0;
-        action = G::A;
         for (int a = 0; a < G::A; a++) {
             acc = __dadd_rn(acc, (double)sm.vec2[a]);
             if (u < __ddiv_rn(acc, last)) { action = a; break; }
         }
     }
-    action = __shfl_sync(gmask, action, 0, L);
+    action = group_bcast<L>(action, 0);
     if (!fast) {
         // histories[i].append((game.clone(), mcts.probs(game)))  -- temp = 1
-        const int hl = d.hist_len[g];
-        if (hl < d.hist_cap) {
-            float *hp = d.hist_pi + ((size_t)g * d.hist_cap + hl) * G::A;
-            probs_group<G>(d, sm.vec, 1.0f, sm.vec2, lane, gmask);
-            for (int a = lane; a < G::A; a += L) hp[a] = sm.vec2[a];
-            if (lane == 0) { d.hist_state[(size_t)g * d.hist_cap + hl] = st; d.hist_len[g] = hl + 1; }
-        } else if (lane == 0) atomicOr(d.err, ERRB_SAMPLES);
+        const int hl = on ? d.hist_len[g] : 0;
+        probs_group<G>(d, sm.vec, 1.0f, sm.vec2, on, lane);
+        if (on) {
+            if (hl < d.hist_cap) {
+                float *hp = d.hist_pi + ((size_t)g * d.hist_cap + hl) * G::A;
+                for (int a = lane; a < G::A; a += L) hp[a] = sm.vec2[a];
+                if (lane == 0) { d.hist_state[(size_t)g * d.hist_cap + hl] = st; d.hist_len[g] = hl + 1; }
+            } else if (lane == 0) atomicOr(d.err, ERRB_SAMPLES);
+        }
     }
     // MCTS.update_root
     int found = -1;
-    for (int k = lane; k < C; k += L) if (meta_action(d.meta[cb + k]) == action) found = k;
 #pragma unroll
-    for (int off = L / 2; off >= 1; off >>= 1) found = max(found, __shfl_xor_sync(gmask, found, off, L));
-    if (found < 0) {
-        if (lane == 0) { atomicOr(d.err, ERRB_ACTION); d.finished[g] = 2; }
-        __syncwarp(gmask);
-        return;
+    for (int i = 0; i < IT; i++) if (ka[i] == action && lane + i * L < C) found = lane + i * L;
+#pragma unroll
+    for (int off = L / 2; off >= 1; off >>= 1) found = max(found, __shfl_xor_sync(FULL, found, off, L));
+    if (on && found < 0) {
+        if (lane == 0) atomicOr(d.err, ERRB_ACTION);
+        H.st.flags |= GF_DEAD;
+        if (lane == 0) store_head(d.head + g, H);
+        on = false;
     }
-    G::play(st, action);
-    const int e = G::win_code(st);
-    if (lane == 0) {
-        d.root[g] = (int)(cb - nb) + found;
-        d.state[g] = st;
+    if (on && lane == 0) {
+        const int nr = H.root_child0 + found;
+        const NodeHot h = load_hot(d.hot + nb + nr);
+        const NodeCold c = load_cold(d.cold + nb + nr);
+        H.root = nr; H.root_n = h.n; H.root_v = c.v; H.root_child0 = h.child0; H.root_meta = c.meta;
+        G::play(st, action);
+        const int e = G::win_code(st);
+        st.flags &= 0xff;
+        if (e != 0) { st.flags |= GF_FINISHED; d.fin_code[g] = e; }
+        H.st = st;
         d.last_action[g] = action;
-        d.stats[g].moves += 1ULL;
+        reinterpret_cast<unsigned *>(d.stats + g)[5] += 1u;     // moves
         if (d.reset_threshold && st.turns >= d.next_reset[g]) {
-            tree_reset(d, g);
+            int *pk = reinterpret_cast<int *>(d.stats + g) + 6;
+            if (H.alloc > *pk) *pk = H.alloc;
+            tree_reset(H);
             d.next_reset[g] = st.turns + d.reset_threshold;
         }
-        if (e != 0) { d.finished[g] = 1; d.fin_code[g] = e; }
+        store_head(d.head + g, H);
     }
-    __syncwarp(gmask);
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------
 template <class G>
-__device__ __forceinline__ bool group_setup(int first, int count, int &g, int &lane, unsigned &gmask, int &gi)
+__device__ __forceinline__ bool group_setup(int first, int count, int &g, bool &active, int &lane, int &sub, int &gi)
 {
     constexpr int L = G::LANES;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int grp = tid / L;
     lane = threadIdx.x % L;
     gi = threadIdx.x / L;
-    const int sub = (threadIdx.x % 32) / L;
-    gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (sub * L));
-    g = first + grp;
-    return grp < count;
+    sub = (threadIdx.x % 32) / L;
+    active = grp < count;
+    g = first + (active ? grp : 0);
+    return __any_sync(FULL, active);          // false: the whole warp is out of range
 }
 
 template <class G>
 __global__ void __launch_bounds__(CTA_THREADS) k_select(DevView d, int first, int count)
 {
     __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
-    int g, lane, gi; unsigned gmask;
-    if (!group_setup<G>(first, count, g, lane, gmask, gi)) return;
-    select_game<G, true>(d, g, lane, gmask, sm[gi]);
+    int g, lane, sub, gi; bool active;
+    if (!group_setup<G>(first, count, g, active, lane, sub, gi)) return;
+    select_game<G, true>(d, g, active, lane, sub, sm[gi]);
 }
 
 template <class G>
 __global__ void __launch_bounds__(CTA_THREADS) k_expand_backup(DevView d, int first, int count, const float *policy, const float *value)
 {
     __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
-    int g, lane, gi; unsigned gmask;
-    if (!group_setup<G>(first, count, g, lane, gmask, gi)) return;
-    expand_backup_game<G>(d, g, lane, gmask, sm[gi], policy + (size_t)g * G::A, value + (size_t)g * 3);
+    int g, lane, sub, gi; bool active;
+    if (!group_setup<G>(first, count, g, active, lane, sub, gi)) return;
+    expand_backup_game<G>(d, g, active, lane, sub, sm[gi], policy + (size_t)g * G::A, value + (size_t)g * 3);
 }
 
 // `sims` simulations per game with constant NN outputs, no NN round trip
@@ -602,11 +796,11 @@ template <class G>
 __global__ void __launch_bounds__(CTA_THREADS) k_warmup_sims(DevView d, int sims)
 {
     __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
-    int g, lane, gi; unsigned gmask;
-    if (!group_setup<G>(0, d.B, g, lane, gmask, gi)) return;
+    int g, lane, sub, gi; bool active;
+    if (!group_setup<G>(0, d.B, g, active, lane, sub, gi)) return;
     for (int s = 0; s < sims; s++) {
-        select_game<G, false>(d, g, lane, gmask, sm[gi]);
-        expand_backup_game<G>(d, g, lane, gmask, sm[gi], d.warm_policy, d.warm_value);
+        select_game<G, false>(d, g, active, lane, sub, sm[gi]);
+        expand_backup_game<G>(d, g, active, lane, sub, sm[gi], d.warm_policy, d.warm_value);
     }
 }
 
@@ -614,9 +808,9 @@ template <class G>
 __global__ void __launch_bounds__(CTA_THREADS) k_play_moves(DevView d, int fast)
 {
     __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
-    int g, lane, gi; unsigned gmask;
-    if (!group_setup<G>(0, d.B, g, lane, gmask, gi)) return;
-    play_move_game<G>(d, g, fast, lane, gmask, sm[gi]);
+    int g, lane, sub, gi; bool active;
+    if (!group_setup<G>(0, d.B, g, active, lane, sub, gi)) return;
+    play_move_game<G>(d, g, active, fast, lane, sub, sm[gi]);
 }
 
 // Terminal handling in slot order (one CTA): result_queue.put for every
@@ -638,8 +832,9 @@ __global__ void __launch_bounds__(1024) k_finalize(DevView d)
     const int per = d.symmetric ? G::NSYM : 1;
     for (int g0 = 0; g0 < d.B; g0 += 1024) {
         const int g = g0 + tid;
-        const int fin = (g < d.B && d.finished[g] == 1) ? 1 : 0;
-        // inclusive scan of fin
+        int flags = 0, turns = 0;
+        if (g < d.B) { flags = d.head[g].st.flags; turns = d.head[g].st.turns; }
+        const int fin = (flags & GF_FINISHED) ? 1 : 0;
         s_scan[tid] = fin;
         __syncthreads();
         for (int off = 1; off < 1024; off <<= 1) {
@@ -668,7 +863,7 @@ __global__ void __launch_bounds__(1024) k_finalize(DevView d)
             if (ri < d.r_cap) {
                 const int code = d.fin_code[g];
                 d.r_slot[ri] = g;
-                d.r_turns[ri] = d.state[g].turns;
+                d.r_turns[ri] = turns;
                 d.r_win[ri * 3 + 0] = code == 1; d.r_win[ri * 3 + 1] = code == 2; d.r_win[ri * 3 + 2] = code == 3;
             } else atomicOr(d.err, ERRB_SAMPLES);
             if (accepted) {
@@ -703,12 +898,14 @@ template <class G>
 __global__ void __launch_bounds__(CTA_THREADS) k_emit(DevView d)
 {
     constexpr int L = G::LANES;
-    int g, lane, gi; unsigned gmask;
-    if (!group_setup<G>(0, d.B, g, lane, gmask, gi)) return;
-    if (d.finished[g] != 1) return;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = tid / L, lane = threadIdx.x % L;
+    if (g >= d.B) return;
+    SlotHead H = load_head(d.head + g);
+    if (!(H.st.flags & GF_FINISHED)) return;
     const long long off = d.emit_off[g];
     if (off == -1) {                    // beyond the quota: the game stays finished
-        if (lane == 0) d.finished[g] = 2;
+        if (lane == 0) { H.st.flags = (H.st.flags & ~GF_FINISHED) | GF_DEAD; store_head(d.head + g, H); }
         return;
     }
     const int code = d.fin_code[g];
@@ -720,11 +917,10 @@ __global__ void __launch_bounds__(CTA_THREADS) k_emit(DevView d)
             const float *hp = d.hist_pi + ((size_t)g * d.hist_cap + h) * G::A;
             for (int k = 0; k < per; k++) {
                 const long long si = off + (long long)h * per + k;
-                const GState ss = G::symmetry(hs, k);
-                float *o = d.s_obs + (size_t)si * G::OBS;
-                for (int i = lane; i < G::OBS; i += L) o[i] = G::obs_value(ss, i);
+                const GState ss = d.symmetric ? G::symmetry(hs, k) : hs;
+                G::write_obs(ss, d.s_obs + (size_t)si * G::OBS, lane);
                 float *pp = d.s_pi + (size_t)si * G::A;
-                for (int a = lane; a < G::A; a += L) pp[G::sym_action(k, a)] = hp[a];
+                for (int a = lane; a < G::A; a += L) pp[d.symmetric ? G::sym_action(k, a) : a] = hp[a];
                 if (lane == 0) {
                     d.s_z[si * 3 + 0] = code == 1 ? 1.0f : 0.0f;
                     d.s_z[si * 3 + 1] = code == 2 ? 1.0f : 0.0f;
@@ -734,13 +930,13 @@ __global__ void __launch_bounds__(CTA_THREADS) k_emit(DevView d)
             }
         }
     }
-    __syncwarp(gmask);
     if (lane == 0) {
-        GState st; G::init(st);
-        d.state[g] = st;
+        int *pk = reinterpret_cast<int *>(d.stats + g) + 6;
+        if (H.alloc > *pk) *pk = H.alloc;
+        G::init(H.st);
+        tree_reset(H);
+        store_head(d.head + g, H);
         d.hist_len[g] = 0;
-        tree_reset(d, g);
-        d.finished[g] = 0;
         d.fin_code[g] = 0;
     }
 }
@@ -752,11 +948,11 @@ __global__ void k_root_counts(DevView d, int *out)
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= d.B) return;
     const size_t nb = (size_t)g * (size_t)d.npg;
-    const int root = d.root[g];
-    const int C = meta_nc(d.meta[nb + root]);
-    const size_t cb = nb + (size_t)d.child0[nb + root];
+    const SlotHead H = load_head(d.head + g);
+    const int C = meta_nc(H.root_meta);
+    const size_t cb = nb + (size_t)(H.root_child0 < 0 ? 0 : H.root_child0);
     for (int a = 0; a < G::A; a++) out[(size_t)g * G::A + a] = 0;
-    for (int k = 0; k < C; k++) out[(size_t)g * G::A + meta_action(d.meta[cb + k])] = d.n[cb + k];
+    for (int k = 0; k < C; k++) out[(size_t)g * G::A + meta_action(d.cold[cb + k].meta)] = d.hot[cb + k].n;
 }
 
 template <class G>
@@ -764,7 +960,7 @@ __global__ void k_boards(DevView d, int8_t *out)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= d.B) return;
-    const GState st = d.state[g];
+    const GState st = d.head[g].st;
     for (int i = 0; i < G::CELLS; i++) out[(size_t)g * G::CELLS + i] = (int8_t)G::cell_code(st, i);
 }
 
@@ -773,11 +969,15 @@ __global__ void k_init_slots(DevView d, const uint32_t *mt_seeds)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= d.B) return;
-    GState st; G::init(st);
-    d.state[g] = st;
-    tree_reset(d, g);
+    SlotHead H;
+    G::init(H.st);
+    tree_reset(H);
+    H.pad0 = H.pad1 = 0;
+    store_head(d.head + g, H);
+    LeafInfo li; li.leaf = -1; li.depth = 0; li.child0 = -1; li.meta = 0u;
+    d.leafinfo[g] = li;
     d.hist_len[g] = 0; d.next_reset[g] = 0; d.noise_event[g] = 0; d.last_action[g] = -1;
-    d.finished[g] = 0; d.fin_code[g] = 0; d.emit_off[g] = -1;
+    d.fin_code[g] = 0; d.emit_off[g] = -1;
     d.ctr[g] = 0ULL;
     SlotStats z = {};
     z.peak_nodes = 1;
