@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--sims", type=int, default=100)
     ap.add_argument("--net", default="default", choices=["default", "connect4_train"])
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
-    ap.add_argument("--cohorts", type=int, default=2)
+    ap.add_argument("--cohorts", type=int, default=1)
     ap.add_argument("--lanes", type=int, default=0, help="threads per game (0 = library default)")
     ap.add_argument("--nchw", action="store_true", help="keep the ResNet in NCHW (default: channels_last)")
     ap.add_argument("--preroll", type=int, default=48, help="cheap tree-only rounds that de-synchronise the games")
