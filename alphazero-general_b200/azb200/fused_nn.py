@@ -1,0 +1,107 @@
+"""FusedResNetEvaluator -- the reference ResNet for Connect4-sized boards as one
+CUDA kernel launch (csrc/azb_resnet.cu, C ABI in include/azb200_nn.h).
+
+Host-side weight preparation (exact algebra, evaluated in float64):
+  stem     conv -> BN -> ReLU          => conv' = conv * s, bias' = beta - mean * s,  s = gamma / sqrt(var + eps)
+  block    BN1 -> ReLU -> conv1 -> BN2 -> ReLU -> conv2 (+x)
+           BN1 stays elementwise (scale, shift); BN2 is folded into conv1
+  heads    conv1x1 -> BN -> flatten -> Linear..Linear with Identity activations
+           (NNetArchitecture.py:86-102) is affine in the trunk output: its matrix
+           is obtained by pushing the canonical basis through the modules.
+Convolution operands are rounded to bf16 (fp32 accumulation); everything else
+is fp32.  This is the bf16 performance mode of the leaf evaluation; parity runs
+use azb200.nnet.LeafEvaluator(precision="fp32")."""
+import ctypes as C
+
+import torch
+
+from . import _capi
+
+
+class _NNWeights(C.Structure):
+    _fields_ = [("channels", C.c_int32), ("depth", C.c_int32), ("in_channels", C.c_int32), ("board_h", C.c_int32),
+                ("board_w", C.c_int32), ("action_size", C.c_int32), ("wconv", C.c_void_p), ("cbias", C.c_void_p),
+                ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p), ("whead", C.c_void_p), ("bhead", C.c_void_p)]
+
+
+def supported(model):
+    ch = model.conv1.out_channels
+    return (ch == 32 and (model.board_x, model.board_y) == (6, 7) and model.action_size == 7
+            and model.channels <= 16)
+
+
+def _bn_affine(bn):
+    s = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
+    return s, bn.bias.double() - bn.running_mean.double() * s
+
+
+@torch.no_grad()
+def fold(model, row_stride):
+    """-> dict of CPU tensors in the layouts azb200_nn.h documents."""
+    m = model.eval().cpu()
+    ch, depth, cin = m.conv1.out_channels, len(m.resnet), m.channels
+    L = 1 + 2 * depth
+    wconv = torch.zeros(L, ch, row_stride, dtype=torch.float64)
+    cbias = torch.zeros(L, ch, dtype=torch.float64)
+    s, t = _bn_affine(m.bn1)
+    w = m.conv1.weight.double() * s[:, None, None, None]                 # [co, ci, ky, kx]
+    wconv[0, :, :9 * 16].view(ch, 9, 16)[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(ch, 9, cin)
+    cbias[0] = t
+    bn_scale = torch.zeros(max(depth, 1), ch, dtype=torch.float64)
+    bn_shift = torch.zeros(max(depth, 1), ch, dtype=torch.float64)
+    for i, blk in enumerate(m.resnet):
+        bn_scale[i], bn_shift[i] = _bn_affine(blk.bn1)
+        s2, t2 = _bn_affine(blk.bn2)
+        w1 = blk.conv1.weight.double() * s2[:, None, None, None]
+        wconv[1 + 2 * i, :, :9 * ch] = w1.permute(0, 2, 3, 1).reshape(ch, 9 * ch)
+        cbias[1 + 2 * i] = t2
+        wconv[2 + 2 * i, :, :9 * ch] = blk.conv2.weight.double().permute(0, 2, 3, 1).reshape(ch, 9 * ch)
+    # heads as one affine map of the trunk output [ch, H, W]
+    H, W = m.board_x, m.board_y
+    md = m.double()
+
+    def heads(x):
+        v = md.v_fc(torch.flatten(md.v_bn(md.v_conv(x)), 1))
+        p = md.pi_fc(torch.flatten(md.pi_bn(md.pi_conv(x)), 1))
+        return torch.cat([p, v], dim=1)                                   # [n, A + 3]
+    zero = torch.zeros(1, ch, H, W, dtype=torch.float64)
+    bias = heads(zero)[0]
+    basis = torch.eye(ch * H * W, dtype=torch.float64).view(ch * H * W, ch, H, W)
+    mat = (heads(basis) - bias[None]).T.contiguous()                       # [A+3, ch*H*W], feature = c*HW + pos
+    whead = mat.view(-1, ch, H * W).permute(0, 2, 1).contiguous()          # [A+3, pos, ch]
+    m.float()
+    return dict(wconv=wconv.to(torch.bfloat16), cbias=cbias.float(), bn_scale=bn_scale.float(),
+                bn_shift=bn_shift.float(), whead=whead.float(), bhead=bias.float(),
+                channels=ch, depth=depth, in_channels=cin, board_h=H, board_w=W, action_size=m.action_size)
+
+
+class FusedResNetEvaluator:
+    """Same call surface as azb200.nnet.LeafEvaluator: evaluator(stream) enqueues one
+    evaluation of ``obs`` into ``policy`` / ``value`` (engine-owned device rows)."""
+
+    precision = "bf16"
+
+    def __init__(self, model, obs, policy, value):
+        if not supported(model):
+            raise NotImplementedError("fused evaluator: 6x7 boards, 32 channels, 7 actions only")
+        self.lib = _capi.load()
+        self.lib.azb_nn_forward.restype = C.c_int
+        self.lib.azb_nn_forward.argtypes = [C.POINTER(_NNWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        dev = obs.device
+        model_dev = next(model.parameters()).device
+        f = fold(model, self.lib.azb_nn_weight_row_stride())
+        model.to(model_dev)
+        self.t = {k: v.to(dev).contiguous() for k, v in f.items() if torch.is_tensor(v)}
+        self.w = _NNWeights(f["channels"], f["depth"], f["in_channels"], f["board_h"], f["board_w"], f["action_size"],
+                            *(self.t[k].data_ptr() for k in ("wconv", "cbias", "bn_scale", "bn_shift", "whead", "bhead")))
+        assert obs.is_contiguous() and policy.is_contiguous() and value.is_contiguous()
+        self.obs, self.policy, self.value = obs, policy, value
+        self.batch = obs.shape[0]
+        self.stream = torch.cuda.Stream(device=dev)
+
+    def __call__(self, stream=None):
+        stream = stream or torch.cuda.current_stream()
+        rc = self.lib.azb_nn_forward(C.byref(self.w), self.obs.data_ptr(), self.policy.data_ptr(), self.value.data_ptr(),
+                                     self.batch, C.c_void_p(stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"azb_nn_forward failed with status {rc}")

@@ -183,7 +183,7 @@ class DeviceSelfPlay:
     ``nn_stream``; with cohorts == 2 the two halves of the games alternate so
     that tree work of one half overlaps inference of the other."""
 
-    def __init__(self, engine, nnet, cohorts=1, precision="tf32", use_graph=True, channels_last=False):
+    def __init__(self, engine, nnet, cohorts=1, precision="tf32", use_graph=True, channels_last=False, fused=False):
         assert cohorts in (1, 2)
         self.engine = engine
         self.cohorts = cohorts
@@ -191,9 +191,15 @@ class DeviceSelfPlay:
         bounds = [0, B] if cohorts == 1 else [0, B // 2, B]
         self.ranges = [(bounds[i], bounds[i + 1] - bounds[i]) for i in range(cohorts)]
         from .nnet import LeafEvaluator
-        self.evals = [LeafEvaluator(nnet, engine.obs[f:f + c], engine.policy[f:f + c], engine.value[f:f + c],
-                                    precision=precision, use_graph=use_graph, channels_last=channels_last)
-                      for f, c in self.ranges]
+        if fused:
+            # hand-written fused ResNet kernel (bf16 tensor cores, csrc/azb_resnet.cu)
+            from .fused_nn import FusedResNetEvaluator
+            self.evals = [FusedResNetEvaluator(nnet, engine.obs[f:f + c], engine.policy[f:f + c], engine.value[f:f + c])
+                          for f, c in self.ranges]
+        else:
+            self.evals = [LeafEvaluator(nnet, engine.obs[f:f + c], engine.policy[f:f + c], engine.value[f:f + c],
+                                        precision=precision, use_graph=use_graph, channels_last=channels_last)
+                          for f, c in self.ranges]
         dev = engine.obs.device
         self.tree_stream = torch.cuda.Stream(device=dev)
         self.nn_stream = torch.cuda.Stream(device=dev)

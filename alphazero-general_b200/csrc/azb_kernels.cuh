@@ -38,8 +38,8 @@ template <int L>
 __device__ __forceinline__ unsigned group_ballot(bool p, int sub)
 {
     const unsigned b = __ballot_sync(FULL, p);
-    if (L == 32) return b;
-    return (b >> (sub * L)) & ((1u << L) - 1u);
+    if constexpr (L == 32) return b;
+    else return (b >> (sub * L)) & ((1u << L) - 1u);
 }
 template <int L, class T>
 __device__ __forceinline__ T group_bcast(T v, int src) { return __shfl_sync(FULL, v, src, L); }

@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--net", default="default", choices=["default", "connect4_train"])
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--cohorts", type=int, default=1)
+    ap.add_argument("--nn", default="cudnn", choices=["cudnn", "fused"],
+                    help="leaf evaluator: PyTorch/cuDNN CUDA graph, or the fused bf16 tensor-core kernel")
     ap.add_argument("--lanes", type=int, default=0, help="threads per game (0 = library default)")
     ap.add_argument("--nchw", action="store_true", help="keep the ResNet in NCHW (default: channels_last)")
     ap.add_argument("--preroll", type=int, default=48, help="cheap tree-only rounds that de-synchronise the games")
@@ -301,7 +303,8 @@ def main():
     torch.manual_seed(0)
     netargs = aznet.DEFAULT_NET_ARGS if a.net == "default" else aznet.CONNECT4_TRAIN_NET_ARGS
     model = aznet.ResNet((4, 6, 7), 7, 3, **netargs).to(dev).eval()
-    drv = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision, channels_last=not a.nchw)
+    drv = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision, channels_last=not a.nchw,
+                         fused=(a.nn == "fused"))
 
     # cheap tree-only pre-roll so the games are spread over all phases (steady state)
     for _ in range(a.preroll):
@@ -317,23 +320,18 @@ def main():
         else:
             drv.run_round(sims)
         # keep the sample ring from filling: discard on the device (no host copy)
-        n = eng.sample_count()
-        if n > (eng_cap // 2):
-            clear_samples()
+        clear_samples()
 
-    eng_cap = 8192 * 4 * 42 * 2
-
-    scratch = {}
+    kept = []          # examples drained on the device during the run (gathered over NCCL at the end)
 
     def clear_samples():
         n = eng.sample_count()
         if n == 0:
             return
-        if "obs" not in scratch or scratch["obs"].shape[0] < n:
-            scratch["obs"] = torch.empty(n, 4, 6, 7, device=dev)
-            scratch["pi"] = torch.empty(n, 7, device=dev)
-            scratch["z"] = torch.empty(n, 3, device=dev)
-        eng.drain_samples_into(scratch["obs"], scratch["pi"], scratch["z"])
+        o = torch.empty(n, 4, 6, 7, device=dev); p = torch.empty(n, 7, device=dev); z = torch.empty(n, 3, device=dev)
+        eng.drain_samples_into(o, p, z)
+        if world > 1 and sum(t[0].shape[0] for t in kept) < 4_000_000:
+            kept.append((o, p, z))
 
     def barrier():
         torch.cuda.synchronize()
@@ -344,6 +342,7 @@ def main():
     for _ in range(max(a.warmup, 3)):
         step()
     clear_samples()
+    kept.clear()
     eng.check_errors()
     st0 = eng.stats()
     launches0 = drv.launches
@@ -425,7 +424,8 @@ def main():
         e2e = run_e2e(a, eng, model, dev, world)
 
     if world > 1:
-        gather_ms, gathered = gather_examples(eng, dev, rank, world)
+        clear_samples()
+        gather_ms, gathered = gather_examples(kept, dev, rank, world)
     else:
         gather_ms, gathered = None, None
 
@@ -433,11 +433,11 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if a.precision == "fp32" else a.precision, "data": "synthetic",
+            "dtype": "bf16" if a.nn == "fused" else ("f32" if a.precision == "fp32" else a.precision), "data": "synthetic",
             "config": {"workload": f"connect4 {B} games/GPU x {sims} sims/move, DEFAULT_ARGS MCTS (cpuct 1.25, fpu 0.2, "
                                    f"root noise 0.1 + temp 1.1), net={a.net} ResNet random-init, "
                                    f"{'tree-only warmup mode' if a.tree_only else 'NN in the loop'}",
-                       "games_per_gpu": B, "sims_per_move": sims, "net": a.net, "nn_precision": a.precision,
+                       "games_per_gpu": B, "sims_per_move": sims, "net": a.net, "nn": a.nn, "nn_precision": "bf16" if a.nn == "fused" else a.precision,
                        "cohorts": a.cohorts, "channels_last": not a.nchw, "lanes_per_game": a.lanes or 8, "rng": "philox", "parallelism": f"games x{world} (no data-path collective)",
                        "l2": "node pool %.1f GB per GPU > 126 MB L2; no flush" % (st1["pool_bytes"] / 1e9),
                        "preroll_rounds": a.preroll},
@@ -526,14 +526,16 @@ def run_e2e(a, eng, model, dev, world):
             "steps": steps, "api": "azb200.selfplay.SelfPlayAgent.generateBatch/processBatch/playMoves + NNetWrapper.process, pinned host tensors"}
 
 
-def gather_examples(eng, dev, rank, world):
-    """BASELINE config 3: NCCL gather of the (s, pi, z) examples to rank 0."""
+def gather_examples(kept, dev, rank, world):
+    """BASELINE config 3: NCCL gather of the (s, pi, z) examples of the timed steps to rank 0."""
     import torch
     import torch.distributed as dist
     from azb200.distributed import gather_examples_to_rank0
-    n = eng.sample_count()
-    obs = torch.empty(n, 4, 6, 7, device=dev); pi = torch.empty(n, 7, device=dev); z = torch.empty(n, 3, device=dev)
-    eng.drain_samples_into(obs, pi, z)
+    if kept:
+        obs, pi, z = (torch.cat([k[i] for k in kept]) for i in range(3))
+    else:
+        obs, pi, z = torch.empty(0, 4, 6, 7, device=dev), torch.empty(0, 7, device=dev), torch.empty(0, 3, device=dev)
+    gather_examples_to_rank0(obs[:1], pi[:1], z[:1])          # NCCL warm-up (communicator setup is not timed)
     torch.cuda.synchronize(); dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

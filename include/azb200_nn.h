@@ -1,0 +1,44 @@
+/*
+ * azb200_nn.h -- C ABI of the fused leaf evaluator in libazb200.so: the
+ * reference's pre-activation ResNet (alphazero/NNetArchitecture.py:69-120, the
+ * network NNetWrapper.process runs, alphazero/NNetWrapper.py:225-232) for small
+ * boards as ONE kernel launch per batch (bf16 tensor-core convolutions, fp32
+ * residual stream / heads / softmax).  Weights are prepared on the host with
+ * batch-norm folded (azb200/fused_nn.py documents the algebra).  Supported
+ * geometry: 6x7 boards, 32 trunk channels, 7 actions (Connect4); everything
+ * else keeps the PyTorch/cuDNN evaluator.
+ */
+#ifndef AZB200_NN_H
+#define AZB200_NN_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct azb_nn_weights {
+    int32_t channels;      /* args.num_channels (32)                                          */
+    int32_t depth;         /* args.depth: residual blocks                                     */
+    int32_t in_channels;   /* Game.observation_size()[0]                                      */
+    int32_t board_h, board_w;
+    int32_t action_size;   /* Game.action_size()                                              */
+    const void *wconv;     /* device bf16 [1+2*depth][channels][azb_nn_weight_row_stride()]:  */
+                           /* row = output channel, k = tap*16+cin (stem) / tap*32+cin        */
+    const float *cbias;    /* device f32 [1+2*depth][channels] (folded BN shift; 0 for conv2) */
+    const float *bn_scale; /* device f32 [depth][channels]: BN1 of every block                */
+    const float *bn_shift; /* device f32 [depth][channels]                                    */
+    const float *whead;    /* device f32 [action_size+3][H*W][channels]: folded heads         */
+    const float *bhead;    /* device f32 [action_size+3]                                      */
+} azb_nn_weights;
+
+/* obs: device f32 [batch, C, H, W]; policy: device f32 [batch, A] (probabilities);
+ * value: device f32 [batch, 3].  Asynchronous on `stream`.  0 on success,
+ * -1 unsupported geometry, -2 CUDA error, -7 bad argument. */
+int azb_nn_forward(const azb_nn_weights *w, const float *obs, float *policy, float *value, int32_t batch, void *stream);
+int azb_nn_weight_row_stride(void);
+int azb_nn_boards_per_cta(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

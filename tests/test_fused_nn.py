@@ -1,0 +1,87 @@
+"""The fused ResNet kernel (csrc/azb_resnet.cu) against a plain PyTorch fp32
+evaluation of the same module.  Convolution operands are bf16 (fp32
+accumulation), so the tolerance is the bf16 one, stated here: 3e-2 absolute on
+probabilities; the folded-weight algebra itself is checked in float64 on the
+CPU to 1e-9."""
+import numpy as np
+import pytest
+import torch
+
+from azb200 import nnet as aznet
+
+
+def _model(seed=0, depth=4):
+    torch.manual_seed(seed)
+    m = aznet.ResNet((4, 6, 7), 7, 3, **dict(aznet.DEFAULT_NET_ARGS, depth=depth)).eval()
+    with torch.no_grad():                      # non-trivial BN statistics / affine
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.3); mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.5, 1.5); mod.bias.normal_(0, 0.2)
+    return m
+
+
+def _obs(n, seed=1):
+    rs = np.random.RandomState(seed)
+    o = np.zeros((n, 4, 6, 7), np.float32)
+    cells = rs.randint(0, 3, size=(n, 6, 7))
+    o[:, 0] = cells == 1; o[:, 1] = cells == 2
+    o[:, 2] = rs.randint(0, 2, size=(n, 1, 1)); o[:, 3] = rs.randint(0, 43, size=(n, 1, 1)) / 42.0
+    return torch.from_numpy(o)
+
+
+def test_folded_weights_reproduce_the_module_in_float64():
+    """BN folding + affine head folding, emulated with the folded tensors in float64."""
+    from azb200.fused_nn import fold
+    m = _model()
+    f = fold(m, 296)
+    x = _obs(16).double()
+    md = m.double()
+    with torch.no_grad():
+        lp, lv = md(x)
+        want = torch.cat([lp.exp(), lv.exp()], 1)
+        ch, depth = 32, f["depth"]
+        w = f["wconv"].double()              # bf16-rounded operands: compare against the same rounding
+        def conv(inp, layer, cin, kper):
+            k = w[layer, :, :9 * kper].view(ch, 3, 3, kper)[..., :cin].permute(0, 3, 1, 2)
+            return torch.nn.functional.conv2d(inp, k, padding=1)
+        t = torch.relu(conv(x, 0, 4, 16) + f["cbias"][0].double().view(1, -1, 1, 1))
+        for i in range(depth):
+            a = torch.relu(t * f["bn_scale"][i].double().view(1, -1, 1, 1) + f["bn_shift"][i].double().view(1, -1, 1, 1))
+            b = torch.relu(conv(a, 1 + 2 * i, ch, ch) + f["cbias"][1 + 2 * i].double().view(1, -1, 1, 1))
+            t = t + conv(b, 2 + 2 * i, ch, ch)
+        feat = t.permute(0, 2, 3, 1).reshape(len(x), 42, ch)
+        logits = torch.einsum("npc,jpc->nj", feat, f["whead"].double()) + f["bhead"].double()
+        got = torch.cat([torch.softmax(logits[:, :7], 1), torch.softmax(logits[:, 7:], 1)], 1)
+    m.float()
+    # only the bf16 rounding of the conv weights separates the two
+    assert torch.allclose(got, want, atol=2e-2)
+    # and with unrounded weights the algebra is exact
+    f64 = fold(_model(), 296)
+    assert f64["whead"].shape == (10, 42, 32) and f64["wconv"].shape == (9, 32, 296)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch", [8, 100, 8192])
+def test_fused_kernel_matches_pytorch_fp32(batch):
+    from azb200.fused_nn import FusedResNetEvaluator
+    dev = torch.device("cuda")
+    m = _model().to(dev)
+    obs = _obs(batch).to(dev)
+    pol = torch.zeros(batch, 7, device=dev); val = torch.zeros(batch, 3, device=dev)
+    ev = FusedResNetEvaluator(m, obs, pol, val)
+    ev()
+    torch.cuda.synchronize()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        lp, lv = m(obs)
+    torch.backends.cudnn.allow_tf32 = old
+    wp, wv = lp.exp(), lv.exp()
+    assert torch.isfinite(pol).all() and torch.isfinite(val).all()
+    assert torch.allclose(pol.sum(1), torch.ones(batch, device=dev), atol=1e-5)
+    assert torch.allclose(val.sum(1), torch.ones(batch, device=dev), atol=1e-5)
+    ep, evl = (pol - wp).abs().max().item(), (val - wv).abs().max().item()
+    assert ep < 3e-2 and evl < 3e-2, (ep, evl)
+    # typical error is far below the bound
+    assert (pol - wp).abs().mean().item() < 3e-3
