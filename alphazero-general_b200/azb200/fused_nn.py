@@ -36,7 +36,7 @@ def _bn_affine(bn):
 
 
 @torch.no_grad()
-def fold(model, row_stride):
+def fold(model, row_stride, head_stride=None):
     """-> dict of CPU tensors in the layouts azb200_nn.h documents."""
     m = model.eval().cpu()
     ch, depth, cin = m.conv1.out_channels, len(m.resnet), m.channels
@@ -70,8 +70,15 @@ def fold(model, row_stride):
     mat = (heads(basis) - bias[None]).T.contiguous()                       # [A+3, ch*H*W], feature = c*HW + pos
     whead = mat.view(-1, ch, H * W).permute(0, 2, 1).contiguous()          # [A+3, pos, ch]
     m.float()
+    nout = whead.shape[0]
+    hs = head_stride or (H * W * ch + 8)
+    whead16 = torch.zeros(16, hs, dtype=torch.float64)                     # padded to two n-tiles, k = pos*ch + c
+    whead16[:nout, :H * W * ch] = whead.reshape(nout, -1)
+    bhead16 = torch.zeros(16, dtype=torch.float64)
+    bhead16[:nout] = bias
     return dict(wconv=wconv.to(torch.bfloat16), cbias=cbias.float(), bn_scale=bn_scale.float(),
                 bn_shift=bn_shift.float(), whead=whead.float(), bhead=bias.float(),
+                whead16=whead16.to(torch.bfloat16), bhead16=bhead16.float(),
                 channels=ch, depth=depth, in_channels=cin, board_h=H, board_w=W, action_size=m.action_size)
 
 
@@ -89,11 +96,12 @@ class FusedResNetEvaluator:
         self.lib.azb_nn_forward.argtypes = [C.POINTER(_NNWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         dev = obs.device
         model_dev = next(model.parameters()).device
-        f = fold(model, self.lib.azb_nn_weight_row_stride())
+        self.lib.azb_nn_head_row_stride.restype = C.c_int
+        f = fold(model, self.lib.azb_nn_weight_row_stride(), self.lib.azb_nn_head_row_stride())
         model.to(model_dev)
         self.t = {k: v.to(dev).contiguous() for k, v in f.items() if torch.is_tensor(v)}
         self.w = _NNWeights(f["channels"], f["depth"], f["in_channels"], f["board_h"], f["board_w"], f["action_size"],
-                            *(self.t[k].data_ptr() for k in ("wconv", "cbias", "bn_scale", "bn_shift", "whead", "bhead")))
+                            *(self.t[k].data_ptr() for k in ("wconv", "cbias", "bn_scale", "bn_shift", "whead16", "bhead16")))
         assert obs.is_contiguous() and policy.is_contiguous() and value.is_contiguous()
         self.obs, self.policy, self.value = obs, policy, value
         self.batch = obs.shape[0]

@@ -96,14 +96,32 @@ class NNetWrapper:
     """Inference half of alphazero/NNetWrapper.py (process / predict); training
     stays with the reference wrapper."""
 
-    def __init__(self, game_cls=None, args=None, nnet=None, cuda=None):
+    def __init__(self, game_cls=None, args=None, nnet=None, cuda=None, fused=False):
         self.game_cls, self.args = game_cls, args
         self.nnet = nnet if nnet is not None else ResNet.for_game(game_cls, args)
         self.cuda = torch.cuda.is_available() if cuda is None else cuda
         if self.cuda:
             self.nnet.cuda()
+        self.fused = fused          # evaluate with the fused bf16 kernel (csrc/azb_resnet.cu) when supported
+        self._fused_eval = {}
+
+    def _process_fused(self, batch):
+        n = batch.shape[0]
+        ev = self._fused_eval.get(n)
+        if ev is None:
+            from .fused_nn import FusedResNetEvaluator
+            dev = next(self.nnet.parameters()).device
+            obs = torch.empty((n,) + tuple(batch.shape[1:]), device=dev)
+            ev = FusedResNetEvaluator(self.nnet, obs, torch.empty(n, self.nnet.action_size, device=dev),
+                                      torch.empty(n, 3, device=dev))
+            self._fused_eval[n] = ev
+        ev.obs.copy_(batch, non_blocking=True)
+        ev()
+        return ev.policy, ev.value
 
     def process(self, batch):
+        if self.fused and self.cuda:
+            return self._process_fused(batch)
         batch = batch.type(torch.FloatTensor) if not batch.is_cuda else batch.float()
         if self.cuda and not batch.is_cuda:
             batch = batch.cuda()

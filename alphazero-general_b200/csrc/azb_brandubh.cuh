@@ -30,6 +30,7 @@ struct Brandubh {
     static constexpr int MAXD = 104;
     static constexpr int NSYM = 8;
     static constexpr int LANES = 32;
+    static constexpr bool LANE_IS_ACTION = false;
     static constexpr unsigned long long BOARD = (1ULL << 49) - 1ULL;
     static constexpr unsigned long long THRONE = 1ULL << 24;
     static constexpr unsigned long long CORNERS = (1ULL << 0) | (1ULL << 6) | (1ULL << 42) | (1ULL << 48);

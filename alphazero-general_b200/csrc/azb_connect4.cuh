@@ -25,6 +25,7 @@ struct Connect4T {
     static constexpr int MAXD = 44;        // path buffer entries per slot
     static constexpr int NSYM = 2;         // symmetries(): identity, mirror
     static constexpr int LANES = LANES_;   // threads cooperating on one game (8, 16 or 32)
+    static constexpr bool LANE_IS_ACTION = true;   // A <= LANES: lane a can own the child of action a
     static constexpr unsigned long long TOP = 0x0810204081020ULL;  // bits col*7+5
 
     __device__ __forceinline__ static void init(GState &s) { s.b0 = s.b1 = s.b2 = 0ULL; s.turns = 0; s.flags = 0; }

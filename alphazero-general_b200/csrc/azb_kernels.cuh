@@ -169,11 +169,12 @@ __device__ __forceinline__ float np_sum_group(const float *vec, int lane)
 // ------------------------------------------------------------------------------
 template <class G, int IT>
 __device__ __forceinline__ void child_order(const DevView &d, int g, int C, bool consume, bool store, int lane,
-                                            GroupSmem<G> &sm, uint32_t valid_mask, int (&cpos)[IT], int (&cact)[IT])
+                                            GroupSmem<G> &sm, uint32_t valid_mask, int (&cpos)[IT], int (&cact)[IT],
+                                            bool (&cwr)[IT])
 {
     constexpr int L = G::LANES;
 #pragma unroll
-    for (int i = 0; i < IT; i++) { cpos[i] = lane + i * L; cact[i] = 0; }
+    for (int i = 0; i < IT; i++) { cpos[i] = lane + i * L; cact[i] = 0; cwr[i] = store && (lane + i * L < C); }
     if (d.rng_mode == 0) {
         if (consume && lane == 0) {
             uint32_t *st = d.mt + (size_t)g * 625;
@@ -197,6 +198,21 @@ __device__ __forceinline__ void child_order(const DevView &d, int g, int C, bool
         __syncwarp();
         if (consume && lane == 0) d.ctr[g] = c0 + (unsigned long long)C;
         uint32_t key[IT];
+        if constexpr (G::LANE_IS_ACTION) {
+            // small action space: lane a owns the child of action a; its ascending index is the
+            // number of valid actions below it
+            const bool valid = (valid_mask >> lane) & 1u;
+            const int j = __popc(valid_mask & ((1u << lane) - 1u));
+            key[0] = (store && valid) ? philox_word(d.seed, (unsigned long long)(d.gid_base + g), c0 + (unsigned long long)j) : 0u;
+            int rank = 0;
+#pragma unroll
+            for (int i = 0; i < G::A; i++) {
+                const uint32_t ki = group_bcast<L>(key[0], i);
+                rank += ((valid_mask >> i) & 1u) && ((ki < key[0]) || (ki == key[0] && i < lane));
+            }
+            cpos[0] = rank; cact[0] = lane; cwr[0] = store && valid;
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < IT; i++) {
             const int j = lane + i * L;
@@ -395,12 +411,12 @@ __device__ __forceinline__ void select_game(const DevView &d, int g, bool active
             else { store = true; nc = C; }
         }
         int cpos[IT], cact[IT];
-        child_order<G, IT>(d, g, C, expd, store, lane, sm, vmask, cpos, cact);
+        bool cwr[IT];
+        child_order<G, IT>(d, g, C, expd, store, lane, sm, vmask, cpos, cact, cwr);
         if (store) {
 #pragma unroll
             for (int i = 0; i < IT; i++) {
-                const int j = lane + i * L;
-                if (j < C) {
+                if (cwr[i]) {
                     const size_t idx = nb + (size_t)(base + cpos[i]);
                     *reinterpret_cast<int4 *>(d.hot + idx) = make_int4(0, 0, 0, -1);
                     *reinterpret_cast<int2 *>(d.cold + idx) = make_int2(0, (int)meta_pack((uint32_t)cact[i], 0u, 0u, 0u));
@@ -602,7 +618,7 @@ __device__ __forceinline__ void expand_backup_game(const DevView &d, int g, bool
     // backup along the stored path; level i updates the node entered at step i.
     // player(node at depth t) = (leaf player - depth + t) & 1: turns alternate.
     const int *path = d.path + (size_t)g * G::MAXD;
-    const float share = f_div(val2, 2.0f);              // value[num_players] / num_players
+    const float share = f_mul(val2, 0.5f);              // value[num_players] / num_players (halving is exact)
     const int root_player = (meta_player(lmeta) - depth) & 1;
     if (on) {
         for (int i = lane; i < depth; i += L) {

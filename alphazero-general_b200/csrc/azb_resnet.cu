@@ -15,9 +15,13 @@
 // the strict-fp32 parity path stays PyTorch/cuDNN (azb200/nnet.py).
 //
 // Tile: NB = 8 boards per CTA -> 8*H*W = 336 output positions = 21 m-tiles of
-// 16 rows for a 6x7 board; 11 warps (a pair of m-tiles each); shared memory: fp32 residual x, bf16
-// activations a / b (zero-padded (H+2)x(W+2) frames, so a 3x3 tap is a constant
-// row offset), double-buffered bf16 weights of the current / next layer.
+// 16 rows for a 6x7 board; 11 warps (a pair of m-tiles each).  Shared memory
+// (218 KB): fp32 residual x, bf16 activations a / b (zero-padded (H+2)x(W+2)
+// frames, so a 3x3 tap is a constant row offset), double-buffered bf16 weights
+// of the current / next layer, the folded head matrix.  BN1 + ReLU of the next
+// block is applied in the epilogue of the convolution that produces x, so a
+// block costs two tensor-core passes and two barriers; the heads are one more
+// small MMA over the bf16 copy of the final x.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,9 +34,13 @@ constexpr int NB = 8;          // boards per CTA
 constexpr int CH = 32;         // trunk channels
 constexpr int THREADS = 352;    // 11 warps: warp w owns m-tiles 2w, 2w+1 of the 21 (6x7 boards)
 constexpr int RS_A = 40;       // bf16 row stride of a / b (80 B: conflict-free ldmatrix rows)
-constexpr int RS_X = 36;       // fp32 row stride of x
+constexpr int RS_X = 40;       // fp32 row stride of x (float2 epilogue accesses conflict-free per half-warp)
 constexpr int KW = 9 * CH;     // 288: K of a full 3x3 conv
 constexpr int RS_W = KW + 8;   // 296: bf16 row stride of the weight matrix [cout][k]
+constexpr int NHEAD = 16;      // head outputs padded to two n-tiles
+constexpr int MAXD = 6;        // residual blocks supported by the shared-memory parameter block
+constexpr int MAXL = 1 + 2 * MAXD;
+constexpr int PRM_FLOATS = MAXL * CH + 2 * MAXD * CH;
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t addr)
 {
@@ -44,12 +52,32 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+// ---- TMA bulk copy (global -> shared, completion on an mbarrier) ---------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(dst), "l"(src));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 template <int H, int W>
 struct Geo {
@@ -66,13 +94,17 @@ struct Geo {
     }
 };
 
-enum { EPI_STEM = 0, EPI_TO_B = 1, EPI_ADD_X = 2 };
+enum { EPI_TO_B = 1, EPI_TO_X = 2 };
 
-// one 3x3 convolution layer over the CTA's tile: out = conv(in) with `kchunks`
-// 16-channel chunks of input channels per tap.
+// one 3x3 convolution layer over the CTA's tile with `kchunks` 16-channel chunks
+// of input channels per tap.
+//   EPI_TO_B : outb = bf16(relu(acc + bias))                      (conv1, BN2 folded)
+//   EPI_TO_X : x = (add ? x : 0) + acc (+ bias, relu for the stem) and, for the next
+//              tensor-core pass, outb = bf16(act(x * nsc + nsh))   (BN1 of the next block)
 template <int H, int W, int EPI>
 __device__ __forceinline__ void conv_layer(const __nv_bfloat16 *in, const __nv_bfloat16 *wsm, const float *bias,
-                                           float *x, __nv_bfloat16 *outb, const int *ptab, int kchunks, int warp, int lane)
+                                           float *x, __nv_bfloat16 *outb, const int *ptab, int kchunks, int warp,
+                                           int lane, bool add, const float *nsc, const float *nsh)
 {
     using G = Geo<H, W>;
     const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(in);
@@ -128,24 +160,30 @@ __device__ __forceinline__ void conv_layer(const __nv_bfloat16 *in, const __nv_b
 #pragma unroll
             for (int nt = 0; nt < 4; nt++) {
                 const int col = nt * 8 + 2 * t;
-                if (EPI == EPI_ADD_X) {
+                const float bx = bias ? bias[col] : 0.0f, by = bias ? bias[col + 1] : 0.0f;
+                float r00 = acc[u][nt][0] + bx, r01 = acc[u][nt][1] + by;
+                float r10 = acc[u][nt][2] + bx, r11 = acc[u][nt][3] + by;
+                if (EPI == EPI_TO_B) {
+                    r00 = fmaxf(r00, 0.0f); r01 = fmaxf(r01, 0.0f); r10 = fmaxf(r10, 0.0f); r11 = fmaxf(r11, 0.0f);
+                } else {
                     float2 *q0 = reinterpret_cast<float2 *>(x + m0 * RS_X + col);
                     float2 *q1 = reinterpret_cast<float2 *>(x + m1 * RS_X + col);
-                    float2 v0 = *q0, v1 = *q1;
-                    v0.x += acc[u][nt][0]; v0.y += acc[u][nt][1]; v1.x += acc[u][nt][2]; v1.y += acc[u][nt][3];
-                    *q0 = v0; *q1 = v1;
-                } else {
-                    const float bx = bias[col], by = bias[col + 1];
-                    const float r00 = fmaxf(acc[u][nt][0] + bx, 0.0f), r01 = fmaxf(acc[u][nt][1] + by, 0.0f);
-                    const float r10 = fmaxf(acc[u][nt][2] + bx, 0.0f), r11 = fmaxf(acc[u][nt][3] + by, 0.0f);
-                    if (EPI == EPI_STEM) {
-                        *reinterpret_cast<float2 *>(x + m0 * RS_X + col) = make_float2(r00, r01);
-                        *reinterpret_cast<float2 *>(x + m1 * RS_X + col) = make_float2(r10, r11);
-                    } else {
-                        *reinterpret_cast<__nv_bfloat162 *>(outb + p0 * RS_A + col) = __floats2bfloat162_rn(r00, r01);
-                        *reinterpret_cast<__nv_bfloat162 *>(outb + p1 * RS_A + col) = __floats2bfloat162_rn(r10, r11);
+                    if (add) {                                      // residual: x += conv2(b)
+                        const float2 v0 = *q0, v1 = *q1;
+                        r00 += v0.x; r01 += v0.y; r10 += v1.x; r11 += v1.y;
+                    } else {                                        // stem: x = relu(conv + bias)
+                        r00 = fmaxf(r00, 0.0f); r01 = fmaxf(r01, 0.0f); r10 = fmaxf(r10, 0.0f); r11 = fmaxf(r11, 0.0f);
+                    }
+                    *q0 = make_float2(r00, r01);
+                    *q1 = make_float2(r10, r11);
+                    if (nsc != nullptr) {                           // relu(bn1(x)) of the block that consumes x next
+                        const float sx = nsc[col], sy = nsc[col + 1], tx = nsh[col], ty = nsh[col + 1];
+                        r00 = fmaxf(fmaf(r00, sx, tx), 0.0f); r01 = fmaxf(fmaf(r01, sy, ty), 0.0f);
+                        r10 = fmaxf(fmaf(r10, sx, tx), 0.0f); r11 = fmaxf(fmaf(r11, sy, ty), 0.0f);
                     }
                 }
+                *reinterpret_cast<__nv_bfloat162 *>(outb + p0 * RS_A + col) = __floats2bfloat162_rn(r00, r01);
+                *reinterpret_cast<__nv_bfloat162 *>(outb + p1 * RS_A + col) = __floats2bfloat162_rn(r10, r11);
             }
         }
     }
@@ -156,29 +194,56 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_resnet_fused(const float *__restrict__ obs, float *__restrict__ policy, float *__restrict__ value, int B, int in_ch,
                int depth, const __nv_bfloat16 *__restrict__ wconv, const float *__restrict__ cbias,
                const float *__restrict__ bn_scale, const float *__restrict__ bn_shift,
-               const float *__restrict__ whead, const float *__restrict__ bhead)
+               const __nv_bfloat16 *__restrict__ whead, const float *__restrict__ bhead)
 {
     using G = Geo<H, W>;
+    constexpr int KH = G::P * CH;                    // head K: pos * CH + ch
+    constexpr int RS_H = KH + 8;                     // bf16 row stride of the head matrix
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *x = reinterpret_cast<float *>(smem_raw);                                   // [M][RS_X] residual stream
     __nv_bfloat16 *a = reinterpret_cast<__nv_bfloat16 *>(x + G::M * RS_X);            // [NB*PP][RS_A]
     __nv_bfloat16 *b = a + NB * G::PP * RS_A;
     __nv_bfloat16 *w0 = b + NB * G::PP * RS_A;                                        // [CH][RS_W] x 2
     __nv_bfloat16 *w1 = w0 + CH * RS_W;
-    int *ptab = reinterpret_cast<int *>(w1 + CH * RS_W);                              // [M] GEMM row -> padded frame row
-    float *red = reinterpret_cast<float *>(ptab + G::M);                              // [warps][NB*NOUT] head partial sums
+    __nv_bfloat16 *wh = w1 + CH * RS_W;                                               // [NHEAD][RS_H]
+    int *ptab = reinterpret_cast<int *>(wh + NHEAD * RS_H);                           // [M] GEMM row -> padded frame row
+    float *prm = reinterpret_cast<float *>(ptab + G::M);                              // biases [L][CH], bn scale/shift [D][CH] x2
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(prm + PRM_FLOATS);   // mbarriers: w0, w1, heads
+    float *red = reinterpret_cast<float *>(w0);                                       // heads: [warps][NB][NHEAD] (aliases w0)
+    float *fin = reinterpret_cast<float *>(w1);                                       // heads: [NB][NHEAD] logits (aliases w1)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int board0 = blockIdx.x * NB;
     const int layers = 1 + 2 * depth;
-    constexpr int WBYTES = CH * RS_W * 2;
+    constexpr uint32_t WBYTES = CH * RS_W * 2;
+    const uint32_t bar_w[2] = {(uint32_t)__cvta_generic_to_shared(bars), (uint32_t)__cvta_generic_to_shared(bars + 1)};
+    const uint32_t bar_h = (uint32_t)__cvta_generic_to_shared(bars + 2);
+    uint32_t phase[2] = {0u, 0u};
 
-    auto prefetch_w = [&](int layer, __nv_bfloat16 *dst) {
-        const char *src = reinterpret_cast<const char *>(wconv) + (size_t)layer * WBYTES;
-        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-        for (int i = tid; i < WBYTES / 16; i += THREADS) cp_async16(d + i * 16, src + i * 16);
-        cp_async_commit();
+    if (tid == 0) {
+        mbar_init(bar_w[0], 1); mbar_init(bar_w[1], 1); mbar_init(bar_h, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    // one thread streams a whole layer's weight matrix with a single bulk copy (all readers of
+    // the destination buffer have passed a __syncthreads before this is called)
+    auto prefetch_w = [&](int layer, __nv_bfloat16 *dst, int buf) {
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar_w[buf], WBYTES);
+            bulk_g2s((uint32_t)__cvta_generic_to_shared(dst), reinterpret_cast<const char *>(wconv) + (size_t)layer * WBYTES,
+                     WBYTES, bar_w[buf]);
+        }
     };
-    prefetch_w(0, w0);
+    auto wait_w = [&](int buf) { mbar_wait(bar_w[buf], phase[buf]); phase[buf] ^= 1u; };
+    prefetch_w(0, w0, 0);
+    if (tid == 0) {   // the folded head matrix, needed only at the very end
+        mbar_expect_tx(bar_h, (uint32_t)(NHEAD * RS_H * 2));
+        bulk_g2s((uint32_t)__cvta_generic_to_shared(wh), whead, (uint32_t)(NHEAD * RS_H * 2), bar_h);
+    }
+    // per-channel parameters -> shared memory
+    for (int i = tid; i < layers * CH; i += THREADS) prm[i] = cbias[i];
+    for (int i = tid; i < depth * CH; i += THREADS) { prm[MAXL * CH + i] = bn_scale[i]; prm[MAXL * CH + MAXD * CH + i] = bn_shift[i]; }
+    const float *s_bias = prm, *s_sc = prm + MAXL * CH, *s_sh = prm + MAXL * CH + MAXD * CH;
 
     // zero the activation frames (borders must read as zero padding), build the row table, load the observation
     {
@@ -192,101 +257,87 @@ k_resnet_fused(const float *__restrict__ obs, float *__restrict__ policy, float 
         const int bl = i / (in_ch * G::P), r = i - bl * in_ch * G::P, c = r / G::P, pos = r - c * G::P;
         const int gb = board0 + bl;
         const float v = gb < B ? obs[(size_t)gb * in_ch * G::P + r] : 0.0f;
-        a[ptab[bl * G::P + pos] * RS_A + c] = __float2bfloat16(v);
+        b[ptab[bl * G::P + pos] * RS_A + c] = __float2bfloat16(v);
     }
 
-    // stem: x = relu(conv(a) + bias0)       (K = 9 taps x 16 channels, channels >= in_ch are zero)
-    cp_async_wait_all();
+    // stem: x = relu(conv(obs) + bias0), a = relu(bn1_0(x))   (K = 9 taps x 16 channels, channels >= in_ch are zero)
     __syncthreads();
-    if (layers > 1) prefetch_w(1, w1);
-    conv_layer<H, W, EPI_STEM>(a, w0, cbias, x, nullptr, ptab, 1, warp, lane);
+    wait_w(0);
+    if (layers > 1) prefetch_w(1, w1, 1);
+    conv_layer<H, W, EPI_TO_X>(b, w0, s_bias, x, a, ptab, 1, warp, lane, false, depth > 0 ? s_sc : nullptr, s_sh);
     __syncthreads();
 
     for (int blk = 0; blk < depth; blk++) {
-        // a = relu(bn1(x))
-        const float *sc = bn_scale + blk * CH, *sh = bn_shift + blk * CH;
-        {
-            const int c2 = (tid & 15) * 2;                 // THREADS % 16 == 0: a thread keeps its channel pair
-            const float s0 = sc[c2], s1 = sc[c2 + 1], t0 = sh[c2], t1 = sh[c2 + 1];
-            for (int m = tid >> 4; m < G::M; m += THREADS / 16) {
-                const float2 v = *reinterpret_cast<const float2 *>(x + m * RS_X + c2);
-                const float r0 = fmaxf(fmaf(v.x, s0, t0), 0.0f), r1 = fmaxf(fmaf(v.y, s1, t1), 0.0f);
-                *reinterpret_cast<__nv_bfloat162 *>(a + ptab[m] * RS_A + c2) = __floats2bfloat162_rn(r0, r1);
-            }
-        }
         const int l1 = 1 + 2 * blk, l2 = l1 + 1;
         __nv_bfloat16 *wl1 = (l1 & 1) ? w1 : w0, *wl2 = (l2 & 1) ? w1 : w0;
-        cp_async_wait_all();
-        __syncthreads();
-        prefetch_w(l2, wl2);
+        prefetch_w(l2, wl2, l2 & 1);
+        wait_w(l1 & 1);
         // b = relu(conv1(a) + bias)   (BN2 folded)
-        conv_layer<H, W, EPI_TO_B>(a, wl1, cbias + l1 * CH, x, b, ptab, 2, warp, lane);
-        cp_async_wait_all();
+        conv_layer<H, W, EPI_TO_B>(a, wl1, s_bias + l1 * CH, x, b, ptab, 2, warp, lane, false, nullptr, nullptr);
         __syncthreads();
-        if (l2 + 1 < layers) prefetch_w(l2 + 1, wl1);
-        // x += conv2(b)
-        conv_layer<H, W, EPI_ADD_X>(b, wl2, nullptr, x, nullptr, ptab, 2, warp, lane);
+        if (l2 + 1 < layers) prefetch_w(l2 + 1, wl1, l1 & 1);
+        wait_w(l2 & 1);
+        // x += conv2(b);  a = relu(bn1_{blk+1}(x))  (the last block leaves a = bf16(x) for the heads)
+        const bool last = blk + 1 == depth;
+        conv_layer<H, W, EPI_TO_X>(b, wl2, nullptr, x, a, ptab, 2, warp, lane, true,
+                                   last ? nullptr : s_sc + (blk + 1) * CH, s_sh + (blk + 1) * CH);
         __syncthreads();
     }
+    mbar_wait(bar_h, 0u);
 
-    // heads: logits[board][j] = sum_f whead[j][f] * x[board][f] + bhead[j],  f = pos*CH + ch.
-    // Each thread owns a slice of the features for ALL boards of the tile, so a head weight is
-    // read once per CTA; partial sums are reduced by shuffles, then across warps in shared memory.
+    // heads: logits[board][j] = sum_k wh[j][k] * a[board][k] + bhead[j], k = pos*CH + ch, as one small MMA
+    // (rows 0-7 = boards, rows 8-15 duplicate them); the 2*P k-steps are split over the warps.
     {
-        float acc[NB][NOUT];
+        const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(a);
+        const uint32_t h_s = (uint32_t)__cvta_generic_to_shared(wh);
+        float acc[2][4];
 #pragma unroll
-        for (int bq = 0; bq < NB; bq++)
-#pragma unroll
-            for (int j = 0; j < NOUT; j++) acc[bq][j] = 0.0f;
-        for (int f = tid; f < G::P * CH; f += THREADS) {
-            const int pos = f / CH, ch = f - pos * CH;
-            float wv[NOUT];
-#pragma unroll
-            for (int j = 0; j < NOUT; j++) wv[j] = whead[(size_t)j * G::P * CH + f];
-#pragma unroll
-            for (int bq = 0; bq < NB; bq++) {
-                const float xv = x[(bq * G::P + pos) * RS_X + ch];
-#pragma unroll
-                for (int j = 0; j < NOUT; j++) acc[bq][j] = fmaf(wv[j], xv, acc[bq][j]);
-            }
+        for (int i = 0; i < 2; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f; }
+        const int brd = lane & 7;
+        const uint32_t h_lane = h_s + (uint32_t)(((((lane >> 4) << 3) + (lane & 7)) * RS_H + ((lane >> 3) & 1) * 8) * 2);
+        for (int ks = warp; ks < 2 * G::P; ks += THREADS / 32) {
+            const int pos = ks >> 1, chunk = ks & 1;
+            const uint32_t addr = a_s + (uint32_t)((ptab[brd * G::P + pos] * RS_A + chunk * 16 + (lane >> 4) * 8) * 2);
+            uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+            ldmatrix_x4(a0, a1, a2, a3, addr);
+            ldmatrix_x4(b0, b1, b2, b3, h_lane + ks * 32);
+            mma_bf16(acc[0], a0, a1, a2, a3, b0, b1);
+            mma_bf16(acc[1], a0, a1, a2, a3, b2, b3);
         }
+        const int g = lane >> 2, t = lane & 3;                     // c0,c1: row g (board g), cols 2t, 2t+1
 #pragma unroll
-        for (int bq = 0; bq < NB; bq++)
+        for (int nt = 0; nt < 2; nt++) {
+            red[(warp * NB + g) * NHEAD + nt * 8 + 2 * t] = acc[nt][0];
+            red[(warp * NB + g) * NHEAD + nt * 8 + 2 * t + 1] = acc[nt][1];
+        }
+        __syncthreads();
+        if (tid < NB * NHEAD) {
+            float v = 0.0f;
+            for (int wq = 0; wq < THREADS / 32; wq++) v += red[wq * NB * NHEAD + tid];
+            fin[tid] = v + ((tid % NHEAD) < NOUT ? bhead[tid % NHEAD] : 0.0f);
+        }
+        __syncthreads();
+        if (tid < NB && board0 + tid < B) {
+            const int gb = board0 + tid;
+            constexpr int A = NOUT - 3;
+            float lg[NOUT];
+#pragma unroll
+            for (int j = 0; j < NOUT; j++) lg[j] = fin[tid * NHEAD + j];
+            float mp = lg[0], mv = lg[A];
+#pragma unroll
+            for (int j = 1; j < A; j++) mp = fmaxf(mp, lg[j]);
+#pragma unroll
+            for (int j = A + 1; j < NOUT; j++) mv = fmaxf(mv, lg[j]);
+            float sp = 0.0f, sv = 0.0f;
 #pragma unroll
             for (int j = 0; j < NOUT; j++) {
-                float v = acc[bq][j];
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                if (lane == 0) red[warp * (NB * NOUT) + bq * NOUT + j] = v;
+                lg[j] = expf(lg[j] - (j < A ? mp : mv));
+                if (j < A) sp += lg[j]; else sv += lg[j];
             }
-        __syncthreads();
-        if (tid < NB) {
-            const int gb = board0 + tid;
-            if (gb < B) {
-                float lg[NOUT];
 #pragma unroll
-                for (int j = 0; j < NOUT; j++) {
-                    float v = bhead[j];
-                    for (int wq = 0; wq < THREADS / 32; wq++) v += red[wq * (NB * NOUT) + tid * NOUT + j];
-                    lg[j] = v;
-                }
-                constexpr int A = NOUT - 3;
-                float mp = lg[0], mv = lg[A];
+            for (int j = 0; j < A; j++) policy[(size_t)gb * A + j] = lg[j] / sp;
 #pragma unroll
-                for (int j = 1; j < A; j++) mp = fmaxf(mp, lg[j]);
-#pragma unroll
-                for (int j = A + 1; j < NOUT; j++) mv = fmaxf(mv, lg[j]);
-                float sp = 0.0f, sv = 0.0f;
-#pragma unroll
-                for (int j = 0; j < NOUT; j++) {
-                    lg[j] = expf(lg[j] - (j < A ? mp : mv));
-                    if (j < A) sp += lg[j]; else sv += lg[j];
-                }
-#pragma unroll
-                for (int j = 0; j < A; j++) policy[(size_t)gb * A + j] = lg[j] / sp;
-#pragma unroll
-                for (int j = A; j < NOUT; j++) value[(size_t)gb * 3 + (j - A)] = lg[j] / sv;
-            }
+            for (int j = A; j < NOUT; j++) value[(size_t)gb * 3 + (j - A)] = lg[j] / sv;
         }
     }
 }
@@ -295,13 +346,14 @@ template <int H, int W, int NOUT>
 constexpr size_t smem_bytes()
 {
     using G = Geo<H, W>;
-    return (size_t)G::M * RS_X * 4 + 2 * (size_t)NB * G::PP * RS_A * 2 + 2 * (size_t)CH * RS_W * 2 + (size_t)G::M * 4 +
-           (size_t)(THREADS / 32) * NB * NOUT * 4;
+    return (size_t)G::M * RS_X * 4 + 2 * (size_t)NB * G::PP * RS_A * 2 + 2 * (size_t)CH * RS_W * 2 +
+           (size_t)NHEAD * (G::P * CH + 8) * 2 + (size_t)G::M * 4 + (size_t)PRM_FLOATS * 4 + 32;
 }
 
 }  // namespace
 
 extern "C" int azb_nn_weight_row_stride(void) { return RS_W; }
+extern "C" int azb_nn_head_row_stride(void) { return 6 * 7 * CH + 8; }
 extern "C" int azb_nn_boards_per_cta(void) { return NB; }
 
 extern "C" int azb_nn_forward(const azb_nn_weights *w, const float *obs, float *policy, float *value, int32_t batch,
@@ -309,7 +361,7 @@ extern "C" int azb_nn_forward(const azb_nn_weights *w, const float *obs, float *
 {
     if (!w || !obs || !policy || !value || batch <= 0) return -7;
     if (w->channels != CH || w->board_h != 6 || w->board_w != 7 || w->action_size != 7 || w->in_channels > 16 ||
-        w->depth < 0)
+        w->depth < 0 || w->depth > MAXD)
         return -1;
     cudaStream_t s = (cudaStream_t)stream;
     static bool configured = false;
@@ -321,7 +373,7 @@ extern "C" int azb_nn_forward(const azb_nn_weights *w, const float *obs, float *
     }
     const int grid = (batch + NB - 1) / NB;
     k_resnet_fused<6, 7, 10><<<grid, THREADS, SM, s>>>(obs, policy, value, batch, w->in_channels, w->depth,
-                                                  reinterpret_cast<const __nv_bfloat16 *>(w->wconv), w->cbias, w->bn_scale,
-                                                  w->bn_shift, w->whead, w->bhead);
+                                                      reinterpret_cast<const __nv_bfloat16 *>(w->wconv), w->cbias, w->bn_scale,
+                                                      w->bn_shift, reinterpret_cast<const __nv_bfloat16 *>(w->whead), w->bhead);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--net", default="default", choices=["default", "connect4_train"])
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--cohorts", type=int, default=1)
-    ap.add_argument("--nn", default="cudnn", choices=["cudnn", "fused"],
+    ap.add_argument("--nn", default="fused", choices=["cudnn", "fused"],
                     help="leaf evaluator: PyTorch/cuDNN CUDA graph, or the fused bf16 tensor-core kernel")
     ap.add_argument("--lanes", type=int, default=0, help="threads per game (0 = library default)")
     ap.add_argument("--nchw", action="store_true", help="keep the ResNet in NCHW (default: channels_last)")
@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-alt", action="store_true")
     ap.add_argument("--no-select-events", action="store_true")
     return ap.parse_args()
 
@@ -303,6 +304,8 @@ def main():
     torch.manual_seed(0)
     netargs = aznet.DEFAULT_NET_ARGS if a.net == "default" else aznet.CONNECT4_TRAIN_NET_ARGS
     model = aznet.ResNet((4, 6, 7), 7, 3, **netargs).to(dev).eval()
+    if a.net != "default":
+        a.nn = "cudnn"                      # the fused kernel covers the 32-channel DEFAULT_ARGS net
     drv = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision, channels_last=not a.nchw,
                          fused=(a.nn == "fused"))
 
@@ -418,6 +421,28 @@ def main():
         except Exception:
             pass
 
+    # secondary: the same step with the PyTorch/cuDNN TF32 evaluator (the reference's default numerics)
+    alt = None
+    if a.nn == "fused" and not a.tree_only and not a.no_alt:
+        model.to(memory_format=torch.channels_last)
+        drv2 = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision="tf32", channels_last=True, fused=False)
+        for _ in range(2):
+            drv2.run_round(sims); clear_samples()
+        s0 = eng.stats()["sims"]
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(3):
+            drv2.run_round(sims); clear_samples()
+        f1.record()
+        barrier()
+        tt = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+        nn_ = torch.tensor([eng.stats()["sims"] - s0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(nn_, op=dist.ReduceOp.SUM)
+        alt = {"nn": "cudnn (CUDA graph, channels_last)", "dtype": "tf32", "value": float(nn_.item()) / (float(tt.item()) / 1000.0),
+               "unit": UNIT, "steps": 3}
+
     # e2e: reference-facing SelfPlayAgent surface with host tensors
     e2e = None
     if not a.no_e2e and not a.tree_only:
@@ -442,7 +467,7 @@ def main():
                        "l2": "node pool %.1f GB per GPU > 126 MB L2; no flush" % (st1["pool_bytes"] / 1e9),
                        "preroll_rounds": a.preroll},
             "clocks": clk, "gpu_launches": drv.launches - launches0,
-            "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e,
+            "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "alt_nn": alt,
             "tree_stats": {"sims": dsims, "mean_depth": dD / max(dsims, 1), "mean_children_scanned": dC / max(dsims, 1),
                            "games_finished": st1["results"] - st0["results"], "peak_nodes_per_game": st1["peak_nodes"]},
         }
@@ -486,7 +511,7 @@ def run_e2e(a, eng, model, dev, world):
     vt = torch.zeros(B, 3).pin_memory()
     args = {"gamesPerIteration": 1 << 40, "probFastSim": 0.0, "numMCTSSims": a.sims, "numFastSims": a.sims}
     ag = SelfPlayAgent(0, _Game, _Q(), _Ev(), bt, pt, vt, _Q(), _Q(), _Val(), _Val(), _Ev(), _Ev(), args, engine=eng)
-    wrap = NNetWrapper(nnet=model, cuda=True)
+    wrap = NNetWrapper(nnet=model, cuda=True, fused=(a.nn == "fused"))
     old_tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = a.precision != "fp32"
 

@@ -27,8 +27,9 @@ typedef struct azb_nn_weights {
     const float *cbias;    /* device f32 [1+2*depth][channels] (folded BN shift; 0 for conv2) */
     const float *bn_scale; /* device f32 [depth][channels]: BN1 of every block                */
     const float *bn_shift; /* device f32 [depth][channels]                                    */
-    const float *whead;    /* device f32 [action_size+3][H*W][channels]: folded heads         */
-    const float *bhead;    /* device f32 [action_size+3]                                      */
+    const void *whead;     /* device bf16 [16][azb_nn_head_row_stride()]: folded heads, row j =  */
+                           /* output j (policy logits, then value logits), k = pos*channels+ch  */
+    const float *bhead;    /* device f32 [16] (action_size+3 used)                               */
 } azb_nn_weights;
 
 /* obs: device f32 [batch, C, H, W]; policy: device f32 [batch, A] (probabilities);
@@ -36,6 +37,7 @@ typedef struct azb_nn_weights {
  * -1 unsupported geometry, -2 CUDA error, -7 bad argument. */
 int azb_nn_forward(const azb_nn_weights *w, const float *obs, float *policy, float *value, int32_t batch, void *stream);
 int azb_nn_weight_row_stride(void);
+int azb_nn_head_row_stride(void);
 int azb_nn_boards_per_cta(void);
 
 #ifdef __cplusplus
