@@ -1,0 +1,135 @@
+"""Self-play phase of alphazero/Coach.py on the engine.
+
+``GpuSelfPlayMixin`` overrides the three self-play phase methods of the
+reference Coach (generateSelfPlayAgents / processSelfPlayBatches /
+killSelfPlayAgents, Coach.py:291-361,401-435) so that
+``class MyCoach(GpuSelfPlayMixin, Coach)`` keeps the rest of the loop
+(saveIterationSamples, processGameResults, train, gating, GUI fields) unchanged:
+samples and results still arrive through ``file_queue`` / ``result_queue`` and
+``games_played`` / ``completed`` / ``sample_time`` are maintained.
+
+``run_selfplay_iteration`` is the same phase without the reference package: it
+plays ``gamesPerIteration`` games on one GPU and returns (and optionally saves,
+in the reference's three-file format, Coach.py:364-386) the training examples.
+"""
+import os
+import pickle
+import time
+
+import numpy as np
+import torch
+
+from .engine import SelfPlayEngine
+from .selfplay import DeviceSelfPlay, FinalState, engine_kwargs_from_args
+
+
+def get_iter_file(iteration):
+    """alphazero/utils.py:15-16"""
+    return f"iteration-{iteration:04d}.pkl"
+
+
+class SelfPlayResult:
+    def __init__(self, obs, pi, z, slot_r, turns_r, win_r, sims, seconds):
+        self.data, self.policy, self.value = obs, pi, z
+        self.result_slots, self.result_turns, self.result_winstates = slot_r, turns_r, win_r
+        self.sims, self.seconds = sims, seconds
+
+    def game_results(self, num_players=2):
+        """alphazero/utils.py:34-54 get_game_results"""
+        wins = [int(self.result_winstates[:, p].sum()) for p in range(num_players)]
+        draws = int(self.result_winstates[:, num_players].sum())
+        n = len(self.result_turns)
+        return wins, draws, (float(self.result_turns.sum()) / n if n else 0)
+
+
+def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup=False, engine=None, fused=None,
+                           precision="tf32", game_id_base=0, stop_event=None, progress=None):
+    """One self-play phase (SelfPlayAgent.run for a single GPU-resident agent):
+    until gamesPerIteration games are counted, draw the fast-move coin, run
+    numFastSims / numMCTSSims (numWarmupSims in a warmup iteration) simulations
+    for every game, play the moves.  Returns a SelfPlayResult (host tensors)."""
+    g = lambda k, d=None: (args[k] if k in args else d)
+    B = int(g("process_batch_size", 256))
+    if engine is None:
+        engine = SelfPlayEngine(**engine_kwargs_from_args(game_cls, args, B, device=device, rng="philox", seed=seed,
+                                                          game_id_base=game_id_base))
+    else:
+        engine.reset_games(seed)
+        engine.set_quota(g("gamesPerIteration", 0))
+    drv = None
+    if not warmup:
+        if fused is None:
+            from .fused_nn import supported
+            fused = supported(nnet_module)
+        drv = DeviceSelfPlay(engine, nnet_module, cohorts=1, precision=precision, channels_last=not fused, fused=fused)
+    rs = np.random.RandomState(seed)
+    quota = int(g("gamesPerIteration"))
+    obs, pi, z, rslot, rturns, rwin = [], [], [], [], [], []
+    t0 = time.time()
+    while engine.games_played() < quota and not (stop_event is not None and stop_event.is_set()):
+        fast = bool(rs.random_sample() < g("probFastSim", 0.0))
+        if warmup:
+            engine.warmup_sims(int(g("numWarmupSims", 5)))
+            engine.play_moves(fast)
+        else:
+            drv.run_round(int(g("numFastSims", 20)) if fast else int(g("numMCTSSims", 100)), fast)
+        engine.check_errors()
+        if engine.sample_count() > 0:
+            o, p, zz, _ = engine.drain_samples()
+            obs.append(o); pi.append(p); z.append(zz)
+        s, t, w = engine.drain_results()
+        if len(s):
+            rslot.append(s); rturns.append(t); rwin.append(w)
+            if progress is not None:
+                progress(engine.games_played())
+    cat = lambda xs, shape, dt: np.concatenate(xs) if xs else np.zeros(shape, dt)
+    A = engine.A
+    return SelfPlayResult(
+        torch.from_numpy(cat(obs, (0,) + engine.obs_shape, np.float32)), torch.from_numpy(cat(pi, (0, A), np.float32)),
+        torch.from_numpy(cat(z, (0, 3), np.float32)), cat(rslot, (0,), np.int32), cat(rturns, (0,), np.int32),
+        cat(rwin, (0, 3), np.uint8), engine.stats()["sims"], time.time() - t0)
+
+
+def save_iteration_samples(result, data_dir, run_name, iteration):
+    """Coach.saveIterationSamples (Coach.py:364-386): three torch.save files."""
+    folder = os.path.join(data_dir, run_name)
+    os.makedirs(folder, exist_ok=True)
+    base = os.path.join(folder, get_iter_file(iteration).replace(".pkl", ""))
+    torch.save(result.data, base + "-data.pkl", pickle_protocol=pickle.HIGHEST_PROTOCOL)
+    torch.save(result.policy, base + "-policy.pkl", pickle_protocol=pickle.HIGHEST_PROTOCOL)
+    torch.save(result.value, base + "-value.pkl", pickle_protocol=pickle.HIGHEST_PROTOCOL)
+    return base
+
+
+class GpuSelfPlayMixin:
+    """Mix into the reference Coach: ``class GpuCoach(GpuSelfPlayMixin, Coach): pass``."""
+
+    def generateSelfPlayAgents(self):
+        self._gpu_engine_args = dict(seed=int(np.random.randint(0, 2 ** 31 - 1)))
+
+    def processSelfPlayBatches(self, iteration):
+        nnet = self.self_play_net if self.args.model_gating else self.train_net
+        t0 = time.time()
+
+        def progress(n):
+            self.games_played.value = int(n)
+            self.sample_time = (time.time() - t0) / max(n, 1)
+
+        res = run_selfplay_iteration(self.game_cls, nnet.nnet, self.args, warmup=self.warmup,
+                                     stop_event=self.stop_train, progress=progress, **self._gpu_engine_args)
+        for i in range(len(res.result_turns)):
+            w = res.result_winstates[i]
+            self.result_queue.put((FinalState(res.result_turns[i], w), w, 0))
+        for i in range(res.data.shape[0]):
+            self.file_queue.put((res.data[i].numpy(), res.policy[i].numpy(), res.value[i].numpy()))
+        self.games_played.value = min(int(self.args.gamesPerIteration), len(res.result_turns))
+        self.completed.value = self.args.workers
+        self.sample_time = res.seconds / max(self.games_played.value, 1)
+        if hasattr(self, "writer"):
+            self.writer.add_scalar("loss/sample_time", self.sample_time, iteration)
+
+    def killSelfPlayAgents(self):
+        import torch.multiprocessing as mp
+        self.agents = []
+        self.file_queue, self.result_queue = mp.Queue(), mp.Queue()
+        self.completed, self.games_played = mp.Value("i", 0), mp.Value("i", 0)

@@ -1,0 +1,68 @@
+"""run_selfplay_iteration (the Coach self-play phase on the engine): quota,
+fast-move coin, sample files in the reference's three-file format, and equality
+with the oracle driven by the same coin sequence."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import _orc
+from _fakenn import warmup_outputs
+
+pytestmark = pytest.mark.gpu
+
+
+class _C4Game:
+    __module__ = "alphazero.envs.connect4.connect4"
+    @staticmethod
+    def max_turns(): return 42
+    @staticmethod
+    def action_size(): return 7
+    @staticmethod
+    def observation_size(): return (4, 6, 7)
+    @staticmethod
+    def num_players(): return 2
+    @staticmethod
+    def has_draw(): return True
+
+
+def test_warmup_iteration_matches_oracle_and_writes_reference_files(tmp_path):
+    from azb200.coach import run_selfplay_iteration, save_iteration_samples
+    args = dict(process_batch_size=64, gamesPerIteration=100, numWarmupSims=12, probFastSim=0.6, numFastSims=4,
+                numMCTSSims=12, add_root_noise=False, add_root_temp=True, symmetricSamples=True)
+    res = run_selfplay_iteration(_C4Game, None, args, seed=9, warmup=True)
+    wins, draws, avg_len = res.game_results()
+    assert len(res.result_turns) >= 100 and wins[0] + wins[1] + draws == len(res.result_turns) and 7 <= avg_len <= 42
+    base = save_iteration_samples(res, str(tmp_path), "run", 3)
+    d, p, v = (torch.load(base + s, weights_only=False) for s in ("-data.pkl", "-policy.pkl", "-value.pkl"))
+    assert os.path.basename(base) == "iteration-0003"
+    assert d.shape[1:] == (4, 6, 7) and p.shape == (d.shape[0], 7) and v.shape == (d.shape[0], 3) and d.dtype == torch.float32
+    # the oracle with the same coin sequence and streams
+    temps = _orc.temp_table(_orc.default_temp_scaling, 1, 42)
+    orc = _orc.OracleAgent(_orc.GAME_CONNECT4, 64, rng_mode=_orc.RNG_PHILOX, seed=9, add_root_temp=True,
+                           games_per_iteration=100, temps=temps)
+    rs = np.random.RandomState(9)
+    while orc.stats()["games_played"] < 100:
+        fast = bool(rs.random_sample() < 0.6)
+        for _ in range(12):                      # warmup iterations always run numWarmupSims (SelfPlayAgent.pyx:85-86)
+            orc.generateBatch(); orc.processBatch(*warmup_outputs(64, 7))
+        orc.playMoves(fast)
+    o, pi, z, _ = orc.samples()
+    assert np.array_equal(d.numpy(), o) and np.array_equal(p.numpy(), pi) and np.array_equal(v.numpy(), z)
+    assert np.array_equal(res.result_turns, orc.results()[1])
+
+
+def test_nn_iteration_with_fused_and_cudnn_evaluators():
+    from azb200 import nnet as aznet
+    from azb200.coach import run_selfplay_iteration
+    torch.manual_seed(0)
+    model = aznet.ResNet((4, 6, 7), 7, 3, **aznet.DEFAULT_NET_ARGS).cuda().eval()
+    args = dict(process_batch_size=128, gamesPerIteration=128, numMCTSSims=16, numFastSims=4, probFastSim=0.5,
+                add_root_noise=True, add_root_temp=True, symmetricSamples=True)
+    for fused in (True, False):
+        res = run_selfplay_iteration(_C4Game, model, args, seed=1, fused=fused)
+        assert len(res.result_turns) >= 128 and res.data.shape[0] == res.policy.shape[0] == res.value.shape[0] > 0
+        assert torch.allclose(res.policy.sum(1), torch.ones(res.policy.shape[0]), atol=1e-5)
+        assert torch.all(res.value.sum(1) == 1)
+        assert res.sims > 0
