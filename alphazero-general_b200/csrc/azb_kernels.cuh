@@ -586,28 +586,32 @@ __device__ __forceinline__ void expand_backup_game(const DevView &d, int g, bool
         if (kin[0]) d.hot[cb + lane].p = pk;
     } else {
         // ---- large action space: action-indexed vector in shared memory ----
+        // sm.vec is all zero outside the children's entries (zero-filled once per launch by the
+        // kernel, restored below), so only the C child entries are ever touched; NumPy's
+        // pairwise sum still reads the whole vector (adding +0.0 is exact).
         if (__any_sync(FULL, ex)) {
-            for (int a = lane; a < G::A; a += L) sm.vec[a] = 0.0f;
-            __syncwarp();
 #pragma unroll
             for (int i = 0; i < IT; i++) if (kin[i]) sm.vec[ak[i]] = pol_row[ak[i]];
             float sum = np_sum_group<G>(sm.vec, lane);
             if (ex && C > 0 && !(sum > 0.0f) && lane == 0) atomicOr(d.err, ERRB_FP);
-            for (int a = lane; a < G::A; a += L) sm.vec[a] = f_div(sm.vec[a], sum);
+            float pk[IT];
+#pragma unroll
+            for (int i = 0; i < IT; i++) pk[i] = kin[i] ? f_div(sm.vec[ak[i]], sum) : 0.0f;     // pi /= np.sum(pi)
             if (__any_sync(FULL, rootx && d.add_temp)) {
                 __syncwarp();
-                for (int a = lane; a < G::A; a += L) sm.vec[a] = pow_det(sm.vec[a], d.root_temp_exp);
+#pragma unroll
+                for (int i = 0; i < IT; i++) if (kin[i]) sm.vec[ak[i]] = pow_det(pk[i], d.root_temp_exp);
                 float sum2 = np_sum_group<G>(sm.vec, lane);
-                for (int a = lane; a < G::A; a += L) sm.vec[a] = f_div(sm.vec[a], sum2);
+#pragma unroll
+                for (int i = 0; i < IT; i++) if (kin[i]) pk[i] = f_div(sm.vec[ak[i]], sum2);
             }
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < IT; i++) {
                 const int k = lane + i * L;
                 if (kin[i]) {
-                    float pk = sm.vec[ak[i]];
-                    pk = root_noise_mix<G>(d, g, C, k, pk, rootx && d.add_noise, gsum, gval[i], nz);
-                    d.hot[cb + k].p = pk;
+                    sm.vec[ak[i]] = 0.0f;                                   // restore the all-zero invariant
+                    d.hot[cb + k].p = root_noise_mix<G>(d, g, C, k, pk[i], rootx && d.add_noise, gsum, gval[i], nz);
                 }
             }
             __syncwarp();
@@ -804,6 +808,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_expand_backup(DevView d, int fi
     __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
     int g, lane, sub, gi; bool active;
     if (!group_setup<G>(first, count, g, active, lane, sub, gi)) return;
+    if (G::A > G::LANES) { for (int a = lane; a < G::A; a += G::LANES) sm[gi].vec[a] = 0.0f; __syncwarp(); }
     expand_backup_game<G>(d, g, active, lane, sub, sm[gi], policy + (size_t)g * G::A, value + (size_t)g * 3);
 }
 
@@ -814,6 +819,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_warmup_sims(DevView d, int sims
     __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
     int g, lane, sub, gi; bool active;
     if (!group_setup<G>(0, d.B, g, active, lane, sub, gi)) return;
+    if (G::A > G::LANES) { for (int a = lane; a < G::A; a += G::LANES) sm[gi].vec[a] = 0.0f; __syncwarp(); }
     for (int s = 0; s < sims; s++) {
         select_game<G, false>(d, g, active, lane, sub, sm[gi]);
         expand_backup_game<G>(d, g, active, lane, sub, sm[gi], d.warm_policy, d.warm_value);

@@ -43,9 +43,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--game", default="connect4", choices=["connect4", "brandubh"],
+                    help="brandubh = BASELINE config 4 (use --games 4096 --sims 200 --net brandubh_train)")
     ap.add_argument("--games", type=int, default=8192)
     ap.add_argument("--sims", type=int, default=100)
-    ap.add_argument("--net", default="default", choices=["default", "connect4_train"])
+    ap.add_argument("--net", default="default", choices=["default", "connect4_train", "brandubh_train"])
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--cohorts", type=int, default=1)
     ap.add_argument("--nn", default="fused", choices=["cudnn", "fused"],
@@ -271,7 +273,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     cpu_base = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and a.game == "connect4":
         # before this process initialises CUDA: the reference agents are forked
         try:
             r = run_reference(a.games, a.sims, a.net, 0, 1, seconds=a.cpu_seconds)
@@ -296,24 +298,23 @@ def main():
     dev = torch.device("cuda", local)
 
     B, sims = a.games, a.sims
+    tafl = a.game == "brandubh"
+    OBS, A = ((5, 7, 7), 588) if tafl else ((4, 6, 7), 7)
     eng = SelfPlayEngine(
-        game="connect4", num_games=B, device=local, rng="philox", seed=0, game_id_base=rank * B,
+        game=a.game, num_games=B, device=local, rng="philox", seed=0, game_id_base=rank * B,
         cpuct=1.25, fpu_reduction=0.2, root_noise_frac=0.1, root_policy_temp=1.1, add_root_noise=True,
         add_root_temp=True, symmetric_samples=True, games_per_iteration=0, max_sims_per_move=sims,
-        temps=temp_table(default_temp_scaling, 1, 42), lanes_per_game=a.lanes)
+        max_nodes_per_game=(120000 if tafl else 0), sample_capacity=(600000 if tafl else 0),
+        temps=temp_table(default_temp_scaling, 1, None if tafl else 42), lanes_per_game=a.lanes)
     torch.manual_seed(0)
-    netargs = aznet.DEFAULT_NET_ARGS if a.net == "default" else aznet.CONNECT4_TRAIN_NET_ARGS
-    model = aznet.ResNet((4, 6, 7), 7, 3, **netargs).to(dev).eval()
-    if a.net != "default":
-        a.nn = "cudnn"                      # the fused kernel covers the 32-channel DEFAULT_ARGS net
+    netargs = {"default": aznet.DEFAULT_NET_ARGS, "connect4_train": aznet.CONNECT4_TRAIN_NET_ARGS,
+               "brandubh_train": aznet.BRANDUBH_TRAIN_NET_ARGS}[a.net]
+    model = aznet.ResNet(OBS, A, 3, **netargs).to(dev).eval()
+    if a.net != "default" or tafl:
+        a.nn = "cudnn"                      # the fused kernel covers the 32-channel DEFAULT_ARGS net on 6x7 boards
+        a.no_e2e = True if tafl else a.no_e2e
     drv = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision, channels_last=not a.nchw,
                          fused=(a.nn == "fused"))
-
-    # cheap tree-only pre-roll so the games are spread over all phases (steady state)
-    for _ in range(a.preroll):
-        eng.warmup_sims(8)
-        eng.play_moves(False)
-    torch.cuda.synchronize()
 
     sel_events = []
 
@@ -331,10 +332,20 @@ def main():
         n = eng.sample_count()
         if n == 0:
             return
-        o = torch.empty(n, 4, 6, 7, device=dev); p = torch.empty(n, 7, device=dev); z = torch.empty(n, 3, device=dev)
+        o = torch.empty((n,) + OBS, device=dev); p = torch.empty(n, A, device=dev); z = torch.empty(n, 3, device=dev)
         eng.drain_samples_into(o, p, z)
         if world > 1 and sum(t[0].shape[0] for t in kept) < 4_000_000:
             kept.append((o, p, z))
+
+    # cheap tree-only pre-roll so the games are spread over all phases (steady state)
+    for _ in range(a.preroll):
+        eng.warmup_sims(8)
+        eng.play_moves(False)
+        if _ % 4 == 3:
+            clear_samples()
+    clear_samples()
+    kept.clear()
+    torch.cuda.synchronize()
 
     def barrier():
         torch.cuda.synchronize()
@@ -405,7 +416,7 @@ def main():
         nl = len(sel_events)
         ach = alg_bytes / (sel_ms / 1000.0) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
-                "traffic": None, "kernel": "k_select<Connect4>", "launches": nl, "avg_launch_us": 1000.0 * sel_ms / nl,
+                "traffic": None, "kernel": f"k_select<{'Brandubh' if tafl else 'Connect4'}>", "launches": nl, "avg_launch_us": 1000.0 * sel_ms / nl,
                 "alg_bytes_per_launch": alg_bytes / nl, "bytes_per_sim": alg_bytes / max(dsims, 1), "peak_source": peak_src,
                 "note": "CUDA-event time of each select launch on the tree stream (NN runs concurrently on another stream)"}
     elif a.tree_only:
@@ -450,7 +461,7 @@ def main():
 
     if world > 1:
         clear_samples()
-        gather_ms, gathered = gather_examples(kept, dev, rank, world)
+        gather_ms, gathered = gather_examples(kept, dev, rank, world, OBS, A)
     else:
         gather_ms, gathered = None, None
 
@@ -459,7 +470,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if a.nn == "fused" else ("f32" if a.precision == "fp32" else a.precision), "data": "synthetic",
-            "config": {"workload": f"connect4 {B} games/GPU x {sims} sims/move, DEFAULT_ARGS MCTS (cpuct 1.25, fpu 0.2, "
+            "config": {"workload": f"{a.game} {B} games/GPU x {sims} sims/move, DEFAULT_ARGS MCTS (cpuct 1.25, fpu 0.2, "
                                    f"root noise 0.1 + temp 1.1), net={a.net} ResNet random-init, "
                                    f"{'tree-only warmup mode' if a.tree_only else 'NN in the loop'}",
                        "games_per_gpu": B, "sims_per_move": sims, "net": a.net, "nn": a.nn, "nn_precision": "bf16" if a.nn == "fused" else a.precision,
@@ -551,7 +562,7 @@ def run_e2e(a, eng, model, dev, world):
             "steps": steps, "api": "azb200.selfplay.SelfPlayAgent.generateBatch/processBatch/playMoves + NNetWrapper.process, pinned host tensors"}
 
 
-def gather_examples(kept, dev, rank, world):
+def gather_examples(kept, dev, rank, world, obs_shape=(4, 6, 7), A=7):
     """BASELINE config 3: NCCL gather of the (s, pi, z) examples of the timed steps to rank 0."""
     import torch
     import torch.distributed as dist
@@ -559,7 +570,7 @@ def gather_examples(kept, dev, rank, world):
     if kept:
         obs, pi, z = (torch.cat([k[i] for k in kept]) for i in range(3))
     else:
-        obs, pi, z = torch.empty(0, 4, 6, 7, device=dev), torch.empty(0, 7, device=dev), torch.empty(0, 3, device=dev)
+        obs, pi, z = torch.empty((0,) + obs_shape, device=dev), torch.empty(0, A, device=dev), torch.empty(0, 3, device=dev)
     gather_examples_to_rank0(obs[:1], pi[:1], z[:1])          # NCCL warm-up (communicator setup is not timed)
     torch.cuda.synchronize(); dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
