@@ -105,12 +105,19 @@ class SelfPlayAgent(threading.Thread):
         self._counted = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.batches = 0            # generateBatch calls (simulation batches) so far
 
     def _check_pause(self):
         while self.pause_event.is_set():
             time.sleep(.1)
 
     def run(self):
+        # the agent's kernels and copies go to its own stream, so several agents and the
+        # NN server overlap on one GPU
+        with torch.cuda.stream(torch.cuda.Stream(device=self.engine.obs.device)):
+            self._run()
+
+    def _run(self):
         try:
             while not self.stop_event.is_set() and self.games_played.value < self.args.gamesPerIteration:
                 self._check_pause()
@@ -143,6 +150,7 @@ class SelfPlayAgent(threading.Thread):
         self.batch_tensor.copy_(self.engine.obs)             # device -> caller's (host) tensor
         if not self.batch_tensor.is_cuda:
             self.d2h_bytes += self.batch_tensor.numel() * 4
+        self.batches += 1
         self.ready_queue.put(self.id)
 
     def processBatch(self):
@@ -151,6 +159,8 @@ class SelfPlayAgent(threading.Thread):
             return
         self.batch_ready.wait()
         self.batch_ready.clear()
+        if self.stop_event.is_set():
+            return
         self.engine.policy.copy_(self.policy_tensor, non_blocking=True)
         self.engine.value.copy_(self.value_tensor, non_blocking=True)
         if not self.policy_tensor.is_cuda:
@@ -183,12 +193,22 @@ class DeviceSelfPlay:
     ``nn_stream``; with cohorts == 2 the two halves of the games alternate so
     that tree work of one half overlaps inference of the other."""
 
-    def __init__(self, engine, nnet, cohorts=1, precision="tf32", use_graph=True, channels_last=False, fused=False):
+    def __init__(self, engine, nnet, cohorts=1, precision="tf32", use_graph=True, channels_last=False, fused=False,
+                 split=None):
         assert cohorts in (1, 2)
         self.engine = engine
         self.cohorts = cohorts
         B = engine.B
-        bounds = [0, B] if cohorts == 1 else [0, B // 2, B]
+        if cohorts == 2 and split is None:
+            split = B // 2
+            if fused:
+                # the fused evaluator runs one 8-board CTA per SM: cut the batch at a whole number of
+                # waves so that two launches cost the same number of waves as one
+                import torch as _t
+                sms = _t.cuda.get_device_properties(engine.obs.device).multi_processor_count
+                waves = -(-(-(-B // 8)) // sms)
+                split = min(B - 8, max(8, ((waves + 1) // 2) * sms * 8))
+        bounds = [0, B] if cohorts == 1 else [0, split, B]
         self.ranges = [(bounds[i], bounds[i + 1] - bounds[i]) for i in range(cohorts)]
         from .nnet import LeafEvaluator
         if fused:

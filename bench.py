@@ -56,7 +56,8 @@ def parse():
     ap.add_argument("--nchw", action="store_true", help="keep the ResNet in NCHW (default: channels_last)")
     ap.add_argument("--preroll", type=int, default=48, help="cheap tree-only rounds that de-synchronise the games")
     ap.add_argument("--tree-only", action="store_true", help="warmup mode (constant NN outputs), one fused kernel per round")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-agents", type=int, default=2, help="reference `workers`: agents sharing the GPU in the e2e leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -491,75 +492,99 @@ def main():
 
 
 def run_e2e(a, eng, model, dev, world):
-    """The loop body of Coach.processSelfPlayBatches (Coach.py:337-342) around the
-    reference-shaped SelfPlayAgent with pinned HOST tensors."""
+    """Coach.processSelfPlayBatches (Coach.py:326-361) as the reference runs it: `workers`
+    reference-shaped SelfPlayAgent objects (here threads, each owning a CUDA engine with its share
+    of the games) exchange observation / policy / value batches with this NN-server loop through
+    pinned HOST tensors, a ready queue and per-agent events."""
+    import queue as pyqueue
     import torch
     import torch.distributed as dist
+    from azb200 import SelfPlayEngine, default_temp_scaling, temp_table
     from azb200.nnet import NNetWrapper
     from azb200.selfplay import SelfPlayAgent
 
-    class _Q:
-        def __init__(self): self.n = 0
-        def put(self, x): self.n += 1
-        def close(self): pass
-        def join_thread(self): pass
-
-    class _Ev:
-        def is_set(self): return False
-        def wait(self): pass
-        def clear(self): pass
-        def set(self): pass
-
     class _Val:
-        def __init__(self): self.value = 0
-        def get_lock(self): return threading.Lock()
+        def __init__(self): self.value = 0; self._l = threading.Lock()
+        def get_lock(self): return self._l
+
+    class _Sink:
+        def put(self, x): pass
 
     class _Game:
         __module__ = "alphazero.envs.connect4.connect4"
-    B = eng.B
-    bt = torch.zeros(B, 4, 6, 7).pin_memory()
-    pt = torch.zeros(B, 7).pin_memory()
-    vt = torch.zeros(B, 3).pin_memory()
-    args = {"gamesPerIteration": 1 << 40, "probFastSim": 0.0, "numMCTSSims": a.sims, "numFastSims": a.sims}
-    ag = SelfPlayAgent(0, _Game, _Q(), _Ev(), bt, pt, vt, _Q(), _Q(), _Val(), _Val(), _Ev(), _Ev(), args, engine=eng)
+    W = max(1, a.e2e_agents)
+    Bw = eng.B // W
+    rank = int(os.environ.get("RANK", "0"))
+    args = type("A", (dict,), {"__getattr__": dict.__getitem__})(
+        gamesPerIteration=1 << 40, probFastSim=0.0, numMCTSSims=a.sims, numFastSims=a.sims, numWarmupSims=a.sims)
+    ready, stop, pause = pyqueue.Queue(), threading.Event(), threading.Event()
+    completed, played = _Val(), _Val()
+    bts, pts, vts, evs, agents = [], [], [], [], []
+    for i in range(W):
+        e = SelfPlayEngine(game="connect4", num_games=Bw, device=dev.index, rng="philox", seed=1,
+                           game_id_base=(rank * W + i) * Bw, add_root_noise=True, add_root_temp=True,
+                           max_sims_per_move=a.sims, temps=temp_table(default_temp_scaling, 1, 42))
+        for _ in range(24):                       # de-synchronise the games cheaply
+            e.warmup_sims(8); e.play_moves(False)
+        e.drain_samples(); e.drain_results()
+        bts.append(torch.zeros(Bw, 4, 6, 7).pin_memory()); pts.append(torch.zeros(Bw, 7).pin_memory())
+        vts.append(torch.zeros(Bw, 3).pin_memory()); evs.append(threading.Event())
+        agents.append(SelfPlayAgent(i, _Game, ready, evs[i], bts[i], pts[i], vts[i], _Sink(), _Sink(), completed, played,
+                                    stop, pause, args, engine=e))
     wrap = NNetWrapper(nnet=model, cuda=True, fused=(a.nn == "fused"))
     old_tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = a.precision != "fp32"
+    srv = torch.cuda.Stream(device=dev)
+    for ag in agents:
+        ag.start()
 
-    def round_():
-        for _ in range(a.sims):
-            ag.generateBatch()
-            policy, value = wrap.process(bt)
-            pt.copy_(policy)
-            vt.copy_(value)
-            ag.processBatch()
-        ag.playMoves()
+    def serve(until):
+        with torch.cuda.stream(srv):
+            while not until():
+                try:
+                    i = ready.get(timeout=0.5)
+                except pyqueue.Empty:
+                    continue
+                policy, value = wrap.process(bts[i])          # host -> device, network
+                pts[i].copy_(policy)                          # device -> host
+                vts[i].copy_(value)
+                evs[i].set()
 
-    round_()
-    ag.h2d_bytes = ag.d2h_bytes = 0
-    s0 = eng.stats()["sims"]
-    torch.cuda.synchronize()
+    serve(lambda: all(ag.batches >= a.sims + 2 for ag in agents))          # one untimed round per agent
     if world > 1:
         dist.barrier()
+    for ag in agents:
+        ag.h2d_bytes = ag.d2h_bytes = 0
+    n0 = sum(ag.batches for ag in agents)
     t0 = time.perf_counter()
-    for _ in range(a.e2e_steps):
-        round_()
+    target = n0 + W * a.sims * a.e2e_steps
+    serve(lambda: sum(ag.batches for ag in agents) >= target)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    n1 = sum(ag.batches for ag in agents)
+    stop.set()
+    for ev in evs:
+        ev.set()
+    for ag in agents:
+        ag.join(timeout=20)
     torch.backends.cudnn.allow_tf32 = old_tf32
     t = torch.tensor([dt], device=dev, dtype=torch.float64)
-    n = torch.tensor([eng.stats()["sims"] - s0], device=dev, dtype=torch.float64)
+    n = torch.tensor([(n1 - n0) * Bw], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(n, op=dist.ReduceOp.SUM)
-    obs_b, pv_b = B * 4 * 6 * 7 * 4, B * 10 * 4
-    steps = a.e2e_steps
+    steps = (n1 - n0) / float(W * a.sims)                 # move-rounds of all 8192 games
+    obs_b, pv_b = eng.B * 4 * 6 * 7 * 4, eng.B * 10 * 4
+    for ag in agents:
+        ag.engine.close()
     return {"value": float(n.item()) / float(t.item()), "unit": UNIT,
             # per step: nnet.process uploads the observation batch, processBatch uploads policy/value
-            "h2d_bytes_per_step": a.sims * obs_b + ag.h2d_bytes // steps,
+            "h2d_bytes_per_step": int(a.sims * obs_b + sum(ag.h2d_bytes for ag in agents) / steps),
             # per step: generateBatch downloads observations, the NN answers go to host tensors, samples are drained
-            "d2h_bytes_per_step": a.sims * pv_b + ag.d2h_bytes // steps,
-            "steps": steps, "api": "azb200.selfplay.SelfPlayAgent.generateBatch/processBatch/playMoves + NNetWrapper.process, pinned host tensors"}
+            "d2h_bytes_per_step": int(a.sims * pv_b + sum(ag.d2h_bytes for ag in agents) / steps),
+            "steps": steps, "agents": W, "games_per_agent": Bw,
+            "api": "Coach.processSelfPlayBatches loop: azb200.selfplay.SelfPlayAgent threads (generateBatch/processBatch/"
+                   "playMoves) + NNetWrapper.process, pinned host tensors, ready queue + events"}
 
 
 def gather_examples(kept, dev, rank, world, obs_shape=(4, 6, 7), A=7):
