@@ -40,7 +40,7 @@ UNIT = "sims/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--game", default="connect4", choices=["connect4", "brandubh"],
@@ -90,7 +90,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region (nvidia-smi itself takes about a second to come up, so the
+        sampler is started long before; only samples taken after this mark are reported)."""
+        self.t_mark = time.time()
 
     def stop(self):
         if not self.proc:
@@ -102,7 +107,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        for ts, ln in self.lines:
+            if ts < t_mark:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -298,6 +306,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     B, sims = a.games, a.sims
     tafl = a.game == "brandubh"
     OBS, A = ((5, 7, 7), 588) if tafl else ((4, 6, 7), 7)
@@ -374,10 +385,8 @@ def main():
             sel_events.append((e0, e1))
         eng.select = timed_select
 
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     barrier()
+    clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(a.steps):
