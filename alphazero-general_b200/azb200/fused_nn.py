@@ -36,16 +36,17 @@ def _bn_affine(bn):
 
 
 @torch.no_grad()
-def fold(model, row_stride, head_stride=None):
-    """-> dict of CPU tensors in the layouts azb200_nn.h documents."""
+def _folded(model):
+    """Folded network in float64, layout-free: conv weights [L][cout][tap][cin], biases, BN1
+    scale / shift per block, the affine head map [A+3][pos][ch] and its bias."""
     m = model.eval().cpu()
     ch, depth, cin = m.conv1.out_channels, len(m.resnet), m.channels
     L = 1 + 2 * depth
-    wconv = torch.zeros(L, ch, row_stride, dtype=torch.float64)
+    convs = []
     cbias = torch.zeros(L, ch, dtype=torch.float64)
     s, t = _bn_affine(m.bn1)
     w = m.conv1.weight.double() * s[:, None, None, None]                 # [co, ci, ky, kx]
-    wconv[0, :, :9 * 16].view(ch, 9, 16)[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(ch, 9, cin)
+    convs.append(w.permute(0, 2, 3, 1).reshape(ch, 9, cin))
     cbias[0] = t
     bn_scale = torch.zeros(max(depth, 1), ch, dtype=torch.float64)
     bn_shift = torch.zeros(max(depth, 1), ch, dtype=torch.float64)
@@ -53,9 +54,9 @@ def fold(model, row_stride, head_stride=None):
         bn_scale[i], bn_shift[i] = _bn_affine(blk.bn1)
         s2, t2 = _bn_affine(blk.bn2)
         w1 = blk.conv1.weight.double() * s2[:, None, None, None]
-        wconv[1 + 2 * i, :, :9 * ch] = w1.permute(0, 2, 3, 1).reshape(ch, 9 * ch)
+        convs.append(w1.permute(0, 2, 3, 1).reshape(ch, 9, ch))
         cbias[1 + 2 * i] = t2
-        wconv[2 + 2 * i, :, :9 * ch] = blk.conv2.weight.double().permute(0, 2, 3, 1).reshape(ch, 9 * ch)
+        convs.append(blk.conv2.weight.double().permute(0, 2, 3, 1).reshape(ch, 9, ch))
     # heads as one affine map of the trunk output [ch, H, W]
     H, W = m.board_x, m.board_y
     md = m.double()
@@ -70,34 +71,95 @@ def fold(model, row_stride, head_stride=None):
     mat = (heads(basis) - bias[None]).T.contiguous()                       # [A+3, ch*H*W], feature = c*HW + pos
     whead = mat.view(-1, ch, H * W).permute(0, 2, 1).contiguous()          # [A+3, pos, ch]
     m.float()
+    return dict(convs=convs, cbias=cbias, bn_scale=bn_scale, bn_shift=bn_shift, whead=whead, bhead=bias,
+                channels=ch, depth=depth, in_channels=cin, board_h=H, board_w=W, action_size=m.action_size)
+
+
+def fold(model, row_stride, head_stride=None):
+    """-> dict of CPU tensors in the layouts azb200_nn.h documents for azb_nn_forward (mma.sync kernel)."""
+    f = _folded(model)
+    ch, depth, cin, H, W = f["channels"], f["depth"], f["in_channels"], f["board_h"], f["board_w"]
+    L = 1 + 2 * depth
+    wconv = torch.zeros(L, ch, row_stride, dtype=torch.float64)
+    wconv[0, :, :9 * 16].view(ch, 9, 16)[:, :, :cin] = f["convs"][0]
+    for l in range(1, L):
+        wconv[l, :, :9 * ch] = f["convs"][l].reshape(ch, 9 * ch)
+    whead, bias = f["whead"], f["bhead"]
     nout = whead.shape[0]
     hs = head_stride or (H * W * ch + 8)
     whead16 = torch.zeros(16, hs, dtype=torch.float64)                     # padded to two n-tiles, k = pos*ch + c
     whead16[:nout, :H * W * ch] = whead.reshape(nout, -1)
     bhead16 = torch.zeros(16, dtype=torch.float64)
     bhead16[:nout] = bias
-    return dict(wconv=wconv.to(torch.bfloat16), cbias=cbias.float(), bn_scale=bn_scale.float(),
-                bn_shift=bn_shift.float(), whead=whead.float(), bhead=bias.float(),
+    return dict(wconv=wconv.to(torch.bfloat16), cbias=f["cbias"].float(), bn_scale=f["bn_scale"].float(),
+                bn_shift=f["bn_shift"].float(), whead=whead.float(), bhead=bias.float(),
                 whead16=whead16.to(torch.bfloat16), bhead16=bhead16.float(),
-                channels=ch, depth=depth, in_channels=cin, board_h=H, board_w=W, action_size=m.action_size)
+                channels=ch, depth=depth, in_channels=cin, board_h=H, board_w=W, action_size=f["action_size"])
+
+
+def fold_tc(model, layer_bytes=18432, head_stride=1800, frame_rows=56):
+    """-> dict of CPU tensors in the layouts of azb_nn_forward_tc (tcgen05 kernel, azb_resnet_tc.cu):
+    conv weights as the K-major no-swizzle UMMA B operand [layer][16-byte K chunk][cout][8 cin]
+    (stem: chunk = tap, cin < 8; trunk: chunk = tap*4 + cin/8), the head matrix over frame rows
+    (k = (y*8 + x)*channels + ch; the frame's padding rows carry zero weights)."""
+    f = _folded(model)
+    ch, depth, cin, H, W = f["channels"], f["depth"], f["in_channels"], f["board_h"], f["board_w"]
+    assert cin <= 8 and ch == 32 and frame_rows == (H + 1) * (W + 1)
+    L = 1 + 2 * depth
+    kch = layer_bytes // (ch * 16)
+    wconv = torch.zeros(L, kch, ch, 8, dtype=torch.float64)
+    wconv[0, :9, :, :cin] = f["convs"][0].permute(1, 0, 2)                  # [tap][cout][cin]
+    for l in range(1, L):
+        wconv[l] = f["convs"][l].view(ch, 9, ch // 8, 8).permute(1, 2, 0, 3).reshape(kch, ch, 8)
+    whead, bias = f["whead"], f["bhead"]
+    nout = whead.shape[0]
+    wh = torch.zeros(16, head_stride, dtype=torch.float64)
+    fr = torch.zeros(nout, H + 1, W + 1, ch, dtype=torch.float64)
+    fr[:, :H, :W] = whead.view(nout, H, W, ch)
+    wh[:nout, :frame_rows * ch] = fr.reshape(nout, -1)
+    bhead16 = torch.zeros(16, dtype=torch.float64)
+    bhead16[:nout] = bias
+    return dict(wconv=wconv.to(torch.bfloat16), cbias=f["cbias"].float(), bn_scale=f["bn_scale"].float(),
+                bn_shift=f["bn_shift"].float(), whead16=wh.to(torch.bfloat16), bhead16=bhead16.float(),
+                channels=ch, depth=depth, in_channels=cin, board_h=H, board_w=W, action_size=f["action_size"])
+
+
+def supported_tc(model):
+    """Geometry the tcgen05 kernel covers (azb_resnet_tc.cu): the mma.sync one, with <= 8 input planes."""
+    return supported(model) and model.channels <= 8
 
 
 class FusedResNetEvaluator:
     """Same call surface as azb200.nnet.LeafEvaluator: evaluator(stream) enqueues one
-    evaluation of ``obs`` into ``policy`` / ``value`` (engine-owned device rows)."""
+    evaluation of ``obs`` into ``policy`` / ``value`` (engine-owned device rows).
+
+    kernel = "tc"  : tcgen05 / TMEM kernel (azb_nn_forward_tc), the default where it applies
+             "mma" : the mma.sync kernel (azb_nn_forward)"""
 
     precision = "bf16"
 
-    def __init__(self, model, obs, policy, value):
+    def __init__(self, model, obs, policy, value, kernel=None):
         if not supported(model):
             raise NotImplementedError("fused evaluator: 6x7 boards, 32 channels, 7 actions only")
+        kernel = kernel or ("tc" if supported_tc(model) else "mma")
+        if kernel == "tc" and not supported_tc(model):
+            raise NotImplementedError("tcgen05 evaluator: at most 8 observation planes")
+        self.kernel = kernel
         self.lib = _capi.load()
-        self.lib.azb_nn_forward.restype = C.c_int
-        self.lib.azb_nn_forward.argtypes = [C.POINTER(_NNWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        sig = [C.POINTER(_NNWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        for fn in (self.lib.azb_nn_forward, self.lib.azb_nn_forward_tc):
+            fn.restype, fn.argtypes = C.c_int, sig
+        self.lib.azb_nn_forward_tc_debug.restype = C.c_int
+        self.lib.azb_nn_forward_tc_debug.argtypes = sig + [C.c_void_p, C.c_int32]
         dev = obs.device
         model_dev = next(model.parameters()).device
-        self.lib.azb_nn_head_row_stride.restype = C.c_int
-        f = fold(model, self.lib.azb_nn_weight_row_stride(), self.lib.azb_nn_head_row_stride())
+        if kernel == "tc":
+            f = fold_tc(model, self.lib.azb_nn_tc_layer_bytes(), self.lib.azb_nn_tc_head_row_stride(),
+                        self.lib.azb_nn_tc_frame_rows_per_board())
+            self._fwd = self.lib.azb_nn_forward_tc
+        else:
+            f = fold(model, self.lib.azb_nn_weight_row_stride(), self.lib.azb_nn_head_row_stride())
+            self._fwd = self.lib.azb_nn_forward
         model.to(model_dev)
         self.t = {k: v.to(dev).contiguous() for k, v in f.items() if torch.is_tensor(v)}
         self.w = _NNWeights(f["channels"], f["depth"], f["in_channels"], f["board_h"], f["board_w"], f["action_size"],
@@ -109,7 +171,21 @@ class FusedResNetEvaluator:
 
     def __call__(self, stream=None):
         stream = stream or torch.cuda.current_stream()
-        rc = self.lib.azb_nn_forward(C.byref(self.w), self.obs.data_ptr(), self.policy.data_ptr(), self.value.data_ptr(),
-                                     self.batch, C.c_void_p(stream.cuda_stream))
+        rc = self._fwd(C.byref(self.w), self.obs.data_ptr(), self.policy.data_ptr(), self.value.data_ptr(),
+                       self.batch, C.c_void_p(stream.cuda_stream))
         if rc != 0:
-            raise RuntimeError(f"azb_nn_forward failed with status {rc}")
+            raise RuntimeError(f"azb_nn_forward ({self.kernel}) failed with status {rc}")
+
+    def debug_layer(self, layer):
+        """tcgen05 kernel only: evaluate and return the fp32 activation the epilogue of `layer`
+        produced, as [batch, 6, 7, 32] (padding rows dropped) -- for layer-by-layer checks."""
+        assert self.kernel == "tc"
+        nb, fb = self.lib.azb_nn_tc_boards_per_cta(), self.lib.azb_nn_tc_frame_rows_per_board()
+        ctas = -(-self.batch // nb)
+        dump = torch.zeros(ctas * nb, fb // 8, 8, 32, device=self.obs.device)
+        rc = self.lib.azb_nn_forward_tc_debug(C.byref(self.w), self.obs.data_ptr(), self.policy.data_ptr(),
+                                              self.value.data_ptr(), self.batch,
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream), dump.data_ptr(), layer)
+        if rc != 0:
+            raise RuntimeError(f"azb_nn_forward_tc_debug failed with status {rc}")
+        return dump[:self.batch, :6, :7]

@@ -36,6 +36,24 @@ typedef struct azb_nn_weights {
  * value: device f32 [batch, 3].  Asynchronous on `stream`.  0 on success,
  * -1 unsupported geometry, -2 CUDA error, -7 bad argument. */
 int azb_nn_forward(const azb_nn_weights *w, const float *obs, float *policy, float *value, int32_t batch, void *stream);
+
+/* The same network on the 5th-generation tensor cores (tcgen05.mma, accumulators and the fp32
+ * residual stream in TMEM; csrc/azb_resnet_tc.cu), 16 boards per CTA, in_channels <= 8.
+ * Weight layouts differ from azb_nn_forward:
+ *   wconv  bf16 [1+2*depth][azb_nn_tc_layer_bytes()/16/channels][channels][8]: K-major no-swizzle
+ *          UMMA operand, 16-byte K chunk = tap (stem, cin < 8) / tap*4 + cin/8 (trunk)
+ *   whead  bf16 [16][azb_nn_tc_head_row_stride()], k = frame_row*channels + ch with
+ *          frame_row = y*8 + x over the azb_nn_tc_frame_rows_per_board() rows of a board frame
+ * Same status codes. */
+int azb_nn_forward_tc(const azb_nn_weights *w, const float *obs, float *policy, float *value, int32_t batch, void *stream);
+/* test hook: also writes the fp32 activation produced by layer `dump_layer`'s epilogue to
+ * dump[ceil(batch/16)*16][frame_rows][channels] (padding rows zero) */
+int azb_nn_forward_tc_debug(const azb_nn_weights *w, const float *obs, float *policy, float *value, int32_t batch,
+                            void *stream, float *dump, int32_t dump_layer);
+int azb_nn_tc_layer_bytes(void);
+int azb_nn_tc_head_row_stride(void);
+int azb_nn_tc_boards_per_cta(void);
+int azb_nn_tc_frame_rows_per_board(void);
 int azb_nn_weight_row_stride(void);
 int azb_nn_head_row_stride(void);
 int azb_nn_boards_per_cta(void);

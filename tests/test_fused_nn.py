@@ -61,15 +61,30 @@ def test_folded_weights_reproduce_the_module_in_float64():
     assert f64["whead"].shape == (10, 42, 32) and f64["wconv"].shape == (9, 32, 296)
 
 
+def test_tc_weight_layouts_match_the_mma_layouts():
+    """fold_tc (UMMA operand chunks, frame-row head matrix) is a pure re-layout of fold."""
+    from azb200.fused_nn import fold, fold_tc
+    m = _model()
+    a, b = fold(m, 296), fold_tc(m)
+    w, t = a["wconv"].float(), b["wconv"].float()
+    for l in range(1, 9):
+        assert torch.equal(w[l, :, :288].view(32, 9, 4, 8).permute(1, 2, 0, 3).reshape(36, 32, 8), t[l])
+    assert torch.equal(w[0, :, :144].view(32, 9, 16)[:, :, :8].permute(1, 0, 2), t[0, :9]) and bool((t[0, 9:] == 0).all())
+    wh = a["whead16"].float()[:, :42 * 32].view(16, 6, 7, 32)
+    th = b["whead16"].float()[:, :56 * 32].view(16, 7, 8, 32)
+    assert torch.equal(wh, th[:, :6, :7]) and bool((th[:, 6] == 0).all()) and bool((th[:, :, 7] == 0).all())
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["tc", "mma"])
 @pytest.mark.parametrize("batch", [8, 100, 8192])
-def test_fused_kernel_matches_pytorch_fp32(batch):
+def test_fused_kernel_matches_pytorch_fp32(batch, kernel):
     from azb200.fused_nn import FusedResNetEvaluator
     dev = torch.device("cuda")
     m = _model().to(dev)
     obs = _obs(batch).to(dev)
     pol = torch.zeros(batch, 7, device=dev); val = torch.zeros(batch, 3, device=dev)
-    ev = FusedResNetEvaluator(m, obs, pol, val)
+    ev = FusedResNetEvaluator(m, obs, pol, val, kernel=kernel)
     ev()
     torch.cuda.synchronize()
     old = torch.backends.cudnn.allow_tf32
@@ -85,3 +100,38 @@ def test_fused_kernel_matches_pytorch_fp32(batch):
     assert ep < 3e-2 and evl < 3e-2, (ep, evl)
     # typical error is far below the bound
     assert (pol - wp).abs().mean().item() < 3e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("depth", [0, 1, 4])
+def test_tc_kernel_layer_by_layer(depth):
+    """Every epilogue of the tcgen05 kernel (stem, conv1, conv2 of each block) against the fp32
+    activations of the PyTorch module; tolerance = bf16 operand rounding, 3e-2 absolute."""
+    import torch.nn.functional as F
+    from azb200.fused_nn import FusedResNetEvaluator
+    dev = torch.device("cuda")
+    m = _model(depth=depth).to(dev)
+    batch = 40
+    obs = _obs(batch).to(dev)
+    pol = torch.zeros(batch, 7, device=dev); val = torch.zeros(batch, 3, device=dev)
+    ev = FusedResNetEvaluator(m, obs, pol, val, kernel="tc")
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    want = []
+    with torch.no_grad():
+        x = F.relu(m.bn1(m.conv1(obs)))
+        blocks = list(m.resnet)
+        a = F.relu(blocks[0].bn1(x)) if blocks else x
+        want.append(a)
+        for i, blk in enumerate(blocks):
+            b = F.relu(blk.bn2(blk.conv1(a)))
+            want.append(b)
+            x = x + blk.conv2(b)
+            a = F.relu(blocks[i + 1].bn1(x)) if i + 1 < len(blocks) else x
+            want.append(a)
+    torch.backends.cudnn.allow_tf32 = old
+    for l, w in enumerate(want):
+        got = ev.debug_layer(l)
+        torch.cuda.synchronize()
+        err = (got - w.permute(0, 2, 3, 1)).abs().max().item()
+        assert err < 3e-2, (l, err)
