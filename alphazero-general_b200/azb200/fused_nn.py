@@ -99,24 +99,27 @@ def fold(model, row_stride, head_stride=None):
 
 def fold_tc(model, layer_bytes=18432, head_stride=1800, frame_rows=56):
     """-> dict of CPU tensors in the layouts of azb_nn_forward_tc (tcgen05 kernel, azb_resnet_tc.cu):
-    conv weights as the K-major no-swizzle UMMA B operand [layer][16-byte K chunk][cout][8 cin]
-    (stem: chunk = tap, cin < 8; trunk: chunk = tap*4 + cin/8), the head matrix over frame rows
-    (k = (y*8 + x)*channels + ch; the frame's padding rows carry zero weights)."""
+    conv weights as the K-major no-swizzle UMMA B operand with the three horizontal taps side by
+    side in N: [layer][16-byte K chunk][dx*32 + cout][8 cin], K chunk = (dy+1)*4 + cin/8 (trunk) or
+    dy+1 with cin < 8 (stem); the head matrix [A+3][k] over frame rows, k = (y*8 + x)*channels + ch
+    (the frame's padding rows carry zero weights)."""
     f = _folded(model)
     ch, depth, cin, H, W = f["channels"], f["depth"], f["in_channels"], f["board_h"], f["board_w"]
     assert cin <= 8 and ch == 32 and frame_rows == (H + 1) * (W + 1)
     L = 1 + 2 * depth
-    kch = layer_bytes // (ch * 16)
-    wconv = torch.zeros(L, kch, ch, 8, dtype=torch.float64)
-    wconv[0, :9, :, :cin] = f["convs"][0].permute(1, 0, 2)                  # [tap][cout][cin]
+    kch = layer_bytes // (3 * ch * 16)
+    wconv = torch.zeros(L, kch, 3 * ch, 8, dtype=torch.float64)
+    w0 = f["convs"][0].view(ch, 3, 3, cin)                                  # [cout][dy][dx][cin]
+    wconv[0, :3, :, :cin] = w0.permute(1, 2, 0, 3).reshape(3, 3 * ch, cin)  # [dy][dx*32+cout][cin]
     for l in range(1, L):
-        wconv[l] = f["convs"][l].view(ch, 9, ch // 8, 8).permute(1, 2, 0, 3).reshape(kch, ch, 8)
+        w = f["convs"][l].view(ch, 3, 3, ch // 8, 8)                        # [cout][dy][dx][cin/8][8]
+        wconv[l] = w.permute(1, 3, 2, 0, 4).reshape(kch, 3 * ch, 8)         # [dy][cin/8][dx][cout][8]
     whead, bias = f["whead"], f["bhead"]
     nout = whead.shape[0]
-    wh = torch.zeros(16, head_stride, dtype=torch.float64)
     fr = torch.zeros(nout, H + 1, W + 1, ch, dtype=torch.float64)
     fr[:, :H, :W] = whead.view(nout, H, W, ch)
-    wh[:nout, :frame_rows * ch] = fr.reshape(nout, -1)
+    wh = torch.zeros(nout, head_stride, dtype=torch.float64)
+    wh[:, :frame_rows * ch] = fr.reshape(nout, -1)
     bhead16 = torch.zeros(16, dtype=torch.float64)
     bhead16[:nout] = bias
     return dict(wconv=wconv.to(torch.bfloat16), cbias=f["cbias"].float(), bn_scale=f["bn_scale"].float(),
@@ -127,6 +130,13 @@ def fold_tc(model, layer_bytes=18432, head_stride=1800, frame_rows=56):
 def supported_tc(model):
     """Geometry the tcgen05 kernel covers (azb_resnet_tc.cu): the mma.sync one, with <= 8 input planes."""
     return supported(model) and model.channels <= 8
+
+
+def boards_per_cta(model, kernel=None):
+    """Boards one CTA of the chosen kernel evaluates (launch-wave arithmetic for batch splits)."""
+    lib = _capi.load()
+    kernel = kernel or ("tc" if supported_tc(model) else "mma")
+    return lib.azb_nn_tc_boards_per_cta() if kernel == "tc" else lib.azb_nn_boards_per_cta()
 
 
 class FusedResNetEvaluator:

@@ -102,7 +102,7 @@ class NNetWrapper:
         self.cuda = torch.cuda.is_available() if cuda is None else cuda
         if self.cuda:
             self.nnet.cuda()
-        self.fused = fused          # evaluate with the fused bf16 kernel (csrc/azb_resnet.cu) when supported
+        self.fused = fused          # evaluate with the fused bf16 kernels (csrc/azb_resnet_tc.cu / azb_resnet.cu) when supported
         self._fused_eval = {}
 
     def _process_fused(self, batch):

@@ -202,19 +202,23 @@ class DeviceSelfPlay:
         if cohorts == 2 and split is None:
             split = B // 2
             if fused:
-                # the fused evaluator runs one 8-board CTA per SM: cut the batch at a whole number of
+                # the fused evaluators run one CTA of `nb` boards per SM: cut the batch at a whole number of
                 # waves so that two launches cost the same number of waves as one
                 import torch as _t
+                from .fused_nn import boards_per_cta
+                nb = boards_per_cta(nnet, None if fused is True else fused)
                 sms = _t.cuda.get_device_properties(engine.obs.device).multi_processor_count
-                waves = -(-(-(-B // 8)) // sms)
-                split = min(B - 8, max(8, ((waves + 1) // 2) * sms * 8))
+                waves = -(-(-(-B // nb)) // sms)
+                split = min(B - nb, max(nb, ((waves + 1) // 2) * sms * nb))
         bounds = [0, B] if cohorts == 1 else [0, split, B]
         self.ranges = [(bounds[i], bounds[i + 1] - bounds[i]) for i in range(cohorts)]
         from .nnet import LeafEvaluator
         if fused:
-            # hand-written fused ResNet kernel (bf16 tensor cores, csrc/azb_resnet.cu)
+            # hand-written fused ResNet kernel: tcgen05 / TMEM (csrc/azb_resnet_tc.cu) where it applies, else the
+            # mma.sync one (csrc/azb_resnet.cu); fused="tc" / "mma" forces one
             from .fused_nn import FusedResNetEvaluator
-            self.evals = [FusedResNetEvaluator(nnet, engine.obs[f:f + c], engine.policy[f:f + c], engine.value[f:f + c])
+            self.evals = [FusedResNetEvaluator(nnet, engine.obs[f:f + c], engine.policy[f:f + c], engine.value[f:f + c],
+                                               kernel=None if fused is True else fused)
                           for f, c in self.ranges]
         else:
             self.evals = [LeafEvaluator(nnet, engine.obs[f:f + c], engine.policy[f:f + c], engine.value[f:f + c],

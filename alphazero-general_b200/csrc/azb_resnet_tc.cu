@@ -14,22 +14,35 @@
 // Shared-memory layout of an activation frame: [8-channel chunk][frame row][16 B]
 // -- exactly the canonical K-major, no-swizzle UMMA operand with the 8 rows of a
 // core matrix contiguous (SBO = 128 B) and the two 16-byte K chunks of one MMA a
-// plane apart (LBO = plane size).  Shifting the operand by a tap is then just
-// `start address += shift * 16 B`, so the nine taps need no im2col and no copies,
-// and the epilogue's stores (one 16-byte chunk per thread, consecutive threads =
-// consecutive rows) are bank-conflict free.  The stem (<= 8 input channels) packs
-// two taps into one K=16 step by pointing LBO at the second tap's shift.
+// plane apart (LBO = plane size).  Shifting the operand by a vertical tap is just
+// `start address += dy * 128 B`: no im2col, no copies; and the epilogue's stores
+// (one 16-byte chunk per thread, consecutive threads = consecutive rows) are
+// bank-conflict free.
 //
-// Tensor memory: the fp32 residual stream x lives in TMEM for the whole network
-// (7 tiles x 32 columns); conv2 of every block accumulates straight onto it (the
-// residual add is the MMA's accumulate input), conv1 uses a second set of 7 x 32
-// columns.  One elected thread issues the MMAs of a layer tile after tile and
-// commits each tile to its own mbarrier; eight epilogue warps (two per TMEM lane
-// quadrant) drain finished tiles (tcgen05.ld -> bias / BN / ReLU -> bf16 ->
-// shared memory) while the tensor core works on the following tiles.  Weights of
-// the next layer are streamed by one bulk copy (UBLKCP) during the current one.
-// The affine heads are one small mma.sync over the final activation, softmax fp32.
+// A tcgen05.mma with M = 128, K = 16 costs ~44 cycles at N = 32 but only ~56 at
+// N = 96 (measured, scripts/umma_bench.cu: the A operand read from shared memory
+// dominates), so the three horizontal taps share one A read: the B operand holds
+// [dx][cout] = 96 columns and the MMA produces P_dx[i] = sum_dy A[i + 8 dy] W[dy,dx];
+// the convolution is D[r] = P_-1[r-1] + P_0[r] + P_+1[r+1], a one-lane shuffle in the
+// epilogue (rows r-1 / r+1 that fall outside the 8-row group are padding, where P is
+// exactly zero).  6 MMAs per tile and layer instead of 18.  The stem (<= 8 input
+// planes) packs two vertical taps into one K = 16 step by pointing LBO at the
+// second tap's rows.
+//
+// Tensor memory (512 columns): the fp32 residual stream x of the 7 tiles (224
+// columns, owned by the epilogue threads for the whole network) + a ring of three
+// 96-column accumulators.  Warp roles: warps 0-2 issue the MMAs, one per ring slot
+// (one elected thread each, uniform registers; issue is blocking and the thread's
+// own latencies would otherwise idle the tensor pipe), tile after tile across
+// layers, throttled only by the ring and by the rows of the previous layer a tile
+// needs (per-tile progress counters, no CTA-wide barrier inside the network);
+// warp 3 streams each layer's weights with one bulk
+// copy (UBLKCP) into a ring of three buffers; three groups of eight warps (TMEM lane
+// quadrant x 16-channel half) drain the accumulators (tcgen05.ld -> shuffle-add ->
+// bias / residual / BN / ReLU in packed f32x2 -> bf16 -> shared memory).  The affine heads are one small mma.sync over the final
+// activation, softmax in fp32.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -46,30 +59,51 @@ constexpr int FB = (BH + 1) * FW;      // 56 frame rows per board: + one shared 
 constexpr int ROWS = NB * FB;          // 896
 constexpr int TILES = ROWS / 128;      // 7
 static_assert(ROWS % 128 == 0, "frame rows of a CTA must fill whole M=128 tiles");
-constexpr int PADR = 16;               // zero rows in front of / behind the boards (|tap shift| <= 9)
+constexpr int PADR = 16;               // zero rows in front of / behind the boards
 constexpr int FROWS = ROWS + 2 * PADR; // 928
 constexpr int PLANE = FROWS * 16;      // bytes of one 8-channel chunk plane (14848)
 constexpr int FRAME = 4 * PLANE;       // 59392
-constexpr int KCH = 36;                // 16-byte K chunks per layer: 9 taps x 4
-constexpr int WL_BYTES = KCH * CH * 16;    // 18432: [k chunk][cout][8 cin] bf16
-constexpr int NHEAD = 16;
+constexpr int NACC = 3 * CH;           // 96 accumulator columns: [dx][cout]
+constexpr int KCH = 12;                // 16-byte K chunks per layer: 3 vertical taps x 4
+constexpr int WCHUNK = NACC * 16;      // 1536 bytes: one K chunk of the B operand
+constexpr int WL_BYTES = KCH * WCHUNK; // 18432: [k chunk][dx*32 + cout][8 cin] bf16
+constexpr int NWBUF = 3, NPBUF = 3;
+constexpr int NOUT = 10;               // 7 policy logits + 3 value logits
 constexpr int KH = FB * CH;            // head K: frame row * 32 + channel (1792)
 constexpr int RS_H = KH + 8;           // bf16 row stride of the head matrix
 constexpr int MAXD = 6, MAXL = 1 + 2 * MAXD;
 constexpr int PRM_FLOATS = MAXL * CH + 2 * MAXD * CH;
-constexpr int WARPS = 9;               // warp 0: control / MMA issue; warps 1-8: epilogue
+constexpr int PROD_WARP = NPBUF;       // warps 0..2: MMA issue for ring slot 0..2; warp 3: weight producer
+constexpr int EPI_WARP0 = NPBUF + 1;   // then the epilogue warps
+constexpr int GRP_WARPS = 8;           // per ring slot: 4 TMEM lane quadrants x 2 column halves
+constexpr int WARPS = EPI_WARP0 + GRP_WARPS * NPBUF;   // 28
 constexpr int THREADS = WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t COL_X = 0, COL_T = 256;   // x tiles at 32*t, conv1 accumulators at 256 + 32*t
+constexpr uint32_t COL_X = 0, COL_P = 224;   // x tiles at 32*t; accumulator ring at 224 + 96*b
+static_assert(COL_P + NPBUF * NACC <= TMEM_COLS, "tensor memory budget");
 
-constexpr size_t SMEM_BYTES = 2 * (size_t)FRAME + 2 * (size_t)WL_BYTES + (size_t)NHEAD * RS_H * 2 +
-                              (size_t)PRM_FLOATS * 4 + 16 * 8 + 16 + 128;
+// mbarriers
+enum { BAR_PFULL = 0, BAR_PEMPTY = BAR_PFULL + NPBUF, BAR_READY = BAR_PEMPTY + NPBUF /* [TILES]: rows 128t-8 .. 128t+135 written */,
+       BAR_WFULL = BAR_READY + TILES, BAR_WEMPTY = BAR_WFULL + NWBUF, BAR_HEAD = BAR_WEMPTY + NWBUF, NBARS };
+// Shared-memory bandwidth is the shared resource: a tcgen05.mma at N = 96 reads 7 KB of operands in 56 cycles (the
+// full 128 B/clk), so anything that polls shared memory steals from the tensor pipe.  Waits are mbarrier waits (the
+// hardware suspends the thread); the only polled word is the turn counter that keeps the MMAs of a tile contiguous.
+enum { CNT_TURN = 0 /* next tile whose MMAs may enter the tensor pipe */, NCNT = 1 };
+constexpr int HB = FB + 1;             // rows per board of the head-input layout (57: board stride 912 B, conflict-free ldmatrix)
+
+constexpr size_t SMEM_BYTES = 2 * (size_t)FRAME + (size_t)NWBUF * WL_BYTES + (size_t)NOUT * RS_H * 2 +
+                              (size_t)PRM_FLOATS * 4 + 32 * 8 + 64 + 128;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 // ---- PTX wrappers --------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
@@ -81,16 +115,36 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-// bounded wait: a barrier that never completes is a programming error -- trap instead of hanging the GPU
+// Bounded wait: a barrier that never completes is a programming error -- trap instead of hanging the GPU.  The
+// suspend-time hint lets the hardware park the thread instead of returning to re-poll: the kernel is bound by
+// instruction issue in the epilogue warps, and every retry of a waiting warp takes issue slots from a working one.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;
-    for (uint32_t it = 0; it < (1u << 26); it++) {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 22); it++) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(done)
-                     : "r"(bar), "r"(parity)
+                     : "r"(bar), "r"(parity), "r"(20000u)
                      : "memory");
         if (done) return;
+    }
+    __trap();
+}
+// the turn counter orders only the *issue* of tcgen05.mma by different threads (a performance matter): relaxed
+// accesses.  (A release store compiles to MEMBAR.ALL.CTA, which stalls the issuing thread until its MMAs retire.)
+__device__ __forceinline__ void turn_store(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void turn_wait(uint32_t addr, uint32_t g)
+{
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 24); it++) {
+        uint32_t v;
+        asm volatile("ld.relaxed.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
+        if (v >= g) return;
+        __nanosleep(64);
     }
     __trap();
 }
@@ -115,7 +169,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 // instruction descriptor, kind::f16: D = f32 [4,6), A = B = bf16 [7,10) [10,13), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CH >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NACC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
 {
@@ -127,36 +181,28 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
-#define AZB_R32(v)                                                                                                     \
+#define AZB_R16(v)                                                                                                     \
     "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),        \
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),         \
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),        \
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-#define AZB_I32(v)                                                                                                     \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+#define AZB_I16(v)                                                                                                     \
     "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),      \
-        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),    \
-        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),    \
-        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-// one accumulator row (this thread's TMEM lane), 32 consecutive fp32 columns
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+// this thread's TMEM lane, 16 consecutive fp32 columns (no wait: the caller batches loads)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-                 "%29,%30,%31}, [%32];\n"
-                 : AZB_R32(v)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : AZB_R16(v)
                  : "r"(taddr)
                  : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
 {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
-                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-                 "%29,%30,%31};\n" ::AZB_I32(v),
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};\n" ::AZB_I16(v),
                  "r"(taddr)
                  : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t addr)
 {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
@@ -173,97 +219,134 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
+// MMAs of one tile (elected thread).  trunk: 3 vertical taps x two 16-channel halves; stem: two K steps over
+// chunk plane 0 ((dy=-1, dy=0) and (dy=+1, zero weights)).
+__device__ __forceinline__ void issue_tile(uint32_t in_s, uint32_t w_s, uint32_t d_tmem, int t, bool stem)
+{
+    const uint32_t row0 = in_s + (uint32_t)((PADR + 128 * t) * 16);
+    if (stem) {
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const uint64_t ad = umma_desc(row0 + (uint32_t)((2 * s - 1) * FW * 16), (uint32_t)(FW * 16), 128u);
+            const uint64_t bd = umma_desc(w_s + (uint32_t)(2 * s * WCHUNK), (uint32_t)WCHUNK, 128u);
+            umma_f16(d_tmem, ad, bd, s > 0 ? 1u : 0u);
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            const int dy = s / 2 - 1, half = s & 1;
+            const uint64_t ad = umma_desc(row0 + (uint32_t)(2 * half * PLANE + dy * FW * 16), (uint32_t)PLANE, 128u);
+            const uint64_t bd = umma_desc(w_s + (uint32_t)(2 * s * WCHUNK), (uint32_t)WCHUNK, 128u);
+            umma_f16(d_tmem, ad, bd, s > 0 ? 1u : 0u);
+        }
+    }
+}
+
 enum { EPI_STEM = 0, EPI_CONV1 = 1, EPI_CONV2 = 2 };
 
-// tap t = (dy+1)*3 + (dx+1) -> frame-row shift dy*8 + dx
-__device__ __forceinline__ int tap_shift(int t) { return (t / 3 - 1) * FW + (t % 3 - 1); }
-
-// All MMAs of one layer, issued by one thread: tile after tile, each tile committed to its own mbarrier.
-//   stem : 5 K-steps, each covering two taps of the <= 8 input channels (chunk plane 0 of `in`)
-//   trunk: 18 K-steps = 9 taps x two 16-channel halves
-__device__ __forceinline__ void issue_layer(uint32_t in_s, uint32_t w_s, uint32_t tmem_d, bool stem, bool accumulate,
-                                            uint32_t bar_tile0)
+__device__ __forceinline__ float2 f2(uint32_t lo, uint32_t hi) { return make_float2(__uint_as_float(lo), __uint_as_float(hi)); }
+__device__ __forceinline__ uint32_t relu_bf16x2(float2 v)      // bf16x2(max(v, 0)): rounding is monotonic, so relu commutes with it
 {
-#pragma unroll 1
-    for (int t = 0; t < TILES; t++) {
-        const uint32_t row0 = in_s + (uint32_t)((PADR + 128 * t) * 16);
-        const uint32_t d = tmem_d + (uint32_t)(32 * t);
-        if (stem) {
-#pragma unroll
-            for (int s = 0; s < 5; s++) {
-                const int sh0 = tap_shift(2 * s), sh1 = s < 4 ? tap_shift(2 * s + 1) : tap_shift(8) + 1;
-                const uint64_t ad = umma_desc(row0 + (uint32_t)(sh0 * 16), (uint32_t)((sh1 - sh0) * 16), 128u);
-                const uint64_t bd = umma_desc(w_s + (uint32_t)(2 * s * CH * 16), (uint32_t)(CH * 16), 128u);
-                umma_f16(d, ad, bd, s > 0 ? 1u : 0u);
-            }
-        } else {
-#pragma unroll
-            for (int s = 0; s < 18; s++) {
-                const int tap = s >> 1, half = s & 1;
-                const uint64_t ad = umma_desc(row0 + (uint32_t)(2 * half * PLANE + tap_shift(tap) * 16), (uint32_t)PLANE, 128u);
-                const uint64_t bd = umma_desc(w_s + (uint32_t)(2 * s * CH * 16), (uint32_t)(CH * 16), 128u);
-                umma_f16(d, ad, bd, (s > 0 || accumulate) ? 1u : 0u);
-            }
-        }
-        umma_commit(bar_tile0 + 8u * (uint32_t)t);
-    }
+    __nv_bfloat162 h = __hmax2(__float22bfloat162_rn(v), __float2bfloat162_rn(0.0f));
+    return *reinterpret_cast<uint32_t *>(&h);
 }
 
-// Epilogue of one layer for the tiles of this warp's group (warps 1-4: tiles 0,2,4,6; warps 5-8: 1,3,5).
-// Each thread owns one frame row of the tile = one TMEM lane (lane quadrant = warp % 4).
-template <int EPI>
-__device__ __forceinline__ void epilogue(uint32_t tmem_base, uint32_t col0, unsigned char *outf, const float *bias,
-                                         const float *nsc, const float *nsh, uint32_t bar_tile0, uint32_t parity, int warp,
-                                         int lane, float *dump)
+// Epilogue of one tile for 16 of its 32 channels: this thread owns frame row `fr` = TMEM lane q*32 + lane and the
+// channels [16*half, 16*half + 16).  Packed f32x2 arithmetic (FADD2 / FFMA2).
+//   stem : x = relu(D + bias) -> TMEM;  a = relu(bn1_0(x))
+//   conv1: b = relu(D + bias)                                   (BN2 folded)
+//   conv2: x += D -> TMEM;  a = relu(bn1_next(x))  (last block: a = x)
+// t_p / t_x / bias / nsc / nsh / out_row / dump_row already point at this thread's column half.
+template <int EPI, bool DBG>
+__device__ __forceinline__ void epilogue_tile(uint32_t t_p, uint32_t t_x, unsigned char *out_row, int out_plane, const float *bias,
+                                              const float *nsc, const float *nsh, bool live, int lane, uint32_t bar_pempty,
+                                              float *dump_row)
 {
-    const int q = warp & 3, grp = (warp - 1) >> 2;
-#pragma unroll 1
-    for (int t = grp; t < TILES; t += 2) {
-        mbar_wait(bar_tile0 + 8u * (uint32_t)t, parity);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col0 + (uint32_t)(32 * t);
-        uint32_t v[32];
-        tmem_ld32(taddr, v);
-        const int fr = t * 128 + q * 32 + lane;
-        const bool live = ((fr & 7) != 7) && (((fr >> 3) % (BH + 1)) != BH);
-        float r[32];
+    uint32_t pm[16], p0[16], pp[16], xv[16];
+    tmem_ld16(t_p, pm);
+    tmem_ld16(t_p + (uint32_t)CH, p0);
+    tmem_ld16(t_p + (uint32_t)(2 * CH), pp);
+    if (EPI == EPI_CONV2) tmem_ld16(t_x, xv);
+    tmem_ld_wait();
+    tc_fence_before();                    // the accumulator is in registers: hand the ring slot back to the MMA warp
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_pempty);
+    // D[r] = P_-1[r-1] + P_0[r] + P_+1[r+1]: rotate by one lane.  Lane 0 receives lane 31's value, a padding-column
+    // row where P is exactly zero -- which is what row r-1 of lane 0 (also a padding column) holds; lane 31 is a
+    // padding row itself and is never stored.
+    // The two neighbour terms travel as packed fp16 pairs (11-bit mantissa, far below the bf16 rounding of the operands):
+    // shuffles go through the shared-memory data pipe, which is the resource this kernel is bound by.
+    const int src_up = (lane + 31) & 31, src_dn = (lane + 1) & 31;
+    float2 r[8];
 #pragma unroll
-        for (int c = 0; c < 32; c++) r[c] = __uint_as_float(v[c]);
-        if (EPI == EPI_STEM) {                                  // x = relu(conv + bias) goes back to TMEM
-#pragma unroll
-            for (int c = 0; c < 32; c++) {
-                r[c] = fmaxf(r[c] + bias[c], 0.0f);
-                v[c] = __float_as_uint(r[c]);
-            }
-            tmem_st32(taddr, v);
-        } else if (EPI == EPI_CONV1) {                          // b = relu(conv1 + bias)   (BN2 folded)
-#pragma unroll
-            for (int c = 0; c < 32; c++) r[c] = fmaxf(r[c] + bias[c], 0.0f);
-        }
-        if (EPI != EPI_CONV1 && nsc != nullptr) {               // a = relu(bn1(x)) of the block that reads x next
-#pragma unroll
-            for (int c = 0; c < 32; c++) r[c] = fmaxf(fmaf(r[c], nsc[c], nsh[c]), 0.0f);
-        }
-        if (dump != nullptr) {
-#pragma unroll
-            for (int c = 0; c < 32; c++) dump[(size_t)fr * 32 + c] = live ? r[c] : 0.0f;
-        }
-        unsigned char *row = outf + (size_t)(PADR + fr) * 16;
+    for (int c = 0; c < 8; c++) {
+        const __half2 hm = __floats2half2_rn(__uint_as_float(pm[2 * c]), __uint_as_float(pm[2 * c + 1]));
+        const __half2 hp = __floats2half2_rn(__uint_as_float(pp[2 * c]), __uint_as_float(pp[2 * c + 1]));
+        const uint32_t um = __shfl_sync(0xffffffffu, *reinterpret_cast<const uint32_t *>(&hm), src_up);
+        const uint32_t up_ = __shfl_sync(0xffffffffu, *reinterpret_cast<const uint32_t *>(&hp), src_dn);
+        const float2 up = __half22float2(*reinterpret_cast<const __half2 *>(&um));
+        const float2 dn = __half22float2(*reinterpret_cast<const __half2 *>(&up_));
+        r[c] = __fadd2_rn(__fadd2_rn(up, f2(p0[2 * c], p0[2 * c + 1])), dn);
+    }
+    float2 prm2[8];                        // 16 per-channel parameters with four 16-byte loads
+    if (EPI != EPI_CONV2) {
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            uint4 o;
-            o.x = live ? pack_bf16(r[8 * c + 0], r[8 * c + 1]) : 0u;
-            o.y = live ? pack_bf16(r[8 * c + 2], r[8 * c + 3]) : 0u;
-            o.z = live ? pack_bf16(r[8 * c + 4], r[8 * c + 5]) : 0u;
-            o.w = live ? pack_bf16(r[8 * c + 6], r[8 * c + 7]) : 0u;
-            *reinterpret_cast<uint4 *>(row + (size_t)c * PLANE) = o;
+            const float4 b4 = reinterpret_cast<const float4 *>(bias)[c];
+            prm2[2 * c] = make_float2(b4.x, b4.y); prm2[2 * c + 1] = make_float2(b4.z, b4.w);
         }
     }
-    fence_proxy_async();      // the next layer's MMAs read these rows through the async proxy
-    tc_fence_before();
+    if (EPI == EPI_STEM) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            r[c] = __fadd2_rn(r[c], prm2[c]);
+            r[c].x = fmaxf(r[c].x, 0.0f); r[c].y = fmaxf(r[c].y, 0.0f);
+            xv[2 * c] = __float_as_uint(r[c].x); xv[2 * c + 1] = __float_as_uint(r[c].y);
+        }
+        tmem_st16(t_x, xv);
+    } else if (EPI == EPI_CONV1) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) r[c] = __fadd2_rn(r[c], prm2[c]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            r[c] = __fadd2_rn(r[c], f2(xv[2 * c], xv[2 * c + 1]));
+            xv[2 * c] = __float_as_uint(r[c].x); xv[2 * c + 1] = __float_as_uint(r[c].y);
+        }
+        tmem_st16(t_x, xv);
+    }
+    uint32_t o[8];
+    if (EPI != EPI_CONV1 && nsc == nullptr) {               // last block: a = bf16(x), no activation
+#pragma unroll
+        for (int c = 0; c < 8; c++) o[c] = pack_bf16(r[c].x, r[c].y);
+    } else {
+        if (EPI != EPI_CONV1) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float4 s4 = reinterpret_cast<const float4 *>(nsc)[c], h4 = reinterpret_cast<const float4 *>(nsh)[c];
+                r[2 * c] = __ffma2_rn(r[2 * c], make_float2(s4.x, s4.y), make_float2(h4.x, h4.y));
+                r[2 * c + 1] = __ffma2_rn(r[2 * c + 1], make_float2(s4.z, s4.w), make_float2(h4.z, h4.w));
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) o[c] = relu_bf16x2(r[c]);
+    }
+    if (DBG && dump_row != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162 *>(&o[c]);
+            dump_row[2 * c] = live ? __low2float(h) : 0.0f;
+            dump_row[2 * c + 1] = live ? __high2float(h) : 0.0f;
+        }
+    }
+    if (live) {                           // padding rows are zero from the start and stay so
+        *reinterpret_cast<uint4 *>(out_row) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4 *>(out_row + out_plane) = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    if (EPI != EPI_CONV1) tmem_st_wait();
 }
 
-template <int NOUT>
+template <bool DBG>
 __global__ void __launch_bounds__(THREADS, 1)
 k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__restrict__ value, int B, int in_ch, int depth,
             const unsigned char *__restrict__ wconv, const float *__restrict__ cbias, const float *__restrict__ bn_scale,
@@ -273,24 +356,34 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *fa = smem;                                            // activation frame a
     unsigned char *fb = fa + FRAME;                                      // activation frame b (first: the observation)
-    unsigned char *w0 = fb + FRAME;                                      // weights of the even / odd layers
-    unsigned char *w1 = w0 + WL_BYTES;
-    __nv_bfloat16 *wh = reinterpret_cast<__nv_bfloat16 *>(w1 + WL_BYTES);   // [NHEAD][RS_H]
-    float *prm = reinterpret_cast<float *>(wh + NHEAD * RS_H);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(prm + PRM_FLOATS);   // tile[7], w[2], head
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
-    float *red = reinterpret_cast<float *>(w0);                          // heads: [WARPS][NB][NHEAD] (after the trunk)
-    float *fin = reinterpret_cast<float *>(w1);                          // heads: [NB][NHEAD]
+    unsigned char *wb = fb + FRAME;                                      // weight ring [NWBUF][WL_BYTES]
+    __nv_bfloat16 *wh = reinterpret_cast<__nv_bfloat16 *>(wb + NWBUF * WL_BYTES);   // [NOUT][RS_H]
+    float *prm = reinterpret_cast<float *>(wh + NOUT * RS_H);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(prm + PRM_FLOATS);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 32);
+    uint32_t *cnts = tmem_slot + 4;                                      // [NCNT] progress counters
+    float *red = reinterpret_cast<float *>(wb);                          // heads: [WARPS][NB][16] (after the trunk)
+    float *fin = red + WARPS * NB * 16;                                  // heads: [NB][16]
 
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int board0 = blockIdx.x * NB;
+    // DBG build (azb_nn_forward_tc_debug): dump_layer = 99 writes per-warp phase clocks, else the activations of a layer
+    const bool timing = DBG && dump != nullptr && dump_layer == 99;
+    long long ts[5];
+    if (timing) ts[0] = clock64();
     const int layers = 1 + 2 * depth;
-    const uint32_t bar_tile0 = smem_u32(bars), bar_w0 = smem_u32(bars + TILES), bar_h = smem_u32(bars + TILES + 2);
-    const uint32_t fa_s = smem_u32(fa), fb_s = smem_u32(fb), w_s[2] = {smem_u32(w0), smem_u32(w1)};
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t fa_s = smem_u32(fa), fb_s = smem_u32(fb), wb_s = smem_u32(wb);
+#define BAR(i) (bar0 + 8u * (uint32_t)(i))
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int i = 0; i < TILES + 3; i++) mbar_init(bar_tile0 + 8u * (uint32_t)i, 1);
+            for (int i = 0; i < NPBUF; i++) { mbar_init(BAR(BAR_PFULL + i), 1); mbar_init(BAR(BAR_PEMPTY + i), GRP_WARPS); }
+            // every epilogue warp of tiles t-1, t, t+1 arrives on READY[t]
+            for (int i = 0; i < TILES; i++) mbar_init(BAR(BAR_READY + i), GRP_WARPS * ((i == 0 || i == TILES - 1) ? 2 : 3));
+            for (int i = 0; i < NWBUF; i++) { mbar_init(BAR(BAR_WFULL + i), 1); mbar_init(BAR(BAR_WEMPTY + i), NPBUF); }
+            mbar_init(BAR(BAR_HEAD), 1);
+            for (int i = 0; i < NCNT; i++) cnts[i] = 0u;
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         }
         __syncwarp();
@@ -314,12 +407,6 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
     const uint32_t tmem_base = *tmem_slot;
     const float *s_bias = prm, *s_sc = prm + MAXL * CH, *s_sh = prm + MAXL * CH + MAXD * CH;
 
-    if (tid == 0) {       // weights of layer 0 and the head matrix
-        mbar_expect_tx(bar_w0, WL_BYTES);
-        bulk_g2s(w_s[0], wconv, WL_BYTES, bar_w0);
-        mbar_expect_tx(bar_h, (uint32_t)(NHEAD * RS_H * 2));
-        bulk_g2s(smem_u32(wh), whead, (uint32_t)(NHEAD * RS_H * 2), bar_h);
-    }
     // observation -> chunk plane 0 of frame b (channels >= in_ch stay zero)
     for (int i = tid; i < NB * BH * BW; i += THREADS) {
         const int bl = i / (BH * BW), pos = i - bl * (BH * BW), y = pos / BW, xx = pos - y * BW;
@@ -333,74 +420,149 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
     }
     fence_proxy_async();
     __syncthreads();
+    if (timing) ts[1] = clock64();
 
-    // ---- trunk: one pass per layer ------------------------------------------------
+    const uint32_t cnt0 = smem_u32(cnts);
+#define CNT(i) (cnt0 + 4u * (uint32_t)(i))
+    if (warp < NPBUF) {
+        // ---- MMA issuers: warp k feeds ring slot k (tiles g = k, k+3, ... across layers) --------------------
+        if (elect_one_sync()) {
+            const int total = layers * TILES;
+            const uint32_t d_tmem = tmem_base + COL_P + (uint32_t)(warp * NACC);
+            int l = 0, t = warp, cur_l = -1;
+            uint32_t w_s = 0;
 #pragma unroll 1
-    for (int l = 0; l < layers; l++) {
-        const bool stem = l == 0, is_c1 = (l & 1) == 1;
-        const uint32_t parity = (uint32_t)(l & 1);
-        if (warp == 0) {
-            if (elect_one_sync()) {
-                if (l + 1 < layers) {      // stream the next layer's weights into the buffer layer l-1 has released
-                    const uint32_t bw = bar_w0 + 8u * (uint32_t)((l + 1) & 1);
-                    mbar_expect_tx(bw, WL_BYTES);
-                    bulk_g2s(w_s[(l + 1) & 1], wconv + (size_t)(l + 1) * WL_BYTES, WL_BYTES, bw);
+            for (int g = warp, use = 0; g < total; g += NPBUF, use++) {
+                if (l != cur_l) {
+                    if (cur_l >= 0) umma_commit(BAR(BAR_WEMPTY + cur_l % NWBUF));   // my MMAs of that layer are all issued
+                    cur_l = l;
+                    mbar_wait(BAR(BAR_WFULL + l % NWBUF), (uint32_t)((l / NWBUF) & 1));
+                    w_s = wb_s + (uint32_t)((l % NWBUF) * WL_BYTES);
                 }
-                mbar_wait(bar_w0 + 8u * (uint32_t)(l & 1), (uint32_t)((l >> 1) & 1));
+                // rows 128t-8 .. 128t+135 of the previous layer's output, and my ring slot drained
+                if (l > 0) mbar_wait(BAR(BAR_READY + t), (uint32_t)((l - 1) & 1));
+                if (use > 0) mbar_wait(BAR(BAR_PEMPTY + warp), (uint32_t)((use - 1) & 1));
                 tc_fence_after();
-                // stem: obs (frame b) -> x;  conv1: a -> T;  conv2: b -> x (+=)
-                issue_layer((stem || !is_c1) ? fb_s : fa_s, w_s[l & 1], tmem_base + (is_c1 ? COL_T : COL_X), stem,
-                            !stem && !is_c1, bar_tile0);
+                // the three issuers overlap their waits, but the MMAs of a tile enter the pipe back to back and in tile
+                // order: interleaved, all three tiles would complete together and the ring would run in lock-step
+                turn_wait(CNT(CNT_TURN), (uint32_t)g);
+                issue_tile((l & 1) ? fa_s : fb_s, w_s, d_tmem, t, l == 0);   // stem: obs (b);  conv1: a;  conv2: b
+                umma_commit(BAR(BAR_PFULL + warp));
+                turn_store(CNT(CNT_TURN), (uint32_t)(g + 1));
+                t += NPBUF;
+                if (t >= TILES) { t -= TILES; l++; }
             }
-            __syncwarp();
-        } else {
-            float *dmp = (dump != nullptr && l == dump_layer) ? dump + (size_t)blockIdx.x * ROWS * 32 : nullptr;
-            if (stem) {
-                epilogue<EPI_STEM>(tmem_base, COL_X, fa, s_bias, depth > 0 ? s_sc : nullptr, s_sh, bar_tile0, parity, warp, lane, dmp);
-            } else if (is_c1) {
-                epilogue<EPI_CONV1>(tmem_base, COL_T, fb, s_bias + l * CH, nullptr, nullptr, bar_tile0, parity, warp, lane, dmp);
-            } else {
-                const int nb = l >> 1;     // the block that consumes x next
-                const bool last = l + 1 == layers;
-                epilogue<EPI_CONV2>(tmem_base, COL_X, fa, nullptr, last ? nullptr : s_sc + nb * CH, s_sh + nb * CH, bar_tile0,
-                                    parity, warp, lane, dmp);
+            umma_commit(BAR(BAR_WEMPTY + cur_l % NWBUF));
+        }
+        __syncwarp();
+    } else if (warp == PROD_WARP) {
+        // ---- weight producer --------------------------------------------------------
+        if (elect_one_sync()) {
+            mbar_expect_tx(BAR(BAR_HEAD), (uint32_t)(NOUT * RS_H * 2));
+            bulk_g2s(smem_u32(wh), whead, (uint32_t)(NOUT * RS_H * 2), BAR(BAR_HEAD));
+#pragma unroll 1
+            for (int l = 0; l < layers; l++) {
+                const int wbuf = l % NWBUF, use = l / NWBUF;
+                if (use > 0) mbar_wait(BAR(BAR_WEMPTY + wbuf), (uint32_t)((use - 1) & 1));
+                mbar_expect_tx(BAR(BAR_WFULL + wbuf), WL_BYTES);
+                bulk_g2s(wb_s + (uint32_t)(wbuf * WL_BYTES), wconv + (size_t)l * WL_BYTES, WL_BYTES, BAR(BAR_WFULL + wbuf));
             }
         }
-        __syncthreads();
-        tc_fence_after();
+        __syncwarp();
+    } else {
+        // ---- epilogue: group `grp` (8 warps) drains ring slot `grp`; a warp owns one TMEM lane quadrant and 16 channels
+        const int e = warp - EPI_WARP0, grp = e / GRP_WARPS, q = warp & 3, half = (e % GRP_WARPS) >> 2;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const uint32_t t_p = tmem_base + lane_off + COL_P + (uint32_t)(grp * NACC + 16 * half);
+        const uint32_t t_x0 = tmem_base + lane_off + COL_X + (uint32_t)(16 * half);
+        const uint32_t bar_full = BAR(BAR_PFULL + grp), bar_empty = BAR(BAR_PEMPTY + grp);
+        const int total = layers * TILES, ho = 16 * half, r0 = q * 32 + lane;
+        unsigned char *const fa_h = fa + (size_t)(2 * half) * PLANE + (size_t)PADR * 16;
+        unsigned char *const fb_h = fb + (size_t)(2 * half) * PLANE + (size_t)PADR * 16;
+        int l = 0, t = grp;
+        uint32_t par = 0;
+#pragma unroll 1
+        for (int g = grp; g < total; g += NPBUF) {
+            const bool is_c1 = (l & 1) == 1, last = l + 1 == layers;
+            mbar_wait(bar_full, par);
+            par ^= 1u;
+            tc_fence_after();
+            const int fr = t * 128 + r0;
+            const bool live = ((fr & 7) != 7) && (((fr >> 3) % (BH + 1)) != BH);
+            const uint32_t t_x = t_x0 + (uint32_t)(CH * t);
+            // the last layer writes the head input: [8-channel chunk][board][HB rows][16 B]
+            unsigned char *out_row;
+            int out_plane = PLANE;
+            if (last) {
+                const int brd = fr / FB;
+                out_row = fa + ((size_t)(2 * half) * (NB * HB) + (size_t)(fr + brd)) * 16;      // brd*HB + fr - brd*FB
+                out_plane = NB * HB * 16;
+            } else {
+                out_row = (is_c1 ? fb_h : fa_h) + (size_t)fr * 16;
+            }
+            float *dmp = (DBG && dump != nullptr && l == dump_layer) ? dump + ((size_t)blockIdx.x * ROWS + fr) * CH + ho : nullptr;
+            if (l == 0) {
+                epilogue_tile<EPI_STEM, DBG>(t_p, t_x, out_row, out_plane, s_bias + ho, depth > 0 ? s_sc + ho : nullptr, s_sh + ho,
+                                             live, lane, bar_empty, dmp);
+            } else if (is_c1) {
+                epilogue_tile<EPI_CONV1, DBG>(t_p, t_x, out_row, out_plane, s_bias + l * CH + ho, nullptr, nullptr, live, lane,
+                                              bar_empty, dmp);
+            } else {
+                const int nb = l >> 1;                        // the block that consumes x next
+                epilogue_tile<EPI_CONV2, DBG>(t_p, t_x, out_row, out_plane, nullptr, last ? nullptr : s_sc + nb * CH + ho,
+                                              s_sh + nb * CH + ho, live, lane, bar_empty, dmp);
+            }
+            fence_proxy_async();              // the next layer's MMAs read these rows through the async proxy
+            __syncwarp();
+            if (lane == 0) {                  // every tile whose MMAs read these rows
+                if (t > 0) mbar_arrive(BAR(BAR_READY + t - 1));
+                mbar_arrive(BAR(BAR_READY + t));
+                if (t + 1 < TILES) mbar_arrive(BAR(BAR_READY + t + 1));
+            }
+            t += NPBUF;
+            if (t >= TILES) { t -= TILES; l++; }
+        }
     }
+#undef CNT
+    if (timing) ts[2] = clock64();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (timing) ts[3] = clock64();
 
     // ---- heads: logits[board][j] = sum_k wh[j][k] * a[board][k] + bhead[j], k = frame row * 32 + channel ----------
-    mbar_wait(bar_h, 0u);
+    mbar_wait(BAR(BAR_HEAD), 0u);
     {
         const uint32_t h_s = smem_u32(wh);
         float acc[2][4];
 #pragma unroll
         for (int i = 0; i < 2; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f; }
         const int brd = lane & 15, khalf = lane >> 4;
-        const uint32_t a_lane = fa_s + (uint32_t)((PADR + brd * FB) * 16 + khalf * PLANE);
-        const uint32_t h_lane = h_s + (uint32_t)(((((lane >> 4) << 3) + (lane & 7)) * RS_H + ((lane >> 3) & 1) * 8) * 2);
+        const uint32_t a_lane = fa_s + (uint32_t)((brd * HB) * 16 + khalf * (NB * HB * 16));
+        int hrow = ((lane >> 4) << 3) + (lane & 7);                     // output row this lane addresses for ldmatrix
+        hrow = hrow < NOUT ? hrow : NOUT - 1;                           // rows >= NOUT: any valid row, result unused
+        const uint32_t h_lane = h_s + (uint32_t)((hrow * RS_H + ((lane >> 3) & 1) * 8) * 2);
         for (int ks = warp; ks < KH / 16; ks += WARPS) {
             const int fr = ks >> 1, half = ks & 1;
             uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
-            ldmatrix_x4(a0, a1, a2, a3, a_lane + (uint32_t)(fr * 16 + 2 * half * PLANE));
+            ldmatrix_x4(a0, a1, a2, a3, a_lane + (uint32_t)(fr * 16 + 2 * half * (NB * HB * 16)));
             ldmatrix_x4(b0, b1, b2, b3, h_lane + (uint32_t)(ks * 32));
             mma_bf16(acc[0], a0, a1, a2, a3, b0, b1);
             mma_bf16(acc[1], a0, a1, a2, a3, b2, b3);
         }
-        const int g = lane >> 2, t = lane & 3;                     // c0,c1: board g; c2,c3: board g+8; cols 2t, 2t+1
+        const int gq = lane >> 2, tq = lane & 3;                   // c0,c1: board gq; c2,c3: board gq+8; cols 2tq, 2tq+1
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
-            red[(warp * NB + g) * NHEAD + nt * 8 + 2 * t] = acc[nt][0];
-            red[(warp * NB + g) * NHEAD + nt * 8 + 2 * t + 1] = acc[nt][1];
-            red[(warp * NB + g + 8) * NHEAD + nt * 8 + 2 * t] = acc[nt][2];
-            red[(warp * NB + g + 8) * NHEAD + nt * 8 + 2 * t + 1] = acc[nt][3];
+            red[(warp * NB + gq) * 16 + nt * 8 + 2 * tq] = acc[nt][0];
+            red[(warp * NB + gq) * 16 + nt * 8 + 2 * tq + 1] = acc[nt][1];
+            red[(warp * NB + gq + 8) * 16 + nt * 8 + 2 * tq] = acc[nt][2];
+            red[(warp * NB + gq + 8) * 16 + nt * 8 + 2 * tq + 1] = acc[nt][3];
         }
         __syncthreads();
-        if (tid < NB * NHEAD) {
+        if (tid < NB * 16) {
             float v = 0.0f;
-            for (int wq = 0; wq < WARPS; wq++) v += red[wq * NB * NHEAD + tid];
-            fin[tid] = v + ((tid % NHEAD) < NOUT ? bhead[tid % NHEAD] : 0.0f);
+            for (int wq = 0; wq < WARPS; wq++) v += red[wq * NB * 16 + tid];
+            fin[tid] = v + ((tid & 15) < NOUT ? bhead[tid & 15] : 0.0f);
         }
         __syncthreads();
         if (tid < NB && board0 + tid < B) {
@@ -408,7 +570,7 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
             constexpr int A = NOUT - 3;
             float lg[NOUT];
 #pragma unroll
-            for (int j = 0; j < NOUT; j++) lg[j] = fin[tid * NHEAD + j];
+            for (int j = 0; j < NOUT; j++) lg[j] = fin[tid * 16 + j];
             float mp = lg[0], mv = lg[A];
 #pragma unroll
             for (int j = 1; j < A; j++) mp = fmaxf(mp, lg[j]);
@@ -426,11 +588,20 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
             for (int j = A; j < NOUT; j++) value[(size_t)gb * 3 + (j - A)] = lg[j] / sv;
         }
     }
+    if (timing && lane == 0) {        // per warp: prologue, own trunk work, wait for the slowest warp, heads; + SM id
+        ts[4] = clock64();
+        float *o = dump + ((size_t)blockIdx.x * 32 + warp) * 8;
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        o[0] = (float)(ts[1] - ts[0]); o[1] = (float)(ts[2] - ts[1]); o[2] = (float)(ts[3] - ts[2]); o[3] = (float)(ts[4] - ts[3]);
+        o[4] = (float)smid;
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+#undef BAR
 }
 
 }  // namespace tc
@@ -451,14 +622,20 @@ static int tc_launch(const azb_nn_weights *w, const float *obs, float *policy, f
     cudaStream_t s = (cudaStream_t)stream;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(tc::k_resnet_tc<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute(tc::k_resnet_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(tc::k_resnet_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES) != cudaSuccess)
             return -2;
         configured = true;
     }
     const int grid = (batch + tc::NB - 1) / tc::NB;
-    tc::k_resnet_tc<10><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(
-        obs, policy, value, batch, w->in_channels, w->depth, reinterpret_cast<const unsigned char *>(w->wconv), w->cbias,
-        w->bn_scale, w->bn_shift, reinterpret_cast<const __nv_bfloat16 *>(w->whead), w->bhead, dump, dump_layer);
+    if (dump != nullptr)
+        tc::k_resnet_tc<true><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(
+            obs, policy, value, batch, w->in_channels, w->depth, reinterpret_cast<const unsigned char *>(w->wconv), w->cbias,
+            w->bn_scale, w->bn_shift, reinterpret_cast<const __nv_bfloat16 *>(w->whead), w->bhead, dump, dump_layer);
+    else
+        tc::k_resnet_tc<false><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(
+            obs, policy, value, batch, w->in_channels, w->depth, reinterpret_cast<const unsigned char *>(w->wconv), w->cbias,
+            w->bn_scale, w->bn_shift, reinterpret_cast<const __nv_bfloat16 *>(w->whead), w->bhead, nullptr, -1);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

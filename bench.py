@@ -50,8 +50,8 @@ def parse():
     ap.add_argument("--net", default="default", choices=["default", "connect4_train", "brandubh_train"])
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--cohorts", type=int, default=1)
-    ap.add_argument("--nn", default="fused", choices=["cudnn", "fused"],
-                    help="leaf evaluator: PyTorch/cuDNN CUDA graph, or the fused bf16 tensor-core kernel")
+    ap.add_argument("--nn", default="fused", choices=["cudnn", "fused", "fused_mma"],
+                    help="leaf evaluator: PyTorch/cuDNN CUDA graph, the fused bf16 tcgen05/TMEM kernel, or the fused mma.sync kernel")
     ap.add_argument("--lanes", type=int, default=0, help="threads per game (0 = library default)")
     ap.add_argument("--nchw", action="store_true", help="keep the ResNet in NCHW (default: channels_last)")
     ap.add_argument("--preroll", type=int, default=48, help="cheap tree-only rounds that de-synchronise the games")
@@ -326,7 +326,7 @@ def main():
         a.nn = "cudnn"                      # the fused kernel covers the 32-channel DEFAULT_ARGS net on 6x7 boards
         a.no_e2e = True if tafl else a.no_e2e
     drv = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision, channels_last=not a.nchw,
-                         fused=(a.nn == "fused"))
+                         fused={"fused": True, "fused_mma": "mma", "cudnn": False}[a.nn])
 
     sel_events = []
 
@@ -444,7 +444,7 @@ def main():
 
     # secondary: the same step with the PyTorch/cuDNN TF32 evaluator (the reference's default numerics)
     alt = None
-    if a.nn == "fused" and not a.tree_only and not a.no_alt:
+    if a.nn != "cudnn" and not a.tree_only and not a.no_alt:
         model.to(memory_format=torch.channels_last)
         drv2 = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision="tf32", channels_last=True, fused=False)
         for _ in range(2):
@@ -479,11 +479,11 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if a.nn == "fused" else ("f32" if a.precision == "fp32" else a.precision), "data": "synthetic",
+            "dtype": "bf16" if a.nn != "cudnn" else ("f32" if a.precision == "fp32" else a.precision), "data": "synthetic",
             "config": {"workload": f"{a.game} {B} games/GPU x {sims} sims/move, DEFAULT_ARGS MCTS (cpuct 1.25, fpu 0.2, "
                                    f"root noise 0.1 + temp 1.1), net={a.net} ResNet random-init, "
                                    f"{'tree-only warmup mode' if a.tree_only else 'NN in the loop'}",
-                       "games_per_gpu": B, "sims_per_move": sims, "net": a.net, "nn": a.nn, "nn_precision": "bf16" if a.nn == "fused" else a.precision,
+                       "games_per_gpu": B, "sims_per_move": sims, "net": a.net, "nn": a.nn, "nn_precision": "bf16" if a.nn != "cudnn" else a.precision,
                        "cohorts": a.cohorts, "channels_last": not a.nchw, "lanes_per_game": a.lanes or 8, "rng": "philox", "parallelism": f"games x{world} (no data-path collective)",
                        "l2": "node pool %.1f GB per GPU > 126 MB L2; no flush" % (st1["pool_bytes"] / 1e9),
                        "preroll_rounds": a.preroll},
@@ -540,7 +540,7 @@ def run_e2e(a, eng, model, dev, world):
         vts.append(torch.zeros(Bw, 3).pin_memory()); evs.append(threading.Event())
         agents.append(SelfPlayAgent(i, _Game, ready, evs[i], bts[i], pts[i], vts[i], _Sink(), _Sink(), completed, played,
                                     stop, pause, args, engine=e))
-    wrap = NNetWrapper(nnet=model, cuda=True, fused=(a.nn == "fused"))
+    wrap = NNetWrapper(nnet=model, cuda=True, fused=(a.nn != "cudnn"))
     old_tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = a.precision != "fp32"
     srv = torch.cuda.Stream(device=dev)

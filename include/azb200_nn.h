@@ -40,9 +40,10 @@ int azb_nn_forward(const azb_nn_weights *w, const float *obs, float *policy, flo
 /* The same network on the 5th-generation tensor cores (tcgen05.mma, accumulators and the fp32
  * residual stream in TMEM; csrc/azb_resnet_tc.cu), 16 boards per CTA, in_channels <= 8.
  * Weight layouts differ from azb_nn_forward:
- *   wconv  bf16 [1+2*depth][azb_nn_tc_layer_bytes()/16/channels][channels][8]: K-major no-swizzle
- *          UMMA operand, 16-byte K chunk = tap (stem, cin < 8) / tap*4 + cin/8 (trunk)
- *   whead  bf16 [16][azb_nn_tc_head_row_stride()], k = frame_row*channels + ch with
+ *   wconv  bf16 [1+2*depth][azb_nn_tc_layer_bytes()/(3*channels*16)][3*channels][8]: K-major no-swizzle
+ *          UMMA B operand with the three horizontal taps side by side, row n = (dx+1)*channels + cout,
+ *          16-byte K chunk = (dy+1)*4 + cin/8 (trunk) or dy+1 with cin < 8 (stem)
+ *   whead  bf16 [action_size+3][azb_nn_tc_head_row_stride()], k = frame_row*channels + ch with
  *          frame_row = y*8 + x over the azb_nn_tc_frame_rows_per_board() rows of a board frame
  * Same status codes. */
 int azb_nn_forward_tc(const azb_nn_weights *w, const float *obs, float *policy, float *value, int32_t batch, void *stream);

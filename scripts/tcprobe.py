@@ -76,7 +76,41 @@ def timeit(kernel, batch=8192, reps=50):
     print(f"{kernel}: {us:.1f} us per {batch} boards = {batch / us:.2f} M evals/s, {batch * 8.1e6 / us / 1e6:.0f} TFLOP/s", flush=True)
 
 
+def phases(batch=8192, code=99, show=True):
+    """Per-CTA / per-warp phase clocks from the kernel's timing hook (dump_layer = 99)."""
+    import ctypes as C
+    m = _model(depth=4).to(dev)
+    obs = _obs(batch).to(dev)
+    pol = torch.zeros(batch, 7, device=dev); val = torch.zeros(batch, 3, device=dev)
+    ev = FusedResNetEvaluator(m, obs, pol, val, kernel="tc")
+    ctas = -(-batch // 16)
+    buf = torch.zeros(ctas * 16 * 56 * 32, device=dev)
+    for _ in range(3):
+        ev()
+    rc = ev.lib.azb_nn_forward_tc_debug(C.byref(ev.w), obs.data_ptr(), pol.data_ptr(), val.data_ptr(), batch,
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream), buf.data_ptr(), code)
+    torch.cuda.synchronize()
+    t = buf[:ctas * 32 * 8].view(ctas, 32, 8).cpu()
+    nw = 28
+    if not show:
+        print(f"dbg {99 - code}: trunk {t[:, :nw, 1].mean().item():.0f} cycles, CTA total {t[:, 0, :4].sum(1).mean().item():.0f}")
+        return
+    names = ["prologue", "trunk(own)", "wait-slowest", "heads"]
+    for i, n in enumerate(names):
+        v = t[:, :nw, i]
+        print(f"{n:14s} mean {v.mean().item():9.0f} max {v.max().item():9.0f} | issuer {t[:, 0:3, i].mean().item():9.0f} producer {t[:, 3, i].mean().item():9.0f} "
+              f"epilogue {t[:, 4:nw, i].mean().item():9.0f}")
+    tot = t[:, 0, :4].sum(1)
+    print(f"CTA total cycles: mean {tot.mean().item():.0f} min {tot.min().item():.0f} max {tot.max().item():.0f}")
+    sm = t[:, 0, 4].long()
+    per_sm = torch.bincount(sm, minlength=148)
+    print("CTAs per SM: min", per_sm.min().item(), "max", per_sm.max().item(), "SMs used", int((per_sm > 0).sum()))
+
+
 if __name__ == "__main__":
+    if "--phases" in sys.argv:
+        phases(code=int(sys.argv[sys.argv.index("--phases") + 1]) if sys.argv[-1] != "--phases" else 99)
+        sys.exit(0)
     if "--time-only" in sys.argv:
         timeit("tc", reps=3)
         sys.exit(0)

@@ -62,16 +62,20 @@ def test_folded_weights_reproduce_the_module_in_float64():
 
 
 def test_tc_weight_layouts_match_the_mma_layouts():
-    """fold_tc (UMMA operand chunks, frame-row head matrix) is a pure re-layout of fold."""
+    """fold_tc (UMMA operand chunks with the horizontal taps side by side, frame-row head matrix)
+    is a pure re-layout of fold."""
     from azb200.fused_nn import fold, fold_tc
     m = _model()
     a, b = fold(m, 296), fold_tc(m)
     w, t = a["wconv"].float(), b["wconv"].float()
+    assert t.shape == (9, 12, 96, 8)
     for l in range(1, 9):
-        assert torch.equal(w[l, :, :288].view(32, 9, 4, 8).permute(1, 2, 0, 3).reshape(36, 32, 8), t[l])
-    assert torch.equal(w[0, :, :144].view(32, 9, 16)[:, :, :8].permute(1, 0, 2), t[0, :9]) and bool((t[0, 9:] == 0).all())
-    wh = a["whead16"].float()[:, :42 * 32].view(16, 6, 7, 32)
-    th = b["whead16"].float()[:, :56 * 32].view(16, 7, 8, 32)
+        ref = w[l, :, :288].view(32, 3, 3, 4, 8)                 # [cout][dy][dx][cin/8][8]
+        assert torch.equal(ref.permute(1, 3, 2, 0, 4).reshape(12, 96, 8), t[l])
+    ref0 = w[0, :, :144].view(32, 3, 3, 16)[..., :8]             # [cout][dy][dx][cin]
+    assert torch.equal(ref0.permute(1, 2, 0, 3).reshape(3, 96, 8), t[0, :3]) and bool((t[0, 3:] == 0).all())
+    wh = a["whead16"].float()[:10, :42 * 32].view(10, 6, 7, 32)
+    th = b["whead16"].float()[:, :56 * 32].view(10, 7, 8, 32)
     assert torch.equal(wh, th[:, :6, :7]) and bool((th[:, 6] == 0).all()) and bool((th[:, :, 7] == 0).all())
 
 
