@@ -76,7 +76,8 @@ class FinalState:
 class SelfPlayAgent(threading.Thread):
     def __init__(self, id, game_cls, ready_queue, batch_ready, batch_tensor, policy_tensor, value_tensor,
                  output_queue, result_queue, complete_count, games_played, stop_event, pause_event, args,
-                 _is_arena=False, _is_warmup=False, engine=None, device=0, rng="philox", seed=None):
+                 _is_arena=False, _is_warmup=False, engine=None, device=0, rng="philox", seed=None,
+                 stream_ordered=False):
         super().__init__(daemon=True)
         if _is_arena:
             raise NotImplementedError("arena mode is served by the reference agent (SURVEY 8f-1)")
@@ -102,6 +103,14 @@ class SelfPlayAgent(threading.Thread):
             # SelfPlayAgent.pyx:48-52: policy = 1/A, value = 1/(P+1) (float32)
             self.engine.policy.copy_(torch.full((engine.A,), 1 / engine.A).expand(engine.B, engine.A))
             self.engine.value.copy_(torch.full((3,), 1 / 3).expand(engine.B, 3))
+        # stream_ordered: the host tensors stay the transport (every batch still crosses PCIe both ways), but their
+        # validity is ordered by CUDA events instead of host synchronisation: generateBatch returns once the copy into
+        # batch_tensor is ENQUEUED and records `batch_event`; the NN server makes its stream wait on that event before
+        # it uploads batch_tensor, and records `answer_event` (set by the server through `set_answer_event`) after it
+        # has enqueued the copies into policy_tensor / value_tensor.  Requires pinned host tensors.
+        self.stream_ordered = stream_ordered
+        self.batch_event = None
+        self.answer_event = None
         self._counted = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -114,7 +123,8 @@ class SelfPlayAgent(threading.Thread):
     def run(self):
         # the agent's kernels and copies go to its own stream, so several agents and the
         # NN server overlap on one GPU
-        with torch.cuda.stream(torch.cuda.Stream(device=self.engine.obs.device)):
+        self.stream = torch.cuda.Stream(device=self.engine.obs.device)
+        with torch.cuda.stream(self.stream):
             self._run()
 
     def _run(self):
@@ -147,7 +157,13 @@ class SelfPlayAgent(threading.Thread):
         self.engine.select()
         if self._is_warmup:
             return
-        self.batch_tensor.copy_(self.engine.obs)             # device -> caller's (host) tensor
+        if self.stream_ordered:
+            self.batch_tensor.copy_(self.engine.obs, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self.batch_event = ev
+        else:
+            self.batch_tensor.copy_(self.engine.obs)             # device -> caller's (host) tensor
         if not self.batch_tensor.is_cuda:
             self.d2h_bytes += self.batch_tensor.numel() * 4
         self.batches += 1
@@ -161,6 +177,8 @@ class SelfPlayAgent(threading.Thread):
         self.batch_ready.clear()
         if self.stop_event.is_set():
             return
+        if self.stream_ordered and self.answer_event is not None:
+            torch.cuda.current_stream().wait_event(self.answer_event)
         self.engine.policy.copy_(self.policy_tensor, non_blocking=True)
         self.engine.value.copy_(self.value_tensor, non_blocking=True)
         if not self.policy_tensor.is_cuda:

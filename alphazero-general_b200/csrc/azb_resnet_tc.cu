@@ -118,6 +118,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 // Bounded wait: a barrier that never completes is a programming error -- trap instead of hanging the GPU.  The
 // suspend-time hint lets the hardware park the thread instead of returning to re-poll: the kernel is bound by
 // instruction issue in the epilogue warps, and every retry of a waiting warp takes issue slots from a working one.
+template <int BACKOFF_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;
@@ -128,6 +129,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                      : "r"(bar), "r"(parity), "r"(20000u)
                      : "memory");
         if (done) return;
+        if (BACKOFF_NS > 0) __nanosleep(BACKOFF_NS);     // waiters with slack: every retry is a shared-memory transaction
     }
     __trap();
 }
@@ -484,7 +486,7 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
 #pragma unroll 1
         for (int g = grp; g < total; g += NPBUF) {
             const bool is_c1 = (l & 1) == 1, last = l + 1 == layers;
-            mbar_wait(bar_full, par);
+            mbar_wait<96>(bar_full, par);
             par ^= 1u;
             tc_fence_after();
             const int fr = t * 128 + r0;

@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--tree-only", action="store_true", help="warmup mode (constant NN outputs), one fused kernel per round")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-agents", type=int, default=2, help="reference `workers`: agents sharing the GPU in the e2e leg")
+    ap.add_argument("--e2e-sync", action="store_true",
+                    help="e2e leg with host-synchronised tensors (default: stream-ordered, see SelfPlayAgent)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -539,7 +541,7 @@ def run_e2e(a, eng, model, dev, world):
         bts.append(torch.zeros(Bw, 4, 6, 7).pin_memory()); pts.append(torch.zeros(Bw, 7).pin_memory())
         vts.append(torch.zeros(Bw, 3).pin_memory()); evs.append(threading.Event())
         agents.append(SelfPlayAgent(i, _Game, ready, evs[i], bts[i], pts[i], vts[i], _Sink(), _Sink(), completed, played,
-                                    stop, pause, args, engine=e))
+                                    stop, pause, args, engine=e, stream_ordered=not a.e2e_sync))
     wrap = NNetWrapper(nnet=model, cuda=True, fused=(a.nn != "cudnn"))
     old_tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = a.precision != "fp32"
@@ -554,14 +556,25 @@ def run_e2e(a, eng, model, dev, world):
                     i = ready.get(timeout=0.5)
                 except pyqueue.Empty:
                     continue
-                policy, value = wrap.process(bts[i])          # host -> device, network
-                pts[i].copy_(policy)                          # device -> host
-                vts[i].copy_(value)
+                if a.e2e_sync:
+                    policy, value = wrap.process(bts[i])      # host -> device, network
+                    pts[i].copy_(policy)                      # device -> host
+                    vts[i].copy_(value)
+                else:
+                    # stream-ordered host tensors: same copies, ordered by CUDA events instead of host syncs
+                    srv.wait_event(agents[i].batch_event)
+                    policy, value = wrap.process(bts[i])
+                    pts[i].copy_(policy, non_blocking=True)
+                    vts[i].copy_(value, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(srv)
+                    agents[i].answer_event = ev
                 evs[i].set()
 
     serve(lambda: all(ag.batches >= a.sims + 2 for ag in agents))          # one untimed round per agent
     if world > 1:
         dist.barrier()
+    torch.cuda.synchronize()          # stream-ordered mode: no backlog of enqueued work may leak into the timed region
     for ag in agents:
         ag.h2d_bytes = ag.d2h_bytes = 0
     n0 = sum(ag.batches for ag in agents)
@@ -592,6 +605,7 @@ def run_e2e(a, eng, model, dev, world):
             # per step: generateBatch downloads observations, the NN answers go to host tensors, samples are drained
             "d2h_bytes_per_step": int(a.sims * pv_b + sum(ag.d2h_bytes for ag in agents) / steps),
             "steps": steps, "agents": W, "games_per_agent": Bw,
+            "host_tensor_protocol": "host-synchronised" if a.e2e_sync else "stream-ordered (CUDA events)",
             "api": "Coach.processSelfPlayBatches loop: azb200.selfplay.SelfPlayAgent threads (generateBatch/processBatch/"
                    "playMoves) + NNetWrapper.process, pinned host tensors, ready queue + events"}
 
