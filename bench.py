@@ -110,6 +110,9 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         t_mark = getattr(self, "t_mark", 0.0)
+        if sum(1 for ts, _ in self.lines if ts >= t_mark) < 3:
+            # short timed region: count the warm-up steps too (same load, run immediately before)
+            t_mark = getattr(self, "t_warm", t_mark)
         for ts, ln in self.lines:
             if ts < t_mark:
                 continue
@@ -367,6 +370,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks.t_warm = time.time()
     for _ in range(max(a.warmup, 3)):
         step()
     clear_samples()
