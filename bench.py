@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-alt", action="store_true")
     ap.add_argument("--no-select-events", action="store_true")
+    ap.add_argument("--roofline-steps", type=int, default=3, help="eager move-rounds timed per select launch for the roofline")
+    ap.add_argument("--no-round-graph", action="store_true", help="launch every kernel of a move-round from the host")
     return ap.parse_args()
 
 
@@ -331,7 +333,8 @@ def main():
         a.nn = "cudnn"                      # the fused kernel covers the 32-channel DEFAULT_ARGS net on 6x7 boards
         a.no_e2e = True if tafl else a.no_e2e
     drv = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision, channels_last=not a.nchw,
-                         fused={"fused": True, "fused_mma": "mma", "cudnn": False}[a.nn])
+                         fused={"fused": True, "fused_mma": "mma", "cudnn": False}[a.nn],
+                         round_graph=False if a.no_round_graph else None)
 
     sel_events = []
 
@@ -379,18 +382,6 @@ def main():
     st0 = eng.stats()
     launches0 = drv.launches
 
-    # optional: CUDA events around every select launch (tree stream) for the roofline
-    if not a.no_select_events and not a.tree_only:
-        orig_select = eng.select
-
-        def timed_select(first=0, count=0, stream=None):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            orig_select(first, count, stream=stream)
-            e1.record(stream)
-            sel_events.append((e0, e1))
-        eng.select = timed_select
-
     barrier()
     clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -401,8 +392,6 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     clk = clocks.stop() if rank == 0 else None
-    if not a.no_select_events and not a.tree_only:
-        eng.select = orig_select
     st1 = eng.stats()
     eng.check_errors()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -427,14 +416,37 @@ def main():
     dD, dC = st1["sum_depth"] - st0["sum_depth"], st1["sum_children"] - st0["sum_children"]
     alg_bytes = 16.0 * dD + 12.0 * dC
     roof = None
+    # Roofline pass: the timed steps replay one CUDA graph per move-round, so the per-launch time of k_select is taken
+    # right after them from eagerly launched rounds of the same workload, with CUDA events around every select launch
+    # on the tree stream (the kernel and its inputs are the same; only the launch path differs).
+    if not a.no_select_events and not a.tree_only:
+        orig_select, was_graph = eng.select, drv.round_graph
+        drv.round_graph = False
+
+        def timed_select(first=0, count=0, stream=None):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            orig_select(first, count, stream=stream)
+            e1.record(stream)
+            sel_events.append((e0, e1))
+        eng.select = timed_select
+        r0 = eng.stats()
+        for _ in range(a.roofline_steps):
+            step()
+        torch.cuda.synchronize()
+        r1 = eng.stats()
+        eng.select, drv.round_graph = orig_select, was_graph
+        alg_bytes = 16.0 * (r1["sum_depth"] - r0["sum_depth"]) + 12.0 * (r1["sum_children"] - r0["sum_children"])
+        roof_sims = r1["sims"] - r0["sims"]
     if sel_events:
         sel_ms = sum(e0.elapsed_time(e1) for e0, e1 in sel_events)
         nl = len(sel_events)
         ach = alg_bytes / (sel_ms / 1000.0) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                 "traffic": None, "kernel": f"k_select<{'Brandubh' if tafl else 'Connect4'}>", "launches": nl, "avg_launch_us": 1000.0 * sel_ms / nl,
-                "alg_bytes_per_launch": alg_bytes / nl, "bytes_per_sim": alg_bytes / max(dsims, 1), "peak_source": peak_src,
-                "note": "CUDA-event time of each select launch on the tree stream (NN runs concurrently on another stream)"}
+                "alg_bytes_per_launch": alg_bytes / nl, "bytes_per_sim": alg_bytes / max(roof_sims, 1), "peak_source": peak_src,
+                "note": f"CUDA-event time of each select launch on the tree stream over {a.roofline_steps} eagerly launched "
+                        "move-rounds right after the timed (graph-replayed) steps"}
     elif a.tree_only:
         ach = alg_bytes / (ms / 1000.0) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
@@ -490,7 +502,7 @@ def main():
                                    f"root noise 0.1 + temp 1.1), net={a.net} ResNet random-init, "
                                    f"{'tree-only warmup mode' if a.tree_only else 'NN in the loop'}",
                        "games_per_gpu": B, "sims_per_move": sims, "net": a.net, "nn": a.nn, "nn_precision": "bf16" if a.nn != "cudnn" else a.precision,
-                       "cohorts": a.cohorts, "channels_last": not a.nchw, "lanes_per_game": a.lanes or 8, "rng": "philox", "parallelism": f"games x{world} (no data-path collective)",
+                       "cohorts": a.cohorts, "round_graph": bool(drv.round_graph), "channels_last": not a.nchw, "lanes_per_game": a.lanes or 8, "rng": "philox", "parallelism": f"games x{world} (no data-path collective)",
                        "l2": "node pool %.1f GB per GPU > 126 MB L2; no flush" % (st1["pool_bytes"] / 1e9),
                        "preroll_rounds": a.preroll},
             "clocks": clk, "gpu_launches": drv.launches - launches0,
