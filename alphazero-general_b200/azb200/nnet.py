@@ -115,7 +115,7 @@ class NNetWrapper:
             ev = FusedResNetEvaluator(self.nnet, obs, torch.empty(n, self.nnet.action_size, device=dev),
                                       torch.empty(n, 3, device=dev))
             self._fused_eval[n] = ev
-        ev.obs.copy_(batch, non_blocking=True)
+        upload(ev.obs, batch)
         ev()
         return ev.policy, ev.value
 
@@ -129,6 +129,80 @@ class NNetWrapper:
         with torch.no_grad():
             pi, v = self.nnet(batch)
             return torch.exp(pi), torch.exp(v)
+
+
+def upload(dst, src):
+    """dst (device) <- src (host), asynchronously on the current stream.  A pinned, contiguous source is read by a
+    copy kernel through its device mapping (azb_upload_pinned: a few-MB cudaMemcpyAsync pays a DMA start-up that the
+    SM path does not); anything else goes through Tensor.copy_."""
+    if (not src.is_cuda and src.is_pinned() and src.is_contiguous() and dst.is_contiguous() and src.dtype == dst.dtype
+            and src.numel() == dst.numel() and src.data_ptr() % 16 == 0 and dst.data_ptr() % 16 == 0):
+        import ctypes as C
+        from . import _capi
+        lib = _capi.load()
+        fn = lib.azb_upload_pinned
+        if fn.restype is not C.c_int or not fn.argtypes:
+            fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        rc = fn(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size(),
+                C.c_void_p(torch.cuda.current_stream(dst.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"azb_upload_pinned failed with status {rc}")
+        return dst
+    return dst.copy_(src, non_blocking=True)
+
+
+_CAPTURE_LOCK = __import__("threading").Lock()
+
+
+def capture_graph(fn, stream):
+    """Capture fn()'s launches on `stream` as a CUDA graph from a worker thread.  Unlike the torch.cuda.graph context
+    manager this does not synchronise the device (not permitted while another thread captures) -- fn must not allocate;
+    thread-local capture mode, so other threads keep launching work meanwhile."""
+    g = torch.cuda.CUDAGraph()
+    with _CAPTURE_LOCK, torch.cuda.stream(stream):
+        g.capture_begin(capture_error_mode="thread_local")
+        try:
+            fn()
+        finally:
+            g.capture_end()
+    return g
+
+
+class HostBatchServer:
+    """The body of Coach.processSelfPlayBatches (Coach.py:337-342) for stream-ordered agents
+    (azb200.selfplay.SelfPlayAgent(stream_ordered=True)): upload the agent's host observation batch, evaluate, download
+    policy / value into the agent's host tensors -- captured once per agent as a CUDA graph on the server stream and
+    ordered against the agent's stream by CUDA events (no host synchronisation)."""
+
+    def __init__(self, wrapper, stream=None):
+        self.wrapper = wrapper
+        dev = next(wrapper.nnet.parameters()).device
+        self.stream = stream or torch.cuda.Stream(device=dev)
+        self._graphs = {}
+
+    def serve(self, agent, batch_ready):
+        """One served batch of `agent` (whose id came out of the ready queue); `batch_ready` is its host event."""
+        S = self.stream
+        S.wait_event(agent.batch_event)
+        g = self._graphs.get(agent.id)
+        with torch.cuda.stream(S):
+            if g is None and agent.id in self._graphs:           # second batch of this agent: capture
+                g = capture_graph(lambda: self._body(agent), S)
+                self._graphs[agent.id] = g
+            if g is not None:
+                g.replay()
+            else:                                                # first batch: eager (lazy one-time setup)
+                self._body(agent)
+                self._graphs[agent.id] = None
+            ev = torch.cuda.Event()
+            ev.record(S)
+        agent.answer_event = ev
+        batch_ready.set()
+
+    def _body(self, agent):
+        policy, value = self.wrapper.process(agent.batch_tensor)
+        agent.policy_tensor.copy_(policy, non_blocking=True)
+        agent.value_tensor.copy_(value, non_blocking=True)
 
 
 class LeafEvaluator:

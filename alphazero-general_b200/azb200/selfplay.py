@@ -77,7 +77,7 @@ class SelfPlayAgent(threading.Thread):
     def __init__(self, id, game_cls, ready_queue, batch_ready, batch_tensor, policy_tensor, value_tensor,
                  output_queue, result_queue, complete_count, games_played, stop_event, pause_event, args,
                  _is_arena=False, _is_warmup=False, engine=None, device=0, rng="philox", seed=None,
-                 stream_ordered=False):
+                 stream_ordered=False, step_graphs=None):
         super().__init__(daemon=True)
         if _is_arena:
             raise NotImplementedError("arena mode is served by the reference agent (SURVEY 8f-1)")
@@ -109,6 +109,12 @@ class SelfPlayAgent(threading.Thread):
         # it uploads batch_tensor, and records `answer_event` (set by the server through `set_answer_event`) after it
         # has enqueued the copies into policy_tensor / value_tensor.  Requires pinned host tensors.
         self.stream_ordered = stream_ordered
+        # step_graphs (stream-ordered mode only): the per-simulation launch sequences of this agent -- upload of the
+        # answers, expand/backup, select, download of the next observation batch -- are captured once as CUDA graphs
+        # and replayed, which removes most of the per-simulation host work
+        self.step_graphs = stream_ordered if step_graphs is None else (step_graphs and stream_ordered)
+        self._g_first = self._g_mid = self._g_last = None
+        self._rounds = 0
         self.batch_event = None
         self.answer_event = None
         self._counted = 0
@@ -136,6 +142,8 @@ class SelfPlayAgent(threading.Thread):
                     if not self._is_warmup else self.args.numWarmupSims
                 if self._is_warmup:
                     self.engine.warmup_sims(sims)
+                elif self.step_graphs and self._rounds > 0:      # the first round runs eagerly (one-time kernel setup)
+                    self._graphed_round(sims)
                 else:
                     for _ in range(sims):
                         if self.stop_event.is_set(): break
@@ -144,6 +152,7 @@ class SelfPlayAgent(threading.Thread):
                         self.processBatch()
                 if self.stop_event.is_set(): break
                 self.playMoves()
+                self._rounds += 1
             with self.complete_count.get_lock():
                 self.complete_count.value += 1
             # the reference closes its process-local end of output_queue here; a thread shares the
@@ -151,6 +160,70 @@ class SelfPlayAgent(threading.Thread):
         except Exception:
             import traceback
             print(traceback.format_exc())
+
+    # ---- stream-ordered protocol with captured step graphs -------------------------------------------
+    def _capture(self, fn):
+        from .nnet import capture_graph
+        return capture_graph(fn, self.stream)
+
+    def _upload_answers(self):
+        from .nnet import upload
+        upload(self.engine.policy, self.policy_tensor)
+        upload(self.engine.value, self.value_tensor)
+
+    def _publish_batch(self):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.batch_event = ev
+        self.d2h_bytes += self.batch_tensor.numel() * 4
+        self.batches += 1
+        self.ready_queue.put(self.id)
+
+    def _await_answers(self):
+        self.batch_ready.wait()
+        self.batch_ready.clear()
+        if self.stop_event.is_set():
+            return False
+        if self.answer_event is not None:
+            torch.cuda.current_stream().wait_event(self.answer_event)
+        self.h2d_bytes += (self.policy_tensor.numel() + self.value_tensor.numel()) * 4
+        return True
+
+    def _graphed_round(self, sims):
+        """generateBatch / processBatch of one move-round, `sims` times, as three replayed graphs:
+        [select, obs -> batch_tensor], [answers -> engine, expand/backup, select, obs -> batch_tensor], [answers -> engine,
+        expand/backup]."""
+        eng = self.engine
+        if self._g_first is None:
+            self._prepare_graphs()
+        self._g_first.replay()
+        self._publish_batch()
+        for _ in range(sims - 1):
+            if not self._await_answers():
+                return
+            self._g_mid.replay()
+            self._publish_batch()
+        if not self._await_answers():
+            return
+        self._g_last.replay()
+
+    def _prepare_graphs(self):
+        eng = self.engine
+
+        def first():
+            eng.select(stream=self.stream)
+            self.batch_tensor.copy_(eng.obs, non_blocking=True)
+
+        def mid():
+            self._upload_answers()
+            eng.expand_backup(stream=self.stream)
+            eng.select(stream=self.stream)
+            self.batch_tensor.copy_(eng.obs, non_blocking=True)
+
+        def last():
+            self._upload_answers()
+            eng.expand_backup(stream=self.stream)
+        self._g_first, self._g_mid, self._g_last = self._capture(first), self._capture(mid), self._capture(last)
 
     def generateBatch(self):
         self._check_pause()
@@ -179,8 +252,7 @@ class SelfPlayAgent(threading.Thread):
             return
         if self.stream_ordered and self.answer_event is not None:
             torch.cuda.current_stream().wait_event(self.answer_event)
-        self.engine.policy.copy_(self.policy_tensor, non_blocking=True)
-        self.engine.value.copy_(self.value_tensor, non_blocking=True)
+        self._upload_answers()
         if not self.policy_tensor.is_cuda:
             self.h2d_bytes += (self.policy_tensor.numel() + self.value_tensor.numel()) * 4
         self.engine.expand_backup()

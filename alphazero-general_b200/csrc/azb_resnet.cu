@@ -377,3 +377,37 @@ extern "C" int azb_nn_forward(const azb_nn_weights *w, const float *obs, float *
                                                       w->bn_shift, reinterpret_cast<const __nv_bfloat16 *>(w->whead), w->bhead);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
+
+// ---- host tensor upload by the SMs --------------------------------------------------------------------------
+// The reference-facing surface hands the network HOST tensors every simulation (Coach.py:339, NNetWrapper.py:227:
+// `batch.cuda()`).  On this platform a cudaMemcpyAsync host->device of a few MB pays ~190 us of DMA start-up
+// (scripts/pcie_probe.py: 2.75 MB in 231 us, 64 MB at 55 GB/s); pinned host memory is mapped into the device's
+// address space, so a kernel can stream it over PCIe directly.
+namespace {
+__global__ void __launch_bounds__(256) k_upload(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16, const unsigned char *src_tail,
+                                                unsigned char *dst_tail, int tail)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i));
+        dst[i] = v;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+}  // namespace
+
+extern "C" int azb_upload_pinned(void *dst_device, const void *src_pinned_host, int64_t bytes, void *stream)
+{
+    if (!dst_device || !src_pinned_host || bytes < 0) return -7;
+    if (bytes == 0) return 0;
+    if ((((uintptr_t)dst_device) | ((uintptr_t)src_pinned_host)) & 15) return -7;
+    const size_t n16 = (size_t)bytes / 16;
+    const int tail = (int)(bytes - (int64_t)n16 * 16);
+    int grid = (int)((n16 + 255) / 256);
+    grid = grid < 1 ? 1 : (grid > 592 ? 592 : grid);
+    k_upload<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4 *>(dst_device), reinterpret_cast<const uint4 *>(src_pinned_host), n16,
+                                                     reinterpret_cast<const unsigned char *>(src_pinned_host) + n16 * 16,
+                                                     reinterpret_cast<unsigned char *>(dst_device) + n16 * 16, tail);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}

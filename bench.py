@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--net", default="default", choices=["default", "connect4_train", "brandubh_train"])
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--cohorts", type=int, default=1)
+    ap.add_argument("--split", type=int, default=0, help="games in the first cohort (0 = automatic)")
     ap.add_argument("--nn", default="fused", choices=["cudnn", "fused", "fused_mma"],
                     help="leaf evaluator: PyTorch/cuDNN CUDA graph, the fused bf16 tcgen05/TMEM kernel, or the fused mma.sync kernel")
     ap.add_argument("--lanes", type=int, default=0, help="threads per game (0 = library default)")
@@ -281,6 +282,10 @@ def reference_main(a):
 # --------------------------------------------------------------------------
 def main():
     a = parse()
+    wd = float(os.environ.get("AZB_BENCH_WATCHDOG", "0"))
+    if wd > 0:      # debugging aid: dump every thread's stack and exit if the run exceeds this many seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     if a.impl == "reference":
         reference_main(a)
         return
@@ -334,7 +339,7 @@ def main():
         a.no_e2e = True if tafl else a.no_e2e
     drv = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision, channels_last=not a.nchw,
                          fused={"fused": True, "fused_mma": "mma", "cudnn": False}[a.nn],
-                         round_graph=False if a.no_round_graph else None)
+                         round_graph=False if a.no_round_graph else None, split=a.split or None)
 
     sel_events = []
 
@@ -562,6 +567,8 @@ def run_e2e(a, eng, model, dev, world):
     old_tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = a.precision != "fp32"
     srv = torch.cuda.Stream(device=dev)
+    from azb200.nnet import HostBatchServer
+    server = HostBatchServer(wrap, stream=srv)
     for ag in agents:
         ag.start()
 
@@ -576,16 +583,10 @@ def run_e2e(a, eng, model, dev, world):
                     policy, value = wrap.process(bts[i])      # host -> device, network
                     pts[i].copy_(policy)                      # device -> host
                     vts[i].copy_(value)
+                    evs[i].set()
                 else:
                     # stream-ordered host tensors: same copies, ordered by CUDA events instead of host syncs
-                    srv.wait_event(agents[i].batch_event)
-                    policy, value = wrap.process(bts[i])
-                    pts[i].copy_(policy, non_blocking=True)
-                    vts[i].copy_(value, non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(srv)
-                    agents[i].answer_event = ev
-                evs[i].set()
+                    server.serve(agents[i], evs[i])
 
     serve(lambda: all(ag.batches >= a.sims + 2 for ag in agents))          # one untimed round per agent
     if world > 1:

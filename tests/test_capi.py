@@ -23,6 +23,17 @@ def test_header_symbols_are_exported():
     assert not missing, f"libazb200.so lacks {missing}"
 
 
+def test_nn_header_symbols_are_exported():
+    """include/azb200_nn.h: the fused leaf evaluators (tcgen05 and mma.sync) and the pinned-tensor upload."""
+    text = open(os.path.join(ROOT, "include", "azb200_nn.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"\b(azb_[a-z0-9_]+)\s*\(", text)))
+    assert {"azb_nn_forward", "azb_nn_forward_tc", "azb_nn_forward_tc_debug", "azb_upload_pinned"} <= set(names)
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"libazb200.so lacks {missing}"
+
+
 def test_binding_table_matches_header():
     assert sorted(_capi.SYMBOLS) == _declared()
 
