@@ -227,13 +227,18 @@ static void node_free_children(node_t *nd)
 
 static int node_terminal(const node_t *nd) { return nd->e[0] | nd->e[1] | nd->e[2]; }
 
-typedef struct slot_t {
-    orc_game game;             /* live game (SelfPlayAgent.games[i]) */
-    orc_game leaf;             /* state returned by find_leaf */
+typedef struct mcts_t {
     node_t root;               /* MCTS._root (owned copy) */
     node_t *cur;               /* MCTS._curnode */
     node_t *path[ORC_MAX_PATH];/* MCTS._path */
     int path_len;
+} mcts_t;
+
+typedef struct slot_t {
+    orc_game game;             /* live game (SelfPlayAgent.games[i]) */
+    orc_game leaf;             /* state returned by find_leaf */
+    mcts_t m[2];               /* SelfPlayAgent.mcts[i]: one tree, or in arena mode one per player
+                                * (SelfPlayAgent._get_mcts, SelfPlayAgent.pyx:62-66) */
     rng_t rng;
     /* SelfPlayAgent per-game state */
     int hist_len;
@@ -258,6 +263,12 @@ struct orc_agent {
     float *s_obs, *s_pi, *s_z; int32_t *s_slot; int64_t s_n, s_cap;
     int32_t *r_slot, *r_turns; uint8_t *r_win; int64_t r_n, r_cap;
 };
+
+/* SelfPlayAgent._mcts (SelfPlayAgent.pyx:68-73): the tree of the player to move in arena mode */
+static mcts_t *slot_mcts(const orc_agent *ag, slot_t *s)
+{
+    return &s->m[ag->args.arena ? s->game.player : 0];
+}
 
 /* Node.add_children (MCTS.pyx:76-79) */
 static void add_children(orc_agent *ag, slot_t *s, node_t *nd, const uint8_t *valid)
@@ -312,28 +323,29 @@ static node_t *best_child(const orc_agent *ag, node_t *nd)
 static void find_leaf(orc_agent *ag, slot_t *s)
 {
     int depth = 0;
-    s->cur = &s->root;
+    mcts_t *m = slot_mcts(ag, s);
+    m->cur = &m->root;
     s->leaf = s->game;                       /* gs.clone() */
-    while (s->cur->n > 0 && !node_terminal(s->cur)) {
-        if (s->path_len >= ORC_MAX_PATH) { fprintf(stderr, "orc: path overflow\n"); abort(); }
-        s->path[s->path_len++] = s->cur;
-        ag->st.sum_children += s->cur->nchildren;
-        s->cur = best_child(ag, s->cur);
-        ag->ops->play(&s->leaf, s->cur->a);
+    while (m->cur->n > 0 && !node_terminal(m->cur)) {
+        if (m->path_len >= ORC_MAX_PATH) { fprintf(stderr, "orc: path overflow\n"); abort(); }
+        m->path[m->path_len++] = m->cur;
+        ag->st.sum_children += m->cur->nchildren;
+        m->cur = best_child(ag, m->cur);
+        ag->ops->play(&s->leaf, m->cur->a);
         depth++;
     }
     ag->st.sum_depth += depth;
-    if (s->cur->n == 0) {
+    if (m->cur->n == 0) {
         uint8_t valid[ORC_MAX_ACTIONS];
-        s->cur->player = s->leaf.player;
-        ag->ops->win_state(&s->leaf, s->cur->e);
+        m->cur->player = s->leaf.player;
+        ag->ops->win_state(&s->leaf, m->cur->e);
         ag->ops->valid_moves(&s->leaf, valid);
-        add_children(ag, s, s->cur, valid);
+        add_children(ag, s, m->cur, valid);
         /* children of a terminal leaf are never used; the engine does not
          * materialise them, so they are left out of the statistic */
-        if (node_terminal(s->cur)) ag->st.nodes_created -= s->cur->nchildren;
+        if (node_terminal(m->cur)) ag->st.nodes_created -= m->cur->nchildren;
     }
-    if (node_terminal(s->cur)) ag->st.terminal_leaves++;
+    if (node_terminal(m->cur)) ag->st.terminal_leaves++;
 }
 
 /* MCTS._get_value (MCTS.pyx:291-295) with value.size == num_players + 1 */
@@ -347,7 +359,8 @@ static float get_value(const float *value, int player)
 static void process_results(orc_agent *ag, slot_t *s, const float *value_in, const float *pi_in)
 {
     float value[3];
-    node_t *cur = s->cur;
+    mcts_t *m = slot_mcts(ag, s);
+    node_t *cur = m->cur;
     if (node_terminal(cur)) {
         for (int i = 0; i < 3; i++) value[i] = (float)cur->e[i];
     } else {
@@ -359,8 +372,8 @@ static void process_results(orc_agent *ag, slot_t *s, const float *value_in, con
         for (int a = 0; a < ag->A; a++) pi[a] = pi_in[a] * valids[a];   /* pi *= valids */
         float sum = np_pairwise_f32(pi, ag->A);
         for (int a = 0; a < ag->A; a++) pi[a] = pi[a] / sum;
-        if (cur == &s->root) {
-            if (ag->args.add_root_temp) {
+        if (cur == &m->root) {
+            if (ag->args.add_root_temp && !ag->args.arena) {
                 /* 1.0 / self.root_temp is a Python float; NumPy casts the weak
                  * scalar exponent to float32 */
                 float e = (float)(1.0 / (double)ag->args.root_policy_temp);
@@ -369,7 +382,7 @@ static void process_results(orc_agent *ag, slot_t *s, const float *value_in, con
                 for (int a = 0; a < ag->A; a++) pi[a] = pi[a] / sum;
             }
             for (int i = 0; i < cur->nchildren; i++) cur->children[i].p = pi[cur->children[i].a];
-            if (ag->args.add_root_noise) {
+            if (ag->args.add_root_noise && !ag->args.arena) {
                 if (!ag->noise || s->noise_event >= ag->noise_events || cur->nchildren > ag->noise_stride) {
                     fprintf(stderr, "orc: root noise requested but not fed (event %d)\n", s->noise_event);
                     abort();
@@ -390,8 +403,8 @@ static void process_results(orc_agent *ag, slot_t *s, const float *value_in, con
     /* backup.  min_discount ** (i / _discount_max_depth) is a C integer
      * division with cdivision=True and i < _discount_max_depth always, so the
      * discount is exactly 1 whatever min_discount is (MCTS.pyx:270-277). */
-    while (s->path_len) {
-        node_t *parent = s->path[--s->path_len];
+    while (m->path_len) {
+        node_t *parent = m->path[--m->path_len];
         float v = get_value(value, parent->player);
         float qn = cur->q * (float)cur->n;
         float vd = v * 1.0f;
@@ -401,25 +414,28 @@ static void process_results(orc_agent *ag, slot_t *s, const float *value_in, con
         cur->n += 1;
         cur = parent;
     }
-    s->cur = cur;
-    s->root.n += 1;
+    m->cur = cur;
+    m->root.n += 1;
 }
 
 /* MCTS.update_root (MCTS.pyx:185-195); returns -1 on ValueError */
-static int update_root(orc_agent *ag, slot_t *s, int a)
+static int update_root(orc_agent *ag, slot_t *s, mcts_t *m, int a)
 {
-    if (s->root.nchildren == 0) {
+    if (m->root.nchildren == 0) {
         uint8_t valid[ORC_MAX_ACTIONS];
         ag->ops->valid_moves(&s->game, valid);
-        add_children(ag, s, &s->root, valid);
+        add_children(ag, s, &m->root, valid);
+        /* only the arena's idle tree gets here with numMCTSSims >= 1; its new children are dropped at once by the
+         * re-root below and the engine does not materialise them, so they are left out of the statistic */
+        if (ag->args.arena) ag->st.nodes_created -= m->root.nchildren;
     }
-    for (int i = 0; i < s->root.nchildren; i++) {
-        if (s->root.children[i].a == a) {
-            node_t keep = s->root.children[i];
-            s->root.children[i].children = NULL;
-            s->root.children[i].nchildren = 0;
-            node_free_children(&s->root);
-            s->root = keep;
+    for (int i = 0; i < m->root.nchildren; i++) {
+        if (m->root.children[i].a == a) {
+            node_t keep = m->root.children[i];
+            m->root.children[i].children = NULL;
+            m->root.children[i].nchildren = 0;
+            node_free_children(&m->root);
+            m->root = keep;
             return 0;
         }
     }
@@ -428,14 +444,17 @@ static int update_root(orc_agent *ag, slot_t *s, int a)
 
 static void mcts_reset(slot_t *s)
 {
-    node_free_children(&s->root);
-    node_init(&s->root, -1);
-    s->cur = &s->root;
-    s->path_len = 0;
+    for (int t = 0; t < 2; t++) {
+        mcts_t *m = &s->m[t];
+        node_free_children(&m->root);
+        node_init(&m->root, -1);
+        m->cur = &m->root;
+        m->path_len = 0;
+    }
 }
 
 /* MCTS.probs (MCTS.pyx:308-327) */
-static void mcts_probs(const orc_agent *ag, const slot_t *s, float temp, float *probs)
+static void mcts_probs(const orc_agent *ag, const mcts_t *s, float temp, float *probs)
 {
     int A = ag->A;
     float counts[ORC_MAX_ACTIONS];
@@ -525,8 +544,7 @@ orc_agent *orc_create(const orc_args *args)
     for (int i = 0; i < args->num_slots; i++) {
         slot_t *s = &ag->slots[i];
         ops->init(&s->game);
-        node_init(&s->root, -1);
-        s->cur = &s->root;
+        for (int t = 0; t < 2; t++) { node_init(&s->m[t].root, -1); s->m[t].cur = &s->m[t].root; }
         s->rng.mode = args->rng_mode;
         s->rng.seed = args->seed;
         s->rng.gid = (uint64_t)(args->game_id_base + i);
@@ -543,7 +561,8 @@ void orc_destroy(orc_agent *ag)
 {
     if (!ag) return;
     for (int i = 0; i < ag->args.num_slots; i++) {
-        node_free_children(&ag->slots[i].root);
+        node_free_children(&ag->slots[i].m[0].root);
+        node_free_children(&ag->slots[i].m[1].root);
         free(ag->slots[i].hist_state);
         free(ag->slots[i].hist_pi);
     }
@@ -568,7 +587,13 @@ void orc_set_root_noise(orc_agent *ag, const float *noise, int events, int strid
     for (int i = 0; i < ag->args.num_slots; i++) ag->slots[i].noise_event = 0;
 }
 
-/* SelfPlayAgent.generateBatch (SelfPlayAgent.pyx:103-135, non-arena) */
+/* arena: env player to move in every slot (its tree searches; player_to_index maps it to a model) */
+void orc_players(const orc_agent *ag, int32_t *players)
+{
+    for (int i = 0; i < ag->args.num_slots; i++) players[i] = ag->slots[i].game.player;
+}
+
+/* SelfPlayAgent.generateBatch (SelfPlayAgent.pyx:103-135; the per-model regrouping of arena mode is the caller's) */
 void orc_generate_batch(orc_agent *ag, float *obs_out)
 {
     for (int i = 0; i < ag->args.num_slots; i++) {
@@ -587,31 +612,37 @@ void orc_process_batch(orc_agent *ag, const float *policy, const float *value)
     }
 }
 
-/* SelfPlayAgent.playMoves (SelfPlayAgent.pyx:153-202, non-arena) */
+/* SelfPlayAgent.playMoves (SelfPlayAgent.pyx:153-202) */
 void orc_play_moves(orc_agent *ag, int fast)
 {
     int A = ag->A;
+    const int arena = ag->args.arena;
     float policy[ORC_MAX_ACTIONS];
     for (int i = 0; i < ag->args.num_slots; i++) {
         slot_t *s = &ag->slots[i];
+        mcts_t *m = slot_mcts(ag, s);
         int t = s->game.turns;
         if (t >= ag->args.temp_table_len) t = ag->args.temp_table_len - 1;
-        float temp = (float)ag->temp_table[t];      /* probs(gs, float temp) */
-        mcts_probs(ag, s, temp, policy);
+        /* probs(gs, float temp); in arena mode the table holds args.arenaTemp (:157-158) */
+        float temp = (float)ag->temp_table[t];
+        mcts_probs(ag, m, temp, policy);
         int action = rng_choice(&s->rng, policy, A);
-        if (!fast) {
+        if (!fast && !arena) {
             if (s->hist_len == s->hist_cap) {
                 s->hist_cap = s->hist_cap ? s->hist_cap * 2 : 64;
                 s->hist_state = (orc_game *)realloc(s->hist_state, sizeof(orc_game) * (size_t)s->hist_cap);
                 s->hist_pi = (float *)realloc(s->hist_pi, sizeof(float) * (size_t)s->hist_cap * A);
             }
             s->hist_state[s->hist_len] = s->game;
-            mcts_probs(ag, s, 1.0f, s->hist_pi + (size_t)s->hist_len * A);
+            mcts_probs(ag, m, 1.0f, s->hist_pi + (size_t)s->hist_len * A);
             s->hist_len++;
         }
-        if (update_root(ag, s, action) != 0) {
-            fprintf(stderr, "orc: invalid action %d while updating root (slot %d)\n", action, i);
-            abort();
+        /* arena: [mcts.update_root(game, action) for mcts in self.mcts[i]] -- both trees, in tuple order (:167-168) */
+        for (int tr = 0; tr < (arena ? 2 : 1); tr++) {
+            if (update_root(ag, s, arena ? &s->m[tr] : m, action) != 0) {
+                fprintf(stderr, "orc: invalid action %d while updating root (slot %d)\n", action, i);
+                abort();
+            }
         }
         ag->ops->play(&s->game, action);
         s->last_action = action;
@@ -651,7 +682,7 @@ void orc_root_counts(const orc_agent *ag, int32_t *counts)
 {
     memset(counts, 0, sizeof(int32_t) * (size_t)ag->args.num_slots * ag->A);
     for (int i = 0; i < ag->args.num_slots; i++) {
-        const node_t *r = &ag->slots[i].root;
+        const node_t *r = &slot_mcts(ag, &ag->slots[i])->root;
         for (int k = 0; k < r->nchildren; k++) counts[(size_t)i * ag->A + r->children[k].a] = r->children[k].n;
     }
 }

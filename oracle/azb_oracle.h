@@ -60,6 +60,9 @@ typedef struct orc_args {
                                /* t >= len uses the last entry                   */
     const uint32_t *mt_seeds;  /* per-slot np.random.seed() values (MT mode);    */
                                /* NULL: seed + game_id_base + slot               */
+    int32_t arena;             /* SelfPlayAgent(_is_arena=True): one tree per     */
+                               /* player, no noise / root temperature / samples,  */
+                               /* temp_table = [args.arenaTemp]                   */
 } orc_args;
 
 typedef struct orc_agent orc_agent;
@@ -95,6 +98,8 @@ void orc_set_root_noise(orc_agent *ag, const float *noise, int events, int strid
 
 /* MCTS.counts for the current root of every slot: counts[B][A] */
 void orc_root_counts(const orc_agent *ag, int32_t *counts);
+/* env player to move per slot (arena: whose tree searches) */
+void orc_players(const orc_agent *ag, int32_t *players);
 /* last action played by play_moves per slot (-1 none) */
 void orc_last_actions(const orc_agent *ag, int32_t *actions);
 /* per-slot turns of the live game */

@@ -27,3 +27,18 @@ def warmup_outputs(batch, action_size):
     p = np.full((batch, action_size), np.float32(1.0 / action_size), dtype=np.float32)
     v = np.full((batch, 3), np.float32(1.0 / 3), dtype=np.float32)
     return p, v
+
+
+class ArenaNN:
+    """Arena.play_games' server loop (Arena.pyx:262-275) for the lock-step drivers: every row is evaluated by the
+    model of the player to move in that game, `agent.models()` says which."""
+
+    def __init__(self, agent, nets):
+        self.agent, self.nets = agent, nets
+
+    def __call__(self, obs):
+        models = self.agent.models()
+        outs = [net(obs) for net in self.nets]
+        p = np.stack([outs[m][0][i] for i, m in enumerate(models)])
+        v = np.stack([outs[m][1][i] for i, m in enumerate(models)])
+        return p, v

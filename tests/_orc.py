@@ -23,6 +23,7 @@ class OrcArgs(C.Structure):
         ("cpuct", C.c_float), ("fpu_reduction", C.c_float),
         ("root_noise_frac", C.c_float), ("root_policy_temp", C.c_float),
         ("temp_table", C.POINTER(C.c_double)), ("mt_seeds", C.POINTER(C.c_uint32)),
+        ("arena", C.c_int32),
     ]
 
 
@@ -51,7 +52,7 @@ def lib():
         L.orc_create.argtypes = [C.POINTER(OrcArgs)]
         for name in ("orc_destroy", "orc_generate_batch", "orc_process_batch", "orc_play_moves",
                      "orc_set_root_noise", "orc_root_counts", "orc_last_actions", "orc_turns",
-                     "orc_boards", "orc_get_stats", "orc_get_samples", "orc_clear_samples",
+                     "orc_boards", "orc_players", "orc_get_stats", "orc_get_samples", "orc_clear_samples",
                      "orc_get_results"):
             getattr(L, name).restype = None
         L.orc_destroy.argtypes = [C.c_void_p]
@@ -65,6 +66,7 @@ def lib():
         L.orc_last_actions.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_turns.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_boards.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_players.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_get_stats.argtypes = [C.c_void_p, C.POINTER(OrcStats)]
         L.orc_num_samples.restype = C.c_int64
         L.orc_num_samples.argtypes = [C.c_void_p]
@@ -122,7 +124,8 @@ class OracleAgent:
     def __init__(self, game=GAME_CONNECT4, num_slots=1, rng_mode=RNG_MT19937, seed=0, mt_seeds=None,
                  game_id_base=0, cpuct=1.25, fpu_reduction=0.2, root_noise_frac=0.1, root_policy_temp=1.1,
                  add_root_noise=False, add_root_temp=False, symmetric_samples=True,
-                 mcts_reset_threshold=0, games_per_iteration=1 << 40, temps=None):
+                 mcts_reset_threshold=0, games_per_iteration=1 << 40, temps=None, arena=False, arena_temp=None,
+                 player_to_index=None):
         L = lib()
         self.L = L
         self.B = num_slots
@@ -133,6 +136,10 @@ class OracleAgent:
         a.games_per_iteration, a.game_id_base, a.seed = games_per_iteration, game_id_base, seed
         a.cpuct, a.fpu_reduction = cpuct, fpu_reduction
         a.root_noise_frac, a.root_policy_temp = root_noise_frac, root_policy_temp
+        a.arena = int(arena)
+        self.player_to_index = list(player_to_index or [0, 1])
+        if arena:                      # playMoves uses args.arenaTemp for every move (SelfPlayAgent.pyx:156-158)
+            temps = np.full(1, 0.25 if arena_temp is None else arena_temp, dtype=np.float64)
         if temps is None:
             temps = np.ones(1, dtype=np.float64)
         temps = np.ascontiguousarray(temps, dtype=np.float64)
@@ -186,6 +193,15 @@ class OracleAgent:
         out = np.zeros(self.B, dtype=np.int32)
         self.L.orc_turns(self.h, _p(out))
         return out
+
+    def players(self):
+        out = np.zeros(self.B, dtype=np.int32)
+        self.L.orc_players(self.h, _p(out))
+        return out
+
+    def models(self):
+        """arena: index of the model that evaluates each slot's leaf (SelfPlayAgent.pyx:117: player_to_index[player])."""
+        return np.asarray(self.player_to_index, dtype=np.int32)[self.players()]
 
     def boards(self):
         out = np.zeros((self.B, self.ncells), dtype=np.int8)

@@ -177,7 +177,8 @@ class RefAgent:
     def __init__(self, game="connect4", num_slots=1, mt_seeds=None, cpuct=1.25, fpu_reduction=0.2,
                  root_noise_frac=0.1, root_policy_temp=1.1, add_root_noise=False, add_root_temp=False,
                  symmetric_samples=True, mcts_reset_threshold=None, games_per_iteration=1 << 40,
-                 temp_scaling_fn=None, start_temp=1, det_pow=False, noise=None):
+                 temp_scaling_fn=None, start_temp=1, det_pow=False, noise=None, arena=False, arena_temp=0.25,
+                 player_to_index=None):
         import torch
         self.ref_mcts, self.ref_spa, dotdict, default_temp_scaling = _import_ref()
         self.game_cls = game_class(game)
@@ -191,8 +192,9 @@ class RefAgent:
             add_root_noise=add_root_noise, add_root_temp=add_root_temp,
             symmetricSamples=symmetric_samples, mctsResetThreshold=mcts_reset_threshold,
             gamesPerIteration=games_per_iteration, numMCTSSims=1, numFastSims=1, probFastSim=0.0,
-            arenaTemp=0.25,
+            arenaTemp=arena_temp,
         ))
+        self.arena = arena
         self.shim = _NpShim(det_pow, noise is not None) if (det_pow or noise is not None) else None
         self.noise = None if noise is None else np.asarray(noise, dtype=np.float32)
         self.noise_event = [0] * num_slots
@@ -213,9 +215,19 @@ class RefAgent:
             pt = torch.zeros((1, self.A))
             vt = torch.zeros((1, 3))
             np.random.seed(int(mt_seeds[i]))
-            ag = self.ref_spa.SelfPlayAgent(i, self.game_cls, _FakeQueue(), _FakeEvent(), bt, pt, vt,
-                                            self.out_q[i], self.res_q[i], self.complete, self.games_played,
-                                            _FakeEvent(), _FakeEvent(), self.args)
+            if arena:
+                # Arena.play_games (Arena.pyx:236-258): batch_tensor is a per-player list, the batches travel through
+                # output_queue; the constructor shuffles player_to_index (SelfPlayAgent.pyx:44-47) -- fixed here, and
+                # the slot's stream is seeded after construction so that the shuffle does not consume from it
+                ag = self.ref_spa.SelfPlayAgent(i, self.game_cls, _FakeQueue(), _FakeEvent(), [[], []], pt, vt,
+                                                self.out_q[i], self.res_q[i], self.complete, self.games_played,
+                                                _FakeEvent(), _FakeEvent(), self.args, _is_arena=True)
+                ag.player_to_index = list(player_to_index or [0, 1])
+                np.random.seed(int(mt_seeds[i]))
+            else:
+                ag = self.ref_spa.SelfPlayAgent(i, self.game_cls, _FakeQueue(), _FakeEvent(), bt, pt, vt,
+                                                self.out_q[i], self.res_q[i], self.complete, self.games_played,
+                                                _FakeEvent(), _FakeEvent(), self.args)
             self.states.append(np.random.get_state())
             self.agents.append(ag)
             self.bt.append(bt); self.pt.append(pt); self.vt.append(vt)
@@ -247,8 +259,21 @@ class RefAgent:
                 ag.generateBatch()
             finally:
                 self._leave(i)
-            obs[i] = self.bt[i][0].numpy()
+            if self.arena:
+                batch = self.out_q[i].items.pop()                 # [per model: tensor or []]
+                model = ag.player_to_index[ag.games[0].player]
+                assert [isinstance(b, list) for b in batch] == [m != model for m in range(len(batch))]
+                obs[i] = batch[model][0].numpy()
+            else:
+                obs[i] = self.bt[i][0].numpy()
         return obs
+
+    def models(self):
+        """arena: index of the model that evaluates each slot's current leaf (player_to_index[game.player])."""
+        return np.asarray([ag.player_to_index[ag.games[0].player] for ag in self.agents], dtype=np.int32)
+
+    def players(self):
+        return np.asarray([ag.games[0].player for ag in self.agents], dtype=np.int32)
 
     def processBatch(self, policy, value):
         import torch
@@ -264,14 +289,14 @@ class RefAgent:
     def playMoves(self, fast=False):
         for i, ag in enumerate(self.agents):
             ag.fast = fast
-            before_s, before_r = self.out_q[i].qsize(), self.res_q[i].qsize()
+            before_s, before_r = (0 if self.arena else self.out_q[i].qsize()), self.res_q[i].qsize()
             turns_before = ag.games[0].turns
             self._enter(i)
             try:
                 ag.playMoves()
             finally:
                 self._leave(i)
-            for k in range(before_s, self.out_q[i].qsize()):
+            for k in range(before_s, 0 if self.arena else self.out_q[i].qsize()):
                 self.sample_order.append((i, k))
             for k in range(before_r, self.res_q[i].qsize()):
                 self.result_order.append((i, k))
@@ -284,7 +309,7 @@ class RefAgent:
     def root_counts(self):
         out = np.zeros((self.B, self.A), dtype=np.int32)
         for i, ag in enumerate(self.agents):
-            out[i] = np.asarray(ag.mcts[0].counts(ag.games[0]))
+            out[i] = np.asarray(ag._mcts(0).counts(ag.games[0]))
         return out
 
     def last_actions(self):
