@@ -24,7 +24,7 @@ class AzbConfig(C.Structure):
         ("rng_mode", C.c_int32), ("add_root_noise", C.c_int32), ("add_root_temp", C.c_int32),
         ("symmetric_samples", C.c_int32), ("mcts_reset_threshold", C.c_int32),
         ("max_sims_per_move", C.c_int32), ("max_nodes_per_game", C.c_int32), ("temp_table_len", C.c_int32),
-        ("lanes_per_game", C.c_int32), ("reserved0", C.c_int32),
+        ("lanes_per_game", C.c_int32), ("arena", C.c_int32),
         ("games_per_iteration", C.c_int64), ("sample_capacity", C.c_int64), ("game_id_base", C.c_int64),
         ("seed", C.c_uint64),
         ("cpuct", C.c_float), ("fpu_reduction", C.c_float), ("root_noise_frac", C.c_float),
@@ -56,6 +56,7 @@ SYMBOLS = {
     "azb_expand_backup": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "azb_play_moves": (C.c_int, [_vp, _i32, _vp]),
     "azb_warmup_sims": (C.c_int, [_vp, _i32, _vp]),
+    "azb_arena_players": (C.c_int, [_vp, _vp, _vp]),
     "azb_set_root_noise": (C.c_int, [_vp, _vp, _i32, _i32]),
     "azb_drain_samples": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _vp]),
     "azb_drain_samples_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _vp]),

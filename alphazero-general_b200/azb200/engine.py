@@ -47,7 +47,7 @@ class SelfPlayEngine:
                  game_id_base=0, cpuct=1.25, fpu_reduction=0.2, root_noise_frac=0.1, root_policy_temp=1.1,
                  add_root_noise=False, add_root_temp=False, symmetric_samples=True,
                  mcts_reset_threshold=None, games_per_iteration=0, max_sims_per_move=100,
-                 max_nodes_per_game=0, sample_capacity=0, temps=None, lanes_per_game=0):
+                 max_nodes_per_game=0, sample_capacity=0, temps=None, lanes_per_game=0, arena=False):
         self.lib = _capi.load()
         self.h = C.c_void_p()
         cfg = AzbConfig()
@@ -62,6 +62,8 @@ class SelfPlayEngine:
         cfg.games_per_iteration, cfg.sample_capacity = int(games_per_iteration or 0), int(sample_capacity)
         cfg.game_id_base, cfg.seed = int(game_id_base), int(seed)
         cfg.lanes_per_game = int(lanes_per_game)
+        cfg.arena = int(bool(arena))
+        self.arena = bool(arena)
         cfg.cpuct, cfg.fpu_reduction = float(cpuct), float(fpu_reduction)
         cfg.root_noise_frac, cfg.root_policy_temp = float(root_noise_frac), float(root_policy_temp)
         if temps is not None:
@@ -154,6 +156,14 @@ class SelfPlayEngine:
 
     def play_moves(self, fast=False, stream=None):
         check(self.lib.azb_play_moves(self.h, int(bool(fast)), self._stream(stream)))
+
+    def arena_players(self, stream=None):
+        """arena mode: device int32 [B]: env player whose tree searches in each slot this round, -1 = idle slot."""
+        import torch
+        if getattr(self, "_arena_players", None) is None:
+            self._arena_players = torch.empty(self.B, dtype=torch.int32, device=f"cuda:{self.device}")
+        check(self.lib.azb_arena_players(self.h, C.c_void_p(self._arena_players.data_ptr()), self._stream(stream)))
+        return self._arena_players
 
     def warmup_sims(self, sims, stream=None):
         check(self.lib.azb_warmup_sims(self.h, int(sims), self._stream(stream)))

@@ -95,6 +95,7 @@ struct DevView {
     // parameters
     float cpuct, fpu_reduction, noise_frac, root_temp_exp;
     int add_noise, add_temp, rng_mode, symmetric, reset_threshold;
+    int arena;       // SelfPlayAgent(_is_arena=True): slots 2i / 2i+1 are the trees of player 0 / 1 of game i
     unsigned long long seed; long long gid_base;
     const float *temp_table; int temp_len;
     long long quota;
@@ -104,6 +105,14 @@ struct DevView {
     Counters *counters;
     uint32_t *err;
 };
+
+// Arena mode: the two trees of a game share the game's RNG stream (the reference draws shuffles and the move from
+// one np.random stream, SelfPlayAgent.pyx:160 / MCTS.pyx:79); it lives in the even slot of the pair.
+__device__ __forceinline__ int rng_slot(const DevView &d, int g) { return d.arena ? (g & ~1) : g; }
+__device__ __forceinline__ unsigned long long rng_gid(const DevView &d, int g)
+{
+    return (unsigned long long)(d.gid_base + (long long)(d.arena ? (g >> 1) : g));
+}
 
 // ---- float32 arithmetic with the reference's rounding -------------------------
 // The reference's Cython compiles to scalar C without FMA contraction; every

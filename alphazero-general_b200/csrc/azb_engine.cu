@@ -97,9 +97,14 @@ template <class G> static void l_expand(azb_engine *e, int first, int count, con
 }
 template <class G> static void l_play(azb_engine *e, int fast, cudaStream_t s)
 {
-    k_play_moves<G><<<grid_for<G>(e->d.B), CTA_THREADS, 0, s>>>(e->d, fast);
+    if (e->d.arena) k_play_moves_arena<G><<<grid_for<G>(e->d.B / 2), CTA_THREADS, 0, s>>>(e->d);
+    else k_play_moves<G><<<grid_for<G>(e->d.B), CTA_THREADS, 0, s>>>(e->d, fast);
     k_finalize<G><<<1, 1024, 0, s>>>(e->d);
     k_emit<G><<<grid_for<G>(e->d.B), CTA_THREADS, 0, s>>>(e->d);
+}
+template <class G> static void l_arena_players(azb_engine *e, int *out, cudaStream_t s)
+{
+    k_arena_players<G><<<(e->d.B + 127) / 128, 128, 0, s>>>(e->d, out);
 }
 template <class G> static void l_warmup(azb_engine *e, int sims, cudaStream_t s)
 {
@@ -150,6 +155,9 @@ extern "C" int azb_create(const azb_config *cfg, azb_engine **out)
     if (cfg->abi_version != AZB_ABI_VERSION)
         return fail(AZB_ERR_BAD_CONFIG, "abi_version %d, library is %d", cfg->abi_version, AZB_ABI_VERSION);
     if (cfg->num_games <= 0) return fail(AZB_ERR_BAD_CONFIG, "num_games must be positive");
+    if (cfg->arena && (cfg->num_games & 1)) return fail(AZB_ERR_BAD_CONFIG, "arena mode: num_games counts slots, two per game");
+    if (cfg->arena && (cfg->add_root_noise || cfg->add_root_temp))
+        return fail(AZB_ERR_BAD_CONFIG, "arena mode runs without root noise / temperature (SelfPlayAgent.pyx:147-150)");
     if (cfg->rng_mode != AZB_RNG_MT19937 && cfg->rng_mode != AZB_RNG_PHILOX)
         return fail(AZB_ERR_BAD_CONFIG, "unknown rng_mode %d", cfg->rng_mode);
     GameDims gd;
@@ -254,6 +262,7 @@ extern "C" int azb_create(const azb_config *cfg, azb_engine **out)
     d.root_temp_exp = (float)(1.0 / (double)cfg->root_policy_temp);
     d.add_noise = cfg->add_root_noise; d.add_temp = cfg->add_root_temp; d.rng_mode = cfg->rng_mode;
     d.symmetric = cfg->symmetric_samples; d.reset_threshold = cfg->mcts_reset_threshold;
+    d.arena = cfg->arena ? 1 : 0;
     d.seed = cfg->seed; d.gid_base = cfg->game_id_base;
     rc = init_slots(e, cfg->mt_seeds);
     if (rc) { azb_destroy(e); return rc; }
@@ -336,6 +345,16 @@ extern "C" int azb_play_moves(azb_engine *e, int32_t fast, void *stream)
     if (!e) return fail(AZB_ERR_BAD_ARGUMENT, "null engine");
     cudaStream_t s = (cudaStream_t)stream;
     DISPATCH(e, l_play, e, fast, s);
+    CK(cudaGetLastError());
+    return AZB_OK;
+}
+
+extern "C" int azb_arena_players(azb_engine *e, int32_t *players_device, void *stream)
+{
+    if (!e || !players_device) return fail(AZB_ERR_BAD_ARGUMENT, "null argument");
+    if (!e->d.arena) return fail(AZB_ERR_BAD_ARGUMENT, "engine is not in arena mode");
+    cudaStream_t s = (cudaStream_t)stream;
+    DISPATCH(e, l_arena_players, e, players_device, s);
     CK(cudaGetLastError());
     return AZB_OK;
 }

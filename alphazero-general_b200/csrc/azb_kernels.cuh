@@ -177,7 +177,7 @@ __device__ __forceinline__ void child_order(const DevView &d, int g, int C, bool
     for (int i = 0; i < IT; i++) { cpos[i] = lane + i * L; cact[i] = 0; cwr[i] = store && (lane + i * L < C); }
     if (d.rng_mode == 0) {
         if (consume && lane == 0) {
-            uint32_t *st = d.mt + (size_t)g * 625;
+            uint32_t *st = d.mt + (size_t)rng_slot(d, g) * 625;
             if (store) for (int k = 0; k < C; k++) sm.order[k] = (short)k;
             for (int i = C - 1; i >= 1; i--) {
                 uint32_t j = mt_interval(st, (uint32_t)i);
@@ -194,16 +194,16 @@ __device__ __forceinline__ void child_order(const DevView &d, int g, int C, bool
         }
     } else {
         unsigned long long c0 = 0ULL;
-        if (consume) c0 = d.ctr[g];
+        if (consume) c0 = d.ctr[rng_slot(d, g)];
         __syncwarp();
-        if (consume && lane == 0) d.ctr[g] = c0 + (unsigned long long)C;
+        if (consume && lane == 0) d.ctr[rng_slot(d, g)] = c0 + (unsigned long long)C;
         uint32_t key[IT];
         if constexpr (G::LANE_IS_ACTION) {
             // small action space: lane a owns the child of action a; its ascending index is the
             // number of valid actions below it
             const bool valid = (valid_mask >> lane) & 1u;
             const int j = __popc(valid_mask & ((1u << lane) - 1u));
-            key[0] = (store && valid) ? philox_word(d.seed, (unsigned long long)(d.gid_base + g), c0 + (unsigned long long)j) : 0u;
+            key[0] = (store && valid) ? philox_word(d.seed, rng_gid(d, g), c0 + (unsigned long long)j) : 0u;
             int rank = 0;
 #pragma unroll
             for (int i = 0; i < G::A; i++) {
@@ -216,7 +216,7 @@ __device__ __forceinline__ void child_order(const DevView &d, int g, int C, bool
 #pragma unroll
         for (int i = 0; i < IT; i++) {
             const int j = lane + i * L;
-            key[i] = (store && j < C) ? philox_word(d.seed, (unsigned long long)(d.gid_base + g), c0 + (unsigned long long)j) : 0u;
+            key[i] = (store && j < C) ? philox_word(d.seed, rng_gid(d, g), c0 + (unsigned long long)j) : 0u;
         }
         if (IT == 1) {
             int rank = 0;
@@ -314,6 +314,7 @@ __device__ __forceinline__ void select_game(const DevView &d, int g, bool active
     const bool in_range = active;               // out-of-range groups alias slot `first`: they must not write
     SlotHead H = load_head(d.head + g);
     if (H.st.flags & (GF_FINISHED | GF_DEAD)) active = false;
+    if (d.arena && ((g ^ H.st.turns) & 1)) active = false;      // arena: only the tree of the player to move searches
     GState st = H.st;
     int *path = d.path + (size_t)g * G::MAXD;
     int cur = H.root, cn = H.root_n, cch = H.root_child0;
@@ -672,11 +673,24 @@ __device__ __forceinline__ void tree_reset(SlotHead &H)
     H.alloc = 1;
 }
 
+// is `action` one of the C valid moves listed by G::list_valid (every lane answers)
+template <class G>
+__device__ __forceinline__ bool vmask_has(const short *act, uint32_t vmask, int C, int action)
+{
+    if constexpr (G::LANE_IS_ACTION) return (vmask >> action) & 1u;
+    for (int k = 0; k < C; k++) if (G::nth_valid(act, vmask, k) == action) return true;
+    return false;
+}
+
 // ------------------------------------------------------------------------------
 // SelfPlayAgent.playMoves, the per-game part up to the terminal test
 // ------------------------------------------------------------------------------
+// `forced` >= 0 (arena, the idle tree of the pair): no sampling -- the root follows the action the searching tree
+// played (MCTS.update_root, MCTS.pyx:185-195; an unexpanded root first gets its children, i.e. their shuffle is
+// drawn, and the chosen child is a fresh node).  Returns the action played (G::A if none).
 template <class G>
-__device__ __forceinline__ void play_move_game(const DevView &d, int g, bool active, int fast, int lane, int sub, GroupSmem<G> &sm)
+__device__ __forceinline__ int play_move_game(const DevView &d, int g, bool active, int fast, int lane, int sub, GroupSmem<G> &sm,
+                                              int forced = -1)
 {
     constexpr int L = G::LANES;
     constexpr int IT = (G::MAXC + L - 1) / L;
@@ -703,22 +717,25 @@ __device__ __forceinline__ void play_move_game(const DevView &d, int g, bool act
     __syncwarp();
     const int t = st.turns < d.temp_len ? st.turns : d.temp_len - 1;
     const float temp = d.temp_table[t < 0 ? 0 : t];
-    probs_group<G>(d, sm.vec, temp, sm.vec2, on, lane);
+    const bool sample = on && forced < 0;
+    probs_group<G>(d, sm.vec, temp, sm.vec2, sample, lane);
     // np.random.choice(A, p=policy): cdf in double, one 53-bit uniform, searchsorted 'right'
     uint32_t wa = 0, wb = 0;
-    if (on && lane == 0) {
+    if (sample && lane == 0) {
+        const int rs = rng_slot(d, g);
         if (d.rng_mode == 0) {
-            uint32_t *ms = d.mt + (size_t)g * 625;
+            uint32_t *ms = d.mt + (size_t)rs * 625;
             wa = mt_next(ms); wb = mt_next(ms);
         } else {
-            const unsigned long long c = d.ctr[g];
-            wa = philox_word(d.seed, (unsigned long long)(d.gid_base + g), c);
-            wb = philox_word(d.seed, (unsigned long long)(d.gid_base + g), c + 1);
-            d.ctr[g] = c + 2;
+            const unsigned long long c = d.ctr[rs];
+            wa = philox_word(d.seed, rng_gid(d, g), c);
+            wb = philox_word(d.seed, rng_gid(d, g), c + 1);
+            d.ctr[rs] = c + 2;
         }
     }
     int action = G::A;
-    if (on && lane == 0) {
+    if (on && forced >= 0) action = forced;
+    if (sample && lane == 0) {
         const double u = u53(wa, wb);
         double last = 0.0;
         for (int a = 0; a < G::A; a++) last = __dadd_rn(last, (double)sm.vec2[a]);
@@ -729,6 +746,19 @@ __device__ __forceinline__ void play_move_game(const DevView &d, int g, bool act
         }
     }
     action = group_bcast<L>(action, 0);
+    // arena, idle tree whose root was never expanded: add_children draws the shuffle of the root's children, the
+    // child `action` becomes the new (fresh) root
+    const bool fresh = on && forced >= 0 && C == 0;
+    if (__any_sync(FULL, fresh)) {
+        uint32_t vmask = 0u;
+        const int Cv = G::list_valid(st, sm.act, vmask, fresh, lane);
+        int cpos[IT], cact[IT];
+        bool cwr[IT];
+        child_order<G, IT>(d, g, Cv, fresh, false, lane, sm, vmask, cpos, cact, cwr);
+        if (fresh && !((vmask_has<G>(sm.act, vmask, Cv, action)))) {
+            if (lane == 0) atomicOr(d.err, ERRB_ACTION);
+        }
+    }
     if (!fast) {
         // histories[i].append((game.clone(), mcts.probs(game)))  -- temp = 1
         const int hl = on ? d.hist_len[g] : 0;
@@ -747,6 +777,7 @@ __device__ __forceinline__ void play_move_game(const DevView &d, int g, bool act
     for (int i = 0; i < IT; i++) if (ka[i] == action && lane + i * L < C) found = lane + i * L;
 #pragma unroll
     for (int off = L / 2; off >= 1; off >>= 1) found = max(found, __shfl_xor_sync(FULL, found, off, L));
+    if (fresh) found = 0;
     if (on && found < 0) {
         if (lane == 0) atomicOr(d.err, ERRB_ACTION);
         H.st.flags |= GF_DEAD;
@@ -754,17 +785,22 @@ __device__ __forceinline__ void play_move_game(const DevView &d, int g, bool act
         on = false;
     }
     if (on && lane == 0) {
-        const int nr = H.root_child0 + found;
-        const NodeHot h = load_hot(d.hot + nb + nr);
-        const NodeCold c = load_cold(d.cold + nb + nr);
-        H.root = nr; H.root_n = h.n; H.root_v = c.v; H.root_child0 = h.child0; H.root_meta = c.meta;
+        if (fresh) {
+            tree_reset(H);
+            H.root_meta = meta_pack((uint32_t)action, 0u, 0u, 0u);
+        } else {
+            const int nr = H.root_child0 + found;
+            const NodeHot h = load_hot(d.hot + nb + nr);
+            const NodeCold c = load_cold(d.cold + nb + nr);
+            H.root = nr; H.root_n = h.n; H.root_v = c.v; H.root_child0 = h.child0; H.root_meta = c.meta;
+        }
         G::play(st, action);
         const int e = G::win_code(st);
         st.flags &= 0xff;
         if (e != 0) { st.flags |= GF_FINISHED; d.fin_code[g] = e; }
         H.st = st;
         d.last_action[g] = action;
-        reinterpret_cast<unsigned *>(d.stats + g)[5] += 1u;     // moves
+        if (forced < 0) reinterpret_cast<unsigned *>(d.stats + g)[5] += 1u;     // moves
         if (d.reset_threshold && st.turns >= d.next_reset[g]) {
             int *pk = reinterpret_cast<int *>(d.stats + g) + 6;
             if (H.alloc > *pk) *pk = H.alloc;
@@ -774,6 +810,7 @@ __device__ __forceinline__ void play_move_game(const DevView &d, int g, bool act
         store_head(d.head + g, H);
     }
     __syncwarp();
+    return on ? action : G::A;
 }
 
 // ------------------------------------------------------------------------------
@@ -835,6 +872,20 @@ __global__ void __launch_bounds__(CTA_THREADS) k_play_moves(DevView d, int fast)
     play_move_game<G>(d, g, active, fast, lane, sub, sm[gi]);
 }
 
+// Arena: one group per game; the tree of the player to move samples the move, then the other tree follows it
+// ([mcts.update_root(game, action) for mcts in self.mcts[i]], SelfPlayAgent.pyx:167-168 -- the searching tree's
+// update never draws, so the order of the two updates does not matter for the game's RNG stream).
+template <class G>
+__global__ void __launch_bounds__(CTA_THREADS) k_play_moves_arena(DevView d)
+{
+    __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
+    int g, lane, sub, gi; bool active;
+    if (!group_setup<G>(0, d.B / 2, g, active, lane, sub, gi)) return;
+    const int mover = d.head[2 * g].st.turns & 1;
+    const int action = play_move_game<G>(d, 2 * g + mover, active, 1, lane, sub, sm[gi]);
+    play_move_game<G>(d, 2 * g + (mover ^ 1), active && action < G::A, 1, lane, sub, sm[gi], action < G::A ? action : 0);
+}
+
 // Terminal handling in slot order (one CTA): result_queue.put for every
 // finished game; the games_played quota decides, in slot order as the
 // reference's worker loop does, which of them emit samples and restart.
@@ -856,7 +907,7 @@ __global__ void __launch_bounds__(1024) k_finalize(DevView d)
         const int g = g0 + tid;
         int flags = 0, turns = 0;
         if (g < d.B) { flags = d.head[g].st.flags; turns = d.head[g].st.turns; }
-        const int fin = (flags & GF_FINISHED) ? 1 : 0;
+        const int fin = ((flags & GF_FINISHED) && !(d.arena && (g & 1))) ? 1 : 0;     // arena: a game is two slots
         s_scan[tid] = fin;
         __syncthreads();
         for (int off = 1; off < 1024; off <<= 1) {
@@ -884,7 +935,7 @@ __global__ void __launch_bounds__(1024) k_finalize(DevView d)
             const long long ri = rbase + rank;
             if (ri < d.r_cap) {
                 const int code = d.fin_code[g];
-                d.r_slot[ri] = g;
+                d.r_slot[ri] = d.arena ? (g >> 1) : g;
                 d.r_turns[ri] = turns;
                 d.r_win[ri * 3 + 0] = code == 1; d.r_win[ri * 3 + 1] = code == 2; d.r_win[ri * 3 + 2] = code == 3;
             } else atomicOr(d.err, ERRB_SAMPLES);
@@ -892,6 +943,7 @@ __global__ void __launch_bounds__(1024) k_finalize(DevView d)
                 if (soff + nsamp <= d.s_cap) d.emit_off[g] = soff;
                 else { d.emit_off[g] = -2; atomicOr(d.err, ERRB_SAMPLES); }
             } else d.emit_off[g] = -1;
+            if (d.arena) d.emit_off[g + 1] = d.emit_off[g];       // the second tree of the game restarts (or dies) with it
         }
         __syncthreads();
         if (tid == 0) {
@@ -975,6 +1027,17 @@ __global__ void k_root_counts(DevView d, int *out)
     const size_t cb = nb + (size_t)(H.root_child0 < 0 ? 0 : H.root_child0);
     for (int a = 0; a < G::A; a++) out[(size_t)g * G::A + a] = 0;
     for (int k = 0; k < C; k++) out[(size_t)g * G::A + meta_action(d.cold[cb + k].meta)] = d.hot[cb + k].n;
+}
+
+// arena: which env player's tree searches in each slot this round (-1: idle tree / finished game)
+template <class G>
+__global__ void k_arena_players(DevView d, int *out)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= d.B) return;
+    const GState st = d.head[g].st;
+    const bool live = !(st.flags & (GF_FINISHED | GF_DEAD));
+    out[g] = (live && !((g ^ st.turns) & 1)) ? (g & 1) : -1;
 }
 
 template <class G>

@@ -69,7 +69,13 @@ typedef struct azb_config {
     int32_t temp_table_len;       /* entries of temp_table (0 = constant 1.0)              */
     int32_t lanes_per_game;       /* threads cooperating on one game: 0 = default, Connect4 */
                                   /* accepts 8, 16, 32 (tuning knob, results are identical) */
-    int32_t reserved0;
+    int32_t arena;                /* 1 = SelfPlayAgent(_is_arena=True), SelfPlayAgent.pyx:23,44-47,62-73,      */
+                                  /* 104-132,144-150,167-168: slots 2i / 2i+1 are the trees of env player 0 / 1 */
+                                  /* of game i (num_games = 2 x games, even); only the tree of the player to    */
+                                  /* move searches (the other slot's obs / policy / value rows are idle), both   */
+                                  /* follow every move; no root noise / temperature, no samples; temp_table =    */
+                                  /* [args.arenaTemp]; results, games_played and the quota count games, result   */
+                                  /* slots are game indices; the pair shares the RNG stream of its even slot     */
     int64_t games_per_iteration;  /* args.gamesPerIteration (quota of counted games)       */
     int64_t sample_capacity;      /* sample ring entries (0 = derive from the quota)       */
     int64_t game_id_base;         /* global id of slot 0 (multi-GPU: rank * num_games)     */
@@ -146,6 +152,11 @@ int azb_expand_backup(azb_engine *e, int32_t first, int32_t count,
  * play_action, terminal handling (result, quota, sample emission with
  * symmetries, game/tree reset). Acts on all slots. */
 int azb_play_moves(azb_engine *e, int32_t fast, void *stream);
+/* arena mode: players[slot] = env player whose tree this slot holds if it searches in the current simulation round
+ * (the player to move of a live game), -1 for the idle tree of the pair and for finished games.  Device int32 [B],
+ * asynchronous on `stream`.  The caller maps players to models (SelfPlayAgent.player_to_index) and evaluates the
+ * active rows of azb_obs_ptr with them (Arena.pyx:262-275). */
+int azb_arena_players(azb_engine *e, int32_t *players_device, void *stream);
 /* `sims` x (generateBatch + processBatch) with the warmup constants policy =
  * 1/A, value = 1/3 (SelfPlayAgent.pyx:48-52,111-114) in ONE kernel launch:
  * the NN-free tree-only mode (numWarmupSims). */

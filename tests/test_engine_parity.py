@@ -156,3 +156,36 @@ def test_brandubh_root_noise_deep_search():
                           max_sims_per_move=sims)
     assert_traces_equal(run_trace(orc, nn, rounds, sims), run_trace(eng, nn, rounds, sims), "tafl noise")
     assert np.array_equal(orc.boards(), eng.boards())
+
+
+@pytest.mark.parametrize("game,rng,p2i,reset", [("connect4", "mt19937", [0, 1], None), ("connect4", "philox", [1, 0], 5),
+                                                ("brandubh", "philox", [0, 1], None)])
+def test_arena_mode_equals_oracle(game, rng, p2i, reset):
+    """SelfPlayAgent(_is_arena=True) on the engine (azb_config.arena): visit counts of the searching tree, sampled
+    actions, leaf observations, results and the quota, bit-equal to the oracle's arena mode (itself pinned against the
+    compiled reference in test_oracle_vs_ref.py)."""
+    from _engine_agent import ArenaEngineAgent
+    from _fakenn import ArenaNN
+    c4 = game == "connect4"
+    B, sims, quota = (6, 9, 14) if c4 else (3, 6, 1 << 40)
+    obs_n, A = (4 * 6 * 7, 7) if c4 else (5 * 7 * 7, 588)
+    seeds = list(range(31, 31 + B))
+    nets = [FakeNN(obs_n, A, seed=70, sharp=3.0 if c4 else 1.0), FakeNN(obs_n, A, seed=71, sharp=3.0 if c4 else 1.0)]
+    kw = dict(mt_seeds=seeds) if rng == "mt19937" else dict(seed=9)
+    orc = _orc.OracleAgent(_orc.GAME_CONNECT4 if c4 else _orc.GAME_BRANDUBH, B, arena=True, arena_temp=0.25,
+                           rng_mode=_orc.RNG_MT19937 if rng == "mt19937" else _orc.RNG_PHILOX, player_to_index=p2i,
+                           mcts_reset_threshold=reset or 0, games_per_iteration=quota, **kw)
+    eng = ArenaEngineAgent(game, B, rng=rng, arena_temp=0.25, player_to_index=p2i, mcts_reset_threshold=reset,
+                           games_per_iteration=quota, max_sims_per_move=sims, **kw)
+    rounds = 200 if c4 else 30
+    until = quota if c4 else None
+    # stop at the first finished-beyond-quota game: the worker loop's exit condition (SelfPlayAgent.pyx:82)
+    ta = run_trace(orc, ArenaNN(orc, nets), rounds, sims, keep_obs=True, until_games=until)
+    tb = run_trace(eng, ArenaNN(eng, nets), rounds, sims, keep_obs=True, until_games=until)
+    assert_traces_equal(ta, tb, f"arena {game} {rng}")
+    for name, x, y in zip(("slot", "turns", "win"), orc.results(), eng.results()):
+        assert np.array_equal(x, y), f"arena results.{name} differ"
+    so, se = orc.stats(), eng.stats()
+    for k in ("sims", "sum_depth", "sum_children", "nodes_created", "terminal_leaves", "games_played", "results", "moves"):
+        assert so[k] == se[k], (k, so[k], se[k])
+    assert se["samples"] == 0
