@@ -77,6 +77,7 @@ class SelfPlayEngine:
             cfg.mt_seeds = self._mt.ctypes.data_as(C.POINTER(C.c_uint32))
         check(self.lib.azb_create(C.byref(cfg), C.byref(self.h)))
         self.device = int(device)
+        self.quota = int(games_per_iteration) if games_per_iteration else (1 << 62)
         self.B = int(num_games)
         self.A = self.lib.azb_action_size(self.h)
         chw = (C.c_int32 * 3)()
@@ -106,6 +107,7 @@ class SelfPlayEngine:
 
     def set_quota(self, games_per_iteration):
         check(self.lib.azb_set_quota(self.h, int(games_per_iteration or 0)))
+        self.quota = int(games_per_iteration) if games_per_iteration else (1 << 62)
 
     # ---- NN I/O buffers as torch tensors (zero copy) -----------------------
     def _wrap(self, ptr, shape):
