@@ -192,7 +192,7 @@ class FusedResNetEvaluator:
         assert self.kernel == "tc"
         nb, fb = self.lib.azb_nn_tc_boards_per_cta(), self.lib.azb_nn_tc_frame_rows_per_board()
         ctas = -(-self.batch // nb)
-        dump = torch.zeros(ctas * nb, fb // 8, 8, 32, device=self.obs.device)
+        dump = torch.zeros(ctas * nb + nb, fb // 8, 8, 32, device=self.obs.device)
         rc = self.lib.azb_nn_forward_tc_debug(C.byref(self.w), self.obs.data_ptr(), self.policy.data_ptr(),
                                               self.value.data_ptr(), self.batch,
                                               C.c_void_p(torch.cuda.current_stream().cuda_stream), dump.data_ptr(), layer)

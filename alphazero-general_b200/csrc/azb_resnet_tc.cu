@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__restrict__ value, int B, int in_ch, int depth,
             const unsigned char *__restrict__ wconv, const float *__restrict__ cbias, const float *__restrict__ bn_scale,
             const float *__restrict__ bn_shift, const __nv_bfloat16 *__restrict__ whead, const float *__restrict__ bhead,
-            float *__restrict__ dump, int dump_layer)
+            float *__restrict__ dump, int dump_layer, int n_full)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *fa = smem;                                            // activation frame a
@@ -368,7 +368,12 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
     float *fin = red + WARPS * NB * 16;                                  // heads: [NB][16]
 
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-    const int board0 = blockIdx.x * NB;
+    // CTAs [0, n_full) evaluate 16 boards (7 M-tiles); the CTAs behind them 8 boards (3.5 -> 4 M-tiles, 4/7 of the
+    // time): the host turns the tiles of a partially filled last wave into twice as many half tiles
+    const bool full = (int)blockIdx.x < n_full;
+    const int nb = full ? NB : NB / 2, tiles = full ? TILES : (TILES + 1) / 2;
+    const int board0 = full ? (int)blockIdx.x * NB : n_full * NB + ((int)blockIdx.x - n_full) * (NB / 2);
+    if (board0 >= B) return;
     // DBG build (azb_nn_forward_tc_debug): dump_layer = 99 writes per-warp phase clocks, else the activations of a layer
     const bool timing = DBG && dump != nullptr && dump_layer == 99;
     long long ts[5];
@@ -382,7 +387,7 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
         if (lane == 0) {
             for (int i = 0; i < NPBUF; i++) { mbar_init(BAR(BAR_PFULL + i), 1); mbar_init(BAR(BAR_PEMPTY + i), GRP_WARPS); }
             // every epilogue warp of tiles t-1, t, t+1 arrives on READY[t]
-            for (int i = 0; i < TILES; i++) mbar_init(BAR(BAR_READY + i), GRP_WARPS * ((i == 0 || i == TILES - 1) ? 2 : 3));
+            for (int i = 0; i < tiles; i++) mbar_init(BAR(BAR_READY + i), GRP_WARPS * ((i == 0 || i == tiles - 1) ? 2 : 3));
             for (int i = 0; i < NWBUF; i++) { mbar_init(BAR(BAR_WFULL + i), 1); mbar_init(BAR(BAR_WEMPTY + i), NPBUF); }
             mbar_init(BAR(BAR_HEAD), 1);
             for (int i = 0; i < NCNT; i++) cnts[i] = 0u;
@@ -410,7 +415,7 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
     const float *s_bias = prm, *s_sc = prm + MAXL * CH, *s_sh = prm + MAXL * CH + MAXD * CH;
 
     // observation -> chunk plane 0 of frame b (channels >= in_ch stay zero)
-    for (int i = tid; i < NB * BH * BW; i += THREADS) {
+    for (int i = tid; i < nb * BH * BW; i += THREADS) {
         const int bl = i / (BH * BW), pos = i - bl * (BH * BW), y = pos / BW, xx = pos - y * BW;
         const int gb = board0 + bl;
         float c[8];
@@ -429,7 +434,7 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
     if (warp < NPBUF) {
         // ---- MMA issuers: warp k feeds ring slot k (tiles g = k, k+3, ... across layers) --------------------
         if (elect_one_sync()) {
-            const int total = layers * TILES;
+            const int total = layers * tiles;
             const uint32_t d_tmem = tmem_base + COL_P + (uint32_t)(warp * NACC);
             int l = 0, t = warp, cur_l = -1;
             uint32_t w_s = 0;
@@ -452,7 +457,7 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
                 umma_commit(BAR(BAR_PFULL + warp));
                 turn_store(CNT(CNT_TURN), (uint32_t)(g + 1));
                 t += NPBUF;
-                if (t >= TILES) { t -= TILES; l++; }
+                if (t >= tiles) { t -= tiles; l++; }
             }
             umma_commit(BAR(BAR_WEMPTY + cur_l % NWBUF));
         }
@@ -478,7 +483,7 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
         const uint32_t t_p = tmem_base + lane_off + COL_P + (uint32_t)(grp * NACC + 16 * half);
         const uint32_t t_x0 = tmem_base + lane_off + COL_X + (uint32_t)(16 * half);
         const uint32_t bar_full = BAR(BAR_PFULL + grp), bar_empty = BAR(BAR_PEMPTY + grp);
-        const int total = layers * TILES, ho = 16 * half, r0 = q * 32 + lane;
+        const int total = layers * tiles, ho = 16 * half, r0 = q * 32 + lane, live_rows = nb * FB;
         unsigned char *const fa_h = fa + (size_t)(2 * half) * PLANE + (size_t)PADR * 16;
         unsigned char *const fb_h = fb + (size_t)(2 * half) * PLANE + (size_t)PADR * 16;
         int l = 0, t = grp;
@@ -490,7 +495,7 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
             par ^= 1u;
             tc_fence_after();
             const int fr = t * 128 + r0;
-            const bool live = ((fr & 7) != 7) && (((fr >> 3) % (BH + 1)) != BH);
+            const bool live = ((fr & 7) != 7) && (((fr >> 3) % (BH + 1)) != BH) && fr < live_rows;
             const uint32_t t_x = t_x0 + (uint32_t)(CH * t);
             // the last layer writes the head input: [8-channel chunk][board][HB rows][16 B]
             unsigned char *out_row;
@@ -502,7 +507,7 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
             } else {
                 out_row = (is_c1 ? fb_h : fa_h) + (size_t)fr * 16;
             }
-            float *dmp = (DBG && dump != nullptr && l == dump_layer) ? dump + ((size_t)blockIdx.x * ROWS + fr) * CH + ho : nullptr;
+            float *dmp = (DBG && dump != nullptr && l == dump_layer && fr < live_rows) ? dump + ((size_t)board0 * FB + fr) * CH + ho : nullptr;
             if (l == 0) {
                 epilogue_tile<EPI_STEM, DBG>(t_p, t_x, out_row, out_plane, s_bias + ho, depth > 0 ? s_sc + ho : nullptr, s_sh + ho,
                                              live, lane, bar_empty, dmp);
@@ -519,10 +524,10 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
             if (lane == 0) {                  // every tile whose MMAs read these rows
                 if (t > 0) mbar_arrive(BAR(BAR_READY + t - 1));
                 mbar_arrive(BAR(BAR_READY + t));
-                if (t + 1 < TILES) mbar_arrive(BAR(BAR_READY + t + 1));
+                if (t + 1 < tiles) mbar_arrive(BAR(BAR_READY + t + 1));
             }
             t += NPBUF;
-            if (t >= TILES) { t -= TILES; l++; }
+            if (t >= tiles) { t -= tiles; l++; }
         }
     }
 #undef CNT
@@ -567,7 +572,7 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
             fin[tid] = v + ((tid & 15) < NOUT ? bhead[tid & 15] : 0.0f);
         }
         __syncthreads();
-        if (tid < NB && board0 + tid < B) {
+        if (tid < nb && board0 + tid < B) {
             const int gb = board0 + tid;
             constexpr int A = NOUT - 3;
             float lg[NOUT];
@@ -629,15 +634,28 @@ static int tc_launch(const azb_nn_weights *w, const float *obs, float *policy, f
             return -2;
         configured = true;
     }
-    const int grid = (batch + tc::NB - 1) / tc::NB;
+    // wave shaping: `rem` = tiles of 16 boards in the partially filled last wave; when twice as many CTAs still fit in
+    // one wave, they run as half tiles of 8 boards (4 M-tiles instead of 7 on the critical path of the launch)
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaDeviceProp prop;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -2;
+        sms = prop.multiProcessorCount;
+    }
+    const int T = (batch + tc::NB - 1) / tc::NB;
+    const int rem = T % sms;
+    int n_full = T, n_half = 0;
+    if (rem > 0 && 2 * rem <= sms) { n_full = T - rem; n_half = 2 * rem; }
+    const int grid = n_full + n_half;
     if (dump != nullptr)
         tc::k_resnet_tc<true><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(
             obs, policy, value, batch, w->in_channels, w->depth, reinterpret_cast<const unsigned char *>(w->wconv), w->cbias,
-            w->bn_scale, w->bn_shift, reinterpret_cast<const __nv_bfloat16 *>(w->whead), w->bhead, dump, dump_layer);
+            w->bn_scale, w->bn_shift, reinterpret_cast<const __nv_bfloat16 *>(w->whead), w->bhead, dump, dump_layer, n_full);
     else
         tc::k_resnet_tc<false><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(
             obs, policy, value, batch, w->in_channels, w->depth, reinterpret_cast<const unsigned char *>(w->wconv), w->cbias,
-            w->bn_scale, w->bn_shift, reinterpret_cast<const __nv_bfloat16 *>(w->whead), w->bhead, nullptr, -1);
+            w->bn_scale, w->bn_shift, reinterpret_cast<const __nv_bfloat16 *>(w->whead), w->bhead, nullptr, -1, n_full);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
