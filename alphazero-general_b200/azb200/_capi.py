@@ -54,6 +54,7 @@ SYMBOLS = {
     "azb_value_ptr": (_vp, [_vp]),
     "azb_select": (C.c_int, [_vp, _i32, _i32, _vp]),
     "azb_expand_backup": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    "azb_expand_backup_select": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "azb_play_moves": (C.c_int, [_vp, _i32, _vp]),
     "azb_warmup_sims": (C.c_int, [_vp, _i32, _vp]),
     "azb_arena_players": (C.c_int, [_vp, _vp, _vp]),

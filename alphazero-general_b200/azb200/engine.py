@@ -156,6 +156,10 @@ class SelfPlayEngine:
             assert tuple(value.shape) == (self.B, 3)
         check(self.lib.azb_expand_backup(self.h, first, count, pp, vp, self._stream(stream)))
 
+    def expand_backup_select(self, first=0, count=0, stream=None):
+        """expand_backup of this simulation + select of the next, one launch (engine-owned policy / value rows)."""
+        check(self.lib.azb_expand_backup_select(self.h, first, count, None, None, self._stream(stream)))
+
     def play_moves(self, fast=False, stream=None):
         check(self.lib.azb_play_moves(self.h, int(bool(fast)), self._stream(stream)))
 

@@ -341,11 +341,11 @@ class DeviceSelfPlay:
                 T.wait_stream(cur)
                 with torch.cuda.graph(g, stream=T):
                     (f, c), = self.ranges
+                    eng.select(f, c, stream=T)
                     for s in range(sims):
-                        if s > 0:
-                            eng.expand_backup(f, c, stream=T)
-                        eng.select(f, c, stream=T)
                         self.evals[0](stream=T)
+                        if s + 1 < sims:
+                            eng.expand_backup_select(f, c, stream=T)      # processBatch(s) + generateBatch(s+1)
                     eng.expand_backup(f, c, stream=T)
                     eng.play_moves(fast, stream=T)
                 self._graphs[key] = g
@@ -354,7 +354,7 @@ class DeviceSelfPlay:
                 with torch.cuda.stream(T):
                     g.replay()
                 cur.wait_stream(T)
-                self.launches += sims * 3 + 3
+                self.launches += sims * 2 + 4
                 return
             self._eager_rounds += 1
         T.wait_stream(cur)

@@ -95,6 +95,10 @@ template <class G> static void l_expand(azb_engine *e, int first, int count, con
 {
     k_expand_backup<G><<<grid_for<G>(count), CTA_THREADS, 0, s>>>(e->d, first, count, pol, val);
 }
+template <class G> static void l_expand_select(azb_engine *e, int first, int count, const float *pol, const float *val, cudaStream_t s)
+{
+    k_expand_select<G><<<grid_for<G>(count), CTA_THREADS, 0, s>>>(e->d, first, count, pol, val);
+}
 template <class G> static void l_play(azb_engine *e, int fast, cudaStream_t s)
 {
     if (e->d.arena) k_play_moves_arena<G><<<grid_for<G>(e->d.B / 2), CTA_THREADS, 0, s>>>(e->d);
@@ -336,6 +340,18 @@ extern "C" int azb_expand_backup(azb_engine *e, int32_t first, int32_t count, co
     const float *pol = policy ? policy : e->d.policy;
     const float *val = value ? value : e->d.value;
     DISPATCH(e, l_expand, e, first, count, pol, val, s);
+    CK(cudaGetLastError());
+    return AZB_OK;
+}
+
+extern "C" int azb_expand_backup_select(azb_engine *e, int32_t first, int32_t count, const float *policy,
+                                        const float *value, void *stream)
+{
+    TRY(range_ok(e, first, count));
+    cudaStream_t s = (cudaStream_t)stream;
+    const float *pol = policy ? policy : e->d.policy;
+    const float *val = value ? value : e->d.value;
+    DISPATCH(e, l_expand_select, e, first, count, pol, val, s);
     CK(cudaGetLastError());
     return AZB_OK;
 }

@@ -849,6 +849,20 @@ __global__ void __launch_bounds__(CTA_THREADS) k_expand_backup(DevView d, int fi
     expand_backup_game<G>(d, g, active, lane, sub, sm[gi], policy + (size_t)g * G::A, value + (size_t)g * 3);
 }
 
+// processBatch of simulation s fused with generateBatch of simulation s+1 for the same slots: one launch instead of
+// two between two network evaluations, and the slot's header / leaf record stay in cache
+template <class G>
+__global__ void __launch_bounds__(CTA_THREADS) k_expand_select(DevView d, int first, int count, const float *policy, const float *value)
+{
+    __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
+    int g, lane, sub, gi; bool active;
+    if (!group_setup<G>(first, count, g, active, lane, sub, gi)) return;
+    if (G::A > G::LANES) { for (int a = lane; a < G::A; a += G::LANES) sm[gi].vec[a] = 0.0f; __syncwarp(); }
+    expand_backup_game<G>(d, g, active, lane, sub, sm[gi], policy + (size_t)g * G::A, value + (size_t)g * 3);
+    __syncwarp();
+    select_game<G, true>(d, g, active, lane, sub, sm[gi]);
+}
+
 // `sims` simulations per game with constant NN outputs, no NN round trip
 template <class G>
 __global__ void __launch_bounds__(CTA_THREADS) k_warmup_sims(DevView d, int sims)

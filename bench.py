@@ -513,7 +513,8 @@ def main():
             "clocks": clk, "gpu_launches": drv.launches - launches0,
             "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "alt_nn": alt,
             "tree_stats": {"sims": dsims, "mean_depth": dD / max(dsims, 1), "mean_children_scanned": dC / max(dsims, 1),
-                           "games_finished": st1["results"] - st0["results"], "peak_nodes_per_game": st1["peak_nodes"]},
+                           "games_finished": st1["results"] - st0["results"], "peak_nodes_per_game": st1["peak_nodes"],
+                           "terminal_leaf_fraction": (st1["terminal_leaves"] - st0["terminal_leaves"]) / max(dsims, 1)},
         }
         if gather_ms is not None:
             line["example_gather"] = {"ms": gather_ms, "samples": gathered}

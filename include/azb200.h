@@ -147,6 +147,11 @@ int azb_select(azb_engine *e, int32_t first, int32_t count, void *stream);
  * engine-owned buffers. */
 int azb_expand_backup(azb_engine *e, int32_t first, int32_t count,
                       const float *policy, const float *value, void *stream);
+/* azb_expand_backup of the current simulation followed by azb_select of the next one for the same slots, as one
+ * launch (the loop of SelfPlayAgent.run, SelfPlayAgent.pyx:88-92, calls them back to back).  The observation rows
+ * are overwritten, so the caller must have consumed them; results are identical to the two separate calls. */
+int azb_expand_backup_select(azb_engine *e, int32_t first, int32_t count,
+                             const float *policy, const float *value, void *stream);
 /* SelfPlayAgent.playMoves (SelfPlayAgent.pyx:153-202): temperature schedule,
  * MCTS.probs, np.random.choice, history append (unless fast), MCTS.update_root,
  * play_action, terminal handling (result, quota, sample emission with

@@ -8,8 +8,11 @@ from azb200 import SelfPlayEngine
 
 
 class EngineAgent:
-    def __init__(self, game="connect4", num_slots=1, rng="mt19937", **kw):
+    def __init__(self, game="connect4", num_slots=1, rng="mt19937", fused_step_sims=0, **kw):
         self.eng = SelfPlayEngine(game=game, num_games=num_slots, rng=rng, **kw)
+        # fused_step_sims = N > 0: processBatch of simulation k < N-1 and generateBatch of k+1 run as ONE launch
+        # (azb_expand_backup_select); rounds must then have exactly N simulations
+        self._fs, self._k = int(fused_step_sims), 0
         self.B, self.A = self.eng.B, self.eng.A
         self.obs_shape = self.eng.obs_shape
 
@@ -17,15 +20,22 @@ class EngineAgent:
         self.eng.set_root_noise(noise)
 
     def generateBatch(self):
-        self.eng.select()
+        if not (self._fs and self._k > 0):
+            self.eng.select()
         return self.eng.obs.cpu().numpy()
 
     def processBatch(self, policy, value):
         self.eng.policy.copy_(torch.from_numpy(np.ascontiguousarray(policy, dtype=np.float32)))
         self.eng.value.copy_(torch.from_numpy(np.ascontiguousarray(value, dtype=np.float32)))
-        self.eng.expand_backup()
+        if self._fs and self._k + 1 < self._fs:
+            self.eng.expand_backup_select()
+            self._k += 1
+        else:
+            self.eng.expand_backup()
+            self._k = 0
 
     def playMoves(self, fast=False):
+        assert self._k == 0
         self.eng.play_moves(fast)
         self.eng.check_errors()
 

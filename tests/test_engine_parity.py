@@ -189,3 +189,24 @@ def test_arena_mode_equals_oracle(game, rng, p2i, reset):
     for k in ("sims", "sum_depth", "sum_children", "nodes_created", "terminal_leaves", "games_played", "results", "moves"):
         assert so[k] == se[k], (k, so[k], se[k])
     assert se["samples"] == 0
+
+
+@pytest.mark.parametrize("game", ["connect4", "brandubh"])
+def test_fused_expand_select_launch_is_identical(game):
+    """azb_expand_backup_select (processBatch of simulation k + generateBatch of k+1 in one launch) against the
+    oracle: traces, samples, results and statistics as with the two separate calls."""
+    from _engine_agent import EngineAgent
+    c4 = game == "connect4"
+    B, sims, rounds = (12, 11, 60) if c4 else (3, 7, 25)
+    obs_n, A = (4 * 6 * 7, 7) if c4 else (5 * 7 * 7, 588)
+    temps = C4_TEMPS if c4 else _orc.temp_table(_orc.default_temp_scaling, 1, None)
+    nn = FakeNN(obs_n, A, seed=21, sharp=3.0 if c4 else 1.0)
+    orc = _orc.OracleAgent(_orc.GAME_CONNECT4 if c4 else _orc.GAME_BRANDUBH, B, rng_mode=_orc.RNG_PHILOX, seed=4,
+                           add_root_temp=True, temps=temps)
+    eng = EngineAgent(game, B, rng="philox", seed=4, add_root_temp=True, temps=temps, max_sims_per_move=sims,
+                      fused_step_sims=sims)
+    assert_traces_equal(run_trace(orc, nn, rounds, sims, keep_obs=True), run_trace(eng, nn, rounds, sims, keep_obs=True), game)
+    assert_queues_equal(orc, eng, game)
+    so, se = orc.stats(), eng.stats()
+    for k in ("sims", "sum_depth", "sum_children", "nodes_created", "terminal_leaves", "moves"):
+        assert so[k] == se[k], (k, so[k], se[k])
