@@ -52,6 +52,8 @@ SYMBOLS = {
     "azb_obs_ptr": (_vp, [_vp]),
     "azb_policy_ptr": (_vp, [_vp]),
     "azb_value_ptr": (_vp, [_vp]),
+    "azb_nn_rows_ptr": (_vp, [_vp]),
+    "azb_nn_count_ptr": (_vp, [_vp]),
     "azb_select": (C.c_int, [_vp, _i32, _i32, _vp]),
     "azb_expand_backup": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "azb_expand_backup_select": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),

@@ -110,9 +110,21 @@ class SelfPlayEngine:
         self.quota = int(games_per_iteration) if games_per_iteration else (1 << 62)
 
     # ---- NN I/O buffers as torch tensors (zero copy) -----------------------
-    def _wrap(self, ptr, shape):
+    def _wrap(self, ptr, shape, typestr="<f4"):
         import torch
-        return torch.as_tensor(_DevArray(ptr, shape, "<f4"), device=f"cuda:{self.device}")
+        return torch.as_tensor(_DevArray(ptr, shape, typestr), device=f"cuda:{self.device}")
+
+    @property
+    def nn_rows(self):
+        """device int32 [B]: slots whose current leaf needs the network (written by select)."""
+        if getattr(self, "_nn_rows", None) is None:
+            self._nn_rows = self._wrap(self.lib.azb_nn_rows_ptr(self.h), (self.B,), "<i4")
+        return self._nn_rows
+
+    def nn_count_ptr(self):
+        """Device address of the int32 count of valid nn_rows entries written by the LAST select call (two counters
+        alternate between consecutive selects; query after every select)."""
+        return int(self.lib.azb_nn_count_ptr(self.h))
 
     @property
     def obs(self):

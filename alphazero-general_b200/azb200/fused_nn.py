@@ -148,7 +148,7 @@ class FusedResNetEvaluator:
 
     precision = "bf16"
 
-    def __init__(self, model, obs, policy, value, kernel=None):
+    def __init__(self, model, obs, policy, value, kernel=None, rows=None, count=None, max_batch=None):
         if not supported(model):
             raise NotImplementedError("fused evaluator: 6x7 boards, 32 channels, 7 actions only")
         kernel = kernel or ("tc" if supported_tc(model) else "mma")
@@ -178,11 +178,28 @@ class FusedResNetEvaluator:
         self.obs, self.policy, self.value = obs, policy, value
         self.batch = obs.shape[0]
         self.stream = torch.cuda.Stream(device=dev)
+        # compact mode (tcgen05 kernel): evaluate only rows[0 .. count) -- device int32 tensors, e.g. the engine's
+        # list of non-terminal leaves (SelfPlayEngine.nn_rows / nn_count); the other rows keep their old answers
+        self.rows, self.count = rows, count
+        if rows is not None:
+            # count: int32 device tensor, or a callable returning the device address of the count (the engine alternates
+            # between two counters, SelfPlayEngine.nn_count_ptr)
+            assert self.kernel == "tc" and count is not None and rows.dtype == torch.int32
+            self.max_batch = int(max_batch or self.batch)
+            self.lib.azb_nn_forward_tc_rows.restype = C.c_int
+            self.lib.azb_nn_forward_tc_rows.argtypes = [C.POINTER(_NNWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                        C.c_void_p, C.c_int32, C.c_void_p]
 
     def __call__(self, stream=None):
         stream = stream or torch.cuda.current_stream()
-        rc = self._fwd(C.byref(self.w), self.obs.data_ptr(), self.policy.data_ptr(), self.value.data_ptr(),
-                       self.batch, C.c_void_p(stream.cuda_stream))
+        if self.rows is not None:
+            rc = self.lib.azb_nn_forward_tc_rows(C.byref(self.w), self.obs.data_ptr(), self.policy.data_ptr(),
+                                                 self.value.data_ptr(), self.rows.data_ptr(),
+                                                 self.count() if callable(self.count) else self.count.data_ptr(),
+                                                 self.max_batch, C.c_void_p(stream.cuda_stream))
+        else:
+            rc = self._fwd(C.byref(self.w), self.obs.data_ptr(), self.policy.data_ptr(), self.value.data_ptr(),
+                           self.batch, C.c_void_p(stream.cuda_stream))
         if rc != 0:
             raise RuntimeError(f"azb_nn_forward ({self.kernel}) failed with status {rc}")
 

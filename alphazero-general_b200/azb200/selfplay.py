@@ -284,7 +284,7 @@ class DeviceSelfPlay:
     that tree work of one half overlaps inference of the other."""
 
     def __init__(self, engine, nnet, cohorts=1, precision="tf32", use_graph=True, channels_last=False, fused=False,
-                 split=None, round_graph=None):
+                 split=None, round_graph=None, skip_terminal=True):
         assert cohorts in (1, 2)
         self.engine = engine
         self.cohorts = cohorts
@@ -306,10 +306,18 @@ class DeviceSelfPlay:
         if fused:
             # hand-written fused ResNet kernel: tcgen05 / TMEM (csrc/azb_resnet_tc.cu) where it applies, else the
             # mma.sync one (csrc/azb_resnet.cu); fused="tc" / "mma" forces one
-            from .fused_nn import FusedResNetEvaluator
-            self.evals = [FusedResNetEvaluator(nnet, engine.obs[f:f + c], engine.policy[f:f + c], engine.value[f:f + c],
-                                               kernel=None if fused is True else fused)
-                          for f, c in self.ranges]
+            from .fused_nn import FusedResNetEvaluator, supported_tc
+            kern = None if fused is True else fused
+            if (kern or ("tc" if supported_tc(nnet) else "mma")) == "tc" and skip_terminal and cohorts == 1:
+                # compact evaluation: only the leaves that need the network (the reference evaluates terminal leaves
+                # too and discards the answers, SelfPlayAgent.pyx:116-123 / MCTS.pyx:234-235)
+                self.evals = [FusedResNetEvaluator(nnet, engine.obs, engine.policy, engine.value, kernel="tc",
+                                                   rows=engine.nn_rows, count=engine.nn_count_ptr, max_batch=c)
+                              for f, c in self.ranges]
+            else:
+                self.evals = [FusedResNetEvaluator(nnet, engine.obs[f:f + c], engine.policy[f:f + c], engine.value[f:f + c],
+                                                   kernel=kern)
+                              for f, c in self.ranges]
         else:
             self.evals = [LeafEvaluator(nnet, engine.obs[f:f + c], engine.policy[f:f + c], engine.value[f:f + c],
                                         precision=precision, use_graph=use_graph, channels_last=channels_last)

@@ -89,6 +89,8 @@ struct DevView {
     SlotStats *stats;
     // NN I/O
     float *obs; float *policy; float *value;
+    int *nn_rows; int *nn_count;       // slots whose leaf needs the network (non-terminal), filled by select;
+    int nn_par;                        // nn_count[2]: select adds to [nn_par] and clears [nn_par ^ 1] for the next one
     const float *warm_policy; const float *warm_value;
     // fed root noise
     const float *noise; int noise_events, noise_stride;

@@ -222,6 +222,7 @@ extern "C" int azb_create(const azb_config *cfg, azb_engine **out)
     const int obs = gd.obs_c * gd.obs_h * gd.obs_w;
     A_(dev_alloc(e, &d.obs, (size_t)B * obs)); A_(dev_alloc(e, &d.policy, (size_t)B * gd.A));
     A_(dev_alloc(e, &d.value, (size_t)B * 3));
+    A_(dev_alloc(e, &d.nn_rows, (size_t)B)); A_(dev_alloc(e, &d.nn_count, 2));
     float *wp = nullptr, *wv = nullptr;
     A_(dev_alloc(e, &wp, gd.A)); A_(dev_alloc(e, &wv, 3));
     // queues
@@ -313,6 +314,8 @@ extern "C" int azb_observation_size(const azb_engine *e, int32_t chw[3])
 extern "C" float *azb_obs_ptr(azb_engine *e) { return e ? e->d.obs : nullptr; }
 extern "C" float *azb_policy_ptr(azb_engine *e) { return e ? e->d.policy : nullptr; }
 extern "C" float *azb_value_ptr(azb_engine *e) { return e ? e->d.value : nullptr; }
+extern "C" int32_t *azb_nn_rows_ptr(azb_engine *e) { return e ? e->d.nn_rows : nullptr; }
+extern "C" int32_t *azb_nn_count_ptr(azb_engine *e) { return e ? e->d.nn_count + e->d.nn_par : nullptr; }
 
 static int range_ok(azb_engine *e, int32_t first, int32_t &count)
 {
@@ -327,6 +330,7 @@ extern "C" int azb_select(azb_engine *e, int32_t first, int32_t count, void *str
 {
     TRY(range_ok(e, first, count));
     cudaStream_t s = (cudaStream_t)stream;
+    e->d.nn_par ^= 1;
     DISPATCH(e, l_select, e, first, count, s);
     CK(cudaGetLastError());
     return AZB_OK;
@@ -351,6 +355,7 @@ extern "C" int azb_expand_backup_select(azb_engine *e, int32_t first, int32_t co
     cudaStream_t s = (cudaStream_t)stream;
     const float *pol = policy ? policy : e->d.policy;
     const float *val = value ? value : e->d.value;
+    e->d.nn_par ^= 1;
     DISPATCH(e, l_expand_select, e, first, count, pol, val, s);
     CK(cudaGetLastError());
     return AZB_OK;
@@ -361,6 +366,7 @@ extern "C" int azb_play_moves(azb_engine *e, int32_t fast, void *stream)
     if (!e) return fail(AZB_ERR_BAD_ARGUMENT, "null engine");
     cudaStream_t s = (cudaStream_t)stream;
     DISPATCH(e, l_play, e, fast, s);
+    e->d.nn_par = 1;                    // the next select uses counter 0 (k_finalize cleared both)
     CK(cudaGetLastError());
     return AZB_OK;
 }

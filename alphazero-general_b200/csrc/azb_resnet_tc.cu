@@ -353,7 +353,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__restrict__ value, int B, int in_ch, int depth,
             const unsigned char *__restrict__ wconv, const float *__restrict__ cbias, const float *__restrict__ bn_scale,
             const float *__restrict__ bn_shift, const __nv_bfloat16 *__restrict__ whead, const float *__restrict__ bhead,
-            float *__restrict__ dump, int dump_layer, int n_full)
+            float *__restrict__ dump, int dump_layer, int n_full, const int *__restrict__ rows, const int *__restrict__ count_ptr,
+            int sms)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *fa = smem;                                            // activation frame a
@@ -370,6 +371,15 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     // CTAs [0, n_full) evaluate 16 boards (7 M-tiles); the CTAs behind them 8 boards (3.5 -> 4 M-tiles, 4/7 of the
     // time): the host turns the tiles of a partially filled last wave into twice as many half tiles
+    // compact mode (rows != nullptr): evaluate boards rows[0 .. *count_ptr) of obs, answers to the same rows; the
+    // batch size lives in device memory (the engine's select kernel counts the non-terminal leaves), so the wave
+    // shaping the host does for a known batch is redone here
+    if (rows != nullptr) {
+        B = *count_ptr;
+        const int T = (B + NB - 1) / NB, rem = T % sms;
+        n_full = T;
+        if (rem > 0 && 2 * rem <= sms) n_full = T - rem;
+    }
     const bool full = (int)blockIdx.x < n_full;
     const int nb = full ? NB : NB / 2, tiles = full ? TILES : (TILES + 1) / 2;
     const int board0 = full ? (int)blockIdx.x * NB : n_full * NB + ((int)blockIdx.x - n_full) * (NB / 2);
@@ -417,10 +427,12 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
     // observation -> chunk plane 0 of frame b (channels >= in_ch stay zero)
     for (int i = tid; i < nb * BH * BW; i += THREADS) {
         const int bl = i / (BH * BW), pos = i - bl * (BH * BW), y = pos / BW, xx = pos - y * BW;
-        const int gb = board0 + bl;
+        int gb = board0 + bl;
+        const bool have = gb < B;
+        if (have && rows != nullptr) gb = rows[gb];
         float c[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) c[k] = (gb < B && k < in_ch) ? obs[((size_t)gb * in_ch + k) * (BH * BW) + pos] : 0.0f;
+        for (int k = 0; k < 8; k++) c[k] = (have && k < in_ch) ? obs[((size_t)gb * in_ch + k) * (BH * BW) + pos] : 0.0f;
         uint4 o;
         o.x = pack_bf16(c[0], c[1]); o.y = pack_bf16(c[2], c[3]); o.z = pack_bf16(c[4], c[5]); o.w = pack_bf16(c[6], c[7]);
         *reinterpret_cast<uint4 *>(fb + (size_t)(PADR + bl * FB + y * FW + xx) * 16) = o;
@@ -573,7 +585,7 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
         }
         __syncthreads();
         if (tid < nb && board0 + tid < B) {
-            const int gb = board0 + tid;
+            const int gb = rows != nullptr ? rows[board0 + tid] : board0 + tid;
             constexpr int A = NOUT - 3;
             float lg[NOUT];
 #pragma unroll
@@ -620,7 +632,7 @@ extern "C" int azb_nn_tc_boards_per_cta(void) { return tc::NB; }
 extern "C" int azb_nn_tc_frame_rows_per_board(void) { return tc::FB; }
 
 static int tc_launch(const azb_nn_weights *w, const float *obs, float *policy, float *value, int32_t batch, void *stream,
-                     float *dump, int dump_layer)
+                     float *dump, int dump_layer, const int *rows = nullptr, const int *count = nullptr)
 {
     if (!w || !obs || !policy || !value || batch <= 0) return -7;
     if (w->channels != tc::CH || w->board_h != tc::BH || w->board_w != tc::BW || w->action_size != 7 || w->in_channels > 8 ||
@@ -647,15 +659,16 @@ static int tc_launch(const azb_nn_weights *w, const float *obs, float *policy, f
     const int rem = T % sms;
     int n_full = T, n_half = 0;
     if (rem > 0 && 2 * rem <= sms) { n_full = T - rem; n_half = 2 * rem; }
-    const int grid = n_full + n_half;
+    int grid = n_full + n_half;
+    if (rows != nullptr) grid = T + sms / 2;       // upper bound over every batch size <= batch; surplus CTAs exit at once
     if (dump != nullptr)
         tc::k_resnet_tc<true><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(
             obs, policy, value, batch, w->in_channels, w->depth, reinterpret_cast<const unsigned char *>(w->wconv), w->cbias,
-            w->bn_scale, w->bn_shift, reinterpret_cast<const __nv_bfloat16 *>(w->whead), w->bhead, dump, dump_layer, n_full);
+            w->bn_scale, w->bn_shift, reinterpret_cast<const __nv_bfloat16 *>(w->whead), w->bhead, dump, dump_layer, n_full, rows, count, sms);
     else
         tc::k_resnet_tc<false><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(
             obs, policy, value, batch, w->in_channels, w->depth, reinterpret_cast<const unsigned char *>(w->wconv), w->cbias,
-            w->bn_scale, w->bn_shift, reinterpret_cast<const __nv_bfloat16 *>(w->whead), w->bhead, nullptr, -1, n_full);
+            w->bn_scale, w->bn_shift, reinterpret_cast<const __nv_bfloat16 *>(w->whead), w->bhead, nullptr, -1, n_full, rows, count, sms);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -663,6 +676,13 @@ extern "C" int azb_nn_forward_tc(const azb_nn_weights *w, const float *obs, floa
                                  void *stream)
 {
     return tc_launch(w, obs, policy, value, batch, stream, nullptr, -1);
+}
+
+extern "C" int azb_nn_forward_tc_rows(const azb_nn_weights *w, const float *obs, float *policy, float *value, const int32_t *rows,
+                                      const int32_t *count, int32_t max_batch, void *stream)
+{
+    if (!rows || !count) return -7;
+    return tc_launch(w, obs, policy, value, max_batch, stream, nullptr, -1, rows, count);
 }
 
 extern "C" int azb_nn_forward_tc_debug(const azb_nn_weights *w, const float *obs, float *policy, float *value, int32_t batch,

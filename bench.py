@@ -68,6 +68,8 @@ def parse():
     ap.add_argument("--no-select-events", action="store_true")
     ap.add_argument("--roofline-steps", type=int, default=3, help="eager move-rounds timed per select launch for the roofline")
     ap.add_argument("--no-round-graph", action="store_true", help="launch every kernel of a move-round from the host")
+    ap.add_argument("--eval-terminal", action="store_true",
+                    help="evaluate the network for terminal leaves too, as the reference does (it discards those answers)")
     return ap.parse_args()
 
 
@@ -339,7 +341,8 @@ def main():
         a.no_e2e = True if tafl else a.no_e2e
     drv = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision, channels_last=not a.nchw,
                          fused={"fused": True, "fused_mma": "mma", "cudnn": False}[a.nn],
-                         round_graph=False if a.no_round_graph else None, split=a.split or None)
+                         round_graph=False if a.no_round_graph else None, split=a.split or None,
+                         skip_terminal=not a.eval_terminal)
 
     sel_events = []
 
@@ -507,7 +510,8 @@ def main():
                                    f"root noise 0.1 + temp 1.1), net={a.net} ResNet random-init, "
                                    f"{'tree-only warmup mode' if a.tree_only else 'NN in the loop'}",
                        "games_per_gpu": B, "sims_per_move": sims, "net": a.net, "nn": a.nn, "nn_precision": "bf16" if a.nn != "cudnn" else a.precision,
-                       "cohorts": a.cohorts, "round_graph": bool(drv.round_graph), "channels_last": not a.nchw, "lanes_per_game": a.lanes or 8, "rng": "philox", "parallelism": f"games x{world} (no data-path collective)",
+                       "cohorts": a.cohorts, "round_graph": bool(drv.round_graph),
+                       "nn_rows": "non-terminal leaves only" if (a.nn == "fused" and not a.eval_terminal and a.cohorts == 1) else "every leaf", "channels_last": not a.nchw, "lanes_per_game": a.lanes or 8, "rng": "philox", "parallelism": f"games x{world} (no data-path collective)",
                        "l2": "node pool %.1f GB per GPU > 126 MB L2; no flush" % (st1["pool_bytes"] / 1e9),
                        "preroll_rounds": a.preroll},
             "clocks": clk, "gpu_launches": drv.launches - launches0,

@@ -133,6 +133,14 @@ int azb_num_games(const azb_engine *e);
 float *azb_obs_ptr(azb_engine *e);
 float *azb_policy_ptr(azb_engine *e);
 float *azb_value_ptr(azb_engine *e);
+/* Written by azb_select (and azb_expand_backup_select) for the slot range of that call: the slots whose leaf needs the
+ * network -- live games with a non-terminal leaf -- in no particular order (device int32 [B]) and their number
+ * (device int32; two counters alternate between consecutive select calls so that none needs a reset launch:
+ * azb_nn_count_ptr returns the one the LAST select call wrote, query it after every select).  A terminal leaf's value is its win state and the reference discards the network's answer for it
+ * (MCTS.pyx:234-235; SelfPlayAgent.generateBatch still evaluates it, SelfPlayAgent.pyx:116-123), so a caller may
+ * evaluate just these rows of azb_obs_ptr (azb_nn_forward_tc_rows does). */
+int32_t *azb_nn_rows_ptr(azb_engine *e);
+int32_t *azb_nn_count_ptr(azb_engine *e);
 
 /* ---- the hot path -------------------------------------------------------- */
 /* SelfPlayAgent.generateBatch (SelfPlayAgent.pyx:103-135) = MCTS.find_leaf

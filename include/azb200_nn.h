@@ -47,6 +47,12 @@ int azb_nn_forward(const azb_nn_weights *w, const float *obs, float *policy, flo
  *          frame_row = y*8 + x over the azb_nn_tc_frame_rows_per_board() rows of a board frame
  * Same status codes. */
 int azb_nn_forward_tc(const azb_nn_weights *w, const float *obs, float *policy, float *value, int32_t batch, void *stream);
+/* Compact evaluation: boards rows[0 .. *count) of obs (device int32 row indices, device int32 count <= max_batch);
+ * policy / value are written to the same rows, all other rows are left untouched.  The engine's select kernel lists
+ * the leaves that need the network (azb_nn_rows_ptr / azb_nn_count_ptr in azb200.h): a terminal leaf's value is its
+ * win state and the reference discards the network's answer for it (MCTS.pyx:234-235). */
+int azb_nn_forward_tc_rows(const azb_nn_weights *w, const float *obs, float *policy, float *value, const int32_t *rows,
+                           const int32_t *count, int32_t max_batch, void *stream);
 /* test hook: also writes the fp32 activation produced by layer `dump_layer`'s epilogue to
  * dump[ceil(batch/16)*16][frame_rows][channels] (padding rows zero) */
 int azb_nn_forward_tc_debug(const azb_nn_weights *w, const float *obs, float *policy, float *value, int32_t batch,

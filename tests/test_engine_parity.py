@@ -210,3 +210,28 @@ def test_fused_expand_select_launch_is_identical(game):
     so, se = orc.stats(), eng.stats()
     for k in ("sims", "sum_depth", "sum_children", "nodes_created", "terminal_leaves", "moves"):
         assert so[k] == se[k], (k, so[k], se[k])
+
+
+def test_select_lists_the_leaves_that_need_the_network():
+    """azb_nn_rows_ptr / azb_nn_count_ptr after every select: exactly the live slots whose leaf is not terminal
+    (the oracle's terminal_leaves statistic counts the complement), across move-rounds and counter parities."""
+    from _engine_agent import EngineAgent
+    B, sims, rounds = 64, 9, 30
+    nn = FakeNN(4 * 6 * 7, 7, seed=33)
+    eng = EngineAgent("connect4", B, rng="philox", seed=6, temps=C4_TEMPS, max_sims_per_move=sims)
+    e = eng.eng
+    total_listed, before = 0, e.stats()
+    for r in range(rounds):
+        for s in range(sims):
+            t0 = e.stats()["terminal_leaves"]
+            obs = eng.generateBatch()
+            n = int(e._wrap(e.nn_count_ptr(), (1,), "<i4").item())
+            rows = e.nn_rows[:n].cpu().numpy()
+            term = e.stats()["terminal_leaves"] - t0
+            assert n == B - term and len(set(rows.tolist())) == n and rows.min() >= 0 and rows.max() < B
+            total_listed += n
+            eng.processBatch(*nn(obs))
+        eng.playMoves(False)
+    st = e.stats()
+    assert total_listed == (st["sims"] - before["sims"]) - (st["terminal_leaves"] - before["terminal_leaves"])
+    assert st["terminal_leaves"] > 0

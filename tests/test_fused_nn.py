@@ -139,3 +139,29 @@ def test_tc_kernel_layer_by_layer(depth):
         torch.cuda.synchronize()
         err = (got - w.permute(0, 2, 3, 1)).abs().max().item()
         assert err < 3e-2, (l, err)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch,keep", [(8192, 0.85), (1000, 0.5), (64, 0.1), (40, 0.0)])
+def test_tc_compact_rows_equal_dense(batch, keep):
+    """azb_nn_forward_tc_rows: the listed rows get bit-identical answers to the dense evaluation, the others are left
+    untouched; the row count is read from device memory (wave shaping on the device)."""
+    from azb200.fused_nn import FusedResNetEvaluator
+    dev = torch.device("cuda")
+    m = _model().to(dev)
+    obs = _obs(batch).to(dev)
+    pol = torch.zeros(batch, 7, device=dev); val = torch.zeros(batch, 3, device=dev)
+    FusedResNetEvaluator(m, obs, pol, val, kernel="tc")()
+    rs = np.random.RandomState(batch)
+    sel = np.flatnonzero(rs.random_sample(batch) < keep).astype(np.int32)
+    rs.shuffle(sel)
+    rows = torch.zeros(batch, dtype=torch.int32, device=dev)
+    rows[:len(sel)] = torch.from_numpy(sel).to(dev)
+    count = torch.tensor([len(sel)], dtype=torch.int32, device=dev)
+    pol2 = torch.full((batch, 7), -1.0, device=dev); val2 = torch.full((batch, 3), -1.0, device=dev)
+    FusedResNetEvaluator(m, obs, pol2, val2, kernel="tc", rows=rows, count=count)()
+    torch.cuda.synchronize()
+    mask = torch.zeros(batch, dtype=torch.bool, device=dev)
+    mask[torch.from_numpy(sel).long().to(dev)] = True
+    assert torch.equal(pol2[mask], pol[mask]) and torch.equal(val2[mask], val[mask])
+    assert bool((pol2[~mask] == -1).all()) and bool((val2[~mask] == -1).all())
