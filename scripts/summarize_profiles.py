@@ -16,7 +16,7 @@ def to_bytes(v, unit):
     m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     return float(v.replace(",", "")) * m.get(unit, 1)
 traffic = {}
-for k in ("select", "expand", "resnet", "warmup"):
+for k in ("select", "expand", "expand_select", "resnet", "warmup"):
     rep = os.path.join(SRC, f"prof_{k}.ncu-rep")
     if not os.path.exists(rep): continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
