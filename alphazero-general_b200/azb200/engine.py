@@ -175,6 +175,18 @@ class SelfPlayEngine:
     def play_moves(self, fast=False, stream=None):
         check(self.lib.azb_play_moves(self.h, int(bool(fast)), self._stream(stream)))
 
+    # ---- single-tree API (azb200.mcts.MCTS) --------------------------------------------------------------
+    def set_state(self, slot, cells, turns, stream=None):
+        cells = np.ascontiguousarray(cells, dtype=np.int8).ravel()
+        assert cells.size == self.ncells
+        check(self.lib.azb_set_state(self.h, int(slot), cells.ctypes.data_as(C.c_void_p), int(turns), self._stream(stream)))
+
+    def force_move(self, slot, action, stream=None):
+        check(self.lib.azb_force_move(self.h, int(slot), int(action), self._stream(stream)))
+
+    def set_root_flags(self, add_root_noise, add_root_temp):
+        check(self.lib.azb_set_root_flags(self.h, int(bool(add_root_noise)), int(bool(add_root_temp))))
+
     def arena_players(self, stream=None):
         """arena mode: device int32 [B]: env player whose tree searches in each slot this round, -1 = idle slot."""
         import torch

@@ -26,14 +26,16 @@ from .engine import SelfPlayEngine, default_temp_scaling, temp_table
 
 def game_name(game_cls):
     """DeviceRules registry: which CUDA rule set implements this Game plugin."""
-    mod = getattr(game_cls, "__module__", "") or ""
     name = getattr(game_cls, "AZB_GAME", None)
     if name:
         return name
-    if "connect4" in mod:
-        return "connect4"
-    if "brandubh" in mod:
-        return "brandubh"
+    mod = getattr(game_cls, "__module__", "") or ""
+    for c in getattr(game_cls, "__mro__", (game_cls,)):          # a subclass of a known plugin keeps its rules
+        m = getattr(c, "__module__", "") or ""
+        if "connect4" in m:
+            return "connect4"
+        if "brandubh" in m:
+            return "brandubh"
     raise NotImplementedError(f"no device rules for game plugin {game_cls!r} (module {mod})")
 
 

@@ -60,6 +60,19 @@ struct Brandubh {
         return 0;
     }
 
+    // inverse of cell_code: Board._state codes -> bitboards (a captured king ends the game, so a state that can be
+    // searched has the flag clear)
+    __device__ __forceinline__ static void from_cells(GState &s, const signed char *cells, int turns)
+    {
+        s.b0 = s.b1 = s.b2 = 0ULL;
+        for (int i = 0; i < CELLS; i++) {
+            const unsigned long long bit = 1ULL << i;
+            const int v = cells[i];
+            if (v == 1) s.b0 |= bit; else if (v == 2) s.b1 |= bit; else if (v == 3 || v == 7 || v == 8) s.b2 |= bit;
+        }
+        s.turns = turns; s.flags = 0;
+    }
+
     // fastafl.pyx get_move
     __device__ __forceinline__ static void decode(int a, int &x, int &y, int &nx, int &ny)
     {

@@ -107,6 +107,18 @@ struct Connect4T {
         return (int)((s.b0 >> bit) & 1ULL) - (int)((s.b1 >> bit) & 1ULL);
     }
 
+    // inverse of cell_code: Board.pieces (row-major, row 0 = top, +1 / -1 / 0) -> bitboards
+    __device__ __forceinline__ static void from_cells(GState &s, const signed char *cells, int turns)
+    {
+        s.b0 = s.b1 = s.b2 = 0ULL;
+        for (int i = 0; i < CELLS; i++) {
+            const int r = i / W, c = i - r * W;
+            const unsigned long long bit = 1ULL << (c * 7 + (H - 1 - r));
+            if (cells[i] > 0) s.b0 |= bit; else if (cells[i] < 0) s.b1 |= bit;
+        }
+        s.turns = turns; s.flags = 0;
+    }
+
     __device__ __forceinline__ static unsigned long long mirror(unsigned long long b)
     {
         unsigned long long r = 0;

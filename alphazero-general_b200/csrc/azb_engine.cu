@@ -110,6 +110,14 @@ template <class G> static void l_arena_players(azb_engine *e, int *out, cudaStre
 {
     k_arena_players<G><<<(e->d.B + 127) / 128, 128, 0, s>>>(e->d, out);
 }
+template <class G> static void l_set_state(azb_engine *e, int slot, const signed char *cells, int turns, cudaStream_t s)
+{
+    k_set_state<G><<<1, 32, 0, s>>>(e->d, slot, cells, turns);
+}
+template <class G> static void l_force_move(azb_engine *e, int slot, int action, cudaStream_t s)
+{
+    k_force_move<G><<<1, CTA_THREADS, 0, s>>>(e->d, slot, action);
+}
 template <class G> static void l_warmup(azb_engine *e, int sims, cudaStream_t s)
 {
     k_warmup_sims<G><<<grid_for<G>(e->d.B), CTA_THREADS, 0, s>>>(e->d, sims);
@@ -368,6 +376,38 @@ extern "C" int azb_play_moves(azb_engine *e, int32_t fast, void *stream)
     DISPATCH(e, l_play, e, fast, s);
     e->d.nn_par = 1;                    // the next select uses counter 0 (k_finalize cleared both)
     CK(cudaGetLastError());
+    return AZB_OK;
+}
+
+extern "C" int azb_set_state(azb_engine *e, int32_t slot, const int8_t *cells, int32_t turns, void *stream)
+{
+    if (!e || !cells) return fail(AZB_ERR_BAD_ARGUMENT, "null argument");
+    if (slot < 0 || slot >= e->d.B || turns < 0) return fail(AZB_ERR_BAD_ARGUMENT, "slot %d / turns %d", slot, turns);
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(e->scratch_i8, cells, (size_t)e->gd.cells, cudaMemcpyHostToDevice, s));
+    DISPATCH(e, l_set_state, e, slot, (const signed char *)e->scratch_i8, turns, s);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    return AZB_OK;
+}
+
+extern "C" int azb_force_move(azb_engine *e, int32_t slot, int32_t action, void *stream)
+{
+    if (!e) return fail(AZB_ERR_BAD_ARGUMENT, "null engine");
+    if (slot < 0 || slot >= e->d.B || action < 0 || action >= e->gd.A)
+        return fail(AZB_ERR_BAD_ARGUMENT, "slot %d / action %d", slot, action);
+    cudaStream_t s = (cudaStream_t)stream;
+    DISPATCH(e, l_force_move, e, slot, action, s);
+    CK(cudaGetLastError());
+    return AZB_OK;
+}
+
+extern "C" int azb_set_root_flags(azb_engine *e, int32_t add_root_noise, int32_t add_root_temp)
+{
+    if (!e) return fail(AZB_ERR_BAD_ARGUMENT, "null engine");
+    if (e->d.arena && (add_root_noise || add_root_temp)) return fail(AZB_ERR_BAD_ARGUMENT, "arena mode has no root noise / temperature");
+    e->d.add_noise = add_root_noise ? 1 : 0;
+    e->d.add_temp = add_root_temp ? 1 : 0;
     return AZB_OK;
 }
 

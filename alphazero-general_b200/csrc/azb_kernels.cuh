@@ -1051,6 +1051,32 @@ __global__ void k_root_counts(DevView d, int *out)
     for (int k = 0; k < C; k++) out[(size_t)g * G::A + meta_action(d.cold[cb + k].meta)] = d.hot[cb + k].n;
 }
 
+// Single-tree API (MCTS.search on an arbitrary position): put a slot on a given position with an empty tree ...
+template <class G>
+__global__ void k_set_state(DevView d, int g, const signed char *cells, int turns)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    SlotHead H = load_head(d.head + g);
+    G::from_cells(H.st, cells, turns);
+    tree_reset(H);
+    store_head(d.head + g, H);
+    LeafInfo li; li.leaf = -1; li.depth = 0; li.child0 = -1; li.meta = 0u;
+    d.leafinfo[g] = li;
+    d.hist_len[g] = 0; d.next_reset[g] = 0; d.noise_event[g] = 0; d.last_action[g] = -1; d.fin_code[g] = 0; d.emit_off[g] = -1;
+}
+
+// ... and MCTS.update_root(gs, action) + gs.play_action(action) for one slot (MCTS.pyx:185-195): the root follows a
+// move decided by the caller; an unexpanded root draws the shuffle of its children first.  No terminal handling:
+// a finished game just stops being searched until the slot is set to a new position.
+template <class G>
+__global__ void __launch_bounds__(CTA_THREADS) k_force_move(DevView d, int g0, int action)
+{
+    __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
+    int g, lane, sub, gi; bool active;
+    if (!group_setup<G>(g0, 1, g, active, lane, sub, gi)) return;
+    play_move_game<G>(d, g, active, 1, lane, sub, sm[gi], action);
+}
+
 // arena: which env player's tree searches in each slot this round (-1: idle tree / finished game)
 template <class G>
 __global__ void k_arena_players(DevView d, int *out)

@@ -165,6 +165,17 @@ int azb_expand_backup_select(azb_engine *e, int32_t first, int32_t count,
  * play_action, terminal handling (result, quota, sample emission with
  * symmetries, game/tree reset). Acts on all slots. */
 int azb_play_moves(azb_engine *e, int32_t fast, void *stream);
+/* ---- single-tree API: MCTS.search / update_root on a caller's position (MCTS.pyx:154-195) -------------------------
+ * azb_set_state: slot `slot` restarts from the position given as the reference's cell codes (the layout azb_boards
+ * returns: Connect4 Board.pieces +1/-1/0; brandubh Board._state codes), host int8 [H*W], with `turns` moves played,
+ * and an empty tree (MCTS.reset).  Synchronous.
+ * azb_force_move: MCTS.update_root(gs, action) followed by gs.play_action(action) for one slot -- the root follows a
+ * move the caller decided (an unexpanded root first draws the shuffle of its children, as update_root does); an
+ * action that is not legal raises AZB_ERR_INVALID_ACTION at the next azb_check_errors (ValueError, MCTS.pyx:195).
+ * azb_set_root_flags: the add_root_noise / add_root_temp arguments of MCTS.search for the following simulations. */
+int azb_set_state(azb_engine *e, int32_t slot, const int8_t *cells, int32_t turns, void *stream);
+int azb_force_move(azb_engine *e, int32_t slot, int32_t action, void *stream);
+int azb_set_root_flags(azb_engine *e, int32_t add_root_noise, int32_t add_root_temp);
 /* arena mode: players[slot] = env player whose tree this slot holds if it searches in the current simulation round
  * (the player to move of a live game), -1 for the idle tree of the pair and for finished games.  Device int32 [B],
  * asynchronous on `stream`.  The caller maps players to models (SelfPlayAgent.player_to_index) and evaluates the
