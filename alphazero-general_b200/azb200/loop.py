@@ -1,0 +1,141 @@
+"""BASELINE config 5 on one process per GPU: the iteration loop of alphazero/Coach.py (learn, Coach.py:225-289) with every
+phase on the device -- self-play on the engine (coach.run_selfplay_iteration), the sample window on the GPU
+(samples.SampleWindow), training through the loop body of NNetWrapper.train (NNetWrapper.py:122-190) over that
+window, the comparison with the self-play model as a batched arena on the engine (arena.play_games) and the
+reference's gating rule (Coach.compareToPast, Coach.py:528-570).
+
+With torch.distributed initialised (one rank per GPU) self-play shards by game and the examples are gathered to rank
+0 (azb200.distributed), which trains and gates and broadcasts the accepted weights; without it everything runs on one
+GPU.  The reference's GUI fields, tensorboard writer and checkpoint files are not part of this loop.
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import nnet as aznet
+from .arena import arena_engine, play_games
+from .coach import run_selfplay_iteration
+from .samples import SampleWindow, loss_pi, loss_v
+
+DEFAULTS = dict(
+    numIters=2, numWarmupIters=1, gamesPerIteration=256, process_batch_size=256, numMCTSSims=100, numFastSims=20,
+    numWarmupSims=5, probFastSim=0.75, train_batch_size=1024, train_steps_per_iteration=64, autoTrainSteps=True,
+    averageTrainSteps=False, minTrainHistoryWindow=4, maxTrainHistoryWindow=20, trainHistoryIncrementIters=2,
+    lr=1e-2, momentum=0.9, weight_decay=1e-4, value_loss_weight=1.5, compareWithPast=True, pastCompareFreq=1,
+    arenaCompare=128, arenaTemp=0.25, model_gating=True, max_gating_iters=None, min_next_model_winrate=0.52,
+    use_draws_for_winrate=True, cpuct=1.25, fpu_reduction=0.2, root_noise_frac=0.1, root_policy_temp=1.1,
+    add_root_noise=True, add_root_temp=True, symmetricSamples=True, mctsResetThreshold=None, startTemp=1)
+
+
+class _A(dict):
+    __getattr__ = dict.__getitem__
+
+
+def train_steps(wrapper, optimizer, loader, steps, value_loss_weight):
+    """The loop body of NNetWrapper.train (NNetWrapper.py:131-165): -> (mean policy loss, mean value loss)."""
+    net = wrapper.nnet
+    net.train()
+    lp_sum = lv_sum = n = 0.0
+    step = 0
+    while step < steps:
+        for boards, target_pis, target_vs in loader:
+            if step == steps:
+                break
+            step += 1
+            out_pi, out_v = net(boards)
+            l_pi, l_v = loss_pi(target_pis, out_pi), loss_v(target_vs, out_v, value_loss_weight)
+            optimizer.zero_grad()
+            (l_pi + l_v).backward()
+            optimizer.step()
+            b = boards.size(0)
+            lp_sum += float(l_pi.detach()) * b; lv_sum += float(l_v.detach()) * b; n += b
+    net.eval()
+    return (lp_sum / n, lv_sum / n) if n else (0.0, 0.0)
+
+
+def winrate_of_first(wins, draws, use_draws):
+    """Arena.__update_winrates / PlayerStats.update (Arena.pyx:124-130): draws count half for everybody."""
+    games = sum(wins) + (draws if use_draws else 0)
+    return ((wins[0] + (draws if use_draws else 0) / len(wins)) / games) if games else 0.0
+
+
+class GpuCoach:
+    def __init__(self, game_cls, args=None, device=0, seed=0, net_args=None):
+        self.game_cls = game_cls
+        self.args = _A(DEFAULTS)
+        self.args.update(args or {})
+        self.device, self.seed = device, seed
+        self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        torch.manual_seed(seed)
+        dev = torch.device("cuda", device)
+        mk = lambda: aznet.NNetWrapper(nnet=aznet.ResNet(tuple(game_cls.observation_size()), game_cls.action_size(), 3,
+                                                         **(net_args or aznet.DEFAULT_NET_ARGS)).to(dev), cuda=True, fused=True)
+        self.train_net, self.self_play_net = mk(), mk()
+        self.self_play_net.nnet.load_state_dict(self.train_net.nnet.state_dict())
+        self.optimizer = torch.optim.SGD(self.train_net.nnet.parameters(), lr=self.args.lr, momentum=self.args.momentum,
+                                         weight_decay=self.args.weight_decay)
+        self.window = SampleWindow(device=dev)
+        self.self_play_iter, self.gating_counter = 0, 0
+        self.history = []
+
+    def _fresh(self, wrapper):
+        wrapper._fused_eval = {}             # folded weights are snapshots: rebuild after the weights changed
+
+    def learn(self):
+        a = self.args
+        for it in range(1, a.numIters + 1):
+            rec = dict(iteration=it)
+            warmup = it <= a.numWarmupIters or self.self_play_iter == 0          # Coach.py:232-238
+            t0 = time.time()
+            res = run_selfplay_iteration(self.game_cls, self.self_play_net.nnet, dict(a, gamesPerIteration=a.gamesPerIteration // self.world),
+                                         device=self.device, seed=self.seed + 1000 * it + self.rank, warmup=warmup,
+                                         game_id_base=self.rank * a.process_batch_size)
+            obs, pi, z = res.data.cuda(self.device), res.policy.cuda(self.device), res.value.cuda(self.device)
+            if self.world > 1:
+                from .distributed import gather_examples_to_rank0
+                obs, pi, z = gather_examples_to_rank0(obs, pi, z)
+            rec.update(selfplay_seconds=time.time() - t0, sims=res.sims, warmup=warmup,
+                       samples=int(obs.shape[0]) if self.rank == 0 else 0, game_results=res.game_results())
+            if self.rank == 0:
+                self.window.add_iteration(it, obs, pi, z)
+                self.window.evict_before(it - a.maxTrainHistoryWindow)
+                loader, used = self.window.loader(it, a)
+                steps = self.window.train_steps(used, a)
+                t0 = time.time()
+                rec["loss_pi"], rec["loss_v"] = train_steps(self.train_net, self.optimizer, loader, steps, a.value_loss_weight)
+                rec.update(train_steps=steps, train_seconds=time.time() - t0, window=used)
+                self._fresh(self.train_net)
+                if a.compareWithPast and (it - 1) % a.pastCompareFreq == 0:
+                    rec.update(self.compare_to_past(it))
+            if self.world > 1:                                                # everybody self-plays with rank 0's decision
+                for p in list(self.self_play_net.nnet.parameters()) + list(self.self_play_net.nnet.buffers()):
+                    torch.distributed.broadcast(p.data, 0)
+                self._fresh(self.self_play_net)
+            self.history.append(rec)
+        return self.history
+
+    def compare_to_past(self, model_iter):
+        """Coach.compareToPast (Coach.py:528-570): new net (model 0) against the self-play net, gating."""
+        a = self.args
+        eng = arena_engine(self.game_cls, dict(a, gamesPerIteration=a.arenaCompare), min(a.arenaCompare, 4096), device=self.device,
+                           rng="philox", seed=self.seed + 7 * model_iter)
+        rs = np.random.RandomState(self.seed + model_iter)
+        p2i = [0, 1]
+        rs.shuffle(p2i)                                                       # SelfPlayAgent.pyx:44-46
+        t0 = time.time()
+        wins, draws, mean_turns, sims = play_games(eng, [self.train_net, self.self_play_net], tuple(p2i), sims=a.numMCTSSims)
+        eng.close()
+        winrate = winrate_of_first(wins, draws, a.use_draws_for_winrate)
+        out = dict(arena_wins=wins, arena_draws=draws, arena_winrate=winrate, arena_seconds=time.time() - t0, arena_sims=sims)
+        if a.model_gating and winrate < a.min_next_model_winrate and (a.max_gating_iters is None or self.gating_counter < a.max_gating_iters):
+            self.gating_counter += 1
+            out["accepted"] = False
+        else:
+            self.self_play_iter = model_iter
+            self.self_play_net.nnet.load_state_dict(self.train_net.nnet.state_dict())
+            self._fresh(self.self_play_net)
+            self.gating_counter = 0
+            out["accepted"] = True
+        return out
