@@ -60,6 +60,9 @@ SYMBOLS = {
     "azb_play_moves": (C.c_int, [_vp, _i32, _vp]),
     "azb_warmup_sims": (C.c_int, [_vp, _i32, _vp]),
     "azb_arena_players": (C.c_int, [_vp, _vp, _vp]),
+    "azb_arena_set_player_to_index": (C.c_int, [_vp, _i32]),
+    "azb_arena_rows_ptr": (_vp, [_vp, _i32]),
+    "azb_arena_count_ptr": (_vp, [_vp, _i32]),
     "azb_set_state": (C.c_int, [_vp, _i32, _vp, _i32, _vp]),
     "azb_force_move": (C.c_int, [_vp, _i32, _i32, _vp]),
     "azb_set_root_flags": (C.c_int, [_vp, _i32, _i32]),

@@ -61,15 +61,22 @@ def play_games(engine, models, player_to_index=(0, 1), sims=None, stop_event=Non
     wins, draws, turns = [0] * len(models), 0, []
     quota = engine.quota
     t0 = time.time()
+    # fast path: both models are NNetWrappers whose network the tcgen05 evaluator covers -- every simulation is
+    # select -> model 0 on its row list -> model 1 on its row list -> expand/backup, all on the device, no host sync
+    evals = _fused_evaluators(engine, models, player_to_index)
     while engine.games_played() < quota and not (stop_event is not None and stop_event.is_set()):
         for _ in range(sims):
             engine.select()
-            for m, rows in enumerate(rnd.rows_by_model()):
-                if rows.numel() == 0:
-                    continue
-                pi, v = models[m].process(engine.obs.index_select(0, rows))
-                engine.policy.index_copy_(0, rows, pi.to(engine.policy.dtype))
-                engine.value.index_copy_(0, rows, v.to(engine.value.dtype))
+            if evals is not None:
+                for ev in evals:
+                    ev()
+            else:
+                for m, rows in enumerate(rnd.rows_by_model()):
+                    if rows.numel() == 0:
+                        continue
+                    pi, v = models[m].process(engine.obs.index_select(0, rows))
+                    engine.policy.index_copy_(0, rows, pi.to(engine.policy.dtype))
+                    engine.value.index_copy_(0, rows, v.to(engine.value.dtype))
             engine.expand_backup()
         engine.play_moves(False)
         engine.check_errors()
@@ -84,6 +91,19 @@ def play_games(engine, models, player_to_index=(0, 1), sims=None, stop_event=Non
         if progress is not None and len(slot):
             progress(len(turns), time.time() - t0)
     return wins, draws, (float(np.mean(turns)) if turns else 0.0), engine.stats()["sims"]
+
+
+def _fused_evaluators(engine, models, player_to_index):
+    """One compact tcgen05 evaluator per model over the engine's per-model row lists, or None."""
+    if len(models) != 2 or not all(getattr(m, "fused", False) and hasattr(m, "nnet") for m in models):
+        return None
+    from .fused_nn import FusedResNetEvaluator, supported_tc
+    if not all(supported_tc(m.nnet) for m in models) or tuple(engine.obs_shape[1:]) != (6, 7):
+        return None
+    engine.arena_set_player_to_index(player_to_index)
+    return [FusedResNetEvaluator(m.nnet, engine.obs, engine.policy, engine.value, kernel="tc", rows=engine.arena_rows(k),
+                                 count=(lambda k=k: engine.arena_count_ptr(k)), max_batch=engine.B // 2)
+            for k, m in enumerate(models)]
 
 
 class ArenaAgent(threading.Thread):

@@ -187,6 +187,17 @@ class SelfPlayEngine:
     def set_root_flags(self, add_root_noise, add_root_temp):
         check(self.lib.azb_set_root_flags(self.h, int(bool(add_root_noise)), int(bool(add_root_temp))))
 
+    def arena_set_player_to_index(self, player_to_index):
+        """arena: SelfPlayAgent.player_to_index = [m, 1 - m]; the per-model row lists follow it."""
+        check(self.lib.azb_arena_set_player_to_index(self.h, int(player_to_index[0])))
+
+    def arena_rows(self, model):
+        """arena: device int32 [B / 2] view of the rows model `model` has to evaluate (after select)."""
+        return self._wrap(self.lib.azb_arena_rows_ptr(self.h, int(model)), (self.B // 2,), "<i4")
+
+    def arena_count_ptr(self, model):
+        return int(self.lib.azb_arena_count_ptr(self.h, int(model)))
+
     def arena_players(self, stream=None):
         """arena mode: device int32 [B]: env player whose tree searches in each slot this round, -1 = idle slot."""
         import torch

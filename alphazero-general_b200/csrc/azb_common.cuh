@@ -90,7 +90,9 @@ struct DevView {
     // NN I/O
     float *obs; float *policy; float *value;
     int *nn_rows; int *nn_count;       // slots whose leaf needs the network (non-terminal), filled by select;
-    int nn_par;                        // nn_count[2]: select adds to [nn_par] and clears [nn_par ^ 1] for the next one
+    int nn_par;                        // nn_count[2][2]: select adds to [nn_par][model] and clears [nn_par ^ 1][*] for the next one
+    int arena_swap;                    // arena: model = env player ^ arena_swap (SelfPlayAgent.player_to_index); rows of model m
+                                       // are listed at nn_rows + m * (B / 2)
     const float *warm_policy; const float *warm_value;
     // fed root noise
     const float *noise; int noise_events, noise_stride;

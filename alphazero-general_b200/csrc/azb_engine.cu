@@ -230,7 +230,7 @@ extern "C" int azb_create(const azb_config *cfg, azb_engine **out)
     const int obs = gd.obs_c * gd.obs_h * gd.obs_w;
     A_(dev_alloc(e, &d.obs, (size_t)B * obs)); A_(dev_alloc(e, &d.policy, (size_t)B * gd.A));
     A_(dev_alloc(e, &d.value, (size_t)B * 3));
-    A_(dev_alloc(e, &d.nn_rows, (size_t)B)); A_(dev_alloc(e, &d.nn_count, 2));
+    A_(dev_alloc(e, &d.nn_rows, (size_t)B)); A_(dev_alloc(e, &d.nn_count, 4));
     float *wp = nullptr, *wv = nullptr;
     A_(dev_alloc(e, &wp, gd.A)); A_(dev_alloc(e, &wv, 3));
     // queues
@@ -323,7 +323,21 @@ extern "C" float *azb_obs_ptr(azb_engine *e) { return e ? e->d.obs : nullptr; }
 extern "C" float *azb_policy_ptr(azb_engine *e) { return e ? e->d.policy : nullptr; }
 extern "C" float *azb_value_ptr(azb_engine *e) { return e ? e->d.value : nullptr; }
 extern "C" int32_t *azb_nn_rows_ptr(azb_engine *e) { return e ? e->d.nn_rows : nullptr; }
-extern "C" int32_t *azb_nn_count_ptr(azb_engine *e) { return e ? e->d.nn_count + e->d.nn_par : nullptr; }
+extern "C" int32_t *azb_nn_count_ptr(azb_engine *e) { return e ? e->d.nn_count + 2 * e->d.nn_par : nullptr; }
+extern "C" int32_t *azb_arena_rows_ptr(azb_engine *e, int32_t model)
+{
+    return (e && e->d.arena && (model == 0 || model == 1)) ? e->d.nn_rows + (size_t)model * (size_t)(e->d.B / 2) : nullptr;
+}
+extern "C" int32_t *azb_arena_count_ptr(azb_engine *e, int32_t model)
+{
+    return (e && e->d.arena && (model == 0 || model == 1)) ? e->d.nn_count + 2 * e->d.nn_par + model : nullptr;
+}
+extern "C" int azb_arena_set_player_to_index(azb_engine *e, int32_t model_of_player0)
+{
+    if (!e || !e->d.arena || (model_of_player0 != 0 && model_of_player0 != 1)) return fail(AZB_ERR_BAD_ARGUMENT, "arena engine, model 0 or 1");
+    e->d.arena_swap = model_of_player0;
+    return AZB_OK;
+}
 
 static int range_ok(azb_engine *e, int32_t first, int32_t &count)
 {

@@ -438,8 +438,11 @@ __device__ __forceinline__ void select_game(const DevView &d, int g, bool active
         if (active) G::write_obs(st, d.obs + (size_t)g * G::OBS, lane);
         // the leaves the network has to evaluate: a terminal leaf's value is its win state (MCTS.pyx:234-235)
         if (active && in_range && lane == 0 && meta_e(cmeta) == 0) {
-            const unsigned idx = (unsigned)atomicAdd(d.nn_count + d.nn_par, 1);
-            if (idx < (unsigned)d.B) d.nn_rows[idx] = g;
+            // arena: one list per model (the model of env player p is p ^ arena_swap), each at most B / 2 long
+            const int m = d.arena ? ((g & 1) ^ d.arena_swap) : 0;
+            const unsigned cap = d.arena ? (unsigned)(d.B / 2) : (unsigned)d.B;
+            const unsigned idx = (unsigned)atomicAdd(d.nn_count + 2 * d.nn_par + m, 1);
+            if (idx < cap) d.nn_rows[(size_t)m * cap + idx] = g;
         }
     }
     if (lane == 0 && in_range) {
@@ -840,7 +843,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_select(DevView d, int first, in
 {
     __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
     int g, lane, sub, gi; bool active;
-    if (blockIdx.x == 0 && threadIdx.x == 0) d.nn_count[d.nn_par ^ 1] = 0;      // consumed by the previous evaluation
+    if (blockIdx.x == 0 && threadIdx.x == 0) { d.nn_count[2 * (d.nn_par ^ 1)] = 0; d.nn_count[2 * (d.nn_par ^ 1) + 1] = 0; }   // consumed
     if (!group_setup<G>(first, count, g, active, lane, sub, gi)) return;
     select_game<G, true>(d, g, active, lane, sub, sm[gi]);
 }
@@ -862,7 +865,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_expand_select(DevView d, int fi
 {
     __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
     int g, lane, sub, gi; bool active;
-    if (blockIdx.x == 0 && threadIdx.x == 0) d.nn_count[d.nn_par ^ 1] = 0;      // consumed by the previous evaluation
+    if (blockIdx.x == 0 && threadIdx.x == 0) { d.nn_count[2 * (d.nn_par ^ 1)] = 0; d.nn_count[2 * (d.nn_par ^ 1) + 1] = 0; }   // consumed
     if (!group_setup<G>(first, count, g, active, lane, sub, gi)) return;
     if (G::A > G::LANES) { for (int a = lane; a < G::A; a += G::LANES) sm[gi].vec[a] = 0.0f; __syncwarp(); }
     expand_backup_game<G>(d, g, active, lane, sub, sm[gi], policy + (size_t)g * G::A, value + (size_t)g * 3);
@@ -978,7 +981,7 @@ __global__ void __launch_bounds__(1024) k_finalize(DevView d)
         __syncthreads();
     }
     if (tid == 0) {
-        d.nn_count[0] = 0; d.nn_count[1] = 0;           // every move-round starts with parity 0 and empty lists
+        d.nn_count[0] = d.nn_count[1] = d.nn_count[2] = d.nn_count[3] = 0;   // every move-round starts with parity 0 and empty lists
         long long rc = s_base[0] < d.r_cap ? s_base[0] : d.r_cap;
         d.counters->results += s_base[0] - d.counters->result_count;
         d.counters->result_count = rc;

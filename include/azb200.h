@@ -181,6 +181,14 @@ int azb_set_root_flags(azb_engine *e, int32_t add_root_noise, int32_t add_root_t
  * asynchronous on `stream`.  The caller maps players to models (SelfPlayAgent.player_to_index) and evaluates the
  * active rows of azb_obs_ptr with them (Arena.pyx:262-275). */
 int azb_arena_players(azb_engine *e, int32_t *players_device, void *stream);
+/* arena mode, device-resident evaluation: SelfPlayAgent.player_to_index is [m, 1 - m] with m = model_of_player0
+ * (default 0); azb_select then lists the slots whose leaf needs model k (non-terminal leaves of the games where the
+ * player of model k is to move) at azb_arena_rows_ptr(e, k) (device int32 [num_games / 2]) with their number at
+ * azb_arena_count_ptr(e, k) (the counter of the LAST select call, as azb_nn_count_ptr) -- the batches
+ * SelfPlayAgent.generateBatch builds per player (SelfPlayAgent.pyx:113-131), without leaving the device. */
+int azb_arena_set_player_to_index(azb_engine *e, int32_t model_of_player0);
+int32_t *azb_arena_rows_ptr(azb_engine *e, int32_t model);
+int32_t *azb_arena_count_ptr(azb_engine *e, int32_t model);
 /* `sims` x (generateBatch + processBatch) with the warmup constants policy =
  * 1/A, value = 1/3 (SelfPlayAgent.pyx:48-52,111-114) in ONE kernel launch:
  * the NN-free tree-only mode (numWarmupSims). */

@@ -119,3 +119,26 @@ def test_arena_agent_under_the_reference_server_loop():
     _, turns, win = orc.results()
     assert [int(r[0].turns) for r in results] == turns.tolist()
     assert np.array_equal(np.stack([r[1] for r in results]), win)
+
+
+def test_fused_two_model_evaluation_equals_the_generic_path(monkeypatch):
+    """play_games with two real networks: the device-resident path (per-model row lists from select, compact tcgen05
+    evaluation, no host synchronisation per simulation) against gather / NNetWrapper.process / scatter."""
+    import azb200.arena as az_arena
+    from azb200 import nnet as aznet
+    B, sims, quota = 96, 10, 150
+    nets = []
+    for s in (1, 2):
+        torch.manual_seed(s)
+        nets.append(aznet.NNetWrapper(nnet=aznet.ResNet((4, 6, 7), 7, 3, **aznet.DEFAULT_NET_ARGS).cuda().eval(), cuda=True,
+                                      fused=True))
+    out = []
+    for fast in (True, False):
+        if not fast:
+            monkeypatch.setattr(az_arena, "_fused_evaluators", lambda *a, **k: None)
+        eng = az_arena.arena_engine(_C4Game, _args(sims, quota), B, rng="philox", seed=11)
+        out.append(az_arena.play_games(eng, nets, (1, 0), sims=sims))
+        eng.close()
+    assert out[0] == out[1]
+    wins, draws, _, nsims = out[0]
+    assert sum(wins) + draws == quota and nsims > quota * sims
