@@ -107,14 +107,17 @@ class NNetWrapper:
 
     def _process_fused(self, batch):
         n = batch.shape[0]
-        ev = self._fused_eval.get(n)
+        # one evaluator (device staging rows + folded weights) per caller tensor: agents served on different streams
+        # must not share staging buffers
+        key = (n, batch.data_ptr() if not batch.is_cuda else 0)
+        ev = self._fused_eval.get(key)
         if ev is None:
             from .fused_nn import FusedResNetEvaluator
             dev = next(self.nnet.parameters()).device
             obs = torch.empty((n,) + tuple(batch.shape[1:]), device=dev)
             ev = FusedResNetEvaluator(self.nnet, obs, torch.empty(n, self.nnet.action_size, device=dev),
                                       torch.empty(n, 3, device=dev))
-            self._fused_eval[n] = ev
+            self._fused_eval[key] = ev
         upload(ev.obs, batch)
         ev()
         return ev.policy, ev.value
@@ -131,11 +134,14 @@ class NNetWrapper:
             return torch.exp(pi), torch.exp(v)
 
 
+_UPLOAD_KERNEL = __import__("os").environ.get("AZB_UPLOAD", "sm") != "dma"
+
+
 def upload(dst, src):
     """dst (device) <- src (host), asynchronously on the current stream.  A pinned, contiguous source is read by a
     copy kernel through its device mapping (azb_upload_pinned: a few-MB cudaMemcpyAsync pays a DMA start-up that the
     SM path does not); anything else goes through Tensor.copy_."""
-    if (not src.is_cuda and src.is_pinned() and src.is_contiguous() and dst.is_contiguous() and src.dtype == dst.dtype
+    if (_UPLOAD_KERNEL and not src.is_cuda and src.is_pinned() and src.is_contiguous() and dst.is_contiguous() and src.dtype == dst.dtype
             and src.numel() == dst.numel() and src.data_ptr() % 16 == 0 and dst.data_ptr() % 16 == 0):
         import ctypes as C
         from . import _capi
@@ -174,15 +180,21 @@ class HostBatchServer:
     policy / value into the agent's host tensors -- captured once per agent as a CUDA graph on the server stream and
     ordered against the agent's stream by CUDA events (no host synchronisation)."""
 
-    def __init__(self, wrapper, stream=None):
+    def __init__(self, wrapper, stream=None, stream_per_agent=True):
         self.wrapper = wrapper
         dev = next(wrapper.nnet.parameters()).device
         self.stream = stream or torch.cuda.Stream(device=dev)
+        # one server stream per agent: the upload of one agent's batch overlaps the evaluation of another's
+        self.stream_per_agent, self._streams, self._dev = stream_per_agent, {}, dev
         self._graphs = {}
 
     def serve(self, agent, batch_ready):
         """One served batch of `agent` (whose id came out of the ready queue); `batch_ready` is its host event."""
         S = self.stream
+        if self.stream_per_agent:
+            S = self._streams.get(agent.id)
+            if S is None:
+                S = self._streams[agent.id] = torch.cuda.Stream(device=self._dev)
         S.wait_event(agent.batch_event)
         g = self._graphs.get(agent.id)
         with torch.cuda.stream(S):

@@ -25,6 +25,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/azb200_nn.h"
 
@@ -404,8 +405,11 @@ extern "C" int azb_upload_pinned(void *dst_device, const void *src_pinned_host, 
     if ((((uintptr_t)dst_device) | ((uintptr_t)src_pinned_host)) & 15) return -7;
     const size_t n16 = (size_t)bytes / 16;
     const int tail = (int)(bytes - (int64_t)n16 * 16);
+    // few CTAs: PCIe needs ~100 KB in flight, not SMs -- the upload should leave the SMs to the kernels it overlaps with
+    static int cap = 0;
+    if (cap == 0) { const char *env = getenv("AZB_UPLOAD_CTAS"); cap = env ? atoi(env) : 32; if (cap < 1) cap = 1; }
     int grid = (int)((n16 + 255) / 256);
-    grid = grid < 1 ? 1 : (grid > 592 ? 592 : grid);
+    grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
     k_upload<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4 *>(dst_device), reinterpret_cast<const uint4 *>(src_pinned_host), n16,
                                                      reinterpret_cast<const unsigned char *>(src_pinned_host) + n16 * 16,
                                                      reinterpret_cast<unsigned char *>(dst_device) + n16 * 16, tail);

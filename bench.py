@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--tree-only", action="store_true", help="warmup mode (constant NN outputs), one fused kernel per round")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-agents", type=int, default=2, help="reference `workers`: agents sharing the GPU in the e2e leg")
+    ap.add_argument("--e2e-mode", default="inline", choices=["inline", "threads"],
+                    help="inline: one host thread runs the Coach loop over the agents (generateBatch -> process -> "
+                         "processBatch, every call asynchronous and stream-ordered); threads: agents are threads, ready queue")
     ap.add_argument("--e2e-sync", action="store_true",
                     help="e2e leg with host-synchronised tensors (default: stream-ordered, see SelfPlayAgent)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -574,6 +577,8 @@ def run_e2e(a, eng, model, dev, world):
     srv = torch.cuda.Stream(device=dev)
     from azb200.nnet import HostBatchServer
     server = HostBatchServer(wrap, stream=srv)
+    if a.e2e_mode == "inline" and not a.e2e_sync:
+        return run_e2e_inline(a, eng, agents, server, evs, ready, dev, world, Bw, old_tf32)
     for ag in agents:
         ag.start()
 
@@ -630,6 +635,65 @@ def run_e2e(a, eng, model, dev, world):
             "host_tensor_protocol": "host-synchronised" if a.e2e_sync else "stream-ordered (CUDA events)",
             "api": "Coach.processSelfPlayBatches loop: azb200.selfplay.SelfPlayAgent threads (generateBatch/processBatch/"
                    "playMoves) + NNetWrapper.process, pinned host tensors, ready queue + events"}
+
+
+def run_e2e_inline(a, eng, agents, server, evs, ready, dev, world, Bw, old_tf32):
+    """The same protocol driven by ONE host thread, the way the parity tests drive the reference in-process: per
+    simulation and agent  generateBatch() -> HostBatchServer.serve() (NNetWrapper.process on the host batch tensor,
+    answers into the host policy / value tensors) -> processBatch(), then playMoves().  Every call only enqueues:
+    the host tensors are ordered by CUDA events, each agent has its own stream, so the copies and kernels of
+    different agents overlap on the GPU while no Python thread ever waits for another."""
+    import torch
+    import torch.distributed as dist
+    W = len(agents)
+    for ag in agents:
+        ag.stream = torch.cuda.Stream(device=dev)
+        ag.step_graphs = False
+
+    def one_round():
+        for _ in range(a.sims):
+            for i, ag in enumerate(agents):
+                with torch.cuda.stream(ag.stream):
+                    ag.generateBatch()
+                j = ready.get_nowait()                       # id = self.ready_queue.get() (Coach.py:336)
+                server.serve(agents[j], evs[j])
+                with torch.cuda.stream(ag.stream):
+                    ag.processBatch()
+        for ag in agents:
+            with torch.cuda.stream(ag.stream):
+                ag.playMoves()
+
+    one_round(); one_round()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for ag in agents:
+        ag.h2d_bytes = ag.d2h_bytes = 0
+    n0 = sum(ag.batches for ag in agents)
+    t0 = time.perf_counter()
+    for _ in range(a.e2e_steps):
+        one_round()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    n1 = sum(ag.batches for ag in agents)
+    torch.backends.cudnn.allow_tf32 = old_tf32
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    n = torch.tensor([(n1 - n0) * Bw], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    steps = (n1 - n0) / float(W * a.sims)
+    obs_b, pv_b = eng.B * 4 * 6 * 7 * 4, eng.B * 10 * 4
+    for ag in agents:
+        ag.engine.close()
+    return {"value": float(n.item()) / float(t.item()), "unit": UNIT,
+            "h2d_bytes_per_step": int(a.sims * obs_b + sum(ag.h2d_bytes for ag in agents) / steps),
+            "d2h_bytes_per_step": int(a.sims * pv_b + sum(ag.d2h_bytes for ag in agents) / steps),
+            "steps": steps, "agents": W, "games_per_agent": Bw,
+            "host_tensor_protocol": "stream-ordered (CUDA events)",
+            "api": "Coach.processSelfPlayBatches data flow driven by one host thread: azb200.selfplay.SelfPlayAgent."
+                   "generateBatch -> HostBatchServer.serve (NNetWrapper.process on the pinned host batch tensor) -> "
+                   "processBatch, playMoves; every batch crosses PCIe in both directions"}
 
 
 def gather_examples(kept, dev, rank, world, obs_shape=(4, 6, 7), A=7):
