@@ -503,7 +503,11 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
 #pragma unroll 1
         for (int g = grp; g < total; g += NPBUF) {
             const bool is_c1 = (l & 1) == 1, last = l + 1 == layers;
-            mbar_wait<96>(bar_full, par);
+            // one warp of the group polls the mbarrier, the other seven sleep in a hardware barrier: a third of all
+            // instructions this kernel issued were wait-loop iterations of epilogue warps, competing for issue slots
+            // with the warps that had work
+            if ((e % GRP_WARPS) == 0) mbar_wait<32>(bar_full, par);
+            asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "r"(GRP_WARPS * 32) : "memory");
             par ^= 1u;
             tc_fence_after();
             const int fr = t * 128 + r0;
