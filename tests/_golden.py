@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 import _orc
-from _fakenn import FakeNN
+from _fakenn import ArenaNN, FakeNN
 from _lockstep import run_trace
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -13,8 +13,12 @@ GAME_IDS = {"connect4": _orc.GAME_CONNECT4, "brandubh": _orc.GAME_BRANDUBH}
 DIMS = {"connect4": (4 * 6 * 7, 7, 42), "brandubh": (5 * 7 * 7, 588, None)}
 
 
-def cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+def cases(arena=False):
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and (f[:-4].endswith("_arena") == arena))
+
+
+def is_arena(g):
+    return "arena" in g.files and bool(g["arena"])
 
 
 def load(name):
@@ -24,6 +28,10 @@ def load(name):
 def agent_kwargs(g):
     game = str(g["game"])
     _, _, max_turns = DIMS[game]
+    if is_arena(g):
+        kw = dict(mcts_reset_threshold=int(g["reset_threshold"]), games_per_iteration=int(g["quota"]) or (1 << 40),
+                  arena_temp=float(g["arena_temp"]), player_to_index=g["player_to_index"].tolist())
+        return game, kw
     kw = dict(add_root_temp=bool(g["add_root_temp"]), add_root_noise=bool(g["add_root_noise"]),
               symmetric_samples=bool(g["symmetric"]), mcts_reset_threshold=int(g["reset_threshold"]),
               games_per_iteration=int(g["quota"]) or (1 << 40),
@@ -36,7 +44,10 @@ def replay(agent, g):
     obs_size, A, _ = DIMS[game]
     if bool(g["add_root_noise"]):
         agent.set_root_noise(g["noise"])
-    nn = FakeNN(obs_size, A, seed=int(g["nn_seed"]), sharp=3.0 if A == 7 else 1.0) if int(g["nn_seed"]) >= 0 else None
+    if is_arena(g):
+        nn = ArenaNN(agent, [FakeNN(obs_size, A, seed=int(sd), sharp=3.0 if A == 7 else 1.0) for sd in g["arena_nn_seeds"]])
+    else:
+        nn = FakeNN(obs_size, A, seed=int(g["nn_seed"]), sharp=3.0 if A == 7 else 1.0) if int(g["nn_seed"]) >= 0 else None
     pat = g["fast_pattern"].tolist()
     return run_trace(agent, nn, len(g["counts"]), int(g["sims"]), fast_pattern=pat if any(pat) else None,
                      until_games=int(g["quota"]) or None)

@@ -39,6 +39,12 @@ CASES = {
                                    add_root_temp=False, add_root_noise=False, det_pow=False),
     "tafl_nn_temp_noise": dict(game="brandubh", B=2, seeds=[51, 52], rounds=60, sims=20, nn=99,
                                add_root_temp=True, add_root_noise=True, det_pow=True),
+    # SelfPlayAgent(_is_arena=True): one tree per player, two networks (model of env player p = player_to_index[p]),
+    # arenaTemp, tree reset threshold, quota (deterministic pow: probs uses ** (1 / arenaTemp))
+    "c4_arena": dict(game="connect4", B=4, seeds=[61, 62, 63, 64], rounds=200, sims=12, nn=[101, 102], arena=True,
+                     arena_temp=0.25, player_to_index=[1, 0], add_root_temp=False, det_pow=True, reset_threshold=6, quota=9),
+    "tafl_arena": dict(game="brandubh", B=2, seeds=[71, 72], rounds=45, sims=8, nn=[111, 112], arena=True,
+                       arena_temp=0.5, player_to_index=[0, 1], add_root_temp=False, det_pow=True),
 }
 GAME_DIMS = {"connect4": (4 * 6 * 7, 7), "brandubh": (5 * 7 * 7, 588)}
 
@@ -51,19 +57,27 @@ def make(name, c):
         noise = rs.dirichlet([10.83 / 7] * 7, size=(c["B"], 24)).astype(np.float32)
         if A > 7:
             noise = rs.dirichlet([10.83 / 40] * 96, size=(c["B"], 8)).astype(np.float32)
+    arena = bool(c.get("arena"))
     ref = _refdriver.RefAgent(c["game"], c["B"], mt_seeds=c["seeds"], add_root_temp=c["add_root_temp"],
                               add_root_noise=c.get("add_root_noise", False), det_pow=c["det_pow"], noise=noise,
                               symmetric_samples=c.get("symmetric", True),
                               mcts_reset_threshold=c.get("reset_threshold"),
-                              games_per_iteration=c.get("quota", 1 << 40))
-    nn = FakeNN(obs_size, A, seed=c["nn"], sharp=3.0 if A == 7 else 1.0) if c["nn"] is not None else None
+                              games_per_iteration=c.get("quota", 1 << 40), arena=arena,
+                              arena_temp=c.get("arena_temp", 0.25), player_to_index=c.get("player_to_index"))
+    if arena:
+        from _fakenn import ArenaNN
+        nn = ArenaNN(ref, [FakeNN(obs_size, A, seed=sd, sharp=3.0 if A == 7 else 1.0) for sd in c["nn"]])
+    else:
+        nn = FakeNN(obs_size, A, seed=c["nn"], sharp=3.0 if A == 7 else 1.0) if c["nn"] is not None else None
     tr = run_trace(ref, nn, c["rounds"], c["sims"], fast_pattern=c.get("fast_pattern"), until_games=c.get("quota"))
     s_obs, s_pi, s_z, s_slot = ref.samples()
     r_slot, r_turns, r_win = ref.results()
     out = dict(counts=np.stack([t["counts"] for t in tr]), actions=np.stack([t["actions"] for t in tr]),
                turns=np.stack([t["turns"] for t in tr]), s_obs=s_obs.astype(np.float16 if False else np.float32),
                s_pi=s_pi, s_z=s_z, s_slot=s_slot, r_slot=r_slot, r_turns=r_turns, r_win=r_win,
-               seeds=np.asarray(c["seeds"]), sims=c["sims"], nn_seed=-1 if c["nn"] is None else c["nn"],
+               seeds=np.asarray(c["seeds"]), sims=c["sims"],
+               nn_seed=-1 if (c["nn"] is None or arena) else c["nn"], arena=arena, arena_temp=c.get("arena_temp", 0.25),
+               arena_nn_seeds=np.asarray(c["nn"] if arena else [0, 0]), player_to_index=np.asarray(c.get("player_to_index") or [0, 1]),
                add_root_temp=c["add_root_temp"], add_root_noise=c.get("add_root_noise", False),
                symmetric=c.get("symmetric", True), reset_threshold=c.get("reset_threshold") or 0,
                quota=c.get("quota", 0), fast_pattern=np.asarray(c.get("fast_pattern", [0])),
