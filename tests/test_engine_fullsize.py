@@ -125,3 +125,47 @@ def test_brandubh_4096_games_properties():
             assert np.array_equal(orc.root_counts()[0], counts[r, s]), (s, r)
             orc.playMoves(False)
             assert orc.last_actions()[0] == actions[r, s]
+
+
+def test_arena_4096_games_properties_and_game_spot_checks():
+    """Arena mode at size (4096 games = 8192 slots, 100 sims/move, warmup constants for both models): bookkeeping
+    properties, and single games of the big engine against the oracle's arena mode on the same stream."""
+    from azb200 import SelfPlayEngine
+    G, sims, rounds = 4096, 100, 24
+    eng = SelfPlayEngine("connect4", 2 * G, rng="philox", seed=8, arena=True, temps=np.full(1, 0.25), max_sims_per_move=sims)
+    counts, actions, movers = [], [], []
+    for _ in range(rounds):
+        pl = eng.arena_players().cpu().numpy().reshape(G, 2)
+        assert np.all((pl >= 0).sum(1) == 1)                               # exactly one tree of every live game searches
+        movers.append(pl.max(1))
+        eng.warmup_sims(sims)
+        counts.append(eng.root_counts().reshape(G, 2, 7)[np.arange(G), movers[-1]])
+        eng.play_moves(False)
+        actions.append(eng.last_actions().reshape(G, 2))
+    eng.check_errors()
+    counts, actions, movers = np.stack(counts), np.stack(actions), np.stack(movers)
+    assert np.array_equal(actions[..., 0], actions[..., 1])                # both trees followed the same move
+    actions = actions[..., 0]
+    st = eng.stats()
+    assert st["sims"] == G * sims * rounds and st["moves"] == G * rounds and st["samples"] == 0
+    assert np.all(counts.sum(-1) >= sims - 1)
+    assert np.all(np.take_along_axis(counts, actions[..., None], axis=-1)[..., 0] > 0)
+    rs, rt, rw = eng.drain_results()
+    assert len(rs) == st["results"] == st["games_played"] > G // 2
+    assert np.all(rw.sum(1) == 1) and np.all((rt >= 7) & (rt <= 42)) and rs.max() < G
+    t = eng.turns().reshape(G, 2)
+    assert np.array_equal(t[:, 0], t[:, 1])
+    for g in (0, 1, 2047, 4095):
+        orc = _orc.OracleAgent(_orc.GAME_CONNECT4, 1, rng_mode=_orc.RNG_PHILOX, seed=8, game_id_base=g, arena=True,
+                               arena_temp=0.25)
+        for r in range(rounds):
+            assert orc.players()[0] == movers[r, g]
+            for _ in range(sims):
+                orc.generateBatch()
+                orc.processBatch(*warmup_outputs(1, 7))
+            assert np.array_equal(orc.root_counts()[0], counts[r, g]), (g, r)
+            orc.playMoves(False)
+            assert orc.last_actions()[0] == actions[r, g], (g, r)
+        _, o_turns, o_win = orc.results()
+        mine = rs == g
+        assert np.array_equal(rt[mine], o_turns) and np.array_equal(rw[mine], o_win)
