@@ -506,7 +506,8 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "metric": METRIC if (a.game == "connect4" and B == 8192) else f"self-play MCTS simulations/sec ({B} {a.game} games)",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if a.nn != "cudnn" else ("f32" if a.precision == "fp32" else a.precision), "data": "synthetic",
             "config": {"workload": f"{a.game} {B} games/GPU x {sims} sims/move, DEFAULT_ARGS MCTS (cpuct 1.25, fpu 0.2, "
