@@ -145,8 +145,7 @@ __device__ __forceinline__ void turn_wait(uint32_t addr, uint32_t g)
     for (uint32_t it = 0; it < (1u << 24); it++) {
         uint32_t v;
         asm volatile("ld.relaxed.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
-        if (v >= g) return;
-        __nanosleep(64);
+        if (v >= g) return;                 // three polling threads per CTA: cheap; a nanosleep here costs ~500 cycles of turn latency
     }
     __trap();
 }
@@ -459,15 +458,22 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
                     w_s = wb_s + (uint32_t)((l % NWBUF) * WL_BYTES);
                 }
                 // rows 128t-8 .. 128t+135 of the previous layer's output, and my ring slot drained
+                const bool trace = DBG && timing && blockIdx.x == 0;
+                float *tl = trace ? dump + (size_t)1024 * 256 + (size_t)g * 16 : nullptr;
+                if (trace) tl[0] = (float)(clock64() - ts[0]);
                 if (l > 0) mbar_wait(BAR(BAR_READY + t), (uint32_t)((l - 1) & 1));
+                if (trace) tl[1] = (float)(clock64() - ts[0]);
                 if (use > 0) mbar_wait(BAR(BAR_PEMPTY + warp), (uint32_t)((use - 1) & 1));
+                if (trace) tl[2] = (float)(clock64() - ts[0]);
                 tc_fence_after();
                 // the three issuers overlap their waits, but the MMAs of a tile enter the pipe back to back and in tile
                 // order: interleaved, all three tiles would complete together and the ring would run in lock-step
                 turn_wait(CNT(CNT_TURN), (uint32_t)g);
+                if (trace) tl[3] = (float)(clock64() - ts[0]);
                 issue_tile((l & 1) ? fa_s : fb_s, w_s, d_tmem, t, l == 0);   // stem: obs (b);  conv1: a;  conv2: b
                 umma_commit(BAR(BAR_PFULL + warp));
                 turn_store(CNT(CNT_TURN), (uint32_t)(g + 1));
+                if (trace) tl[4] = (float)(clock64() - ts[0]);
                 t += NPBUF;
                 if (t >= tiles) { t -= tiles; l++; }
             }
@@ -506,10 +512,11 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
             // one warp of the group polls the mbarrier, the other seven sleep in a hardware barrier: a third of all
             // instructions this kernel issued were wait-loop iterations of epilogue warps, competing for issue slots
             // with the warps that had work
-            if ((e % GRP_WARPS) == 0) mbar_wait<32>(bar_full, par);
-            asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "r"(GRP_WARPS * 32) : "memory");
-            par ^= 1u;
-            tc_fence_after();
+            const bool trace = DBG && timing && blockIdx.x == 0 && lane == 0;
+            float *tl = trace ? dump + (size_t)1024 * 256 + (size_t)g * 16 : nullptr;
+            // everything that does not need the accumulator is computed before the wait: once the tile is complete, the
+            // ring slot is held until every warp has its loads, so the instructions in front of them are on the
+            // critical path of the tensor pipe
             const int fr = t * 128 + r0;
             const bool live = ((fr & 7) != 7) && (((fr >> 3) % (BH + 1)) != BH) && fr < live_rows;
             const uint32_t t_x = t_x0 + (uint32_t)(CH * t);
@@ -524,6 +531,13 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
                 out_row = (is_c1 ? fb_h : fa_h) + (size_t)fr * 16;
             }
             float *dmp = (DBG && dump != nullptr && l == dump_layer && fr < live_rows) ? dump + ((size_t)board0 * FB + fr) * CH + ho : nullptr;
+            if (trace && (e % GRP_WARPS) == 0) tl[5] = (float)(clock64() - ts[0]);
+            if ((e % GRP_WARPS) == 0) mbar_wait<32>(bar_full, par);
+            if (trace && (e % GRP_WARPS) == 0) tl[6] = (float)(clock64() - ts[0]);
+            asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "r"(GRP_WARPS * 32) : "memory");
+            par ^= 1u;
+            tc_fence_after();
+            if (trace && (e % GRP_WARPS) == 7) tl[7] = (float)(clock64() - ts[0]);
             if (l == 0) {
                 epilogue_tile<EPI_STEM, DBG>(t_p, t_x, out_row, out_plane, s_bias + ho, depth > 0 ? s_sc + ho : nullptr, s_sh + ho,
                                              live, lane, bar_empty, dmp);
@@ -542,6 +556,7 @@ k_resnet_tc(const float *__restrict__ obs, float *__restrict__ policy, float *__
                 mbar_arrive(BAR(BAR_READY + t));
                 if (t + 1 < tiles) mbar_arrive(BAR(BAR_READY + t + 1));
             }
+            if (trace) tl[8 + (e % GRP_WARPS)] = (float)(clock64() - ts[0]);
             t += NPBUF;
             if (t >= tiles) { t -= tiles; l++; }
         }

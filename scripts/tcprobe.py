@@ -100,6 +100,11 @@ def phases(batch=8192, code=99, show=True):
         v = t[:, :nw, i]
         print(f"{n:14s} mean {v.mean().item():9.0f} max {v.max().item():9.0f} | issuer {t[:, 0:3, i].mean().item():9.0f} producer {t[:, 3, i].mean().item():9.0f} "
               f"epilogue {t[:, 4:nw, i].mean().item():9.0f}")
+    tl = buf[1024 * 256: 1024 * 256 + 63 * 16].view(63, 16).cpu()
+    print(" g  l t | issuer: start  rows-ok ring-ok turn-ok committed | epilogue: poll-start full   released(after bar) | done: first..last warp")
+    for g in range(14, 44):
+        r = tl[g].tolist()
+        print(f"{g:2d} {g // 7:2d} {g % 7} | {r[0]:7.0f} {r[1]:7.0f} {r[2]:7.0f} {r[3]:7.0f} {r[4]:7.0f} | {r[5]:7.0f} {r[6]:7.0f} {r[7]:7.0f} | {min(r[8:16]):7.0f} {max(r[8:16]):7.0f}")
     tot = t[:, 0, :4].sum(1)
     print(f"CTA total cycles: mean {tot.mean().item():.0f} min {tot.min().item():.0f} max {tot.max().item():.0f}")
     sm = t[:, 0, 4].long()
