@@ -52,7 +52,7 @@ class _Round:
         return [rows[model == m] for m in range(len(self.p2i))]
 
 
-def play_games(engine, models, player_to_index=(0, 1), sims=None, stop_event=None, progress=None):
+def play_games(engine, models, player_to_index=(0, 1), sims=None, stop_event=None, progress=None, round_graph=True):
     """Arena.play_games on the device: `models[m].process(batch) -> (pi, v)` (NNetWrapper surface), model
     `player_to_index[p]` moves for env player p.  Plays until the engine's games_per_iteration quota is reached.
     -> (wins per model index, draws, mean turns, simulations run)."""
@@ -64,21 +64,50 @@ def play_games(engine, models, player_to_index=(0, 1), sims=None, stop_event=Non
     # fast path: both models are NNetWrappers whose network the tcgen05 evaluator covers -- every simulation is
     # select -> model 0 on its row list -> model 1 on its row list -> expand/backup, all on the device, no host sync
     evals = _fused_evaluators(engine, models, player_to_index)
+    # ... and then a whole move-round (sims x (select, model 0, model 1, expand/backup) + playMoves) is ONE CUDA graph:
+    # every launch argument is constant (row lists and counters live on the device), so after one eager round the
+    # graph is captured and replayed per move -- same kernels, same order, same results (tests/test_arena.py)
+    graph, rounds = None, 0
+    use_graph = round_graph and evals is not None
+    gstream = torch.cuda.Stream(device=engine.obs.device) if use_graph else None
+
+    def fused_round(stream=None):
+        engine.select(stream=stream)
+        for s in range(sims):
+            for ev in evals:
+                ev(stream=stream)
+            if s + 1 < sims:
+                engine.expand_backup_select(stream=stream)          # processBatch(s) + generateBatch(s+1), one launch
+        engine.expand_backup(stream=stream)
+        engine.play_moves(False, stream=stream)
+
     while engine.games_played() < quota and not (stop_event is not None and stop_event.is_set()):
-        for _ in range(sims):
-            engine.select()
-            if evals is not None:
-                for ev in evals:
-                    ev()
+        if evals is not None:
+            if use_graph and graph is None and rounds >= 1:
+                graph = torch.cuda.CUDAGraph()
+                gstream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.graph(graph, stream=gstream):
+                    fused_round(gstream)
+            if graph is not None:
+                cur = torch.cuda.current_stream()
+                gstream.wait_stream(cur)
+                with torch.cuda.stream(gstream):
+                    graph.replay()
+                cur.wait_stream(gstream)
             else:
+                fused_round()
+            rounds += 1
+        else:
+            for _ in range(sims):
+                engine.select()
                 for m, rows in enumerate(rnd.rows_by_model()):
                     if rows.numel() == 0:
                         continue
                     pi, v = models[m].process(engine.obs.index_select(0, rows))
                     engine.policy.index_copy_(0, rows, pi.to(engine.policy.dtype))
                     engine.value.index_copy_(0, rows, v.to(engine.value.dtype))
-            engine.expand_backup()
-        engine.play_moves(False)
+                engine.expand_backup()
+            engine.play_moves(False)
         engine.check_errors()
         slot, t, win = engine.drain_results()
         for i in range(len(slot)):

@@ -51,3 +51,76 @@ def allreduce_game_stats(stats, device, group=None):
     for k, v in zip(keys, t.tolist()):
         out[k] = int(v) if k not in ("peak_nodes",) else stats[k]
     return out
+
+
+def train_steps_sharded(net, optimizer, loader, steps, value_loss_weight, device, group=None, sync_bn_stats=True,
+                        bn_eval=False):
+    """Data-parallel form of the loop body of NNetWrapper.train (NNetWrapper.py:131-165) over all ranks.
+
+    Rank 0 owns the sample window and draws the batches exactly as the single-process loop does (``loader`` is its
+    WindowLoader; the other ranks pass None); every step it broadcasts the batch, rank r computes the forward /
+    backward pass of its contiguous slice with the losses normalised by the FULL batch size, the gradients are summed
+    over ranks and every rank takes the same optimizer step -- so the parameters stay identical on all ranks and the
+    step equals the single-process one up to the summation order of the gradient (and, in train mode, BatchNorm's
+    per-rank batch statistics; the running statistics are averaged over ranks after the last step when
+    ``sync_bn_stats``; ``bn_eval`` freezes BatchNorm, which makes the step independent of the split).  -> (mean policy loss, mean value loss) over the steps, as NNetWrapper.train reports them.
+    """
+    from .samples import loss_pi, loss_v
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    head = torch.zeros(6, dtype=torch.int64, device=device)      # batch rows, obs C/H/W, actions, values
+    params = [p for p in net.parameters() if p.requires_grad]
+    net.train(not bn_eval)
+    it = None
+    acc = torch.zeros(2, device=device, dtype=torch.float64)       # sum of batch-weighted losses, kept on the device
+    n = 0
+    for step in range(int(_bcast_int(steps if rank == 0 else 0, device, group))):
+        if rank == 0:
+            try:
+                batch = next(it) if it is not None else None
+            except StopIteration:
+                batch = None
+            if batch is None:                                  # a new epoch of the loader (new permutation)
+                it = iter(loader)
+                batch = next(it)
+            boards, pis, vs = (t.to(device).contiguous() for t in batch)
+            head.copy_(torch.tensor([boards.shape[0], *boards.shape[1:], pis.shape[1], vs.shape[1]], dtype=torch.int64))
+        dist.broadcast(head, 0, group=group)
+        b, c, h, w, na, nv = head.tolist()
+        if rank != 0:
+            boards = torch.empty((b, c, h, w), device=device)
+            pis = torch.empty((b, na), device=device)
+            vs = torch.empty((b, nv), device=device)
+        for t in (boards, pis, vs):
+            dist.broadcast(t, 0, group=group)
+        first, count = shard_games(b, rank, world)             # same contiguous, balanced split as the games
+        optimizer.zero_grad()
+        stat = torch.zeros(2, device=device)
+        if count:
+            out_pi, out_v = net(boards[first:first + count])
+            l_pi = loss_pi(pis[first:first + count], out_pi) * (count / b)      # sum over my rows / full batch size
+            l_v = loss_v(vs[first:first + count], out_v, value_loss_weight) * (count / b)
+            (l_pi + l_v).backward()
+            stat[0], stat[1] = l_pi.detach(), l_v.detach()
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params] + [stat])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)               # one bucket: the net is < 25 MB
+        off = 0
+        for p in params:
+            k = p.numel()
+            p.grad = flat[off:off + k].view_as(p).clone()
+            off += k
+        optimizer.step()
+        acc += flat[off:off + 2].double() * b
+        n += b
+    if sync_bn_stats and world > 1:
+        for name, buf in net.named_buffers():
+            if buf.dtype.is_floating_point:                    # running_mean / running_var
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+                buf /= world
+    net.eval()
+    return (float(acc[0]) / n, float(acc[1]) / n) if n else (0.0, 0.0)
+
+
+def _bcast_int(v, device, group=None):
+    t = torch.tensor([int(v)], dtype=torch.int64, device=device)
+    dist.broadcast(t, 0, group=group)
+    return int(t.item())

@@ -5,8 +5,9 @@ window, the comparison with the self-play model as a batched arena on the engine
 reference's gating rule (Coach.compareToPast, Coach.py:528-570).
 
 With torch.distributed initialised (one rank per GPU) self-play shards by game and the examples are gathered to rank
-0 (azb200.distributed), which trains and gates and broadcasts the accepted weights; without it everything runs on one
-GPU.  The reference's GUI fields, tensorboard writer and checkpoint files are not part of this loop.
+0 (azb200.distributed), which trains and gates and broadcasts the accepted weights (``ddp_train=True``: every rank
+trains on its slice of each batch, gradients summed over NCCL, azb200.distributed.train_steps_sharded); without it
+everything runs on one GPU.  The reference's GUI fields, tensorboard writer and checkpoint files are not part of this loop.
 """
 import time
 
@@ -25,7 +26,8 @@ DEFAULTS = dict(
     lr=1e-2, momentum=0.9, weight_decay=1e-4, value_loss_weight=1.5, compareWithPast=True, pastCompareFreq=1,
     arenaCompare=128, arenaTemp=0.25, model_gating=True, max_gating_iters=None, min_next_model_winrate=0.52,
     use_draws_for_winrate=True, cpuct=1.25, fpu_reduction=0.2, root_noise_frac=0.1, root_policy_temp=1.1,
-    add_root_noise=True, add_root_temp=True, symmetricSamples=True, mctsResetThreshold=None, startTemp=1)
+    add_root_noise=True, add_root_temp=True, symmetricSamples=True, mctsResetThreshold=None, startTemp=1,
+    ddp_train=False)
 
 
 class _A(dict):
@@ -98,15 +100,26 @@ class GpuCoach:
                 obs, pi, z = gather_examples_to_rank0(obs, pi, z)
             rec.update(selfplay_seconds=time.time() - t0, sims=res.sims, warmup=warmup,
                        samples=int(obs.shape[0]) if self.rank == 0 else 0, game_results=res.game_results())
+            loader, steps, used = None, 0, []
             if self.rank == 0:
                 self.window.add_iteration(it, obs, pi, z)
                 self.window.evict_before(it - a.maxTrainHistoryWindow)
                 loader, used = self.window.loader(it, a)
                 steps = self.window.train_steps(used, a)
-                t0 = time.time()
-                rec["loss_pi"], rec["loss_v"] = train_steps(self.train_net, self.optimizer, loader, steps, a.value_loss_weight)
-                rec.update(train_steps=steps, train_seconds=time.time() - t0, window=used)
+            t0 = time.time()
+            if self.world > 1 and a.ddp_train:
+                # every rank trains: rank 0 draws the batches from its window, the rows of each batch are split
+                # over the ranks, gradients summed (azb200.distributed.train_steps_sharded)
+                from .distributed import train_steps_sharded
+                losses = train_steps_sharded(self.train_net.nnet, self.optimizer, loader, steps, a.value_loss_weight,
+                                             torch.device("cuda", self.device))
                 self._fresh(self.train_net)
+            elif self.rank == 0:
+                losses = train_steps(self.train_net, self.optimizer, loader, steps, a.value_loss_weight)
+                self._fresh(self.train_net)
+            if self.rank == 0:
+                rec["loss_pi"], rec["loss_v"] = losses
+                rec.update(train_steps=steps, train_seconds=time.time() - t0, window=used)
                 if a.compareWithPast and (it - 1) % a.pastCompareFreq == 0:
                     rec.update(self.compare_to_past(it))
             if self.world > 1:                                                # everybody self-plays with rank 0's decision

@@ -347,7 +347,7 @@ def main():
                          round_graph=False if a.no_round_graph else None, split=a.split or None,
                          skip_terminal=not a.eval_terminal)
 
-    sel_events = []
+    sel_events, nn_events = [], []
 
     def step():
         if a.tree_only:
@@ -441,12 +441,23 @@ def main():
             e1.record(stream)
             sel_events.append((e0, e1))
         eng.select = timed_select
+        orig_evals = list(drv.evals)
+
+        def timed_eval(ev):
+            def call(stream=None):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                ev(stream=stream)
+                e1.record(stream)
+                nn_events.append((e0, e1))
+            return call
+        drv.evals = [timed_eval(ev) for ev in orig_evals]
         r0 = eng.stats()
         for _ in range(a.roofline_steps):
             step()
         torch.cuda.synchronize()
         r1 = eng.stats()
-        eng.select, drv.round_graph = orig_select, was_graph
+        eng.select, drv.round_graph, drv.evals = orig_select, was_graph, orig_evals
         alg_bytes = 16.0 * (r1["sum_depth"] - r0["sum_depth"]) + 12.0 * (r1["sum_children"] - r0["sum_children"])
         roof_sims = r1["sims"] - r0["sims"]
     if sel_events:
@@ -464,6 +475,23 @@ def main():
                 "traffic": None, "kernel": "k_warmup_sims<Connect4> (select+expand+backup fused)", "launches": a.steps,
                 "avg_launch_us": 1000.0 * ms / a.steps, "alg_bytes_per_launch": alg_bytes / a.steps,
                 "bytes_per_sim": alg_bytes / max(dsims, 1), "peak_source": peak_src}
+    # secondary roofline: the leaf evaluator (the kernel that takes most of the step) against the measured dense bf16
+    # tensor throughput; flops = conv / linear multiply-adds of the ResNet x the rows it evaluated (non-terminal leaves
+    # in compact mode, every leaf otherwise), time = CUDA events around its launches in the same eager rounds
+    roof_nn = None
+    if nn_events:
+        nn_ms = sum(e0.elapsed_time(e1) for e0, e1 in nn_events)
+        compact = a.nn == "fused" and not a.eval_terminal and a.cohorts == 1
+        rows = roof_sims - ((r1["terminal_leaves"] - r0["terminal_leaves"]) if compact else 0)
+        fl = model_flops(model, OBS)
+        tf = fl * rows / (nn_ms / 1000.0) / 1e12
+        sustained = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1388.0)))
+        roof_nn = {"bound": "tensor", "achieved": tf, "peak": sustained, "unit": "TFLOP/s", "frac": tf / sustained, "traffic": None,
+                   "kernel": {"fused": "k_resnet_tc (tcgen05/TMEM)", "fused_mma": "k_resnet_fused (mma.sync)"}.get(a.nn, "cuDNN " + a.precision),
+                   "launches": len(nn_events), "avg_launch_us": 1000.0 * nn_ms / len(nn_events), "flops_per_eval": fl,
+                   "rows_per_launch": rows / len(nn_events), "evals_per_s": rows / (nn_ms / 1000.0),
+                   "peak_source": ("measured sustained bf16" if "bf16_tflops_sustained" in peaks else "fallback"),
+                   "note": "useful flops of the network (2 x multiply-adds of its convolutions and linear layers), not issued MMA flops"}
     traffic_file = os.path.join(ROOT, "profiles", "select_traffic.json")
     if roof is not None and os.path.exists(traffic_file):
         try:
@@ -519,7 +547,7 @@ def main():
                        "l2": "node pool %.1f GB per GPU > 126 MB L2; no flush" % (st1["pool_bytes"] / 1e9),
                        "preroll_rounds": a.preroll},
             "clocks": clk, "gpu_launches": drv.launches - launches0,
-            "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "alt_nn": alt,
+            "roofline": roof, "roofline_nn": roof_nn, "cpu_baseline": cpu_base, "e2e": e2e, "alt_nn": alt,
             "tree_stats": {"sims": dsims, "mean_depth": dD / max(dsims, 1), "mean_children_scanned": dC / max(dsims, 1),
                            "games_finished": st1["results"] - st0["results"], "peak_nodes_per_game": st1["peak_nodes"],
                            "terminal_leaf_fraction": (st1["terminal_leaves"] - st0["terminal_leaves"]) / max(dsims, 1)},
@@ -530,6 +558,27 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def model_flops(model, obs_shape):
+    """2 x multiply-adds of every Conv2d / Linear in one evaluation of `model` (hooks over a one-board forward)."""
+    import torch
+    total = [0]
+
+    def hook(m, inp, out):
+        if isinstance(m, torch.nn.Conv2d):
+            total[0] += 2 * out.numel() * (m.in_channels // m.groups) * m.kernel_size[0] * m.kernel_size[1]
+        elif isinstance(m, torch.nn.Linear):
+            total[0] += 2 * out.numel() * m.in_features
+    hs = [m.register_forward_hook(hook) for m in model.modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))]
+    try:
+        p = next(model.parameters())
+        with torch.no_grad():
+            model(torch.zeros((1,) + tuple(obs_shape), device=p.device, dtype=p.dtype))
+    finally:
+        for h in hs:
+            h.remove()
+    return float(total[0])
 
 
 def run_e2e(a, eng, model, dev, world):

@@ -133,12 +133,12 @@ def test_fused_two_model_evaluation_equals_the_generic_path(monkeypatch):
         nets.append(aznet.NNetWrapper(nnet=aznet.ResNet((4, 6, 7), 7, 3, **aznet.DEFAULT_NET_ARGS).cuda().eval(), cuda=True,
                                       fused=True))
     out = []
-    for fast in (True, False):
-        if not fast:
+    for mode in ("graph", "eager", "generic"):      # one CUDA graph per move-round / launch by launch / PyTorch gather-scatter
+        if mode == "generic":
             monkeypatch.setattr(az_arena, "_fused_evaluators", lambda *a, **k: None)
         eng = az_arena.arena_engine(_C4Game, _args(sims, quota), B, rng="philox", seed=11)
-        out.append(az_arena.play_games(eng, nets, (1, 0), sims=sims))
+        out.append(az_arena.play_games(eng, nets, (1, 0), sims=sims, round_graph=(mode == "graph")))
         eng.close()
-    assert out[0] == out[1]
+    assert out[0] == out[1] == out[2]
     wins, draws, _, nsims = out[0]
     assert sum(wins) + draws == quota and nsims > quota * sims

@@ -63,3 +63,75 @@ def test_two_rank_gloo_gather_and_sharding():
     assert np.array_equal(r0["obs"][5:, 0, 0, 0], 1 + np.arange(8))
     assert r0["st"]["sims"] == 300 and r0["st"]["games_played"] == 21 and r0["st"]["peak_nodes"] == 7
     assert r0["empty"] == 0
+
+
+def _train_worker(rank, world, port, out):
+    sys.path.insert(0, os.path.join(ROOT, "alphazero-general_b200"))
+    from azb200 import nnet as aznet
+    from azb200.distributed import train_steps_sharded
+    from azb200.samples import WindowLoader
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = aznet.ResNet((4, 6, 7), 7, 3, num_channels=8, depth=1, value_dense_layers=(16,), policy_dense_layers=(16,))
+    opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4)
+    loader = None
+    if rank == 0:                                       # only rank 0 owns the sample window
+        g = torch.Generator().manual_seed(5)
+        n = 150                                         # 150 rows, batches of 64: a ragged last batch (22 rows)
+        obs = torch.rand(n, 4, 6, 7, generator=g)
+        pi = torch.softmax(torch.randn(n, 7, generator=g), 1)
+        z = torch.softmax(torch.randn(n, 3, generator=g), 1)
+        torch.manual_seed(9)
+        loader = WindowLoader((obs, pi, z), 64)
+    losses = train_steps_sharded(net, opt, loader, 5 if rank == 0 else 0, 1.5, torch.device("cpu"), bn_eval=True)
+    out.put(dict(rank=rank, losses=losses, params=torch.cat([p.detach().reshape(-1) for p in net.parameters()]).numpy(),
+                 training=net.training))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_training_equals_single_process():
+    """train_steps_sharded over two ranks = the loop body of NNetWrapper.train in one process on the same batches
+    (BatchNorm frozen, so the only difference is the summation order of the gradient)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in procs), key=lambda r: r["rank"])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(res[0]["params"], res[1]["params"])          # the ranks stay in lock-step
+    assert res[0]["losses"] == res[1]["losses"] and not res[0]["training"]
+
+    sys.path.insert(0, os.path.join(ROOT, "alphazero-general_b200"))
+    from azb200 import nnet as aznet
+    from azb200.samples import WindowLoader, loss_pi, loss_v
+    torch.manual_seed(0)
+    net = aznet.ResNet((4, 6, 7), 7, 3, num_channels=8, depth=1, value_dense_layers=(16,), policy_dense_layers=(16,))
+    opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4)
+    g = torch.Generator().manual_seed(5)
+    obs = torch.rand(150, 4, 6, 7, generator=g)
+    pi = torch.softmax(torch.randn(150, 7, generator=g), 1)
+    z = torch.softmax(torch.randn(150, 3, generator=g), 1)
+    torch.manual_seed(9)
+    loader = WindowLoader((obs, pi, z), 64)
+    net.eval()                                                           # BatchNorm frozen as in the workers
+    step, lp, lv, n = 0, 0.0, 0.0, 0
+    while step < 5:
+        for b, tp, tv in loader:
+            if step == 5:
+                break
+            step += 1
+            op, ov = net(b)
+            l1, l2 = loss_pi(tp, op), loss_v(tv, ov, 1.5)
+            opt.zero_grad(); (l1 + l2).backward(); opt.step()
+            lp += float(l1.detach()) * len(b); lv += float(l2.detach()) * len(b); n += len(b)
+    ref = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).numpy()
+    assert n == 64 + 64 + 22 + 64 + 64
+    np.testing.assert_allclose(res[0]["params"], ref, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(res[0]["losses"], (lp / n, lv / n), rtol=1e-5)
