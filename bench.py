@@ -357,16 +357,27 @@ def main():
         # keep the sample ring from filling: discard on the device (no host copy)
         clear_samples()
 
-    kept = []          # examples drained on the device during the run (gathered over NCCL at the end)
+    # Examples are drained on the device into buffers allocated ONCE (a fresh torch.empty per step that is never
+    # freed means a cudaMalloc -- a device-wide synchronisation -- inside the timed region): a scratch triple when the
+    # examples are discarded (N = 1), a keep buffer for the NCCL gather at the end (N > 1).
+    keep_cap = 1_200_000 if world > 1 else 0
+    keep = [torch.empty((keep_cap,) + OBS, device=dev), torch.empty(keep_cap, A, device=dev), torch.empty(keep_cap, 3, device=dev)]
+    scratch = [None]
+    kept = [0]
 
     def clear_samples():
         n = eng.sample_count()
         if n == 0:
             return
-        o = torch.empty((n,) + OBS, device=dev); p = torch.empty(n, A, device=dev); z = torch.empty(n, 3, device=dev)
-        eng.drain_samples_into(o, p, z)
-        if world > 1 and sum(t[0].shape[0] for t in kept) < 4_000_000:
-            kept.append((o, p, z))
+        k = kept[0]
+        if k + n <= keep_cap:
+            eng.drain_samples_into(keep[0][k:k + n], keep[1][k:k + n], keep[2][k:k + n])
+            kept[0] = k + n
+            return
+        if scratch[0] is None or scratch[0][0].shape[0] < n:
+            m = int(n * 1.5) + 1024
+            scratch[0] = (torch.empty((m,) + OBS, device=dev), torch.empty(m, A, device=dev), torch.empty(m, 3, device=dev))
+        eng.drain_samples_into(*scratch[0])
 
     # cheap tree-only pre-roll so the games are spread over all phases (steady state)
     for _ in range(a.preroll):
@@ -375,7 +386,7 @@ def main():
         if _ % 4 == 3:
             clear_samples()
     clear_samples()
-    kept.clear()
+    kept[0] = 0
     torch.cuda.synchronize()
 
     def barrier():
@@ -388,7 +399,7 @@ def main():
     for _ in range(max(a.warmup, 3)):
         step()
     clear_samples()
-    kept.clear()
+    kept[0] = 0
     eng.check_errors()
     st0 = eng.stats()
     launches0 = drv.launches
@@ -528,7 +539,7 @@ def main():
 
     if world > 1:
         clear_samples()
-        gather_ms, gathered = gather_examples(kept, dev, rank, world, OBS, A)
+        gather_ms, gathered = gather_examples([t[:kept[0]] for t in keep], dev, rank, world)
     else:
         gather_ms, gathered = None, None
 
@@ -746,15 +757,12 @@ def run_e2e_inline(a, eng, agents, server, evs, ready, dev, world, Bw, old_tf32)
                    "processBatch, playMoves; every batch crosses PCIe in both directions"}
 
 
-def gather_examples(kept, dev, rank, world, obs_shape=(4, 6, 7), A=7):
-    """BASELINE config 3: NCCL gather of the (s, pi, z) examples of the timed steps to rank 0."""
+def gather_examples(kept, dev, rank, world):
+    """BASELINE config 3: NCCL gather of the (s, pi, z) examples of the run to rank 0."""
     import torch
     import torch.distributed as dist
     from azb200.distributed import gather_examples_to_rank0
-    if kept:
-        obs, pi, z = (torch.cat([k[i] for k in kept]) for i in range(3))
-    else:
-        obs, pi, z = torch.empty((0,) + obs_shape, device=dev), torch.empty(0, A, device=dev), torch.empty(0, 3, device=dev)
+    obs, pi, z = kept
     gather_examples_to_rank0(obs[:1], pi[:1], z[:1])          # NCCL warm-up (communicator setup is not timed)
     torch.cuda.synchronize(); dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
