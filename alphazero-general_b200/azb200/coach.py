@@ -42,12 +42,39 @@ class SelfPlayResult:
         return wins, draws, (float(self.result_turns.sum()) / n if n else 0)
 
 
+class _DeviceSampleSink:
+    """Examples stay on the GPU: drained device-to-device from the engine's sample ring into chunks allocated ahead of
+    the rounds that fill them (no allocation, no host copy of the examples inside the loop)."""
+
+    def __init__(self, engine, chunk=1 << 18):
+        self.eng, self.chunk = engine, int(chunk)
+        self.dev = engine.obs.device
+        self.chunks, self.fill = [], 0
+        self._grow(self.chunk)
+
+    def _grow(self, rows):
+        self.chunks.append([torch.empty((rows,) + self.eng.obs_shape, device=self.dev), torch.empty(rows, self.eng.A, device=self.dev),
+                            torch.empty(rows, 3, device=self.dev), 0])
+
+    def drain(self, n):
+        o, p, z, k = self.chunks[-1]
+        if k + n > o.shape[0]:
+            self._grow(max(self.chunk, n))
+            o, p, z, k = self.chunks[-1]
+        got = self.eng.drain_samples_into(o[k:k + n], p[k:k + n], z[k:k + n])
+        self.chunks[-1][3] = k + got
+
+    def tensors(self):
+        return tuple(torch.cat([c[i][:c[3]] for c in self.chunks]) for i in range(3))
+
+
 def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup=False, engine=None, fused=None,
-                           precision="tf32", game_id_base=0, stop_event=None, progress=None):
+                           precision="tf32", game_id_base=0, stop_event=None, progress=None, device_samples=False):
     """One self-play phase (SelfPlayAgent.run for a single GPU-resident agent):
     until gamesPerIteration games are counted, draw the fast-move coin, run
     numFastSims / numMCTSSims (numWarmupSims in a warmup iteration) simulations
-    for every game, play the moves.  Returns a SelfPlayResult (host tensors)."""
+    for every game, play the moves.  Returns a SelfPlayResult (host tensors; CUDA
+    tensors that never left the device with ``device_samples``)."""
     g = lambda k, d=None: (args[k] if k in args else d)
     B = int(g("process_batch_size", 256))
     if engine is None:
@@ -65,6 +92,7 @@ def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup
     rs = np.random.RandomState(seed)
     quota = int(g("gamesPerIteration"))
     obs, pi, z, rslot, rturns, rwin = [], [], [], [], [], []
+    sink = _DeviceSampleSink(engine) if device_samples else None
     t0 = time.time()
     while engine.games_played() < quota and not (stop_event is not None and stop_event.is_set()):
         fast = bool(rs.random_sample() < g("probFastSim", 0.0))
@@ -74,7 +102,10 @@ def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup
         else:
             drv.run_round(int(g("numFastSims", 20)) if fast else int(g("numMCTSSims", 100)), fast)
         engine.check_errors()
-        if engine.sample_count() > 0:
+        n = engine.sample_count()
+        if n > 0 and sink is not None:
+            sink.drain(n)
+        elif n > 0:
             o, p, zz, _ = engine.drain_samples()
             obs.append(o); pi.append(p); z.append(zz)
         s, t, w = engine.drain_results()
@@ -84,6 +115,9 @@ def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup
                 progress(engine.games_played())
     cat = lambda xs, shape, dt: np.concatenate(xs) if xs else np.zeros(shape, dt)
     A = engine.A
+    if sink is not None:
+        return SelfPlayResult(*sink.tensors(), cat(rslot, (0,), np.int32), cat(rturns, (0,), np.int32),
+                              cat(rwin, (0, 3), np.uint8), engine.stats()["sims"], time.time() - t0)
     return SelfPlayResult(
         torch.from_numpy(cat(obs, (0,) + engine.obs_shape, np.float32)), torch.from_numpy(cat(pi, (0, A), np.float32)),
         torch.from_numpy(cat(z, (0, 3), np.float32)), cat(rslot, (0,), np.int32), cat(rturns, (0,), np.int32),

@@ -93,8 +93,8 @@ class GpuCoach:
             t0 = time.time()
             res = run_selfplay_iteration(self.game_cls, self.self_play_net.nnet, dict(a, gamesPerIteration=a.gamesPerIteration // self.world),
                                          device=self.device, seed=self.seed + 1000 * it + self.rank, warmup=warmup,
-                                         game_id_base=self.rank * a.process_batch_size)
-            obs, pi, z = res.data.cuda(self.device), res.policy.cuda(self.device), res.value.cuda(self.device)
+                                         game_id_base=self.rank * a.process_batch_size, device_samples=True)
+            obs, pi, z = res.data, res.policy, res.value                        # CUDA tensors, never copied to the host
             if self.world > 1:
                 from .distributed import gather_examples_to_rank0
                 obs, pi, z = gather_examples_to_rank0(obs, pi, z)

@@ -66,3 +66,21 @@ def test_nn_iteration_with_fused_and_cudnn_evaluators():
         assert torch.allclose(res.policy.sum(1), torch.ones(res.policy.shape[0]), atol=1e-5)
         assert torch.all(res.value.sum(1) == 1)
         assert res.sims > 0
+
+
+def test_device_resident_examples_equal_the_host_drain():
+    """device_samples=True keeps the examples on the GPU (chunked device-to-device drain): same tensors, same order."""
+    from azb200.coach import run_selfplay_iteration
+    import azb200.coach as coach
+    args = dict(process_batch_size=64, gamesPerIteration=150, numWarmupSims=6, probFastSim=0.3, symmetricSamples=True)
+    host = run_selfplay_iteration(_C4Game, None, args, seed=4, warmup=True)
+    orig = coach._DeviceSampleSink.__init__
+    try:
+        coach._DeviceSampleSink.__init__ = lambda self, engine, chunk=0: orig(self, engine, chunk=700)   # several chunks
+        dev = run_selfplay_iteration(_C4Game, None, args, seed=4, warmup=True, device_samples=True)
+    finally:
+        coach._DeviceSampleSink.__init__ = orig
+    assert dev.data.is_cuda and dev.data.shape[0] == host.data.shape[0] > 1400
+    for a, b in ((dev.data, host.data), (dev.policy, host.policy), (dev.value, host.value)):
+        assert torch.equal(a.cpu(), b)
+    assert np.array_equal(dev.result_turns, host.result_turns) and dev.sims == host.sims

@@ -62,7 +62,8 @@ def test_bad_configurations_are_refused():
     from azb200._capi import AzbError
     for kw in (dict(num_games=0), dict(num_games=-4), dict(num_games=3, arena=True),
                dict(num_games=4, arena=True, add_root_noise=True), dict(num_games=4, game=99),
-               dict(num_games=4, max_sims_per_move=0), dict(num_games=4, lanes_per_game=5)):
+               dict(num_games=4, max_nodes_per_game=3), dict(num_games=4, lanes_per_game=5),
+               dict(num_games=4, root_policy_temp=0.0), dict(num_games=4, device=99)):
         with pytest.raises(AzbError) as ei:
             SelfPlayEngine(**kw)
         assert ei.value.status == -1, kw                        # AZB_ERR_BAD_CONFIG
@@ -123,7 +124,8 @@ def test_sample_ring_overflow_is_reported():
 def test_fed_root_noise_underrun_is_reported():
     from azb200 import SelfPlayEngine
     from azb200._capi import AzbError
-    eng = SelfPlayEngine(num_games=4, max_sims_per_move=3, add_root_noise=True, temps=C4_TEMPS)
+    # the tree is rebuilt after every move (mctsResetThreshold = 1), so every move expands a root and takes a noise row
+    eng = SelfPlayEngine(num_games=4, max_sims_per_move=3, add_root_noise=True, temps=C4_TEMPS, mcts_reset_threshold=1)
     eng.set_root_noise(np.full((4, 2, 7), 1.0 / 7, dtype=np.float32))       # two root expansions per game, then dry
     with pytest.raises(AzbError) as ei:
         for _ in range(6):
