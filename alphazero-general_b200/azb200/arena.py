@@ -64,6 +64,7 @@ def play_games(engine, models, player_to_index=(0, 1), sims=None, stop_event=Non
     # fast path: both models are NNetWrappers whose network the tcgen05 evaluator covers -- every simulation is
     # select -> model 0 on its row list -> model 1 on its row list -> expand/backup, all on the device, no host sync
     evals = _fused_evaluators(engine, models, player_to_index)
+    play_games.setup_seconds = time.time() - t0
     # ... and then a whole move-round (sims x (select, model 0, model 1, expand/backup) + playMoves) is ONE CUDA graph:
     # every launch argument is constant (row lists and counters live on the device), so after one eager round the
     # graph is captured and replayed per move -- same kernels, same order, same results (tests/test_arena.py)
@@ -71,23 +72,36 @@ def play_games(engine, models, player_to_index=(0, 1), sims=None, stop_event=Non
     use_graph = round_graph and evals is not None
     gstream = torch.cuda.Stream(device=engine.obs.device) if use_graph else None
 
+    side = torch.cuda.Stream(device=engine.obs.device) if evals is not None else None
+    e_fork, e_join = torch.cuda.Event(), torch.cuda.Event()
+
     def fused_round(stream=None):
+        stream = stream or torch.cuda.current_stream()
         engine.select(stream=stream)
         for s in range(sims):
-            for ev in evals:
-                ev(stream=stream)
+            # the two models read disjoint row lists and write disjoint rows: evaluate them side by side (a fork /
+            # join in the captured graph) -- at gating sizes each evaluation is a handful of CTAs
+            e_fork.record(stream)
+            side.wait_event(e_fork)
+            evals[1](stream=side)
+            e_join.record(side)
+            evals[0](stream=stream)
+            stream.wait_event(e_join)
             if s + 1 < sims:
                 engine.expand_backup_select(stream=stream)          # processBatch(s) + generateBatch(s+1), one launch
         engine.expand_backup(stream=stream)
         engine.play_moves(False, stream=stream)
 
+    stamps = []
     while engine.games_played() < quota and not (stop_event is not None and stop_event.is_set()):
+        stamps.append(time.time())
         if evals is not None:
             if use_graph and graph is None and rounds >= 1:
-                graph = torch.cuda.CUDAGraph()
+                # not the torch.cuda.graph context manager: it runs gc.collect() and torch.cuda.empty_cache() first
+                # (hundreds of ms right after a training phase); nothing here allocates through torch
+                from .nnet import capture_graph
                 gstream.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.graph(graph, stream=gstream):
-                    fused_round(gstream)
+                graph = capture_graph(lambda: fused_round(gstream), gstream)
             if graph is not None:
                 cur = torch.cuda.current_stream()
                 gstream.wait_stream(cur)
@@ -119,6 +133,8 @@ def play_games(engine, models, player_to_index=(0, 1), sims=None, stop_event=Non
             turns.append(int(t[i]))
         if progress is not None and len(slot):
             progress(len(turns), time.time() - t0)
+    stamps.append(time.time())
+    play_games.last_round_seconds = np.diff(np.asarray(stamps))                 # diagnostic: host time per move-round
     return wins, draws, (float(np.mean(turns)) if turns else 0.0), engine.stats()["sims"]
 
 

@@ -77,7 +77,8 @@ def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup
     tensors that never left the device with ``device_samples``)."""
     g = lambda k, d=None: (args[k] if k in args else d)
     B = int(g("process_batch_size", 256))
-    if engine is None:
+    own_engine = engine is None
+    if own_engine:
         engine = SelfPlayEngine(**engine_kwargs_from_args(game_cls, args, B, device=device, rng="philox", seed=seed,
                                                           game_id_base=game_id_base))
     else:
@@ -94,7 +95,9 @@ def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup
     obs, pi, z, rslot, rturns, rwin = [], [], [], [], [], []
     sink = _DeviceSampleSink(engine) if device_samples else None
     t0 = time.time()
+    round_times = []
     while engine.games_played() < quota and not (stop_event is not None and stop_event.is_set()):
+        round_times.append(time.time())
         fast = bool(rs.random_sample() < g("probFastSim", 0.0))
         if warmup:
             engine.warmup_sims(int(g("numWarmupSims", 5)))
@@ -114,14 +117,20 @@ def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup
             if progress is not None:
                 progress(engine.games_played())
     cat = lambda xs, shape, dt: np.concatenate(xs) if xs else np.zeros(shape, dt)
-    A = engine.A
+    A, obs_shape, nsims = engine.A, engine.obs_shape, engine.stats()["sims"]
+    dt = time.time() - t0
+    round_times.append(time.time())
+    SelfPlayResult.last_round_seconds = np.diff(np.asarray(round_times))        # diagnostic: host time per move-round
+    if own_engine:
+        torch.cuda.synchronize(engine.obs.device)
+        engine.close()                                   # the node pool goes back to the driver now, not at some later GC
     if sink is not None:
         return SelfPlayResult(*sink.tensors(), cat(rslot, (0,), np.int32), cat(rturns, (0,), np.int32),
-                              cat(rwin, (0, 3), np.uint8), engine.stats()["sims"], time.time() - t0)
+                              cat(rwin, (0, 3), np.uint8), nsims, dt)
     return SelfPlayResult(
-        torch.from_numpy(cat(obs, (0,) + engine.obs_shape, np.float32)), torch.from_numpy(cat(pi, (0, A), np.float32)),
+        torch.from_numpy(cat(obs, (0,) + obs_shape, np.float32)), torch.from_numpy(cat(pi, (0, A), np.float32)),
         torch.from_numpy(cat(z, (0, 3), np.float32)), cat(rslot, (0,), np.int32), cat(rturns, (0,), np.int32),
-        cat(rwin, (0, 3), np.uint8), engine.stats()["sims"], time.time() - t0)
+        cat(rwin, (0, 3), np.uint8), nsims, dt)
 
 
 def save_iteration_samples(result, data_dir, run_name, iteration):

@@ -17,6 +17,8 @@ import torch
 from . import nnet as aznet
 from .arena import arena_engine, play_games
 from .coach import run_selfplay_iteration
+from .engine import SelfPlayEngine
+from .selfplay import engine_kwargs_from_args
 from .samples import SampleWindow, loss_pi, loss_v
 
 DEFAULTS = dict(
@@ -81,6 +83,7 @@ class GpuCoach:
         self.window = SampleWindow(device=dev)
         self.self_play_iter, self.gating_counter = 0, 0
         self.history = []
+        self._sp_engine = None
 
     def _fresh(self, wrapper):
         wrapper._fused_eval = {}             # folded weights are snapshots: rebuild after the weights changed
@@ -91,14 +94,20 @@ class GpuCoach:
             rec = dict(iteration=it)
             warmup = it <= a.numWarmupIters or self.self_play_iter == 0          # Coach.py:232-238
             t0 = time.time()
-            res = run_selfplay_iteration(self.game_cls, self.self_play_net.nnet, dict(a, gamesPerIteration=a.gamesPerIteration // self.world),
+            sp_args = dict(a, gamesPerIteration=a.gamesPerIteration // self.world)
+            if self._sp_engine is None:                                          # one node pool for all iterations
+                self._sp_engine = SelfPlayEngine(**engine_kwargs_from_args(
+                    self.game_cls, sp_args, int(a.process_batch_size), device=self.device, rng="philox", seed=self.seed,
+                    game_id_base=self.rank * a.process_batch_size))
+            res = run_selfplay_iteration(self.game_cls, self.self_play_net.nnet, sp_args,
                                          device=self.device, seed=self.seed + 1000 * it + self.rank, warmup=warmup,
-                                         game_id_base=self.rank * a.process_batch_size, device_samples=True)
+                                         engine=self._sp_engine, device_samples=True)
             obs, pi, z = res.data, res.policy, res.value                        # CUDA tensors, never copied to the host
             if self.world > 1:
                 from .distributed import gather_examples_to_rank0
                 obs, pi, z = gather_examples_to_rank0(obs, pi, z)
-            rec.update(selfplay_seconds=time.time() - t0, sims=res.sims, warmup=warmup,
+            rec.update(selfplay_seconds=time.time() - t0, selfplay_loop_seconds=res.seconds, sims=res.sims, warmup=warmup,
+                       selfplay_rounds=int(len(res.last_round_seconds)), slowest_round_seconds=float(np.max(res.last_round_seconds, initial=0.0)),
                        samples=int(obs.shape[0]) if self.rank == 0 else 0, game_results=res.game_results())
             loader, steps, used = None, 0, []
             if self.rank == 0:
@@ -139,9 +148,12 @@ class GpuCoach:
         rs.shuffle(p2i)                                                       # SelfPlayAgent.pyx:44-46
         t0 = time.time()
         wins, draws, mean_turns, sims = play_games(eng, [self.train_net, self.self_play_net], tuple(p2i), sims=a.numMCTSSims)
+        t_play = time.time() - t0
         eng.close()
         winrate = winrate_of_first(wins, draws, a.use_draws_for_winrate)
-        out = dict(arena_wins=wins, arena_draws=draws, arena_winrate=winrate, arena_seconds=time.time() - t0, arena_sims=sims)
+        out = dict(arena_wins=wins, arena_draws=draws, arena_winrate=winrate, arena_seconds=time.time() - t0, arena_play_seconds=t_play, arena_setup_seconds=play_games.setup_seconds, arena_sims=sims,
+                   arena_rounds=int(len(play_games.last_round_seconds)),
+                   arena_slowest_round_seconds=float(np.max(play_games.last_round_seconds, initial=0.0)))
         if a.model_gating and winrate < a.min_next_model_winrate and (a.max_gating_iters is None or self.gating_counter < a.max_gating_iters):
             self.gating_counter += 1
             out["accepted"] = False

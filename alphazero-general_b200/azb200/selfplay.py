@@ -347,9 +347,11 @@ class DeviceSelfPlay:
             key = (sims, bool(fast))
             g = self._graphs.get(key)
             if g is None and self._eager_rounds >= 1:      # capture after one eager round (lazy one-time setup done)
-                g = torch.cuda.CUDAGraph()
-                T.wait_stream(cur)
-                with torch.cuda.graph(g, stream=T):
+                # capture_graph, not the torch.cuda.graph context manager (which runs gc.collect() and
+                # torch.cuda.empty_cache() first): the kernels are launched through the C ABI, nothing allocates
+                from .nnet import capture_graph
+
+                def whole_round():
                     (f, c), = self.ranges
                     eng.select(f, c, stream=T)
                     for s in range(sims):
@@ -358,6 +360,8 @@ class DeviceSelfPlay:
                             eng.expand_backup_select(f, c, stream=T)      # processBatch(s) + generateBatch(s+1)
                     eng.expand_backup(f, c, stream=T)
                     eng.play_moves(fast, stream=T)
+                T.wait_stream(cur)
+                g = capture_graph(whole_round, T)
                 self._graphs[key] = g
             if g is not None:
                 T.wait_stream(cur)
