@@ -67,6 +67,18 @@ class _DeviceSampleSink:
     def tensors(self):
         return tuple(torch.cat([c[i][:c[3]] for c in self.chunks]) for i in range(3))
 
+    def to_host(self):
+        """-> pinned host tensors (one copy per chunk and tensor, then one synchronisation)."""
+        n = sum(c[3] for c in self.chunks)
+        out = tuple(torch.empty((n,) + tuple(self.chunks[0][i].shape[1:]), pin_memory=True) for i in range(3))
+        k = 0
+        for c in self.chunks:
+            for i in range(3):
+                out[i][k:k + c[3]].copy_(c[i][:c[3]], non_blocking=True)
+            k += c[3]
+        torch.cuda.synchronize(self.dev)
+        return out
+
 
 def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup=False, engine=None, fused=None,
                            precision="tf32", game_id_base=0, stop_event=None, progress=None, device_samples=False):
@@ -92,8 +104,10 @@ def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup
         drv = DeviceSelfPlay(engine, nnet_module, cohorts=1, precision=precision, channels_last=not fused, fused=fused)
     rs = np.random.RandomState(seed)
     quota = int(g("gamesPerIteration"))
-    obs, pi, z, rslot, rturns, rwin = [], [], [], [], [], []
-    sink = _DeviceSampleSink(engine) if device_samples else None
+    rslot, rturns, rwin = [], [], []
+    # the examples are drained device-to-device inside the loop either way; for host results they cross PCIe once at
+    # the end, into pinned memory (torch's caching host allocator keeps the block for the next iteration)
+    sink = _DeviceSampleSink(engine)
     t0 = time.time()
     round_times = []
     while engine.games_played() < quota and not (stop_event is not None and stop_event.is_set()):
@@ -106,11 +120,8 @@ def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup
             drv.run_round(int(g("numFastSims", 20)) if fast else int(g("numMCTSSims", 100)), fast)
         engine.check_errors()
         n = engine.sample_count()
-        if n > 0 and sink is not None:
+        if n > 0:
             sink.drain(n)
-        elif n > 0:
-            o, p, zz, _ = engine.drain_samples()
-            obs.append(o); pi.append(p); z.append(zz)
         s, t, w = engine.drain_results()
         if len(s):
             rslot.append(s); rturns.append(t); rwin.append(w)
@@ -124,13 +135,9 @@ def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup
     if own_engine:
         torch.cuda.synchronize(engine.obs.device)
         engine.close()                                   # the node pool goes back to the driver now, not at some later GC
-    if sink is not None:
-        return SelfPlayResult(*sink.tensors(), cat(rslot, (0,), np.int32), cat(rturns, (0,), np.int32),
-                              cat(rwin, (0, 3), np.uint8), nsims, dt)
-    return SelfPlayResult(
-        torch.from_numpy(cat(obs, (0,) + obs_shape, np.float32)), torch.from_numpy(cat(pi, (0, A), np.float32)),
-        torch.from_numpy(cat(z, (0, 3), np.float32)), cat(rslot, (0,), np.int32), cat(rturns, (0,), np.int32),
-        cat(rwin, (0, 3), np.uint8), nsims, dt)
+    tensors = sink.tensors() if device_samples else sink.to_host()
+    return SelfPlayResult(*tensors, cat(rslot, (0,), np.int32), cat(rturns, (0,), np.int32), cat(rwin, (0, 3), np.uint8),
+                          nsims, dt)
 
 
 def save_iteration_samples(result, data_dir, run_name, iteration):

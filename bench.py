@@ -537,6 +537,14 @@ def main():
     if not a.no_e2e and not a.tree_only:
         e2e = run_e2e(a, eng, model, dev, world)
 
+    # e2e_coach: the call a user of the drop-in Coach makes (GpuSelfPlayMixin.processSelfPlayBatches)
+    e2e_coach = None
+    if not a.no_e2e and not a.tree_only and a.game == "connect4" and a.net == "default":
+        try:
+            e2e_coach = run_e2e_coach(a, model, dev, local, rank, world)
+        except Exception as ex:          # a secondary number must never take the bench down
+            e2e_coach = {"value": None, "error": repr(ex)}
+
     if world > 1:
         clear_samples()
         gather_ms, gathered = gather_examples([t[:kept[0]] for t in keep], dev, rank, world)
@@ -558,7 +566,7 @@ def main():
                        "l2": "node pool %.1f GB per GPU > 126 MB L2; no flush" % (st1["pool_bytes"] / 1e9),
                        "preroll_rounds": a.preroll},
             "clocks": clk, "gpu_launches": drv.launches - launches0,
-            "roofline": roof, "roofline_nn": roof_nn, "cpu_baseline": cpu_base, "e2e": e2e, "alt_nn": alt,
+            "roofline": roof, "roofline_nn": roof_nn, "cpu_baseline": cpu_base, "e2e": e2e, "e2e_coach": e2e_coach, "alt_nn": alt,
             "tree_stats": {"sims": dsims, "mean_depth": dD / max(dsims, 1), "mean_children_scanned": dC / max(dsims, 1),
                            "games_finished": st1["results"] - st0["results"], "peak_nodes_per_game": st1["peak_nodes"],
                            "terminal_leaf_fraction": (st1["terminal_leaves"] - st0["terminal_leaves"]) / max(dsims, 1)},
@@ -590,6 +598,58 @@ def model_flops(model, obs_shape):
         for h in hs:
             h.remove()
     return float(total[0])
+
+
+def run_e2e_coach(a, model, dev, local, rank, world):
+    """Secondary end-to-end number: the self-play phase as a user of the drop-in Coach calls it
+    (azb200.coach.GpuSelfPlayMixin.processSelfPlayBatches -> run_selfplay_iteration): per iteration the network's
+    weights come from HOST memory (pinned state_dict -> device), the engine plays gamesPerIteration games, and the
+    training examples + game results are returned in HOST memory (what saveIterationSamples consumes).  Wall clock
+    around the whole call, max over ranks."""
+    import time
+    import torch
+    import torch.distributed as dist
+    from azb200 import SelfPlayEngine
+    from azb200 import nnet as aznet
+    from azb200.coach import run_selfplay_iteration
+    from azb200.selfplay import engine_kwargs_from_args
+
+    class Connect4:
+        __module__ = "alphazero.envs.connect4.connect4"
+        observation_size = staticmethod(lambda: (4, 6, 7))
+        action_size = staticmethod(lambda: 7)
+        num_players = staticmethod(lambda: 2)
+        max_turns = staticmethod(lambda: 42)
+
+    B, sims = a.games, a.sims
+    args = dict(process_batch_size=B, gamesPerIteration=2 * B, numMCTSSims=sims, numFastSims=sims, probFastSim=0.0,
+                cpuct=1.25, fpu_reduction=0.2, root_noise_frac=0.1, root_policy_temp=1.1, add_root_noise=True,
+                add_root_temp=True, symmetricSamples=True)
+    host_weights = {k: v.detach().cpu().pin_memory() for k, v in model.state_dict().items()}
+    net = aznet.ResNet((4, 6, 7), 7, 3, **aznet.DEFAULT_NET_ARGS).to(dev).eval()
+    eng = SelfPlayEngine(**engine_kwargs_from_args(Connect4, args, B, device=local, rng="philox", seed=1, game_id_base=rank * B))
+    run_selfplay_iteration(Connect4, net, args, device=local, seed=1, engine=eng)   # warm-up: a previous iteration of the same size
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    sd = net.state_dict()
+    for k, v in host_weights.items():                                    # H2D: this iteration's network
+        sd[k].copy_(v, non_blocking=True)
+    res = run_selfplay_iteration(Connect4, net, args, device=local, seed=2, engine=eng)      # D2H: examples, results
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    eng.close()
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    n = torch.tensor([float(res.sims)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    h2d = sum(v.numel() * v.element_size() for v in host_weights.values())
+    d2h = sum(x.numel() * x.element_size() for x in (res.data, res.policy, res.value)) + res.result_turns.nbytes + res.result_winstates.nbytes
+    return {"value": float(n.item()) / float(t.item()), "unit": UNIT, "seconds": float(t.item()), "games": int(len(res.result_turns)),
+            "examples": int(res.data.shape[0]), "h2d_bytes": int(h2d), "d2h_bytes": int(d2h),
+            "api": "azb200.coach.run_selfplay_iteration (the body of GpuSelfPlayMixin.processSelfPlayBatches): network weights from "
+                   "pinned host memory, gamesPerIteration = 2 x games, examples and results returned in host memory; wall clock"}
 
 
 def run_e2e(a, eng, model, dev, world):
