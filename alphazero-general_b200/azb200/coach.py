@@ -151,6 +151,52 @@ def save_iteration_samples(result, data_dir, run_name, iteration):
     return base
 
 
+class ExampleQueue:
+    """``file_queue`` of the reference Coach (an mp.Queue of (obs, pi, z) numpy triples, SelfPlayAgent.pyx:194-196) backed
+    by the iteration's example tensors: ``qsize / empty / get / put`` behave like the queue for the reference's
+    saveIterationSamples loop (Coach.py:366-376), but three tensors are stored instead of one pickled item per example
+    (an iteration of 8192 Connect4 games is ~400 k examples)."""
+
+    def __init__(self):
+        self.blocks, self.row, self.singles = [], 0, []
+
+    def put_block(self, data, policy, value):
+        if data.shape[0]:
+            self.blocks.append((data, policy, value))
+
+    def put(self, item, *a, **k):
+        self.singles.append(item)
+
+    def qsize(self):
+        return sum(int(b[0].shape[0]) for b in self.blocks) - self.row + len(self.singles)
+
+    def empty(self):
+        return self.qsize() == 0
+
+    def get(self, *a, **k):
+        if self.blocks:
+            d, p, v = self.blocks[0]
+            i = self.row
+            self.row += 1
+            if self.row == d.shape[0]:
+                self.blocks.pop(0)
+                self.row = 0
+            return d[i].numpy(), p[i].numpy(), v[i].numpy()
+        if self.singles:
+            return self.singles.pop(0)
+        import queue
+        raise queue.Empty
+
+    def take_tensors(self):
+        """Everything queued, as three tensors (None if single items are queued too); empties the queue."""
+        if self.singles or not self.blocks:
+            return None
+        blocks, self.blocks = self.blocks, []
+        row, self.row = self.row, 0
+        blocks[0] = tuple(t[row:] for t in blocks[0])
+        return tuple(torch.cat([b[i] for b in blocks]) for i in range(3))
+
+
 class GpuSelfPlayMixin:
     """Mix into the reference Coach: ``class GpuCoach(GpuSelfPlayMixin, Coach): pass``."""
 
@@ -170,16 +216,32 @@ class GpuSelfPlayMixin:
         for i in range(len(res.result_turns)):
             w = res.result_winstates[i]
             self.result_queue.put((FinalState(res.result_turns[i], w), w, 0))
-        for i in range(res.data.shape[0]):
-            self.file_queue.put((res.data[i].numpy(), res.policy[i].numpy(), res.value[i].numpy()))
+        if not isinstance(self.file_queue, ExampleQueue):
+            self.file_queue = ExampleQueue()
+        self.file_queue.put_block(res.data, res.policy, res.value)
         self.games_played.value = min(int(self.args.gamesPerIteration), len(res.result_turns))
         self.completed.value = self.args.workers
         self.sample_time = res.seconds / max(self.games_played.value, 1)
         if hasattr(self, "writer"):
             self.writer.add_scalar("loss/sample_time", self.sample_time, iteration)
 
+    def saveIterationSamples(self, iteration):
+        """Coach.saveIterationSamples (Coach.py:364-386): the same three files, written from the tensors."""
+        t = self.file_queue.take_tensors() if isinstance(self.file_queue, ExampleQueue) else None
+        if t is None:
+            return super().saveIterationSamples(iteration)
+        print(f'Saving {t[0].shape[0]} samples')
+        try:                                                    # the GUI polls coach.state (Coach.py:128-137)
+            from alphazero.Coach import TrainState
+            self.state = TrainState.SAVE_SAMPLES
+        except ImportError:
+            TrainState = None
+        save_iteration_samples(SelfPlayResult(*t, None, None, None, 0, 0.0), self.args.data, self.args.run_name, iteration)
+        if TrainState is not None:
+            self.state = TrainState.STANDBY
+
     def killSelfPlayAgents(self):
         import torch.multiprocessing as mp
         self.agents = []
-        self.file_queue, self.result_queue = mp.Queue(), mp.Queue()
+        self.file_queue, self.result_queue = ExampleQueue(), mp.Queue()
         self.completed, self.games_played = mp.Value("i", 0), mp.Value("i", 0)

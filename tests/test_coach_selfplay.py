@@ -84,3 +84,66 @@ def test_device_resident_examples_equal_the_host_drain():
     for a, b in ((dev.data, host.data), (dev.policy, host.policy), (dev.value, host.value)):
         assert torch.equal(a.cpu(), b)
     assert np.array_equal(dev.result_turns, host.result_turns) and dev.sims == host.sims
+
+
+class _RefShapedCoach:
+    """The slice of the reference Coach the mixin plugs into: its fields (Coach.py:176-207) and the consumer side of
+    saveIterationSamples / get_game_results (Coach.py:366-376, utils.py:34-54), restated for the test."""
+
+    def __init__(self, game_cls, args, tmp):
+        import torch.multiprocessing as mp
+        self.game_cls, self.args = game_cls, args
+        self.args.data, self.args.run_name = str(tmp), "run"
+        self.warmup, self.sample_time = True, 0
+        import types
+        self.train_net = self.self_play_net = types.SimpleNamespace(nnet=None)       # warmup iterations never call it
+        self.stop_train = mp.Event()
+        self.file_queue, self.result_queue = mp.Queue(), mp.Queue()
+        self.completed, self.games_played = mp.Value("i", 0), mp.Value("i", 0)
+
+    def saveIterationSamples(self, iteration):              # the reference's loop: one queue item per example
+        n = self.file_queue.qsize()
+        data = torch.zeros([n, *self.game_cls.observation_size()])
+        pol, val = torch.zeros([n, self.game_cls.action_size()]), torch.zeros([n, 3])
+        for i in range(n):
+            d, p, v = self.file_queue.get()
+            data[i], pol[i], val[i] = torch.from_numpy(d), torch.from_numpy(p), torch.from_numpy(v)
+        return data, pol, val
+
+
+def test_mixin_fills_the_coach_fields_queues_and_files(tmp_path):
+    """class MyCoach(GpuSelfPlayMixin, Coach): the three self-play phase methods + saveIterationSamples."""
+    from azb200.coach import ExampleQueue, GpuSelfPlayMixin
+
+    class Args(dict):
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+
+    class MyCoach(GpuSelfPlayMixin, _RefShapedCoach):
+        pass
+
+    args = Args(process_batch_size=48, gamesPerIteration=100, numWarmupSims=5, probFastSim=0.4, symmetricSamples=True,
+                model_gating=True, workers=3)
+    c = MyCoach(_C4Game, args, tmp_path)
+    np.random.seed(3)
+    c.generateSelfPlayAgents()
+    c.processSelfPlayBatches(1)
+    assert c.games_played.value == 100 and c.completed.value == 3 and c.sample_time > 0
+    n = c.file_queue.qsize()
+    assert isinstance(c.file_queue, ExampleQueue) and n > 100 * 7
+    first = c.file_queue.get()                              # the per-example queue protocol still works ...
+    assert first[0].shape == (4, 6, 7) and first[1].shape == (7,) and first[2].shape == (3,) and c.file_queue.qsize() == n - 1
+    rest = _RefShapedCoach.saveIterationSamples(c, 1)       # ... for the reference's own consumer loop
+    assert rest[0].shape[0] == n - 1 and c.file_queue.empty()
+    results = [c.result_queue.get(timeout=10) for _ in range(100)]
+    assert all(r[1].sum() == 1 and 7 <= r[0].turns <= 42 and np.array_equal(r[0].win_state(), r[1]) for r in results)
+    # second iteration: the mixin's saveIterationSamples writes the reference's three files from the tensors
+    c.killSelfPlayAgents()
+    c.generateSelfPlayAgents()
+    c.processSelfPlayBatches(2)
+    n2 = c.file_queue.qsize()
+    c.saveIterationSamples(2)
+    base = tmp_path / "run" / "iteration-0002"
+    d, p, v = (torch.load(str(base) + s, weights_only=False) for s in ("-data.pkl", "-policy.pkl", "-value.pkl"))
+    assert d.shape == (n2, 4, 6, 7) and p.shape == (n2, 7) and v.shape == (n2, 3) and c.file_queue.empty()
+    assert torch.allclose(p.sum(1), torch.ones(n2), atol=1e-5) and torch.all(v.sum(1) == 1)
