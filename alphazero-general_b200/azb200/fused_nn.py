@@ -39,7 +39,10 @@ def _bn_affine(bn):
 def _folded(model):
     """Folded network in float64, layout-free: conv weights [L][cout][tap][cin], biases, BN1
     scale / shift per block, the affine head map [A+3][pos][ch] and its bias."""
-    m = model.eval().cpu()
+    # a private copy: nn.Module.cpu() / .double() replace the parameters' storage in place, which would leave every
+    # pointer captured from the caller's model (optimizer state aside: a CUDA-graphed training step) dangling
+    import copy
+    m = copy.deepcopy(model).eval().cpu()
     ch, depth, cin = m.conv1.out_channels, len(m.resnet), m.channels
     L = 1 + 2 * depth
     convs = []
@@ -70,7 +73,6 @@ def _folded(model):
     basis = torch.eye(ch * H * W, dtype=torch.float64).view(ch * H * W, ch, H, W)
     mat = (heads(basis) - bias[None]).T.contiguous()                       # [A+3, ch*H*W], feature = c*HW + pos
     whead = mat.view(-1, ch, H * W).permute(0, 2, 1).contiguous()          # [A+3, pos, ch]
-    m.float()
     return dict(convs=convs, cbias=cbias, bn_scale=bn_scale, bn_shift=bn_shift, whead=whead, bhead=bias,
                 channels=ch, depth=depth, in_channels=cin, board_h=H, board_w=W, action_size=m.action_size)
 

@@ -29,33 +29,79 @@ DEFAULTS = dict(
     arenaCompare=128, arenaTemp=0.25, model_gating=True, max_gating_iters=None, min_next_model_winrate=0.52,
     use_draws_for_winrate=True, cpuct=1.25, fpu_reduction=0.2, root_noise_frac=0.1, root_policy_temp=1.1,
     add_root_noise=True, add_root_temp=True, symmetricSamples=True, mctsResetThreshold=None, startTemp=1,
-    ddp_train=False)
+    ddp_train=False, graph_train=False)
 
 
 class _A(dict):
     __getattr__ = dict.__getitem__
 
 
-def train_steps(wrapper, optimizer, loader, steps, value_loss_weight):
-    """The loop body of NNetWrapper.train (NNetWrapper.py:131-165): -> (mean policy loss, mean value loss)."""
+class _GraphedStep:
+    """One training step (forward, both losses, backward, SGD update) on static input tensors, captured as a CUDA
+    graph: the DEFAULT_ARGS net is ~200 small kernels per step, i.e. launch-bound when issued one by one."""
+
+    def __init__(self, net, optimizer, boards, pis, vs, value_loss_weight):
+        self.boards, self.pis, self.vs = (torch.empty_like(t) for t in (boards, pis, vs))
+        self.losses = torch.zeros(2, device=boards.device)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            out_pi, out_v = net(self.boards)
+            l_pi, l_v = loss_pi(self.pis, out_pi), loss_v(self.vs, out_v, value_loss_weight)
+            (l_pi + l_v).backward()
+            optimizer.step()
+            self.losses.copy_(torch.stack((l_pi.detach(), l_v.detach())))
+
+    def __call__(self, boards, pis, vs):
+        self.boards.copy_(boards); self.pis.copy_(pis); self.vs.copy_(vs)
+        self.graph.replay()
+        return self.losses
+
+
+def _eager_step(net, optimizer, boards, target_pis, target_vs, value_loss_weight):
+    # a function of its own: when it returns nothing references the step's autograd graph any more, so the
+    # parameters' AccumulateGrad nodes (bound to the stream of this step) are gone before a capture builds its own
+    out_pi, out_v = net(boards)
+    l_pi, l_v = loss_pi(target_pis, out_pi), loss_v(target_vs, out_v, value_loss_weight)
+    optimizer.zero_grad()
+    (l_pi + l_v).backward()
+    optimizer.step()
+    return torch.stack((l_pi.detach(), l_v.detach()))
+
+
+def train_steps(wrapper, optimizer, loader, steps, value_loss_weight, graph_after=3):
+    """The loop body of NNetWrapper.train (NNetWrapper.py:131-165): -> (mean policy loss, mean value loss).
+    After `graph_after` eager steps on full batches (cuDNN has chosen its algorithms, the momentum buffers exist) the
+    step is captured once per (wrapper, batch shape) and replayed; ragged last batches of an epoch run eagerly.
+    graph_after=None: every step eager."""
     net = wrapper.nnet
     net.train()
-    lp_sum = lv_sum = n = 0.0
-    step = 0
+    acc = None                                        # device-side sum of batch-weighted (l_pi, l_v): no sync per step
+    n = 0
+    step = full_eager = 0
+    cache = wrapper.__dict__.setdefault("_graphed_steps", {})
     while step < steps:
         for boards, target_pis, target_vs in loader:
             if step == steps:
                 break
             step += 1
-            out_pi, out_v = net(boards)
-            l_pi, l_v = loss_pi(target_pis, out_pi), loss_v(target_vs, out_v, value_loss_weight)
-            optimizer.zero_grad()
-            (l_pi + l_v).backward()
-            optimizer.step()
             b = boards.size(0)
-            lp_sum += float(l_pi.detach()) * b; lv_sum += float(l_v.detach()) * b; n += b
+            key = (tuple(boards.shape), id(optimizer))
+            g = cache.get(key)
+            if g is None and graph_after is not None and boards.is_cuda and b == loader.batch_size and full_eager >= graph_after:
+                g = cache[key] = _GraphedStep(net, optimizer, boards, target_pis, target_vs, value_loss_weight)
+            if g is not None:
+                losses = g(boards, target_pis, target_vs)
+            else:
+                losses = _eager_step(net, optimizer, boards, target_pis, target_vs, value_loss_weight)
+                full_eager += int(b == loader.batch_size)
+            acc = losses.double() * b if acc is None else acc + losses.double() * b
+            n += b
     net.eval()
-    return (lp_sum / n, lv_sum / n) if n else (0.0, 0.0)
+    if not n:
+        return 0.0, 0.0
+    lp, lv = (acc / n).tolist()
+    return lp, lv
 
 
 def winrate_of_first(wins, draws, use_draws):
@@ -124,7 +170,8 @@ class GpuCoach:
                                              torch.device("cuda", self.device))
                 self._fresh(self.train_net)
             elif self.rank == 0:
-                losses = train_steps(self.train_net, self.optimizer, loader, steps, a.value_loss_weight)
+                losses = train_steps(self.train_net, self.optimizer, loader, steps, a.value_loss_weight,
+                                     graph_after=3 if a.graph_train else None)
                 self._fresh(self.train_net)
             if self.rank == 0:
                 rec["loss_pi"], rec["loss_v"] = losses

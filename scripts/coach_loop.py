@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="concurrent games per GPU")
     ap.add_argument("--sims", type=int, default=100)
     ap.add_argument("--arena", type=int, default=128)
+    ap.add_argument("--graph-train", action="store_true", help="replay the training step as a CUDA graph (3.3 vs 4 ms per step)")
     ap.add_argument("--ddp-train", action="store_true", help="N > 1: every rank trains on its slice of each batch")
     a = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -37,7 +38,7 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     from azb200.loop import GpuCoach
     coach = GpuCoach(Connect4, dict(numIters=a.iters, gamesPerIteration=a.games, process_batch_size=a.batch, numMCTSSims=a.sims,
-                                    arenaCompare=a.arena, ddp_train=a.ddp_train), device=local)
+                                    arenaCompare=a.arena, ddp_train=a.ddp_train, graph_train=a.graph_train), device=local)
     for rec in coach.learn():
         if coach.rank == 0:
             print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in rec.items()}))
