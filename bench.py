@@ -14,8 +14,14 @@ value     device-resident throughput: NN reads/writes the engine buffers in HBM.
 e2e       same metric through the reference-facing SelfPlayAgent surface with
           HOST batch/policy/value tensors (Coach.processSelfPlayBatches' loop
           body), host<->device copies and sample drains inside the timed region.
+e2e_coach (N = 1, secondary) the self-play phase as the drop-in Coach calls it
+          (azb200.coach.run_selfplay_iteration): weights from host memory, the
+          iteration's examples and results back in host memory; wall clock.
 roofline  k_select (PUCT scan): algorithmic bytes 16*sumD + 12*sumC from the
           engine's exact counters / CUDA-event time of the select launches.
+roofline_nn  the leaf evaluator against the measured sustained bf16 tensor
+          throughput: useful flops of the ResNet x rows evaluated / CUDA-event
+          time of its launches (same eager rounds as `roofline`).
 cpu_baseline / --impl reference
           the reference's own Cython SelfPlayAgent processes (oracle/_ref) served
           by the reference's ResNet as Coach.processSelfPlayBatches does, on
@@ -539,7 +545,8 @@ def main():
 
     # e2e_coach: the call a user of the drop-in Coach makes (GpuSelfPlayMixin.processSelfPlayBatches)
     e2e_coach = None
-    if not a.no_e2e and not a.tree_only and a.game == "connect4" and a.net == "default":
+    if not a.no_e2e and not a.tree_only and a.game == "connect4" and a.net == "default" and world == 1:
+        # (N = 1 only: a secondary leg with its own collectives is not worth a rank-asymmetric failure in a scaling run)
         try:
             e2e_coach = run_e2e_coach(a, model, dev, local, rank, world)
         except Exception as ex:          # a secondary number must never take the bench down
