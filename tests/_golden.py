@@ -32,10 +32,13 @@ def agent_kwargs(g):
         kw = dict(mcts_reset_threshold=int(g["reset_threshold"]), games_per_iteration=int(g["quota"]) or (1 << 40),
                   arena_temp=float(g["arena_temp"]), player_to_index=g["player_to_index"].tolist())
         return game, kw
+    hp = lambda k, d: float(g["hyper_" + k]) if ("hyper_" + k) in g.files else d       # older files: DEFAULT_ARGS
     kw = dict(add_root_temp=bool(g["add_root_temp"]), add_root_noise=bool(g["add_root_noise"]),
               symmetric_samples=bool(g["symmetric"]), mcts_reset_threshold=int(g["reset_threshold"]),
               games_per_iteration=int(g["quota"]) or (1 << 40),
-              temps=_orc.temp_table(_orc.default_temp_scaling, 1, max_turns))
+              cpuct=hp("cpuct", 1.25), fpu_reduction=hp("fpu_reduction", 0.2), root_noise_frac=hp("root_noise_frac", 0.1),
+              root_policy_temp=hp("root_policy_temp", 1.1),
+              temps=_orc.temp_table(_orc.default_temp_scaling, hp("start_temp", 1.0), max_turns))
     return game, kw
 
 

@@ -43,6 +43,15 @@ CASES = {
     # arenaTemp, tree reset threshold, quota (deterministic pow: probs uses ** (1 / arenaTemp))
     "c4_arena": dict(game="connect4", B=4, seeds=[61, 62, 63, 64], rounds=200, sims=12, nn=[101, 102], arena=True,
                      arena_temp=0.25, player_to_index=[1, 0], add_root_temp=False, det_pow=True, reset_threshold=6, quota=9),
+    # non-default search hyper-parameters (cpuct, fpu_reduction, noise fraction, root temperature, start temperature 2
+    # on the halving schedule): nothing on the path may have the DEFAULT_ARGS values baked in
+    "c4_hyper": dict(game="connect4", B=4, seeds=[81, 82, 83, 84], rounds=45, sims=40, nn=4321,
+                     add_root_temp=True, add_root_noise=True, det_pow=True,
+                     hyper=dict(cpuct=2.5, fpu_reduction=0.45, root_noise_frac=0.3, root_policy_temp=1.6, start_temp=2.0)),
+    "tafl_hyper_fast": dict(game="brandubh", B=3, seeds=[91, 92, 93], rounds=140, sims=10, nn=555,
+                            add_root_temp=True, add_root_noise=False, det_pow=True, symmetric=False, reset_threshold=7,
+                            quota=4, fast_pattern=[1, 0, 0, 1],
+                            hyper=dict(cpuct=0.8, fpu_reduction=0.0, root_noise_frac=0.1, root_policy_temp=0.9, start_temp=1.0)),
     "tafl_arena": dict(game="brandubh", B=2, seeds=[71, 72], rounds=45, sims=8, nn=[111, 112], arena=True,
                        arena_temp=0.5, player_to_index=[0, 1], add_root_temp=False, det_pow=True),
 }
@@ -58,7 +67,9 @@ def make(name, c):
         if A > 7:
             noise = rs.dirichlet([10.83 / 40] * 96, size=(c["B"], 8)).astype(np.float32)
     arena = bool(c.get("arena"))
-    ref = _refdriver.RefAgent(c["game"], c["B"], mt_seeds=c["seeds"], add_root_temp=c["add_root_temp"],
+    hyper = dict(cpuct=1.25, fpu_reduction=0.2, root_noise_frac=0.1, root_policy_temp=1.1, start_temp=1.0)
+    hyper.update(c.get("hyper", {}))
+    ref = _refdriver.RefAgent(c["game"], c["B"], mt_seeds=c["seeds"], add_root_temp=c["add_root_temp"], **hyper,
                               add_root_noise=c.get("add_root_noise", False), det_pow=c["det_pow"], noise=noise,
                               symmetric_samples=c.get("symmetric", True),
                               mcts_reset_threshold=c.get("reset_threshold"),
@@ -81,7 +92,8 @@ def make(name, c):
                add_root_temp=c["add_root_temp"], add_root_noise=c.get("add_root_noise", False),
                symmetric=c.get("symmetric", True), reset_threshold=c.get("reset_threshold") or 0,
                quota=c.get("quota", 0), fast_pattern=np.asarray(c.get("fast_pattern", [0])),
-               noise=noise if noise is not None else np.zeros((0, 0, 0), np.float32), game=c["game"])
+               noise=noise if noise is not None else np.zeros((0, 0, 0), np.float32), game=c["game"],
+               **{"hyper_" + k: np.float64(v) for k, v in hyper.items()})
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(name, "rounds", len(tr), "samples", len(s_obs), "results", len(r_slot))
 
