@@ -726,13 +726,18 @@ void orc_get_results(const orc_agent *ag, int32_t *slot, int32_t *turns, uint8_t
     if (win) memcpy(win, ag->r_win, (size_t)ag->r_n * 3);
 }
 
-int orc_rules_play(int game, const int32_t *actions, int n, int8_t *cells_out,
-                   uint8_t *valid_out, uint8_t *win_out, float *obs_out)
+int orc_rules_play_from(int game, const int8_t *cells, int turns, const int32_t *actions, int n, int8_t *cells_out,
+                        uint8_t *valid_out, uint8_t *win_out, float *obs_out)
 {
     const orc_game_ops *ops = orc_get_game_ops(game);
     if (!ops) return -2;
     orc_game g;
     ops->init(&g);
+    if (cells) {                      /* a constructed position: the game's cell codes, `turns` plies played */
+        memcpy(g.cells, cells, (size_t)ops->num_cells);
+        g.turns = turns;
+        g.player = turns % 2;
+    }
     for (int i = 0; i < n; i++)
         if (ops->play(&g, actions[i]) != 0) return -1;
     if (cells_out) ops->cells(&g, cells_out);
@@ -740,4 +745,10 @@ int orc_rules_play(int game, const int32_t *actions, int n, int8_t *cells_out,
     if (win_out) ops->win_state(&g, win_out);
     if (obs_out) ops->observation(&g, obs_out);
     return 0;
+}
+
+int orc_rules_play(int game, const int32_t *actions, int n, int8_t *cells_out,
+                   uint8_t *valid_out, uint8_t *win_out, float *obs_out)
+{
+    return orc_rules_play_from(game, NULL, 0, actions, n, cells_out, valid_out, win_out, obs_out);
 }

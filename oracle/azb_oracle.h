@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-enum { ORC_GAME_CONNECT4 = 0, ORC_GAME_BRANDUBH = 1 };
+enum { ORC_GAME_CONNECT4 = 0, ORC_GAME_BRANDUBH = 1, ORC_GAME_HNEFATAFL = 2 };
 enum { ORC_RNG_MT19937 = 0, ORC_RNG_PHILOX = 1 };
 
 typedef struct orc_args {
@@ -122,6 +122,9 @@ void orc_get_results(const orc_agent *ag, int32_t *slot, int32_t *turns, uint8_t
  * cells_out[H*W] int8, valid_out[A] u8, win_out[3] u8 */
 int orc_rules_play(int game, const int32_t *actions, int n, int8_t *cells_out,
                    uint8_t *valid_out, uint8_t *win_out, float *obs_out);
+/* the same from a constructed tafl position (cell codes, plies played so far) instead of the start position */
+int orc_rules_play_from(int game, const int8_t *cells, int turns, const int32_t *actions, int n, int8_t *cells_out,
+                        uint8_t *valid_out, uint8_t *win_out, float *obs_out);
 /* connect4 win scan on an arbitrary h x w board (cells +1/-1/0), win length k:
  * returns 0 none, 1 player +1, -1 player -1, 2 draw */
 int orc_c4_win_state(const int32_t *cells, int h, int w, int k);

@@ -1,6 +1,7 @@
 /*
- * orc_brandubh.c -- brandubh (7x7 tafl) rules of the reference restated on a
- * cell-code board.  TEST INFRASTRUCTURE ONLY -- see azb_oracle.h.
+ * orc_brandubh.c -- the tafl rules of the reference restated on a cell-code
+ * board: brandubh (7x7) and hnefatafl (11x11).  TEST INFRASTRUCTURE ONLY -- see
+ * azb_oracle.h.
  *
  * Follows fastafl/cengine.pyx (Board: legal_moves :109-132, _has_legals_check
  * :134-141, get_winner :146-169, _check_capture :174-199, _check_surround
@@ -10,42 +11,56 @@
  * :84-99, valid_moves :176-183, play_action :185-189, win_state :191-203,
  * symmetries :213-256) with the brandubh variant flags of fastafl/variants.py:22
  * (king_two_sided_capture=True, move_over_throne=True, king_can_enter_throne=False).
+ * hnefatafl = alphazero/envs/hnefatafl/fastafl.pyx (the same env code with
+ * variants.hnefatafl_args, fastafl/variants.py:1-11,21: 11x11 board,
+ * king_two_sided_capture=False, DRAW_MOVE_COUNT = 512 :43): the king is never
+ * taken by a sandwich; Board.king_captured (cengine.pyx:153-161) instead tests,
+ * when the winner is asked for, whether every in-bounds neighbour of the king
+ * is in KING_CAPTURE = (side 2, throne, escape) (cengine.pyx:42).
  *
  * Cell codes (cengine.pyx:24-32): 0 empty, 1 king's side ("attacker" in the
  * reference's naming), 2 edge side ("defender", moves first = env player 0),
  * 3 king, 7 king on throne, 8 king on escape, 4 empty throne, 5 empty escape.
- * cells[y * 7 + x]; Square(x, y).
+ * cells[y * N + x]; Square(x, y).  orc_game.variant selects the variant (set by init).
  */
 #include "azb_oracle.h"
 #include "orc_game.h"
 #include <string.h>
 
-#define N 7
-#define A_SIZE 588
-#define DRAW_MOVE_COUNT 100
+#define MAXN 11
 #define FLAG_KING_CAPTURED 1
+
+typedef struct { int n, draw_moves, two_sided; const char *start; } tafl_variant;
+static const tafl_variant VAR[2] = {
+    { 7, 100, 1, "5002005" "0002000" "0001000" "2217122" "0001000" "0002000" "5002005" },
+    { 11, 512, 0, "50022222005" "00000200000" "00000000000" "20000100002" "20001110002" "22011711022"
+                  "20001110002" "20000100002" "00000000000" "00000200000" "50022222005" },
+};
+#define N (VAR[g->variant].n)
+#define A_SIZE (N * N * (2 * N - 2))
+#define DRAW_MOVE_COUNT (VAR[g->variant].draw_moves)
 
 static const int DX[4] = { 0, 1, 0, -1 };   /* DIRECTIONS (cengine.pyx:46) as (dx, dy) */
 static const int DY[4] = { 1, 0, -1, 0 };
 
-static const char *START =
-    "5002005" "0002000" "0001000" "2217122" "0001000" "0002000" "5002005";
-
-static int inb(int x, int y) { return x >= 0 && x < N && y >= 0 && y < N; }
+#define inb(x, y) ((x) >= 0 && (x) < N && (y) >= 0 && (y) < N)
 static int is_king_val(int v) { return v == 3 || v == 7 || v == 8; }
 static int in_attackers(int v) { return v == 1 || is_king_val(v); }   /* ATTACKERS */
 
-static void tafl_init(orc_game *g)
+static void tafl_init_variant(orc_game *g, int variant)
 {
     memset(g, 0, sizeof(*g));
-    for (int i = 0; i < N * N; i++) g->cells[i] = (int8_t)(START[i] - '0');
+    g->variant = variant;
+    for (int i = 0; i < N * N; i++) g->cells[i] = (int8_t)(VAR[variant].start[i] - '0');
 }
+static void tafl_init(orc_game *g) { tafl_init_variant(g, 0); }
+static void hnefatafl_init(orc_game *g) { tafl_init_variant(g, 1); }
 
 /* Board.to_play: 2 - num_turns % 2  (side 2 moves first) */
 static int to_play(const orc_game *g) { return 2 - (g->turns % 2); }
 
 /* fastafl.pyx get_action */
-static int encode_action(int x, int y, int nx, int ny)
+static int encode_action(const orc_game *g, int x, int y, int nx, int ny)
 {
     int mt;
     if (x == nx) mt = ny < y ? ny : ny - 1;
@@ -54,7 +69,7 @@ static int encode_action(int x, int y, int nx, int ny)
 }
 
 /* fastafl.pyx get_move */
-static void decode_action(int a, int *x, int *y, int *nx, int *ny)
+static void decode_action(const orc_game *g, int a, int *x, int *y, int *nx, int *ny)
 {
     int size = 2 * N - 2, mt = a % size, sq = a / size;
     *x = sq % N; *y = sq / N;
@@ -87,7 +102,7 @@ static void tafl_valid(const orc_game *g, uint8_t *valid)
                 int cx = x + DX[d], cy = y + DY[d];
                 int throne = inb(cx, cy) && g->cells[cy * N + cx] == 4;   /* move_over_throne */
                 while (throne || sq_valid(g, cx, cy, king)) {
-                    if (!throne) valid[encode_action(x, y, cx, cy)] = 1;
+                    if (!throne) valid[encode_action(g, x, y, cx, cy)] = 1;
                     cx += DX[d]; cy += DY[d];
                     throne = inb(cx, cy) && g->cells[cy * N + cx] == 4;
                 }
@@ -105,7 +120,7 @@ static void check_capture(orc_game *g, int mx, int my)
         int ex = mx + DX[d], ey = my + DY[d];
         if (!inb(ex, ey)) continue;
         int v = g->cells[ey * N + ex];
-        int do_capture = v == 3;                         /* king_two_sided_capture and value == piece_king */
+        int do_capture = VAR[g->variant].two_sided && v == 3;   /* king_two_sided_capture and value == piece_king */
         if (v == enemy || do_capture) {
             int fx = ex + DX[d], fy = ey + DY[d];
             if (!inb(fx, fy)) continue;
@@ -127,7 +142,7 @@ static void check_surround(orc_game *g, int mx, int my)
 {
     int pv = g->cells[my * N + mx];
     int enemy_is_att = pv == 2;                          /* _get_team(piece, enemy=True) */
-    uint8_t seen[N * N];
+    uint8_t seen[MAXN * MAXN];
     memset(seen, 0, sizeof(seen));
     for (int d = 0; d < 4; d++) {
         int sx = mx + DX[d], sy = my + DY[d];
@@ -136,7 +151,7 @@ static void check_surround(orc_game *g, int mx, int my)
         if (!(enemy_is_att ? in_attackers(v) : v == 2)) continue;
         if (seen[sy * N + sx]) continue;
         /* flood the group */
-        int stack[N * N], sp = 0, group[N * N], gn = 0, free_nb = 0;
+        int stack[MAXN * MAXN], sp = 0, group[MAXN * MAXN], gn = 0, free_nb = 0;
         stack[sp++] = sy * N + sx;
         seen[sy * N + sx] = 1;
         while (sp) {
@@ -168,7 +183,7 @@ static void check_surround(orc_game *g, int mx, int my)
 static int tafl_play(orc_game *g, int action)
 {
     int x, y, nx, ny;
-    decode_action(action, &x, &y, &nx, &ny);
+    decode_action(g, action, &x, &y, &nx, &ny);
     int sv = g->cells[y * N + x];
     int piece = sv, left = 0;
     if (sv == 7) { left = 4; piece = 3; } else if (sv == 8) { left = 5; piece = 3; }   /* remove_piece */
@@ -209,7 +224,22 @@ static int get_winner(const orc_game *g)
     int escaped = 0;
     for (int i = 0; i < N * N; i++) escaped |= g->cells[i] == 8;
     if (escaped || !has_legal(g, 2)) return 1;
-    if ((g->flags & FLAG_KING_CAPTURED) || !has_legal(g, 1)) return 2;
+    int captured = (g->flags & FLAG_KING_CAPTURED) != 0;
+    if (!captured && !VAR[g->variant].two_sided) {
+        /* Board.king_captured: all(in-bounds neighbours of a king in KING_CAPTURE = (2, 4, 5)) */
+        for (int i = 0; i < N * N && !captured; i++) {
+            if (!is_king_val(g->cells[i])) continue;
+            int all_in = 1;
+            for (int d = 0; d < 4; d++) {
+                int x = i % N + DX[d], y = i / N + DY[d];
+                if (!inb(x, y)) continue;
+                int w = g->cells[y * N + x];
+                if (!(w == 2 || w == 4 || w == 5)) all_in = 0;
+            }
+            captured = all_in;
+        }
+    }
+    if (captured || !has_legal(g, 1)) return 2;
     return 0;
 }
 
@@ -246,7 +276,7 @@ static void tafl_sym(const orc_game *g, const float *pi, int k, orc_game *g2, fl
 {
     int rot = k / 2 + 1, flip = k & 1;
     *g2 = *g;
-    int8_t cur[N * N], nxt[N * N];
+    int8_t cur[MAXN * MAXN], nxt[MAXN * MAXN];
     memcpy(cur, g->cells, N * N);
     for (int r = 0; r < rot; r++) {
         /* np.rot90: out[i][j] = in[j][N-1-i] */
@@ -260,22 +290,26 @@ static void tafl_sym(const orc_game *g, const float *pi, int k, orc_game *g2, fl
         memcpy(cur, nxt, N * N);
     }
     memcpy(g2->cells, cur, N * N);
-    for (int a = 0; a < A_SIZE; a++) pi2[a] = 0.0f;
-    for (int a = 0; a < A_SIZE; a++) {
+    const int asz = A_SIZE;
+    for (int a = 0; a < asz; a++) pi2[a] = 0.0f;
+    for (int a = 0; a < asz; a++) {
         int x, y, nx, ny;
-        decode_action(a, &x, &y, &nx, &ny);
+        decode_action(g, a, &x, &y, &nx, &ny);
         for (int r = 0; r < rot; r++) {
             int tx = x, tnx = nx;
             x = N - 1 - y; nx = N - 1 - ny;
             y = tx; ny = tnx;
         }
         if (flip) { x = N - 1 - x; nx = N - 1 - nx; }
-        pi2[encode_action(x, y, nx, ny)] = pi[a];
+        pi2[encode_action(g, x, y, nx, ny)] = pi[a];
     }
 }
 
 static void tafl_cells(const orc_game *g, int8_t *out) { memcpy(out, g->cells, N * N); }
 
 const orc_game_ops orc_brandubh_ops = {
-    A_SIZE, 5 * N * N, N * N, 8, tafl_init, tafl_play, tafl_valid, tafl_win, tafl_obs, tafl_sym, tafl_cells
+    588, 5 * 49, 49, 8, tafl_init, tafl_play, tafl_valid, tafl_win, tafl_obs, tafl_sym, tafl_cells
+};
+const orc_game_ops orc_hnefatafl_ops = {
+    2420, 5 * 121, 121, 8, hnefatafl_init, tafl_play, tafl_valid, tafl_win, tafl_obs, tafl_sym, tafl_cells
 };

@@ -127,6 +127,7 @@ const orc_game_ops *orc_get_game_ops(int game)
     if (game == ORC_GAME_CONNECT4) return &orc_connect4_ops;
 #ifdef ORC_HAVE_BRANDUBH
     if (game == ORC_GAME_BRANDUBH) return &orc_brandubh_ops;
+    if (game == ORC_GAME_HNEFATAFL) return &orc_hnefatafl_ops;
 #endif
     return 0;
 }

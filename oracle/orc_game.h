@@ -7,16 +7,17 @@
 #define ORC_GAME_H
 #include <stdint.h>
 
-#define ORC_MAX_ACTIONS 588
-#define ORC_MAX_CHILDREN 128
-#define ORC_MAX_PATH 512
-#define ORC_MAX_CELLS 49
+#define ORC_MAX_ACTIONS 2420     /* hnefatafl: 11 * 11 * 20 */
+#define ORC_MAX_CHILDREN 512
+#define ORC_MAX_PATH 1024
+#define ORC_MAX_CELLS 121
 
 typedef struct orc_game {
     int8_t cells[ORC_MAX_CELLS]; /* row-major board; meaning is per game       */
     int32_t player;              /* GameState._player                            */
     int32_t turns;               /* GameState._turns                             */
     int32_t flags;               /* game specific (tafl: king captured / escaped)*/
+    int32_t variant;             /* tafl: 0 brandubh, 1 hnefatafl (set by init)  */
 } orc_game;
 
 typedef struct orc_game_ops {
@@ -33,5 +34,6 @@ typedef struct orc_game_ops {
 const orc_game_ops *orc_get_game_ops(int game);
 extern const orc_game_ops orc_connect4_ops;
 extern const orc_game_ops orc_brandubh_ops;
+extern const orc_game_ops orc_hnefatafl_ops;
 
 #endif

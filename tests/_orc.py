@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB = os.path.join(ORACLE_DIR, "liborc.so")
 
-GAME_CONNECT4, GAME_BRANDUBH = 0, 1
+GAME_CONNECT4, GAME_BRANDUBH, GAME_HNEFATAFL = 0, 1, 2
 RNG_MT19937, RNG_PHILOX = 0, 1
 
 
@@ -76,6 +76,7 @@ def lib():
         L.orc_num_results.argtypes = [C.c_void_p]
         L.orc_get_results.argtypes = [C.c_void_p] + [C.c_void_p] * 3
         L.orc_rules_play.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        L.orc_rules_play_from.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4
         L.orc_c4_win_state.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orc_np_sum_f32.restype = C.c_float
         L.orc_np_sum_f32.argtypes = [C.c_void_p, C.c_int]
@@ -91,12 +92,27 @@ def lib():
     return _lib
 
 
+def rules_from_cells(game, cells0, turns, actions):
+    """Like rules_play, from a constructed position (tafl cell codes, `turns` plies played)."""
+    d = GAME_DIMS[game]
+    acts = np.ascontiguousarray(actions, dtype=np.int32)
+    c0 = np.ascontiguousarray(cells0, dtype=np.int8)
+    assert c0.size == d["cells"]
+    cells = np.zeros(d["cells"], dtype=np.int8)
+    valid = np.zeros(d["A"], dtype=np.uint8)
+    win = np.zeros(3, dtype=np.uint8)
+    obs = np.zeros(d["obs"], dtype=np.float32)
+    rc = lib().orc_rules_play_from(game, _p(c0), int(turns), _p(acts), len(acts), _p(cells), _p(valid), _p(win), _p(obs))
+    return rc, cells, valid, win, obs
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
 GAME_DIMS = {GAME_CONNECT4: dict(A=7, obs=(4, 6, 7), cells=42),
-             GAME_BRANDUBH: dict(A=588, obs=(5, 7, 7), cells=49)}
+             GAME_BRANDUBH: dict(A=588, obs=(5, 7, 7), cells=49),
+             GAME_HNEFATAFL: dict(A=2420, obs=(5, 11, 11), cells=121)}
 
 
 def temp_table(temp_scaling_fn, start_temp, max_turns, n=512):

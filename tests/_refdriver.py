@@ -154,8 +154,11 @@ def game_class(name):
     if name == "connect4":
         from alphazero.envs.connect4.connect4 import Game
         return Game
-    if name == "brandubh":
-        from alphazero.envs.brandubh.fastafl import Game as _G
+    if name in ("brandubh", "hnefatafl"):
+        if name == "brandubh":
+            from alphazero.envs.brandubh.fastafl import Game as _G
+        else:
+            from alphazero.envs.hnefatafl.fastafl import Game as _G
 
         class Game(_G):
             # the reference env lacks these two GameState statics (Game.py:55-63)
