@@ -513,6 +513,11 @@ def main():
     if roof is not None and os.path.exists(traffic_file):
         try:
             roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            roof["traffic_note"] = ("ncu dram read+write per launch (profiles/select_traffic.json). `achieved` counts only the PUCT scan "
+                                    "(16 B header + 12 B per scanned child, SURVEY 8d); the same launch also expands the leaf (24 B per "
+                                    "new child record), writes the leaf observation (obs floats x 4 B per game), the path and the slot "
+                                    "header: whole-simulation algorithmic traffic is ~1.5 KB per Connect4 simulation = ~12 MB per launch "
+                                    "of 8192 games, so the measured traffic is not re-reads of the scan")
         except Exception:
             pass
 
