@@ -269,8 +269,14 @@ class SelfPlayAgent(threading.Thread):
         if len(slot):
             obs, pi, z, _ = self.engine.drain_samples()
             self.d2h_bytes += obs.nbytes + pi.nbytes + z.nbytes
-            for i in range(len(obs)):
-                self.output_queue.put((obs[i], pi[i], z[i]))
+            if hasattr(self.output_queue, "put_block"):
+                # azb200.coach.ExampleQueue: the same examples in the same order as one block instead of one queue
+                # item each (a move-round of 8192 games ends ~400 games = ~16 k examples; the per-item loop costs the
+                # host longer than the GPU needs for the next 30 simulations)
+                self.output_queue.put_block(torch.from_numpy(obs), torch.from_numpy(pi), torch.from_numpy(z))
+            else:
+                for i in range(len(obs)):
+                    self.output_queue.put((obs[i], pi[i], z[i]))
             played = self.engine.games_played()
             new = played - self._counted
             self._counted = played

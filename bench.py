@@ -64,10 +64,13 @@ def parse():
     ap.add_argument("--preroll", type=int, default=48, help="cheap tree-only rounds that de-synchronise the games")
     ap.add_argument("--tree-only", action="store_true", help="warmup mode (constant NN outputs), one fused kernel per round")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-agents", type=int, default=2, help="reference `workers`: agents sharing the GPU in the e2e leg")
+    ap.add_argument("--e2e-agents", type=int, default=4, help="reference `workers`: agents sharing the GPU in the e2e leg")
     ap.add_argument("--e2e-mode", default="inline", choices=["inline", "threads"],
                     help="inline: one host thread runs the Coach loop over the agents (generateBatch -> process -> "
                          "processBatch, every call asynchronous and stream-ordered); threads: agents are threads, ready queue")
+    ap.add_argument("--e2e-eager", action="store_true", help="inline e2e leg without the agents' captured step graphs")
+    ap.add_argument("--e2e-item-queue", action="store_true",
+                    help="e2e leg: the agents put one queue item per example (reference file_queue protocol) instead of blocks")
     ap.add_argument("--e2e-sync", action="store_true",
                     help="e2e leg with host-synchronised tensors (default: stream-ordered, see SelfPlayAgent)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -693,6 +696,10 @@ def run_e2e(a, eng, model, dev, world):
     ready, stop, pause = pyqueue.Queue(), threading.Event(), threading.Event()
     completed, played = _Val(), _Val()
     bts, pts, vts, evs, agents = [], [], [], [], []
+    # Coach.file_queue: azb200.coach.ExampleQueue (what GpuSelfPlayMixin installs) keeps every example, block-wise;
+    # --e2e-item-queue: an mp.Queue-like sink that takes one (obs, pi, z) item per example, as the reference's does
+    from azb200.coach import ExampleQueue
+    file_queue = _Sink() if a.e2e_item_queue else ExampleQueue()
     for i in range(W):
         e = SelfPlayEngine(game="connect4", num_games=Bw, device=dev.index, rng="philox", seed=1,
                            game_id_base=(rank * W + i) * Bw, add_root_noise=True, add_root_temp=True,
@@ -702,7 +709,7 @@ def run_e2e(a, eng, model, dev, world):
         e.drain_samples(); e.drain_results()
         bts.append(torch.zeros(Bw, 4, 6, 7).pin_memory()); pts.append(torch.zeros(Bw, 7).pin_memory())
         vts.append(torch.zeros(Bw, 3).pin_memory()); evs.append(threading.Event())
-        agents.append(SelfPlayAgent(i, _Game, ready, evs[i], bts[i], pts[i], vts[i], _Sink(), _Sink(), completed, played,
+        agents.append(SelfPlayAgent(i, _Game, ready, evs[i], bts[i], pts[i], vts[i], file_queue, _Sink(), completed, played,
                                     stop, pause, args, engine=e, stream_ordered=not a.e2e_sync))
     wrap = NNetWrapper(nnet=model, cuda=True, fused=(a.nn != "cudnn"))
     old_tf32 = torch.backends.cudnn.allow_tf32
@@ -765,6 +772,7 @@ def run_e2e(a, eng, model, dev, world):
             # per step: generateBatch downloads observations, the NN answers go to host tensors, samples are drained
             "d2h_bytes_per_step": int(a.sims * pv_b + sum(ag.d2h_bytes for ag in agents) / steps),
             "steps": steps, "agents": W, "games_per_agent": Bw,
+            "file_queue": "one item per example" if a.e2e_item_queue else "azb200.coach.ExampleQueue (one block per move-round, every example kept)",
             "host_tensor_protocol": "host-synchronised" if a.e2e_sync else "stream-ordered (CUDA events)",
             "api": "Coach.processSelfPlayBatches loop: azb200.selfplay.SelfPlayAgent threads (generateBatch/processBatch/"
                    "playMoves) + NNetWrapper.process, pinned host tensors, ready queue + events"}
@@ -796,6 +804,36 @@ def run_e2e_inline(a, eng, agents, server, evs, ready, dev, world, Bw, old_tf32)
             with torch.cuda.stream(ag.stream):
                 ag.playMoves()
 
+    def one_round_graphed():
+        # the agents' own captured step graphs (SelfPlayAgent._graphed_round: [select, obs -> batch_tensor] /
+        # [answers -> engine, expand/backup, select, obs -> batch_tensor] / [answers -> engine, expand/backup]),
+        # interleaved by this one thread instead of one thread per agent: per simulation and agent the host issues two
+        # graph launches and two event records
+        for ag in agents:
+            with torch.cuda.stream(ag.stream):
+                if ag._g_first is None:
+                    ag._prepare_graphs()
+                ag._g_first.replay()
+                ag._publish_batch()
+        for s in range(a.sims):
+            for _ in agents:
+                j = ready.get_nowait()
+                server.serve(agents[j], evs[j])
+            for ag in agents:
+                with torch.cuda.stream(ag.stream):
+                    ag._await_answers()                  # batch_ready is already set: only the stream waits (answer_event)
+                    if s + 1 < a.sims:
+                        ag._g_mid.replay()
+                        ag._publish_batch()
+                    else:
+                        ag._g_last.replay()
+        for ag in agents:
+            with torch.cuda.stream(ag.stream):
+                ag.playMoves()
+
+    one_round()                                           # eager: one-time kernel / evaluator setup
+    if not a.e2e_eager:
+        one_round = one_round_graphed
     one_round(); one_round()
     if world > 1:
         dist.barrier()
@@ -823,6 +861,7 @@ def run_e2e_inline(a, eng, agents, server, evs, ready, dev, world, Bw, old_tf32)
             "h2d_bytes_per_step": int(a.sims * obs_b + sum(ag.h2d_bytes for ag in agents) / steps),
             "d2h_bytes_per_step": int(a.sims * pv_b + sum(ag.d2h_bytes for ag in agents) / steps),
             "steps": steps, "agents": W, "games_per_agent": Bw,
+            "file_queue": "one item per example" if a.e2e_item_queue else "azb200.coach.ExampleQueue (one block per move-round, every example kept)",
             "host_tensor_protocol": "stream-ordered (CUDA events)",
             "api": "Coach.processSelfPlayBatches data flow driven by one host thread: azb200.selfplay.SelfPlayAgent."
                    "generateBatch -> HostBatchServer.serve (NNetWrapper.process on the pinned host batch tensor) -> "
