@@ -480,13 +480,27 @@ def main():
         eng.select, drv.round_graph, drv.evals = orig_select, was_graph, orig_evals
         alg_bytes = 16.0 * (r1["sum_depth"] - r0["sum_depth"]) + 12.0 * (r1["sum_children"] - r0["sum_children"])
         roof_sims = r1["sims"] - r0["sims"]
+    def launch_times(events):
+        """CUDA-event time per launch.  In these eagerly launched rounds the start event can execute before the host
+        has issued the kernel behind it (a Python / scheduler pause between the two calls then counts as kernel time),
+        so launches longer than 3x the median are set aside; their number and the untrimmed mean are reported."""
+        ts = [e0.elapsed_time(e1) for e0, e1 in events]
+        med = statistics.median(ts)
+        kept_ts = [t for t in ts if t <= 3.0 * med]
+        q = sorted(ts)
+        launch_times.last_percentiles = [1000.0 * q[int(f * (len(q) - 1))] for f in (0.1, 0.5, 0.9)]
+        return sum(kept_ts), len(kept_ts), len(ts) - len(kept_ts), 1000.0 * sum(ts) / len(ts)
+
     if sel_events:
-        sel_ms = sum(e0.elapsed_time(e1) for e0, e1 in sel_events)
-        nl = len(sel_events)
+        sel_ms, nl, sel_dropped, sel_mean_all = launch_times(sel_events)
+        sel_pct = launch_times.last_percentiles
+        alg_bytes *= nl / float(len(sel_events))
         ach = alg_bytes / (sel_ms / 1000.0) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                 "traffic": None, "kernel": f"k_select<{'Brandubh' if tafl else 'Connect4'}>", "launches": nl, "avg_launch_us": 1000.0 * sel_ms / nl,
-                "alg_bytes_per_launch": alg_bytes / nl, "bytes_per_sim": alg_bytes / max(roof_sims, 1), "peak_source": peak_src,
+                "alg_bytes_per_launch": alg_bytes / nl, "bytes_per_sim": alg_bytes * (len(sel_events) / float(nl)) / max(roof_sims, 1), "peak_source": peak_src,
+                "launches_set_aside": sel_dropped, "mean_launch_us_untrimmed": sel_mean_all,
+                "launch_us_p10_p50_p90": sel_pct,
                 "note": f"CUDA-event time of each select launch on the tree stream over {a.roofline_steps} eagerly launched "
                         "move-rounds right after the timed (graph-replayed) steps"}
     elif a.tree_only:
@@ -500,16 +514,18 @@ def main():
     # in compact mode, every leaf otherwise), time = CUDA events around its launches in the same eager rounds
     roof_nn = None
     if nn_events:
-        nn_ms = sum(e0.elapsed_time(e1) for e0, e1 in nn_events)
+        nn_ms, nn_n, nn_dropped, nn_mean_all = launch_times(nn_events)
+        nn_pct = launch_times.last_percentiles
         compact = a.nn == "fused" and not a.eval_terminal and a.cohorts == 1
-        rows = roof_sims - ((r1["terminal_leaves"] - r0["terminal_leaves"]) if compact else 0)
+        rows = (roof_sims - ((r1["terminal_leaves"] - r0["terminal_leaves"]) if compact else 0)) * (nn_n / float(len(nn_events)))
         fl = model_flops(model, OBS)
         tf = fl * rows / (nn_ms / 1000.0) / 1e12
         sustained = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1388.0)))
         roof_nn = {"bound": "tensor", "achieved": tf, "peak": sustained, "unit": "TFLOP/s", "frac": tf / sustained, "traffic": None,
                    "kernel": {"fused": "k_resnet_tc (tcgen05/TMEM)", "fused_mma": "k_resnet_fused (mma.sync)"}.get(a.nn, "cuDNN " + a.precision),
-                   "launches": len(nn_events), "avg_launch_us": 1000.0 * nn_ms / len(nn_events), "flops_per_eval": fl,
-                   "rows_per_launch": rows / len(nn_events), "evals_per_s": rows / (nn_ms / 1000.0),
+                   "launches": nn_n, "avg_launch_us": 1000.0 * nn_ms / nn_n, "flops_per_eval": fl,
+                   "rows_per_launch": rows / nn_n, "evals_per_s": rows / (nn_ms / 1000.0),
+                   "launches_set_aside": nn_dropped, "mean_launch_us_untrimmed": nn_mean_all, "launch_us_p10_p50_p90": nn_pct,
                    "peak_source": ("measured sustained bf16" if "bf16_tflops_sustained" in peaks else "fallback"),
                    "note": "useful flops of the network (2 x multiply-adds of its convolutions and linear layers), not issued MMA flops"}
     traffic_file = os.path.join(ROOT, "profiles", "select_traffic.json")
