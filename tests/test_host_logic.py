@@ -85,3 +85,31 @@ def test_resnet_mirror_matches_reference_module(preset):
     got = aznet.NNetWrapper(nnet=ours, cuda=False).process(x)
     assert torch.allclose(got[0], want[0], atol=1e-5, rtol=0) and torch.allclose(got[1], want[1], atol=1e-5, rtol=0)
     assert torch.allclose(got[0].sum(1), torch.ones(64), atol=1e-5)
+
+
+def test_example_queue_keeps_the_per_example_protocol():
+    """azb200.coach.ExampleQueue: Coach.file_queue backed by tensors -- qsize / empty / get hand out the reference's
+    (obs, pi, z) numpy triples in emission order across blocks and single items; take_tensors drains the blocks."""
+    import queue
+    import torch
+    from azb200.coach import ExampleQueue
+    q = ExampleQueue()
+    assert q.empty() and q.qsize() == 0 and q.take_tensors() is None
+    with pytest.raises(queue.Empty):
+        q.get()
+    mk = lambda n, base: (torch.arange(n * 4 * 6 * 7, dtype=torch.float32).view(n, 4, 6, 7) + base,
+                          torch.full((n, 7), float(base)), torch.full((n, 3), float(base)))
+    q.put_block(*mk(3, 100))
+    q.put_block(*mk(0, 0))                                  # an empty block is not queued
+    q.put_block(*mk(2, 200))
+    assert q.qsize() == 5 and not q.empty()
+    d, p, v = q.get()
+    assert d.shape == (4, 6, 7) and d[0, 0, 0] == 100 and p.tolist() == [100.0] * 7 and v.tolist() == [100.0] * 3
+    assert q.qsize() == 4
+    t = q.take_tensors()                                     # the rest, still in order, the consumed row left out
+    assert t[0].shape == (4, 4, 6, 7) and t[1][:, 0].tolist() == [100.0, 100.0, 200.0, 200.0] and q.empty()
+    assert float(t[0][0, 0, 0, 0]) == 100 + 4 * 6 * 7
+    q.put_block(*mk(1, 7))
+    q.put((np.zeros((4, 6, 7), np.float32), np.ones(7, np.float32), np.ones(3, np.float32)))      # a reference-style item
+    assert q.qsize() == 2 and q.take_tensors() is None      # mixed content: only the per-item path serves it
+    assert q.get()[1][0] == 7 and q.get()[1][0] == 1 and q.empty()
