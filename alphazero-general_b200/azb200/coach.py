@@ -33,6 +33,7 @@ class SelfPlayResult:
         self.data, self.policy, self.value = obs, pi, z
         self.result_slots, self.result_turns, self.result_winstates = slot_r, turns_r, win_r
         self.sims, self.seconds = sims, seconds
+        self.last_round_seconds = np.zeros(0)        # host time per move-round (diagnostic, set by run_selfplay_iteration)
 
     def game_results(self, num_players=2):
         """alphazero/utils.py:34-54 get_game_results"""
@@ -131,13 +132,15 @@ def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup
     A, obs_shape, nsims = engine.A, engine.obs_shape, engine.stats()["sims"]
     dt = time.time() - t0
     round_times.append(time.time())
-    SelfPlayResult.last_round_seconds = np.diff(np.asarray(round_times))        # diagnostic: host time per move-round
+    round_seconds = np.diff(np.asarray(round_times))                            # diagnostic: host time per move-round
     if own_engine:
         torch.cuda.synchronize(engine.obs.device)
         engine.close()                                   # the node pool goes back to the driver now, not at some later GC
     tensors = sink.tensors() if device_samples else sink.to_host()
-    return SelfPlayResult(*tensors, cat(rslot, (0,), np.int32), cat(rturns, (0,), np.int32), cat(rwin, (0, 3), np.uint8),
-                          nsims, dt)
+    res = SelfPlayResult(*tensors, cat(rslot, (0,), np.int32), cat(rturns, (0,), np.int32), cat(rwin, (0, 3), np.uint8),
+                         nsims, dt)
+    res.last_round_seconds = round_seconds
+    return res
 
 
 def save_iteration_samples(result, data_dir, run_name, iteration):
