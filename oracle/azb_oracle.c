@@ -747,6 +747,20 @@ int orc_rules_play_from(int game, const int8_t *cells, int turns, const int32_t 
     return 0;
 }
 
+int orc_rules_symmetry(int game, const int8_t *cells, int turns, const float *pi, int k, int8_t *cells_out, float *pi_out)
+{
+    const orc_game_ops *ops = orc_get_game_ops(game);
+    if (!ops || k < 0 || k >= ops->num_symmetries) return -2;
+    orc_game g, g2;
+    ops->init(&g);
+    memcpy(g.cells, cells, (size_t)ops->num_cells);
+    g.turns = turns;
+    g.player = turns % 2;
+    ops->symmetry(&g, pi, k, &g2, pi_out);
+    ops->cells(&g2, cells_out);
+    return 0;
+}
+
 int orc_rules_play(int game, const int32_t *actions, int n, int8_t *cells_out,
                    uint8_t *valid_out, uint8_t *win_out, float *obs_out)
 {

@@ -125,6 +125,8 @@ int orc_rules_play(int game, const int32_t *actions, int n, int8_t *cells_out,
 /* the same from a constructed tafl position (cell codes, plies played so far) instead of the start position */
 int orc_rules_play_from(int game, const int8_t *cells, int turns, const int32_t *actions, int n, int8_t *cells_out,
                         uint8_t *valid_out, uint8_t *win_out, float *obs_out);
+/* Game.symmetries entry k of (position, pi): transformed cells and permuted policy */
+int orc_rules_symmetry(int game, const int8_t *cells, int turns, const float *pi, int k, int8_t *cells_out, float *pi_out);
 /* connect4 win scan on an arbitrary h x w board (cells +1/-1/0), win length k:
  * returns 0 none, 1 player +1, -1 player -1, 2 draw */
 int orc_c4_win_state(const int32_t *cells, int h, int w, int k);

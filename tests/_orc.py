@@ -106,6 +106,19 @@ def rules_from_cells(game, cells0, turns, actions):
     return rc, cells, valid, win, obs
 
 
+def symmetry(game, cells0, turns, pi, k):
+    """Game.symmetries entry k of (position given as cell codes, pi) -> (cells, pi)."""
+    d = GAME_DIMS[game]
+    c0 = np.ascontiguousarray(cells0, dtype=np.int8)
+    p0 = np.ascontiguousarray(pi, dtype=np.float32)
+    cells = np.zeros(d["cells"], dtype=np.int8)
+    p2 = np.zeros(d["A"], dtype=np.float32)
+    L = lib()
+    L.orc_rules_symmetry.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    assert L.orc_rules_symmetry(game, _p(c0), int(turns), _p(p0), int(k), _p(cells), _p(p2)) == 0
+    return cells, p2
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
