@@ -9,12 +9,16 @@ from _fakenn import ArenaNN, FakeNN
 from _lockstep import run_trace
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GAME_IDS = {"connect4": _orc.GAME_CONNECT4, "brandubh": _orc.GAME_BRANDUBH}
-DIMS = {"connect4": (4 * 6 * 7, 7, 42), "brandubh": (5 * 7 * 7, 588, None)}
+GAME_IDS = {"connect4": _orc.GAME_CONNECT4, "brandubh": _orc.GAME_BRANDUBH, "hnefatafl": _orc.GAME_HNEFATAFL}
+DIMS = {"connect4": (4 * 6 * 7, 7, 42), "brandubh": (5 * 7 * 7, 588, None), "hnefatafl": (5 * 11 * 11, 2420, None)}
+ENGINE_GAMES = ("connect4", "brandubh")      # what libazb200.so serves; hnefatafl fixtures wait for the engine
 
 
-def cases(arena=False):
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and (f[:-4].endswith("_arena") == arena))
+def cases(arena=False, engine=False):
+    names = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and (f[:-4].endswith("_arena") == arena))
+    if engine:
+        names = [n for n in names if not n.startswith("hnefatafl")]
+    return names
 
 
 def is_arena(g):

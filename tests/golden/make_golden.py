@@ -52,10 +52,16 @@ CASES = {
                             add_root_temp=True, add_root_noise=False, det_pow=True, symmetric=False, reset_threshold=7,
                             quota=4, fast_pattern=[1, 0, 0, 1],
                             hyper=dict(cpuct=0.8, fpu_reduction=0.0, root_noise_frac=0.1, root_policy_temp=0.9, start_temp=1.0)),
+    # hnefatafl 11x11: fixtures for the oracle now and for the engine once it serves 121-cell boards --
+    # warmup constants (unmodified reference) and a network with root temperature + fed noise, fast moves interleaved
+    "hnefatafl_warmup_unmodified": dict(game="hnefatafl", B=2, seeds=[101, 102], rounds=40, sims=8, nn=None,
+                                        add_root_temp=False, add_root_noise=False, det_pow=False),
+    "hnefatafl_nn_temp_noise": dict(game="hnefatafl", B=2, seeds=[111, 112], rounds=30, sims=10, nn=777,
+                                    add_root_temp=True, add_root_noise=True, det_pow=True, fast_pattern=[0, 0, 1]),
     "tafl_arena": dict(game="brandubh", B=2, seeds=[71, 72], rounds=45, sims=8, nn=[111, 112], arena=True,
                        arena_temp=0.5, player_to_index=[0, 1], add_root_temp=False, det_pow=True),
 }
-GAME_DIMS = {"connect4": (4 * 6 * 7, 7), "brandubh": (5 * 7 * 7, 588)}
+GAME_DIMS = {"connect4": (4 * 6 * 7, 7), "brandubh": (5 * 7 * 7, 588), "hnefatafl": (5 * 11 * 11, 2420)}
 
 
 def make(name, c):
@@ -66,6 +72,9 @@ def make(name, c):
         noise = rs.dirichlet([10.83 / 7] * 7, size=(c["B"], 24)).astype(np.float32)
         if A > 7:
             noise = rs.dirichlet([10.83 / 40] * 96, size=(c["B"], 8)).astype(np.float32)
+        if A > 588:                       # hnefatafl: up to ~150 legal moves at a root
+            with np.errstate(under="ignore"):       # the reference runs under np.seterr(all='raise') (MCTS.pyx:23)
+                noise = rs.dirichlet([10.83 / 116] * 256, size=(c["B"], 8)).astype(np.float32)
     arena = bool(c.get("arena"))
     hyper = dict(cpuct=1.25, fpu_reduction=0.2, root_noise_frac=0.1, root_policy_temp=1.1, start_temp=1.0)
     hyper.update(c.get("hyper", {}))

@@ -17,7 +17,7 @@ def test_oracle_reproduces_reference_golden(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", _golden.cases())
+@pytest.mark.parametrize("name", _golden.cases(engine=True))
 def test_engine_reproduces_reference_golden(name):
     from _engine_agent import EngineAgent
     g = _golden.load(name)
@@ -38,7 +38,7 @@ def test_oracle_reproduces_reference_arena_golden(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", _golden.cases(arena=True))
+@pytest.mark.parametrize("name", _golden.cases(arena=True, engine=True))
 def test_engine_reproduces_reference_arena_golden(name):
     from _engine_agent import ArenaEngineAgent
     g = _golden.load(name)
