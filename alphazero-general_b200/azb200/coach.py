@@ -201,12 +201,26 @@ class ExampleQueue:
 
 
 class GpuSelfPlayMixin:
-    """Mix into the reference Coach: ``class GpuCoach(GpuSelfPlayMixin, Coach): pass``."""
+    """Mix into the reference Coach: ``class GpuCoach(GpuSelfPlayMixin, Coach): pass``.
+    A Game plugin without device rules (anything but Connect4 / brandubh today) keeps the reference's own
+    SelfPlayAgent processes: every override below then defers to the Coach it is mixed into."""
+
+    def _has_device_rules(self):
+        from .selfplay import game_name
+        try:
+            game_name(self.game_cls)
+            return True
+        except NotImplementedError:
+            return False
 
     def generateSelfPlayAgents(self):
+        if not self._has_device_rules():
+            return super().generateSelfPlayAgents()
         self._gpu_engine_args = dict(seed=int(np.random.randint(0, 2 ** 31 - 1)))
 
     def processSelfPlayBatches(self, iteration):
+        if not self._has_device_rules():
+            return super().processSelfPlayBatches(iteration)
         nnet = self.self_play_net if self.args.model_gating else self.train_net
         t0 = time.time()
 
@@ -244,6 +258,8 @@ class GpuSelfPlayMixin:
             self.state = TrainState.STANDBY
 
     def killSelfPlayAgents(self):
+        if not self._has_device_rules():
+            return super().killSelfPlayAgents()
         import torch.multiprocessing as mp
         self.agents = []
         self.file_queue, self.result_queue = ExampleQueue(), mp.Queue()

@@ -113,3 +113,26 @@ def test_example_queue_keeps_the_per_example_protocol():
     q.put((np.zeros((4, 6, 7), np.float32), np.ones(7, np.float32), np.ones(3, np.float32)))      # a reference-style item
     assert q.qsize() == 2 and q.take_tensors() is None      # mixed content: only the per-item path serves it
     assert q.get()[1][0] == 7 and q.get()[1][0] == 1 and q.empty()
+
+
+def test_mixin_defers_to_the_reference_coach_for_games_without_device_rules():
+    """GpuSelfPlayMixin: a plugin the engine has no rules for keeps the reference's own agents."""
+    from azb200.coach import GpuSelfPlayMixin
+    calls = []
+
+    class Base:
+        def generateSelfPlayAgents(self): calls.append("gen")
+        def processSelfPlayBatches(self, iteration): calls.append(("proc", iteration))
+        def killSelfPlayAgents(self): calls.append("kill")
+        def saveIterationSamples(self, iteration): calls.append(("save", iteration))
+
+    class Othello:
+        __module__ = "alphazero.envs.othello.othello"
+
+    class Coach(GpuSelfPlayMixin, Base):
+        game_cls = Othello
+        file_queue = object()
+
+    c = Coach()
+    c.generateSelfPlayAgents(); c.processSelfPlayBatches(3); c.saveIterationSamples(3); c.killSelfPlayAgents()
+    assert calls == ["gen", ("proc", 3), ("save", 3), "kill"] and not hasattr(c, "_gpu_engine_args")
