@@ -319,4 +319,35 @@ struct Hnefatafl {
     }
 };
 
+// ---- NumPy float32 add.reduce over the 2420-entry policy vector ---------------------------------------------------
+// np.sum's pairwise_sum (numpy/core/src/umath/loops_utils.h.src) halves n (rounding the left half down to a multiple
+// of 8) until a block has <= 128 elements; for n = 2420 that recursion is a PERFECT binary tree of depth 5 whose 32
+// leaves have 72, 80 or 84 elements -- so lane b of a warp sums leaf b (eight strided accumulators, then the serial
+// tail, exactly as the leaf loop does) and the tree is five xor-shuffle steps (a + b is commutative in IEEE
+// arithmetic, only the tree shape matters).  np2420_leaf gives leaf b's [offset, offset + len).
+AZB_HD void np2420_leaf(int b, int &off, int &len)
+{
+    int o = 0, n = Hnefatafl::A;
+    for (int level = 4; level >= 0; level--) {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        if ((b >> level) & 1) { o += n2; n -= n2; }
+        else n = n2;
+    }
+    off = o;
+    len = n;
+}
+// the <= 128-element leaf loop of pairwise_sum (n >= 8 here); every add rounds once
+AZB_HD float np_leaf_sum_f32(const float *a, int n)
+{
+    float r[8];
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; j++) r[j] = r[j] + a[i + j];
+    float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res = res + a[i];
+    return res;
+}
+
 }  // namespace azb

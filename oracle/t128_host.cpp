@@ -71,3 +71,22 @@ extern "C" int t128_codec_roundtrip(void)
     }
     return 0;
 }
+
+/* np.sum(float32[2420]) evaluated the way a warp will: lane b sums leaf b, then five xor-shuffle steps */
+extern "C" float t128_np_sum_2420(const float *a, int32_t *leaf_off, int32_t *leaf_len)
+{
+    float lane[32];
+    for (int b = 0; b < 32; b++) {
+        int off, len;
+        np2420_leaf(b, off, len);
+        if (leaf_off) leaf_off[b] = off;
+        if (leaf_len) leaf_len[b] = len;
+        lane[b] = np_leaf_sum_f32(a + off, len);
+    }
+    for (int step = 1; step < 32; step <<= 1) {
+        float nxt[32];
+        for (int b = 0; b < 32; b++) nxt[b] = lane[b] + lane[b ^ step];      /* __shfl_xor_sync(.., step) */
+        for (int b = 0; b < 32; b++) lane[b] = nxt[b];
+    }
+    return lane[0];
+}

@@ -137,3 +137,24 @@ def test_symmetries_equal_the_oracle(t128):
         t128.t128_symmetry(_p(cells), len(acts), _p(pi), k, _p(c2), _p(p2))
         oc, op = _orc.symmetry(HN, cells, len(acts), pi, k)
         assert np.array_equal(c2, oc) and np.array_equal(p2, op), k
+
+
+def test_policy_sum_plan_equals_numpy(t128):
+    """np.sum over float32[2420] as a warp will evaluate it (32 leaves of NumPy's pairwise recursion, one per lane, then
+    five xor-shuffle steps) is bit-equal to NumPy -- and to the oracle's restatement of the recursion."""
+    t128.t128_np_sum_2420.restype = C.c_float
+    t128.t128_np_sum_2420.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    off, ln = np.zeros(32, np.int32), np.zeros(32, np.int32)
+    rs = np.random.RandomState(11)
+    L = _orc.lib()
+    L.orc_np_sum_f32.restype = C.c_float
+    L.orc_np_sum_f32.argtypes = [C.c_void_p, C.c_int]
+    for trial in range(200):
+        a = (rs.rand(A) ** (1 + trial % 5)).astype(np.float32)
+        if trial % 3 == 0:
+            a *= (rs.rand(A) < 0.05)                          # a masked policy: mostly zeros, as after pi *= valids
+        got = t128.t128_np_sum_2420(_p(a), _p(off), _p(ln))
+        assert np.float32(got) == np.sum(a, dtype=np.float32), trial
+        assert np.float32(got) == np.float32(L.orc_np_sum_f32(_p(a), A)), trial
+    assert off[0] == 0 and np.array_equal(off[1:], np.cumsum(ln)[:-1]) and int(ln.sum()) == A
+    assert set(ln.tolist()) <= {72, 80, 84} and all(int(v) % 8 == 0 for v in off)
