@@ -80,6 +80,22 @@ SYMBOLS = {
     "azb_check_errors": (C.c_int, [_vp, _vp]),
     "azb_last_error": (C.c_char_p, []),
     "azb_abi_version": (C.c_int, []),
+    # include/azb200_nn.h (weight structs are passed by address: fused_nn._NNWeights / nn_tc._NNGNet)
+    "azb_nn_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
+    "azb_nn_forward_tc": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
+    "azb_nn_forward_tc_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "azb_nn_forward_tc_debug": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32]),
+    "azb_nn_tc_layer_bytes": (C.c_int, []),
+    "azb_nn_tc_head_row_stride": (C.c_int, []),
+    "azb_nn_tc_boards_per_cta": (C.c_int, []),
+    "azb_nn_tc_frame_rows_per_board": (C.c_int, []),
+    "azb_nn_weight_row_stride": (C.c_int, []),
+    "azb_nn_head_row_stride": (C.c_int, []),
+    "azb_nn_boards_per_cta": (C.c_int, []),
+    "azb_upload_pinned": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "azb_nng_layout": (C.c_int, [_i32, _i32, _vp]),
+    "azb_nng_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "azb_nng_forward_debug": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32]),
 }
 
 _lib = None

@@ -158,11 +158,6 @@ class FusedResNetEvaluator:
             raise NotImplementedError("tcgen05 evaluator: at most 8 observation planes")
         self.kernel = kernel
         self.lib = _capi.load()
-        sig = [C.POINTER(_NNWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
-        for fn in (self.lib.azb_nn_forward, self.lib.azb_nn_forward_tc):
-            fn.restype, fn.argtypes = C.c_int, sig
-        self.lib.azb_nn_forward_tc_debug.restype = C.c_int
-        self.lib.azb_nn_forward_tc_debug.argtypes = sig + [C.c_void_p, C.c_int32]
         dev = obs.device
         model_dev = next(model.parameters()).device
         if kernel == "tc":
@@ -188,9 +183,6 @@ class FusedResNetEvaluator:
             # between two counters, SelfPlayEngine.nn_count_ptr)
             assert self.kernel == "tc" and count is not None and rows.dtype == torch.int32
             self.max_batch = int(max_batch or self.batch)
-            self.lib.azb_nn_forward_tc_rows.restype = C.c_int
-            self.lib.azb_nn_forward_tc_rows.argtypes = [C.POINTER(_NNWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                                        C.c_void_p, C.c_int32, C.c_void_p]
 
     def __call__(self, stream=None):
         stream = stream or torch.cuda.current_stream()

@@ -146,10 +146,7 @@ def upload(dst, src):
         import ctypes as C
         from . import _capi
         lib = _capi.load()
-        fn = lib.azb_upload_pinned
-        if fn.restype is not C.c_int or not fn.argtypes:
-            fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
-        rc = fn(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size(),
+        rc = lib.azb_upload_pinned(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size(),
                 C.c_void_p(torch.cuda.current_stream(dst.device).cuda_stream))
         if rc != 0:
             raise RuntimeError(f"azb_upload_pinned failed with status {rc}")

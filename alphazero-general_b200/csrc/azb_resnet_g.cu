@@ -1,0 +1,737 @@
+// azb_resnet_g.cu -- the reference's pre-activation ResNet (alphazero/NNetArchitecture.py:69-120, the network
+// NNetWrapper.process evaluates, alphazero/NNetWrapper.py:225-232) on the 5th-generation tensor cores for every
+// shipped geometry: boards up to 7x7, 32 or 64 trunk channels, any action size -- and at the reference's numerics.
+//
+// Precision.  PREC_BF16X2 (the default) keeps every convolution / head operand as a pair of bf16 values hi + lo
+// (16 significant bits; TF32, what the reference gets from cuDNN, has 11) and evaluates a.w as
+// a_hi.w_hi + a_hi.w_lo + a_lo.w_hi with fp32 accumulation in TMEM: three tcgen05.mma per K step, probabilities within
+// 1e-5 of the fp32 module (tests/test_nn_tc.py states and checks the bound).  PREC_F16 (one pass, 11-bit significand =
+// TF32's) and PREC_BF16 (one pass, 8 bits) are opt-in performance modes.
+//
+// Trunk kernel (k_trunk_tc).  A board is an 8 x 8 frame of positions (live H x W corner, the rest zero): one zero
+// column and >= one zero row per board are all the padding a 3x3 convolution needs, a tap (dy, dx) is a shift of
+// 8 dy + dx frame rows, and an M = 128 tile is exactly two boards, so tiles never exchange data: a tile's
+// activation is rewritten IN PLACE by its own epilogue (one frame instead of two: this is what lets the split operands
+// fit in shared memory), and tile t of layer l+1 waits only for tile t of layer l.  Frame layout in shared memory:
+// [part hi|lo][8-channel chunk][frame row][16 B] = the canonical K-major no-swizzle UMMA operand (core matrix = 8 rows,
+// SBO = 128 B, LBO = plane size); a vertical tap is `start address += 128 dy`.  The three horizontal taps share one A
+// read: B holds [dx][cout] (N = 3 CH) and the epilogue forms D[r] = P_-1[r-1] + P_0[r] + P_+1[r+1] with one-lane
+// rotations (rows that wrap are padding columns, where P is exactly zero).  TMEM holds the fp32 residual stream
+// (CH columns per tile) and a ring of N = 3 CH accumulators.  Weights stream through a ring of slabs (1 or 3 vertical
+// taps each, cp.async.bulk) so that a 64-channel layer (144 KB of split operands) fits beside the activations.
+// Roles: up to three MMA-issuing warps (one elected thread each; a turn counter keeps a tile's MMAs contiguous), one
+// weight producer, NGROUPS epilogue groups of 4 x CH/16 warps (TMEM lane quadrant x 16-channel group).
+// The last layer's epilogue writes the trunk output straight into the head GEMM's operand layout in global memory.
+//
+// Head kernel (k_head_tc).  The heads (conv1x1 -> BN -> flatten -> Linear .. Linear with Identity activations,
+// NNetArchitecture.py:86-102,110-118) are one affine map of the trunk output, folded on the host in float64
+// (azb200/fused_nn.py): logits[B, A+3] = act[B, H W CH] . Wh^T + b as a tcgen05 GEMM with M = 128 boards per CTA,
+// bulk-copy staged operands (4-stage ring), same split arithmetic; softmax in fp32 (in the epilogue when all outputs fit
+// one N tile, else k_softmax over the logits).
+#include "azb_tc_ptx.cuh"
+#include "../../include/azb200_nn.h"
+
+namespace {
+namespace g {
+using namespace azbtc;
+
+constexpr int MAXD = 6, MAXL = 1 + 2 * MAXD;
+
+template <int CH_, int TILES_, int PREC_, int NGROUPS_, int DYS_, int NSLOT_>
+struct TrunkCfg {
+    static constexpr int CH = CH_, TILES = TILES_, PREC = PREC_, NGROUPS = NGROUPS_, DYS = DYS_, NSLOT = NSLOT_;
+    static constexpr int PARTS = PREC == AZB_NN_BF16X2 ? 2 : 1;
+    static constexpr bool F16 = PREC == AZB_NN_F16;
+    static constexpr int C8 = CH / 8, KST = CH / 16;
+    static constexpr int ROWS = TILES * 128, PADR = 16, FROWS = ROWS + 2 * PADR;
+    static constexpr int PLANE = FROWS * 16, FPART = C8 * PLANE, FRAME = PARTS * FPART;
+    static constexpr int NACC = 3 * CH, WCHUNK = NACC * 16;
+    static constexpr int SLABS = 3 / DYS;                               // weight slabs per trunk layer
+    static constexpr int SLAB_PART = DYS * C8 * WCHUNK, SLAB = PARTS * SLAB_PART;
+    static constexpr int STEM_PART = 4 * WCHUNK;                        // stem slab: [part][4 K chunks][NACC][8]
+    static constexpr int NRING = (512 - TILES * CH) / NACC >= 3 ? 3 : (512 - TILES * CH) / NACC;
+    static constexpr int NISSUE = TILES < 3 ? TILES : 3;
+    static constexpr int GW = 4 * (CH / 16);                            // warps of one epilogue group
+    static constexpr int EPI_WARP0 = 4;                                 // warps 0..2 issue, warp 3 produces
+    static constexpr int WARPS = EPI_WARP0 + NGROUPS * GW, THREADS = WARPS * 32;
+    static constexpr uint32_t COL_X = 0, COL_P = TILES * CH;
+    static constexpr int PRM_FLOATS = MAXL * CH + 2 * MAXD * CH;
+    static constexpr size_t SMEM = (size_t)FRAME + (size_t)NSLOT * SLAB + (size_t)PRM_FLOATS * 4 + 40 * 8 + 64;
+    static constexpr uint32_t IDESC = umma_idesc(NACC, F16);
+    static_assert(3 % DYS == 0 && STEM_PART <= SLAB_PART && NSLOT >= SLABS, "slab geometry");
+    static_assert(NRING >= 2 && COL_P + NRING * NACC <= 512, "tensor memory budget");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    static_assert(NACC <= 256 && NACC % 16 == 0 && WARPS <= 32, "shape limits");
+};
+
+enum { EPI_STEM = 0, EPI_CONV1 = 1, EPI_CONV2 = 2 };
+
+__device__ __forceinline__ float2 f2(uint32_t lo, uint32_t hi) { return make_float2(__uint_as_float(lo), __uint_as_float(hi)); }
+__device__ __forceinline__ uint32_t bf2_bits(__nv_bfloat162 h) { return *reinterpret_cast<uint32_t *>(&h); }
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
+__device__ __forceinline__ uint32_t f16x2_sat(float2 v)      // round to nearest, clamp to the largest finite fp16
+{
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(v.y), "f"(v.x));
+    return r;
+}
+
+// 16 fp32 values (8 pairs) -> operand format, stored as two 16-byte K chunks per part
+template <class C>
+__device__ __forceinline__ void store_operand(const float2 (&r)[8], unsigned char *dst, size_t part_stride, size_t chunk_stride,
+                                              bool live, float *dump_row)
+{
+    uint32_t o[8], o2[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        if (C::PREC == AZB_NN_F16) {
+            o[c] = f16x2_sat(r[c]);
+        } else {
+            const __nv_bfloat162 h = __float22bfloat162_rn(r[c]);
+            o[c] = bf2_bits(h);
+            if (C::PARTS == 2) {
+                const float2 hf = __bfloat1622float2(h);
+                o2[c] = bf2_bits(__float22bfloat162_rn(make_float2(__fsub_rn(r[c].x, hf.x), __fsub_rn(r[c].y, hf.y))));
+            }
+        }
+    }
+    if (dump_row != nullptr) {                 // test hook: the value the next layer's MMAs see
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            float2 v;
+            if (C::PREC == AZB_NN_F16) {
+                v = __half22float2(*reinterpret_cast<__half2 *>(&o[c]));
+            } else {
+                v = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&o[c]));
+                if (C::PARTS == 2) {
+                    const float2 w = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&o2[c]));
+                    v.x += w.x; v.y += w.y;
+                }
+            }
+            dump_row[2 * c] = live ? v.x : 0.0f;
+            dump_row[2 * c + 1] = live ? v.y : 0.0f;
+        }
+    }
+    if (live) {                                // padding rows are zero from the start and stay so
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4 *>(dst + chunk_stride) = make_uint4(o[4], o[5], o[6], o[7]);
+        if (C::PARTS == 2) {
+            *reinterpret_cast<uint4 *>(dst + part_stride) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+            *reinterpret_cast<uint4 *>(dst + part_stride + chunk_stride) = make_uint4(o2[4], o2[5], o2[6], o2[7]);
+        }
+    }
+}
+
+// Epilogue of one tile for 16 of its channels: this thread owns tile row q*32 + lane (= its TMEM lane) and the channels
+// [16 cg, 16 cg + 16).
+//   stem : x = relu(D + bias) -> TMEM;  a = relu(bn1_0(x))      (depth 0: a = x)
+//   conv1: b = relu(D + bias)                                   (BN2 folded into conv1)
+//   conv2: x += D -> TMEM;  a = relu(bn1_next(x))               (last block: a = x, the head input)
+template <class C, int EPI, bool DBG>
+__device__ __forceinline__ void epilogue_tile(uint32_t t_p, uint32_t t_x, unsigned char *dst, size_t part_stride, size_t chunk_stride,
+                                              const float *bias, const float *nsc, const float *nsh, bool live, int lane,
+                                              uint32_t bar_pempty, float *dump_row)
+{
+    uint32_t pm[16], p0[16], pp[16], xv[16];
+    tmem_ld16(t_p, pm);
+    tmem_ld16(t_p + (uint32_t)C::CH, p0);
+    tmem_ld16(t_p + (uint32_t)(2 * C::CH), pp);
+    if (EPI == EPI_CONV2) tmem_ld16(t_x, xv);
+    tmem_ld_wait();
+    tc_fence_before();                    // the accumulator is in registers: hand the ring slot back to the MMA warps
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_pempty);
+    const int src_up = (lane + 31) & 31, src_dn = (lane + 1) & 31;
+    float2 r[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        float2 up, dn;
+        if (C::PREC == AZB_NN_BF16) {     // neighbour terms as packed fp16 pairs: far below the bf16 operand rounding
+            const __half2 hm = __floats2half2_rn(__uint_as_float(pm[2 * c]), __uint_as_float(pm[2 * c + 1]));
+            const __half2 hp = __floats2half2_rn(__uint_as_float(pp[2 * c]), __uint_as_float(pp[2 * c + 1]));
+            const uint32_t um = __shfl_sync(0xffffffffu, h2_bits(hm), src_up);
+            const uint32_t ud = __shfl_sync(0xffffffffu, h2_bits(hp), src_dn);
+            up = __half22float2(*reinterpret_cast<const __half2 *>(&um));
+            dn = __half22float2(*reinterpret_cast<const __half2 *>(&ud));
+        } else {
+            up = f2(__shfl_sync(0xffffffffu, pm[2 * c], src_up), __shfl_sync(0xffffffffu, pm[2 * c + 1], src_up));
+            dn = f2(__shfl_sync(0xffffffffu, pp[2 * c], src_dn), __shfl_sync(0xffffffffu, pp[2 * c + 1], src_dn));
+        }
+        r[c] = __fadd2_rn(__fadd2_rn(up, f2(p0[2 * c], p0[2 * c + 1])), dn);
+    }
+    if (EPI != EPI_CONV2) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float4 b4 = reinterpret_cast<const float4 *>(bias)[c];
+            r[2 * c] = __fadd2_rn(r[2 * c], make_float2(b4.x, b4.y));
+            r[2 * c + 1] = __fadd2_rn(r[2 * c + 1], make_float2(b4.z, b4.w));
+        }
+    }
+    if (EPI == EPI_STEM) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            r[c].x = fmaxf(r[c].x, 0.0f); r[c].y = fmaxf(r[c].y, 0.0f);
+            xv[2 * c] = __float_as_uint(r[c].x); xv[2 * c + 1] = __float_as_uint(r[c].y);
+        }
+        tmem_st16(t_x, xv);
+    } else if (EPI == EPI_CONV2) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            r[c] = __fadd2_rn(r[c], f2(xv[2 * c], xv[2 * c + 1]));
+            xv[2 * c] = __float_as_uint(r[c].x); xv[2 * c + 1] = __float_as_uint(r[c].y);
+        }
+        tmem_st16(t_x, xv);
+    }
+    if (EPI == EPI_CONV1 || nsc != nullptr) {
+        if (EPI != EPI_CONV1) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float4 s4 = reinterpret_cast<const float4 *>(nsc)[c], h4 = reinterpret_cast<const float4 *>(nsh)[c];
+                r[2 * c] = __ffma2_rn(r[2 * c], make_float2(s4.x, s4.y), make_float2(h4.x, h4.y));
+                r[2 * c + 1] = __ffma2_rn(r[2 * c + 1], make_float2(s4.z, s4.w), make_float2(h4.z, h4.w));
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) { r[c].x = fmaxf(r[c].x, 0.0f); r[c].y = fmaxf(r[c].y, 0.0f); }
+    }
+    store_operand<C>(r, dst, part_stride, chunk_stride, live, DBG ? dump_row : nullptr);
+    if (EPI != EPI_CONV1) tmem_st_wait();
+}
+
+// MMAs of one (tile, slab).  Trunk slab: [part][dy in slab][K chunk][NACC][8]; per 16-channel K step the passes
+// hi.hi (+ hi.lo + lo.hi when the operands are split).  Stem slab: [part][4 K chunks][NACC][8], two K steps over chunk
+// plane 0: (dy=-1, dy=0) and (dy=+1, zero weights) -- the second K chunk of a step is the first one 8 rows further.
+template <class C>
+__device__ __forceinline__ void issue_slab(uint32_t frame_s, uint32_t w_s, uint32_t d_tmem, int t, int layer, int j)
+{
+    const uint32_t row0 = frame_s + (uint32_t)((C::PADR + 128 * t) * 16);
+    if (layer == 0) {
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+#pragma unroll
+            for (int pass = 0; pass < (C::PARTS == 2 ? 3 : 1); pass++) {
+                const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
+                const uint64_t ad = umma_desc(row0 + (uint32_t)(pa * C::FPART + (2 * s - 1) * 128), 128u, 128u);
+                const uint64_t bd = umma_desc(w_s + (uint32_t)(pb * C::STEM_PART + 2 * s * C::WCHUNK), (uint32_t)C::WCHUNK, 128u);
+                umma_f16(d_tmem, ad, bd, C::IDESC, (s > 0 || pass > 0) ? 1u : 0u);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int dl = 0; dl < C::DYS; dl++) {
+            const int dy = j * C::DYS + dl - 1;
+#pragma unroll
+            for (int ks = 0; ks < C::KST; ks++) {
+#pragma unroll
+                for (int pass = 0; pass < (C::PARTS == 2 ? 3 : 1); pass++) {
+                    const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
+                    const uint64_t ad = umma_desc(row0 + (uint32_t)(pa * C::FPART + 2 * ks * C::PLANE + dy * 128), (uint32_t)C::PLANE, 128u);
+                    const uint64_t bd = umma_desc(w_s + (uint32_t)(pb * C::SLAB_PART + (dl * C::C8 + 2 * ks) * C::WCHUNK),
+                                                  (uint32_t)C::WCHUNK, 128u);
+                    umma_f16(d_tmem, ad, bd, C::IDESC, (j > 0 || dl > 0 || ks > 0 || pass > 0) ? 1u : 0u);
+                }
+            }
+        }
+    }
+}
+
+// how the global list of tiles (two boards each) is dealt to CTAs: whole waves of `sms` CTAs with equal shares, so a
+// partially filled last wave costs max-tiles-per-CTA, not a full CTA
+struct TileShare { int nct, base, extra; };
+__host__ __device__ inline TileShare tile_share(int boards, int tiles_per_cta, int sms)
+{
+    TileShare s;
+    const int T2 = (boards + 1) / 2;
+    const int waves = (T2 + tiles_per_cta * sms - 1) / (tiles_per_cta * sms);
+    s.nct = waves * sms < T2 ? waves * sms : T2;
+    s.base = s.nct > 0 ? T2 / s.nct : 0;
+    s.extra = s.nct > 0 ? T2 % s.nct : 0;
+    return s;
+}
+
+template <class C, bool DBG>
+__global__ void __launch_bounds__(C::THREADS, 1)
+k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int depth, const unsigned char *__restrict__ wtrunk,
+           const float *__restrict__ cbias, const float *__restrict__ bn_scale, const float *__restrict__ bn_shift,
+           unsigned char *__restrict__ gact, int MT, int KC, float *__restrict__ dump, int dump_layer,
+           const int *__restrict__ rows, const int *__restrict__ count_ptr, int sms)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *frame = smem;
+    unsigned char *wb = frame + C::FRAME;                                       // weight slab ring
+    float *prm = reinterpret_cast<float *>(wb + (size_t)C::NSLOT * C::SLAB);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(prm + C::PRM_FLOATS);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 40);
+    uint32_t *cnts = tmem_slot + 4;
+
+    enum { BAR_PFULL = 0, BAR_PEMPTY = BAR_PFULL + C::NRING, BAR_READY = BAR_PEMPTY + C::NRING,
+           BAR_WFULL = BAR_READY + C::TILES, BAR_WEMPTY = BAR_WFULL + C::NSLOT, NBARS = BAR_WEMPTY + C::NSLOT };
+    static_assert(NBARS <= 40, "barrier storage");
+
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    if (rows != nullptr) B = *count_ptr;                 // compact mode: the batch size lives in device memory
+    const TileShare sh = tile_share(B, C::TILES, sms);
+    if ((int)blockIdx.x >= sh.nct) return;
+    const int tiles = sh.base + ((int)blockIdx.x < sh.extra ? 1 : 0);
+    const int tile0 = (int)blockIdx.x * sh.base + ((int)blockIdx.x < sh.extra ? (int)blockIdx.x : sh.extra);
+    const int board0 = 2 * tile0;
+    const int layers = 1 + 2 * depth, total = layers * tiles;
+    const int nissue = tiles < C::NISSUE ? tiles : C::NISSUE;
+    const uint32_t bar0 = smem_u32(bars), frame_s = smem_u32(frame), wb_s = smem_u32(wb);
+#define BAR(i) (bar0 + 8u * (uint32_t)(i))
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < C::NRING; i++) { mbar_init(BAR(BAR_PFULL + i), 1); mbar_init(BAR(BAR_PEMPTY + i), C::GW); }
+            for (int i = 0; i < C::TILES; i++) mbar_init(BAR(BAR_READY + i), C::GW);
+            for (int i = 0; i < C::NSLOT; i++) { mbar_init(BAR(BAR_WFULL + i), 1); mbar_init(BAR(BAR_WEMPTY + i), (uint32_t)nissue); }
+            cnts[0] = 0u;
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncwarp();
+        tmem_alloc<512>(smem_u32(tmem_slot));
+    }
+    {   // zero the frame (padding rows / columns must read as zero), stage the per-channel parameters
+        uint4 *z = reinterpret_cast<uint4 *>(frame);
+        for (int i = tid; i < C::FRAME / 16; i += C::THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < layers * C::CH; i += C::THREADS) prm[i] = cbias[i];
+        for (int i = tid; i < depth * C::CH; i += C::THREADS) {
+            prm[MAXL * C::CH + i] = bn_scale[i];
+            prm[MAXL * C::CH + MAXD * C::CH + i] = bn_shift[i];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const float *s_bias = prm, *s_sc = prm + MAXL * C::CH, *s_sh = prm + MAXL * C::CH + MAXD * C::CH;
+
+    // observation -> chunk plane 0 (channels >= in_ch stay zero)
+    const int HW = H * W;
+    for (int i = tid; i < tiles * 2 * HW; i += C::THREADS) {
+        const int bl = i / HW, pos = i - bl * HW, y = pos / W, xx = pos - y * W;
+        int gb = board0 + bl;
+        const bool have = gb < B;
+        if (have && rows != nullptr) gb = rows[gb];
+        float2 c[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            c[k].x = (have && 2 * k < in_ch) ? obs[((size_t)gb * in_ch + 2 * k) * HW + pos] : 0.0f;
+            c[k].y = (have && 2 * k + 1 < in_ch) ? obs[((size_t)gb * in_ch + 2 * k + 1) * HW + pos] : 0.0f;
+        }
+        uint32_t o[4], o2[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (C::PREC == AZB_NN_F16) {
+                o[k] = f16x2_sat(c[k]);
+            } else {
+                const __nv_bfloat162 h = __float22bfloat162_rn(c[k]);
+                o[k] = bf2_bits(h);
+                const float2 hf = __bfloat1622float2(h);
+                o2[k] = bf2_bits(__float22bfloat162_rn(make_float2(c[k].x - hf.x, c[k].y - hf.y)));
+            }
+        }
+        unsigned char *d = frame + (size_t)(C::PADR + bl * 64 + y * 8 + xx) * 16;
+        *reinterpret_cast<uint4 *>(d) = make_uint4(o[0], o[1], o[2], o[3]);
+        if (C::PARTS == 2) *reinterpret_cast<uint4 *>(d + C::FPART) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    const uint32_t turn_s = smem_u32(cnts);
+    const int nslabs = 1 + (layers - 1) * C::SLABS;
+    if (warp < 3) {
+        // ---- MMA issuers: warp k feeds the tiles g = k, k + nissue, ... (g = layer * tiles + tile) ---------------
+        if (warp < nissue && elect_one_sync()) {
+            int l = warp / tiles, t = warp - l * tiles, seen = 0;
+#pragma unroll 1
+            for (int g = warp; g < total; g += nissue) {
+                const int slot = g % C::NRING, use = g / C::NRING;
+                const uint32_t d_tmem = tmem_base + C::COL_P + (uint32_t)(slot * C::NACC);
+                if (l > 0) mbar_wait(BAR(BAR_READY + t), (uint32_t)((l - 1) & 1));         // my tile's previous epilogue
+                if (use > 0) mbar_wait(BAR(BAR_PEMPTY + slot), (uint32_t)((use - 1) & 1));  // ring slot drained
+                tc_fence_after();
+                turn_wait(turn_s, (uint32_t)g);
+                const int s0 = l == 0 ? 0 : 1 + (l - 1) * C::SLABS, ns = l == 0 ? 1 : C::SLABS;
+                const bool my_last = t + nissue >= tiles;          // my last tile of this layer: release its slabs
+#pragma unroll 1
+                for (int j = 0; j < ns; j++) {
+                    const int s = s0 + j, ws = s % C::NSLOT;
+                    if (s >= seen) { mbar_wait(BAR(BAR_WFULL + ws), (uint32_t)((s / C::NSLOT) & 1)); seen = s + 1; tc_fence_after(); }
+                    issue_slab<C>(frame_s, wb_s + (uint32_t)(ws * C::SLAB), d_tmem, t, l, j);
+                    if (my_last) umma_commit(BAR(BAR_WEMPTY + ws));
+                }
+                umma_commit(BAR(BAR_PFULL + slot));
+                turn_store(turn_s, (uint32_t)(g + 1));
+                t += nissue;
+                while (t >= tiles) { t -= tiles; l++; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3) {
+        // ---- weight producer ------------------------------------------------------------------------------------
+        if (elect_one_sync()) {
+#pragma unroll 1
+            for (int s = 0; s < nslabs; s++) {
+                const int ws = s % C::NSLOT, use = s / C::NSLOT;
+                if (use > 0) mbar_wait(BAR(BAR_WEMPTY + ws), (uint32_t)((use - 1) & 1));
+                const uint32_t bytes = s == 0 ? (uint32_t)(C::PARTS * C::STEM_PART) : (uint32_t)C::SLAB;
+                mbar_expect_tx(BAR(BAR_WFULL + ws), bytes);
+                bulk_g2s(wb_s + (uint32_t)(ws * C::SLAB), wtrunk + (size_t)s * C::SLAB, bytes, BAR(BAR_WFULL + ws));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- epilogue groups --------------------------------------------------------------------------------------
+        const int e = warp - C::EPI_WARP0, grp = e / C::GW, within = e % C::GW, q = warp & 3, cg = within >> 2;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const int r0 = q * 32 + lane, fy = (r0 & 63) >> 3, fx = r0 & 7;
+        const bool live_pos = fx < W && fy < H;
+        const int pos = fy * W + fx;
+        int l = grp / tiles, t = grp - l * tiles;
+#pragma unroll 1
+        for (int g = grp; g < total; g += C::NGROUPS) {
+            const int slot = g % C::NRING, use = g / C::NRING;
+            const bool is_c1 = (l & 1) == 1, last = l + 1 == layers;
+            const uint32_t t_p = tmem_base + lane_off + C::COL_P + (uint32_t)(slot * C::NACC + 16 * cg);
+            const uint32_t t_x = tmem_base + lane_off + C::COL_X + (uint32_t)(C::CH * t + 16 * cg);
+            const int brd = board0 + 2 * t + (r0 >> 6);                 // (compact) board index of this row
+            const bool live = live_pos && brd < B;
+            unsigned char *dst;
+            size_t part_stride, chunk_stride;
+            if (last) {     // head GEMM A operand: [part][M tile of 128 boards][K chunk = pos * C8 + c][board][16 B]
+                chunk_stride = (size_t)128 * 16;
+                part_stride = (size_t)MT * KC * chunk_stride;
+                dst = gact + ((size_t)(brd >> 7) * KC + (size_t)(pos * C::C8 + 2 * cg)) * chunk_stride + (size_t)(brd & 127) * 16;
+            } else {
+                chunk_stride = C::PLANE;
+                part_stride = C::FPART;
+                dst = frame + (size_t)(2 * cg) * C::PLANE + (size_t)(C::PADR + 128 * t + r0) * 16;
+            }
+            float *dmp = nullptr;
+            if (DBG && dump != nullptr && l == dump_layer && brd < B) dmp = dump + ((size_t)brd * 64 + (r0 & 63)) * C::CH + 16 * cg;
+            if (within == 0) mbar_wait<32>(BAR(BAR_PFULL + slot), (uint32_t)(use & 1));
+            asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "r"(C::GW * 32) : "memory");
+            tc_fence_after();
+            const int ho = 16 * cg;
+            if (l == 0) {
+                epilogue_tile<C, EPI_STEM, DBG>(t_p, t_x, dst, part_stride, chunk_stride, s_bias + ho, depth > 0 ? s_sc + ho : nullptr,
+                                                s_sh + ho, live, lane, BAR(BAR_PEMPTY + slot), dmp);
+            } else if (is_c1) {
+                epilogue_tile<C, EPI_CONV1, DBG>(t_p, t_x, dst, part_stride, chunk_stride, s_bias + l * C::CH + ho, nullptr, nullptr, live,
+                                                 lane, BAR(BAR_PEMPTY + slot), dmp);
+            } else {
+                const int nblk = l >> 1;                      // the block that consumes x next
+                epilogue_tile<C, EPI_CONV2, DBG>(t_p, t_x, dst, part_stride, chunk_stride, nullptr, last ? nullptr : s_sc + nblk * C::CH + ho,
+                                                 s_sh + nblk * C::CH + ho, live, lane, BAR(BAR_PEMPTY + slot), dmp);
+            }
+            fence_proxy_async();              // the next layer's MMAs read these rows through the async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(BAR_READY + t));
+            t += C::NGROUPS;
+            while (t >= tiles) { t -= tiles; l++; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+#undef BAR
+}
+
+// ---- heads ---------------------------------------------------------------------------------------------------------
+constexpr int HSTAGES = 4, HKC = 4;                        // K chunks (of 8) per pipeline stage
+constexpr int HTHREADS = 192;
+
+template <int PREC>
+__global__ void __launch_bounds__(HTHREADS, 1)
+k_head_tc(const unsigned char *__restrict__ gact, const unsigned char *__restrict__ whead, const float *__restrict__ bhead,
+          float *__restrict__ logits, float *__restrict__ policy, float *__restrict__ value, int B, const int *__restrict__ rows,
+          const int *__restrict__ count_ptr, int MT, int KC, int NT, int ntiles, int nout_pad, int A, uint32_t tmem_cols)
+{
+    constexpr int PARTS = PREC == AZB_NN_BF16X2 ? 2 : 1;
+    constexpr bool F16 = PREC == AZB_NN_F16;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int a_part = HKC * 128 * 16, b_part = HKC * NT * 16, stage_bytes = PARTS * (a_part + b_part);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + (size_t)HSTAGES * stage_bytes);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * HSTAGES + 1);
+    enum { BAR_FULL = 0, BAR_EMPTY = HSTAGES, BAR_DONE = 2 * HSTAGES };
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    const int mt = blockIdx.x, nt = blockIdx.y;
+    if (rows != nullptr) B = *count_ptr;
+    if (mt * 128 >= B) return;
+    const uint32_t bar0 = smem_u32(bars), st_s = smem_u32(smem);
+#define BAR(i) (bar0 + 8u * (uint32_t)(i))
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < HSTAGES; i++) { mbar_init(BAR(BAR_FULL + i), 1); mbar_init(BAR(BAR_EMPTY + i), 1); }
+            mbar_init(BAR(BAR_DONE), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nk = KC / HKC;
+    if (warp == 0) {
+        if (elect_one_sync()) {
+#pragma unroll 1
+            for (int i = 0; i < nk; i++) {
+                const int st = i % HSTAGES, use = i / HSTAGES;
+                if (use > 0) mbar_wait(BAR(BAR_EMPTY + st), (uint32_t)((use - 1) & 1));
+                mbar_expect_tx(BAR(BAR_FULL + st), (uint32_t)stage_bytes);
+                const uint32_t dst = st_s + (uint32_t)(st * stage_bytes);
+#pragma unroll
+                for (int p = 0; p < PARTS; p++) {
+                    bulk_g2s(dst + (uint32_t)(p * a_part), gact + (((size_t)p * MT + mt) * KC + (size_t)i * HKC) * 2048, (uint32_t)a_part,
+                             BAR(BAR_FULL + st));
+                    bulk_g2s(dst + (uint32_t)(PARTS * a_part + p * b_part),
+                             whead + (((size_t)p * ntiles + nt) * KC + (size_t)i * HKC) * (size_t)NT * 16, (uint32_t)b_part, BAR(BAR_FULL + st));
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one_sync()) {
+            const uint32_t idesc = umma_idesc(NT, F16);
+#pragma unroll 1
+            for (int i = 0; i < nk; i++) {
+                const int st = i % HSTAGES, use = i / HSTAGES;
+                mbar_wait(BAR(BAR_FULL + st), (uint32_t)(use & 1));
+                tc_fence_after();
+                const uint32_t a_s = st_s + (uint32_t)(st * stage_bytes), b_s = a_s + (uint32_t)(PARTS * a_part);
+#pragma unroll
+                for (int ks = 0; ks < HKC / 2; ks++) {
+#pragma unroll
+                    for (int pass = 0; pass < (PARTS == 2 ? 3 : 1); pass++) {
+                        const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
+                        const uint64_t ad = umma_desc(a_s + (uint32_t)(pa * a_part + 2 * ks * 2048), 2048u, 128u);
+                        const uint64_t bd = umma_desc(b_s + (uint32_t)(pb * b_part + 2 * ks * NT * 16), (uint32_t)(NT * 16), 128u);
+                        umma_f16(tmem_base, ad, bd, idesc, (i > 0 || ks > 0 || pass > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(BAR(BAR_EMPTY + st));
+            }
+            umma_commit(BAR(BAR_DONE));
+        }
+        __syncwarp();
+    } else {
+        // epilogue: warp w reads TMEM lanes 32 (w % 4) ..; lane = board within the M tile
+        const int q = warp & 3, row = q * 32 + lane, i = mt * 128 + row;
+        mbar_wait<64>(BAR(BAR_DONE), 0u);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool have = i < B;
+        if (ntiles == 1 && NT == 16) {             // all outputs in one thread: softmax here
+            uint32_t v[16];
+            tmem_ld16(t_row, v);
+            tmem_ld_wait();
+            if (have) {
+                const int gb = rows != nullptr ? rows[i] : i;
+                float lg[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) lg[j] = __uint_as_float(v[j]) + bhead[j];
+                float mp = -INFINITY, mv = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    if (j < A) mp = fmaxf(mp, lg[j]);
+                    else if (j < A + 3) mv = fmaxf(mv, lg[j]);
+                }
+                float sp = 0.0f, sv = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    if (j < A) { lg[j] = expf(lg[j] - mp); sp += lg[j]; }
+                    else if (j < A + 3) { lg[j] = expf(lg[j] - mv); sv += lg[j]; }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    if (j < A) policy[(size_t)gb * A + j] = lg[j] / sp;
+                    else if (j < A + 3) value[(size_t)gb * 3 + (j - A)] = lg[j] / sv;
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < NT / 16; c++) {
+                uint32_t v[16];
+                tmem_ld16(t_row + (uint32_t)(16 * c), v);
+                tmem_ld_wait();
+                if (have) {
+                    float *o = logits + (size_t)i * nout_pad + (size_t)nt * NT + 16 * c;
+                    const float *bb = bhead + nt * NT + 16 * c;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4 *>(bb + j);
+                        *reinterpret_cast<float4 *>(o + j) = make_float4(__uint_as_float(v[j]) + b4.x, __uint_as_float(v[j + 1]) + b4.y,
+                                                                         __uint_as_float(v[j + 2]) + b4.z, __uint_as_float(v[j + 3]) + b4.w);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+#undef BAR
+}
+
+// exp(log_softmax) of the policy logits [0, A) and the value logits [A, A+3): one warp per board
+__global__ void __launch_bounds__(256)
+k_softmax(const float *__restrict__ logits, float *__restrict__ policy, float *__restrict__ value, int B, const int *__restrict__ rows,
+          const int *__restrict__ count_ptr, int nout_pad, int A)
+{
+    if (rows != nullptr) B = *count_ptr;
+    const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (i >= B) return;
+    const int gb = rows != nullptr ? rows[i] : i;
+    const float *lg = logits + (size_t)i * nout_pad;
+    float m = -INFINITY;
+    for (int j = lane; j < A; j += 32) m = fmaxf(m, lg[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.0f;
+    for (int j = lane; j < A; j += 32) s += expf(lg[j] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float inv = 1.0f / s;
+    for (int j = lane; j < A; j += 32) policy[(size_t)gb * A + j] = expf(lg[j] - m) * inv;
+    if (lane == 0) {
+        const float v0 = lg[A], v1 = lg[A + 1], v2 = lg[A + 2], mv = fmaxf(v0, fmaxf(v1, v2));
+        const float e0 = expf(v0 - mv), e1 = expf(v1 - mv), e2 = expf(v2 - mv), sv = e0 + e1 + e2;
+        value[(size_t)gb * 3] = e0 / sv; value[(size_t)gb * 3 + 1] = e1 / sv; value[(size_t)gb * 3 + 2] = e2 / sv;
+    }
+}
+
+// ---- launch ----------------------------------------------------------------------------------------------------------
+//                          CH  TILES PREC NGROUPS DYS NSLOT
+template <int PREC> using Cfg32 = TrunkCfg<32, 7, PREC, 3, 3, PREC == AZB_NN_BF16X2 ? 2 : 3>;
+template <int PREC> using Cfg64 = TrunkCfg<64, 2, PREC, 1, 1, PREC == AZB_NN_BF16X2 ? 3 : 6>;
+
+int sm_count()
+{
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaDeviceProp prop;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
+        sms = prop.multiProcessorCount;
+    }
+    return sms;
+}
+
+template <class C>
+int launch_trunk(const azb_nng_net *n, const float *obs, int batch, const int *rows, const int *count, cudaStream_t s, float *dump,
+                 int dump_layer)
+{
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_trunk_tc<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(k_trunk_tc<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess)
+            return -2;
+        configured = true;
+    }
+    const int sms = sm_count();
+    if (sms <= 0) return -2;
+    const int grid = tile_share(batch, C::TILES, sms).nct;      // compact mode: upper bound, surplus CTAs exit at once
+    const int MT = (n->max_boards + 127) / 128;
+    if (dump != nullptr)
+        k_trunk_tc<C, true><<<grid, C::THREADS, C::SMEM, s>>>(obs, batch, n->in_channels, n->board_h, n->board_w, n->depth,
+                                                             reinterpret_cast<const unsigned char *>(n->wtrunk), n->cbias, n->bn_scale,
+                                                             n->bn_shift, reinterpret_cast<unsigned char *>(n->gact), MT, n->head_kc, dump,
+                                                             dump_layer, rows, count, sms);
+    else
+        k_trunk_tc<C, false><<<grid, C::THREADS, C::SMEM, s>>>(obs, batch, n->in_channels, n->board_h, n->board_w, n->depth,
+                                                              reinterpret_cast<const unsigned char *>(n->wtrunk), n->cbias, n->bn_scale,
+                                                              n->bn_shift, reinterpret_cast<unsigned char *>(n->gact), MT, n->head_kc, nullptr,
+                                                              -1, rows, count, sms);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+template <int PREC>
+int launch_head(const azb_nng_net *n, float *policy, float *value, int batch, const int *rows, const int *count, cudaStream_t s)
+{
+    constexpr int PARTS = PREC == AZB_NN_BF16X2 ? 2 : 1;
+    const int NT = n->head_nt, ntiles = n->head_ntiles, nout_pad = NT * ntiles;
+    const size_t smem = (size_t)HSTAGES * PARTS * (HKC * 128 * 16 + HKC * NT * 16) + (2 * HSTAGES + 1) * 8 + 64;
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(k_head_tc<PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+        configured = smem;
+    }
+    uint32_t cols = 32;
+    while ((int)cols < NT) cols <<= 1;
+    const int MT = (n->max_boards + 127) / 128, mtiles = (batch + 127) / 128;
+    k_head_tc<PREC><<<dim3(mtiles, ntiles), HTHREADS, smem, s>>>(reinterpret_cast<const unsigned char *>(n->gact),
+                                                                 reinterpret_cast<const unsigned char *>(n->whead), n->bhead, n->logits, policy,
+                                                                 value, batch, rows, count, MT, n->head_kc, NT, ntiles, nout_pad, n->action_size,
+                                                                 cols);
+    if (cudaGetLastError() != cudaSuccess) return -2;
+    if (!(ntiles == 1 && NT == 16)) {
+        k_softmax<<<(batch + 7) / 8, 256, 0, s>>>(n->logits, policy, value, batch, rows, count, nout_pad, n->action_size);
+        if (cudaGetLastError() != cudaSuccess) return -2;
+    }
+    return 0;
+}
+
+template <int PREC>
+int forward_prec(const azb_nng_net *n, const float *obs, float *policy, float *value, int batch, const int *rows, const int *count,
+                 cudaStream_t s, float *dump, int dump_layer)
+{
+    int rc;
+    if (n->channels == 32) rc = launch_trunk<Cfg32<PREC>>(n, obs, batch, rows, count, s, dump, dump_layer);
+    else rc = launch_trunk<Cfg64<PREC>>(n, obs, batch, rows, count, s, dump, dump_layer);
+    if (rc != 0) return rc;
+    return launch_head<PREC>(n, policy, value, batch, rows, count, s);
+}
+
+int forward(const azb_nng_net *n, const float *obs, float *policy, float *value, int batch, const int *rows, const int *count, void *stream,
+            float *dump, int dump_layer)
+{
+    if (!n || !obs || !policy || !value || batch <= 0 || (rows != nullptr) != (count != nullptr)) return -7;
+    if ((n->channels != 32 && n->channels != 64) || n->board_h < 1 || n->board_h > 7 || n->board_w < 1 || n->board_w > 7 ||
+        n->in_channels < 1 || n->in_channels > 8 || n->depth < 0 || n->depth > MAXD || n->action_size < 1 || batch > n->max_boards ||
+        n->head_nt % 16 != 0 || n->head_nt < 16 || n->head_nt > 256 || n->head_ntiles < 1 || n->head_kc % HKC != 0 ||
+        n->head_kc < n->board_h * n->board_w * (n->channels / 8) || n->head_nt * n->head_ntiles < n->action_size + 3 ||
+        !n->wtrunk || !n->cbias || !n->bn_scale || !n->bn_shift || !n->whead || !n->bhead || !n->gact ||
+        (!(n->head_ntiles == 1 && n->head_nt == 16) && !n->logits))
+        return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (n->precision) {
+    case AZB_NN_BF16: return forward_prec<AZB_NN_BF16>(n, obs, policy, value, batch, rows, count, s, dump, dump_layer);
+    case AZB_NN_F16: return forward_prec<AZB_NN_F16>(n, obs, policy, value, batch, rows, count, s, dump, dump_layer);
+    case AZB_NN_BF16X2: return forward_prec<AZB_NN_BF16X2>(n, obs, policy, value, batch, rows, count, s, dump, dump_layer);
+    default: return -1;
+    }
+}
+
+}  // namespace g
+}  // namespace
+
+extern "C" int azb_nng_layout(int32_t channels, int32_t precision, int32_t *out)
+{
+    if (!out || (channels != 32 && channels != 64) || precision < AZB_NN_BF16 || precision > AZB_NN_BF16X2) return -1;
+    const int parts = precision == AZB_NN_BF16X2 ? 2 : 1;
+    const int dys = channels == 32 ? 3 : 1, tiles = channels == 32 ? 7 : 2;
+    out[0] = parts;
+    out[1] = dys;                                           /* vertical taps per weight slab */
+    out[2] = parts * dys * (channels / 8) * 3 * channels * 16;   /* slab bytes */
+    out[3] = 2 * tiles;                                     /* boards per CTA */
+    out[4] = g::HKC;                                        /* head K chunks per stage: head_kc is a multiple */
+    out[5] = g::MAXD;
+    return 0;
+}
+
+extern "C" int azb_nng_forward(const azb_nng_net *net, const float *obs, float *policy, float *value, int32_t batch, const int32_t *rows,
+                               const int32_t *count, void *stream)
+{
+    return g::forward(net, obs, policy, value, batch, rows, count, stream, nullptr, -1);
+}
+
+extern "C" int azb_nng_forward_debug(const azb_nng_net *net, const float *obs, float *policy, float *value, int32_t batch, void *stream,
+                                     float *dump, int32_t dump_layer)
+{
+    if (!dump) return -7;
+    return g::forward(net, obs, policy, value, batch, nullptr, nullptr, stream, dump, dump_layer);
+}

@@ -1,0 +1,132 @@
+// azb_tc_ptx.cuh -- inline-PTX wrappers shared by the tcgen05 leaf-evaluator kernels
+// (mbarrier, bulk async copy, tcgen05.mma / ld / st / commit, UMMA descriptors).  sm_100a only.
+#ifndef AZB_TC_PTX_CUH
+#define AZB_TC_PTX_CUH
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace azbtc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// Bounded wait: a barrier that never completes is a programming error -- trap instead of hanging the GPU.
+template <int BACKOFF_NS = 0>
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 22); it++) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity), "r"(20000u)
+                     : "memory");
+        if (done) return;
+        if (BACKOFF_NS > 0) __nanosleep(BACKOFF_NS);
+    }
+    __trap();
+}
+// relaxed accesses for the MMA turn counter (a release store compiles to MEMBAR.ALL.CTA, which stalls the issuing
+// thread until its MMAs retire)
+__device__ __forceinline__ void turn_store(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void turn_wait(uint32_t addr, uint32_t g)
+{
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 24); it++) {
+        uint32_t v;
+        asm volatile("ld.relaxed.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
+        if (v >= g) return;
+    }
+    __trap();
+}
+// one lane of a converged warp; inside the guarded region addresses and descriptors stay in uniform registers
+__device__ __forceinline__ uint32_t elect_one_sync()
+{
+    uint32_t pred = 0;
+    asm volatile("{\n.reg .pred px;\nelect.sync _|px, 0xFFFFFFFF;\nselp.u32 %0, 1, 0, px;\n}\n" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory operand descriptor: start address [0,14) and the two strides [16,30) / [32,46) in
+// 16-byte units (LBO: between core matrices adjacent in K; SBO: between 8-row groups), version 1 at [46,48)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::f16: D = f32 [4,6); A / B format at [7,10) / [10,13) (0 = f16, 1 = bf16), both
+// K-major; N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc(int n, bool f16)
+{
+    return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+#define AZBTC_R16(v)                                                                                                   \
+    "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),        \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+#define AZBTC_I16(v)                                                                                                   \
+    "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),      \
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+// this thread's TMEM lane, 16 consecutive fp32 columns (no wait: the caller batches loads)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : AZBTC_R16(v)
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};\n" ::AZBTC_I16(v),
+                 "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(slot_smem), "r"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t base)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(base), "r"(COLS) : "memory");
+}
+
+}  // namespace azbtc
+#endif

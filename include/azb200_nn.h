@@ -61,6 +61,51 @@ int azb_nn_tc_layer_bytes(void);
 int azb_nn_tc_head_row_stride(void);
 int azb_nn_tc_boards_per_cta(void);
 int azb_nn_tc_frame_rows_per_board(void);
+/* ---- generic tcgen05 evaluator (csrc/azb_resnet_g.cu): boards up to 7x7, 32 or 64 trunk channels, any action
+ * size, at the reference's numerics.  Replaces NNetWrapper.process (alphazero/NNetWrapper.py:225-232) for the ResNet of
+ * alphazero/NNetArchitecture.py:69-120 with the presets of Coach.py:103-116 (32 ch), envs/hnefatafl/train_brandubh.py:50-55
+ * (64 ch, 7x7, 588 actions).  Operand precision of the convolutions and the head GEMM (accumulation is always fp32):
+ *   AZB_NN_BF16X2  every operand as hi + lo bf16 (16 significant bits; TF32 -- what cuDNN gives the reference -- has
+ *                  11), a.w = a_hi.w_hi + a_hi.w_lo + a_lo.w_hi: probabilities within 1e-5 of the fp32 module.  Default.
+ *   AZB_NN_F16     fp16 operands (11 significant bits = TF32's), one pass; activations saturate at 65504.
+ *   AZB_NN_BF16    bf16 operands (8 bits), one pass.                                                              */
+enum { AZB_NN_BF16 = 0, AZB_NN_F16 = 1, AZB_NN_BF16X2 = 2 };
+
+typedef struct azb_nng_net {
+    int32_t channels, depth, in_channels, board_h, board_w, action_size;
+    int32_t precision;      /* AZB_NN_*                                                                       */
+    int32_t max_boards;     /* capacity of gact / logits                                                      */
+    int32_t head_nt;        /* head GEMM N tile (multiple of 16, <= 256)                                      */
+    int32_t head_ntiles;    /* head_nt * head_ntiles >= action_size + 3                                       */
+    int32_t head_kc;        /* head K in 8-element chunks, >= H*W*channels/8, multiple of layout[4]           */
+    int32_t reserved;
+    const void *wtrunk;     /* device, slab stream: slab s at s * layout[2] bytes; slab 0 = stem               */
+                            /*   [part][4 K chunks: dy=-1,0,+1,zero][3*channels][8 cin], the others, layer by     */
+                            /*   layer, [part][dy in slab][cin/8][dx*channels + cout][8 cin]; part = hi, lo        */
+    const float *cbias;     /* device f32 [1+2*depth][channels] (folded BN shift; 0 for conv2)                 */
+    const float *bn_scale;  /* device f32 [max(depth,1)][channels]: BN1 of every block                         */
+    const float *bn_shift;
+    const void *whead;      /* device [part][n tile][head_kc][head_nt][8]: folded heads, output j = tile*nt + row, */
+                            /*   K chunk = (y*W + x)*channels/8 + ch/8                                           */
+    const float *bhead;     /* device f32 [head_nt * head_ntiles]                                              */
+    void *gact;             /* scratch, device: parts * ceil(max_boards/128) * head_kc * 2048 bytes             */
+    float *logits;          /* scratch, device f32 [max_boards][head_nt*head_ntiles]; may be NULL when all outputs */
+                            /*   fit one 16-wide tile                                                            */
+} azb_nng_net;
+
+/* out[0] = operand parts, out[1] = vertical taps per weight slab, out[2] = slab bytes, out[3] = boards per CTA,
+ * out[4] = head K-chunk granularity, out[5] = max depth.  -1: unsupported channels / precision. */
+int azb_nng_layout(int32_t channels, int32_t precision, int32_t *out);
+/* obs f32 [batch, C, H, W] -> policy f32 [batch, A], value f32 [batch, 3] (probabilities).  rows / count (both or
+ * neither): compact evaluation of boards rows[0 .. *count) as azb_nn_forward_tc_rows, batch = upper bound.
+ * Asynchronous on `stream` (two or three kernel launches).  Status codes as azb_nn_forward. */
+int azb_nng_forward(const azb_nng_net *net, const float *obs, float *policy, float *value, int32_t batch, const int32_t *rows,
+                    const int32_t *count, void *stream);
+/* test hook: also writes the activation layer `dump_layer`'s epilogue hands to the next layer (operand rounding
+ * included) to dump f32 [batch][64 frame rows][channels] (padding rows zero) */
+int azb_nng_forward_debug(const azb_nng_net *net, const float *obs, float *policy, float *value, int32_t batch, void *stream,
+                          float *dump, int32_t dump_layer);
+
 /* Upload of a caller-owned PINNED host tensor (the batch_tensor / policy_tensor / value_tensor of the reference's
  * SelfPlayAgent protocol, SelfPlayAgent.pyx:14-16; NNetWrapper.process does `batch.cuda()`, NNetWrapper.py:227) by a
  * kernel that reads the mapped host memory over PCIe -- a small cudaMemcpyAsync host->device pays ~190 us of DMA

@@ -1,0 +1,227 @@
+"""The generic tcgen05 leaf evaluator (csrc/azb_resnet_g.cu, azb200/nn_tc.py) against the reference network.
+
+Oracle for this floating-point kernel: the PyTorch module of alphazero/NNetArchitecture.py:69-120 (mirror in
+azb200.nnet, state_dict-compatible, checked equal to the reference's own module in test_host_logic.py) evaluated in
+strict fp32 (no TF32), i.e. NNetWrapper.process (NNetWrapper.py:225-232).
+
+Stated tolerances on probabilities (absolute):
+  bf16x2  1e-5   the north star's bound -- the default precision of every product path
+  fp16    max(2 x the error of cuDNN's TF32 evaluation of the same boards, 1e-4): TF32-class (11-bit significand)
+  bf16    3e-2   performance mode
+CPU half: the folded operand layouts, decoded again, reproduce the module in float64."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from azb200 import nnet as aznet
+from azb200 import nn_tc
+
+GEOMS = {
+    "connect4": dict(obs=(4, 6, 7), A=7, args=aznet.DEFAULT_NET_ARGS),
+    "brandubh": dict(obs=(5, 7, 7), A=588, args=aznet.BRANDUBH_TRAIN_NET_ARGS),
+    "brandubh32": dict(obs=(5, 7, 7), A=588, args=aznet.DEFAULT_NET_ARGS),
+    "connect4_64": dict(obs=(4, 6, 7), A=7, args=aznet.BRANDUBH_TRAIN_NET_ARGS),
+}
+
+
+def _model(geom, seed=0, depth=None, sharpen=1.0):
+    g = GEOMS[geom]
+    torch.manual_seed(seed)
+    args = dict(g["args"])
+    if depth is not None:
+        args["depth"] = depth
+    m = aznet.ResNet(g["obs"], g["A"], 3, **args).eval()
+    with torch.no_grad():                      # non-trivial BN statistics / affine, optionally peaked outputs
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.3); mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.5, 1.5); mod.bias.normal_(0, 0.2)
+        for fc in (m.pi_fc, m.v_fc):
+            [l for l in fc if isinstance(l, torch.nn.Linear)][-1].weight.mul_(sharpen)
+    return m
+
+
+def _obs(geom, n, seed=1):
+    c, h, w = GEOMS[geom]["obs"]
+    rs = np.random.RandomState(seed)
+    o = np.zeros((n, c, h, w), np.float32)
+    cells = rs.randint(0, c, size=(n, h, w))
+    for k in range(c - 2):
+        o[:, k] = cells == k + 1
+    o[:, c - 2] = rs.randint(0, 2, size=(n, 1, 1))
+    o[:, c - 1] = (rs.randint(0, 43, size=(n, 1, 1)) / 42.0).astype(np.float32)
+    return torch.from_numpy(o)
+
+
+def _want(m, obs):
+    """strict-fp32 evaluation on the device the module lives on"""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            lp, lv = m(obs)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return lp.exp(), lv.exp()
+
+
+@pytest.mark.parametrize("geom", ["connect4", "brandubh"])
+@pytest.mark.parametrize("precision", ["bf16x2", "fp16"])
+def test_folded_operand_layouts_reproduce_the_module(geom, precision):
+    """Decode wtrunk / whead exactly as the kernel addresses them and evaluate in float64."""
+    m = _model(geom)
+    f = nn_tc.fold_g(m, precision)
+    lay = nn_tc.layout(f["channels"], precision)
+    assert lay["parts"] == f["parts"] and lay["slab_bytes"] == f["wtrunk"].shape[1] * 2
+    ch, depth, cin, H, W, A = (f[k] for k in ("channels", "depth", "in_channels", "board_h", "board_w", "action_size"))
+    parts, dys, c8, nacc = lay["parts"], lay["dys"], ch // 8, 3 * ch
+    wt = f["wtrunk"].double()
+
+    def stem_w():
+        sp = 4 * nacc * 8
+        w = sum(wt[0, p * sp:(p + 1) * sp] for p in range(parts)).view(4, 3, ch, 8)       # [dy][dx][cout][cin]
+        assert bool((w[3] == 0).all())
+        return w[:3, :, :, :cin].permute(2, 3, 0, 1)                                      # [cout][cin][dy][dx]
+
+    def layer_w(l):
+        sp = dys * c8 * nacc * 8
+        per = 3 // dys
+        rows = []
+        for j in range(per):
+            s = 1 + (l - 1) * per + j
+            rows.append(sum(wt[s, p * sp:(p + 1) * sp] for p in range(parts)).view(dys, c8, 3, ch, 8))
+        w = torch.cat(rows, 0)                                                            # [dy][cin/8][dx][cout][8]
+        return w.permute(3, 1, 4, 0, 2).reshape(ch, ch, 3, 3)
+
+    x = _obs(geom, 8).double()
+    b = lambda v: v.double().view(1, -1, 1, 1)
+    t = torch.relu(F.conv2d(x, stem_w(), padding=1) + b(f["cbias"][0]))
+    for i in range(depth):
+        a = torch.relu(t * b(f["bn_scale"][i]) + b(f["bn_shift"][i]))
+        bb = torch.relu(F.conv2d(a, layer_w(1 + 2 * i), padding=1) + b(f["cbias"][1 + 2 * i]))
+        t = t + F.conv2d(bb, layer_w(2 + 2 * i), padding=1)
+    nt, ntiles, kc = f["head_nt"], f["head_ntiles"], f["head_kc"]
+    assert (nt, ntiles) == nn_tc.head_tiles(A + 3) and kc % lay["head_kgran"] == 0 and nt * ntiles >= A + 3
+    wh = f["whead"].double().sum(0)                                                       # [n tile][kc][row][8]
+    wh = wh.permute(0, 2, 1, 3).reshape(ntiles * nt, kc * 8)[:, :H * W * ch]              # [out][pos*ch + c]
+    feat = t.permute(0, 2, 3, 1).reshape(len(x), -1)
+    logits = feat @ wh.T + f["bhead"].double()
+    got = torch.cat([torch.softmax(logits[:, :A], 1), torch.softmax(logits[:, A:A + 3], 1)], 1)
+    with torch.no_grad():
+        lp, lv = m.double()(x)
+    want = torch.cat([lp.exp(), lv.exp()], 1)
+    # only the rounding of the weights to 16 (bf16x2) / 11 (fp16) significant bits separates the two
+    tol = 2e-6 if precision == "bf16x2" else 2e-4
+    assert (got - want).abs().max().item() < tol
+    assert bool((wh[A + 3:] == 0).all())
+
+
+def _tol(precision, m, obs, want):
+    if precision == "bf16x2":
+        return 1e-5
+    if precision == "bf16":
+        return 3e-2
+    # fp16 = TF32-class: measured against what the reference's own default (cuDNN TF32) does on the same boards
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    with torch.no_grad():
+        lp, lv = m(obs)
+    torch.backends.cudnn.allow_tf32 = old
+    err = max((lp.exp() - want[0]).abs().max().item(), (lv.exp() - want[1]).abs().max().item())
+    return max(2 * err, 1e-4)
+
+
+def _run(geom, batch, precision, sharpen=1.0, depth=None):
+    dev = torch.device("cuda")
+    m = _model(geom, depth=depth, sharpen=sharpen).to(dev)
+    obs = _obs(geom, batch).to(dev)
+    A = GEOMS[geom]["A"]
+    pol = torch.zeros(batch, A, device=dev); val = torch.zeros(batch, 3, device=dev)
+    ev = nn_tc.TensorCoreEvaluator(m, obs, pol, val, precision=precision)
+    ev()
+    torch.cuda.synchronize()
+    return m, obs, pol, val, ev
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", ["connect4", "brandubh", "brandubh32", "connect4_64"])
+@pytest.mark.parametrize("precision", ["bf16x2", "fp16", "bf16"])
+@pytest.mark.parametrize("batch", [6, 1000])
+def test_evaluator_matches_the_fp32_module(geom, precision, batch):
+    m, obs, pol, val, _ = _run(geom, batch, precision)
+    want = _want(m, obs)
+    tol = _tol(precision, m, obs, want)
+    assert torch.isfinite(pol).all() and torch.isfinite(val).all()
+    assert torch.allclose(pol.sum(1), torch.ones(batch, device=pol.device), atol=1e-5)
+    assert torch.allclose(val.sum(1), torch.ones(batch, device=pol.device), atol=1e-5)
+    ep, evl = (pol - want[0]).abs().max().item(), (val - want[1]).abs().max().item()
+    assert ep < tol and evl < tol, (geom, precision, ep, evl, tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom,batch", [("connect4", 8192), ("brandubh", 4096)])
+def test_default_precision_at_baseline_sizes_and_peaked_outputs(geom, batch):
+    """BASELINE batch sizes, heads sharpened x8 so that the probabilities are peaked like a trained network's:
+    the default precision stays within 1e-5 of the fp32 module."""
+    m, obs, pol, val, ev = _run(geom, batch, None, sharpen=8.0)
+    assert ev.precision == "bf16x2"
+    want = _want(m, obs)
+    assert want[0].max().item() > 2.0 / GEOMS[geom]["A"]            # visibly non-uniform
+    ep, evl = (pol - want[0]).abs().max().item(), (val - want[1]).abs().max().item()
+    assert ep < 1e-5 and evl < 1e-5, (ep, evl)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", ["connect4", "brandubh"])
+@pytest.mark.parametrize("depth", [0, 1, 4])
+def test_layer_by_layer(geom, depth):
+    """Every epilogue (stem, conv1, conv2 of each block) against the fp32 activations of the module; reports all layers."""
+    dev = torch.device("cuda")
+    m, obs, pol, val, ev = _run(geom, 10, "bf16x2", depth=depth)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    want = []
+    with torch.no_grad():
+        x = F.relu(m.bn1(m.conv1(obs)))
+        blocks = list(m.resnet)
+        a = F.relu(blocks[0].bn1(x)) if blocks else x
+        want.append(a)
+        for i, blk in enumerate(blocks):
+            b = F.relu(blk.bn2(blk.conv1(a)))
+            want.append(b)
+            x = x + blk.conv2(b)
+            a = F.relu(blocks[i + 1].bn1(x)) if i + 1 < len(blocks) else x
+            want.append(a)
+    torch.backends.cudnn.allow_tf32 = old
+    errs = []
+    for l, w in enumerate(want):
+        got = ev.debug_layer(l)
+        torch.cuda.synchronize()
+        errs.append((got - w.permute(0, 2, 3, 1)).abs().max().item() / max(w.abs().max().item(), 1.0))
+    assert max(errs) < 2e-5, errs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom,batch,keep", [("connect4", 8192, 0.85), ("connect4", 1000, 0.5), ("brandubh", 300, 0.7),
+                                             ("connect4", 40, 0.0)])
+def test_compact_rows_equal_dense(geom, batch, keep):
+    """rows / count: the listed rows get bit-identical answers to the dense evaluation, the others are left untouched;
+    the row count is read from device memory."""
+    dev = torch.device("cuda")
+    m, obs, pol, val, _ = _run(geom, batch, "bf16x2")
+    A = GEOMS[geom]["A"]
+    rs = np.random.RandomState(batch)
+    sel = np.flatnonzero(rs.random_sample(batch) < keep).astype(np.int32)
+    rs.shuffle(sel)
+    rows = torch.zeros(batch, dtype=torch.int32, device=dev)
+    rows[:len(sel)] = torch.from_numpy(sel).to(dev)
+    count = torch.tensor([len(sel)], dtype=torch.int32, device=dev)
+    pol2 = torch.full((batch, A), -1.0, device=dev); val2 = torch.full((batch, 3), -1.0, device=dev)
+    nn_tc.TensorCoreEvaluator(m, obs, pol2, val2, precision="bf16x2", rows=rows, count=count)()
+    torch.cuda.synchronize()
+    mask = torch.zeros(batch, dtype=torch.bool, device=dev)
+    mask[torch.from_numpy(sel).long().to(dev)] = True
+    assert torch.equal(pol2[mask], pol[mask]) and torch.equal(val2[mask], val[mask])
+    assert bool((pol2[~mask] == -1).all()) and bool((val2[~mask] == -1).all())
