@@ -142,12 +142,13 @@ def _fused_evaluators(engine, models, player_to_index):
     """One compact tcgen05 evaluator per model over the engine's per-model row lists, or None."""
     if len(models) != 2 or not all(getattr(m, "fused", False) and hasattr(m, "nnet") for m in models):
         return None
-    from .fused_nn import FusedResNetEvaluator, supported_tc
-    if not all(supported_tc(m.nnet) for m in models) or tuple(engine.obs_shape[1:]) != (6, 7):
+    from .nn_tc import TensorCoreEvaluator, supported
+    if not all(supported(m.nnet) for m in models):
         return None
     engine.arena_set_player_to_index(player_to_index)
-    return [FusedResNetEvaluator(m.nnet, engine.obs, engine.policy, engine.value, kernel="tc", rows=engine.arena_rows(k),
-                                 count=(lambda k=k: engine.arena_count_ptr(k)), max_batch=engine.B // 2)
+    return [TensorCoreEvaluator(m.nnet, engine.obs, engine.policy, engine.value, precision=getattr(m, "precision", None),
+                                rows=engine.arena_rows(k), count=(lambda k=k: engine.arena_count_ptr(k)),
+                                max_batch=engine.B // 2)
             for k, m in enumerate(models)]
 
 

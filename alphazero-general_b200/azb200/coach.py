@@ -82,7 +82,7 @@ class _DeviceSampleSink:
 
 
 def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup=False, engine=None, fused=None,
-                           precision="tf32", game_id_base=0, stop_event=None, progress=None, device_samples=False):
+                           precision=None, game_id_base=0, stop_event=None, progress=None, device_samples=False):
     """One self-play phase (SelfPlayAgent.run for a single GPU-resident agent):
     until gamesPerIteration games are counted, draw the fast-move coin, run
     numFastSims / numMCTSSims (numWarmupSims in a warmup iteration) simulations
@@ -99,10 +99,11 @@ def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup
         engine.set_quota(g("gamesPerIteration", 0))
     drv = None
     if not warmup:
-        if fused is None:
-            from .fused_nn import supported
-            fused = supported(nnet_module)
-        drv = DeviceSelfPlay(engine, nnet_module, cohorts=1, precision=precision, channels_last=not fused, fused=fused)
+        # leaf evaluator: the hand-written tcgen05 kernels at their default precision ("bf16x2": within 1e-5 of the
+        # reference's fp32 module) wherever they cover the network, else cuDNN TF32 (the reference's own arithmetic);
+        # a narrower type only when the caller asks for it (args.nn_precision / precision=)
+        drv = DeviceSelfPlay(engine, nnet_module, cohorts=1, precision=precision or g("nn_precision"), channels_last=True,
+                             fused=fused)
     rs = np.random.RandomState(seed)
     quota = int(g("gamesPerIteration"))
     rslot, rturns, rwin = [], [], []

@@ -168,3 +168,27 @@ class TensorCoreEvaluator:
         if rc != 0:
             raise RuntimeError(f"azb_nng_forward_debug failed with status {rc}")
         return dump[:, :self.net.board_h, :self.net.board_w]
+
+
+def make_evaluator(model, obs, policy, value, precision=None, kernel=None, rows=None, count=None, max_batch=None,
+                   use_graph=True, channels_last=False):
+    """The leaf evaluator for `model` at `precision`:
+      "bf16x2" (default) / "fp16" / "bf16"  hand-written tcgen05 kernels (TensorCoreEvaluator); kernel = "tc-r1" / "mma"
+                                          selects the round-1 bf16-only kernels of fused_nn (6x7 boards, 32 channels)
+      "fp32" / "tf32" / "cudnn-bf16"         PyTorch / cuDNN (azb200.nnet.LeafEvaluator; strict fp32 = the parity oracle)
+    A geometry the hand-written kernels do not cover falls back to cuDNN TF32 -- the reference's own arithmetic -- never
+    to a narrower type."""
+    precision = precision or DEFAULT_PRECISION
+    if kernel in ("tc-r1", "mma"):
+        from .fused_nn import FusedResNetEvaluator
+        if precision != "bf16":
+            raise ValueError("the round-1 kernels compute in bf16 only")
+        return FusedResNetEvaluator(model, obs, policy, value, kernel="tc" if kernel == "tc-r1" else "mma", rows=rows,
+                                    count=count, max_batch=max_batch)
+    if precision in PRECISIONS and supported(model):
+        return TensorCoreEvaluator(model, obs, policy, value, precision=precision, rows=rows, count=count, max_batch=max_batch)
+    if rows is not None:
+        raise NotImplementedError("compact evaluation needs the tcgen05 evaluator")
+    from .nnet import LeafEvaluator
+    lib_prec = {"cudnn-bf16": "bf16"}.get(precision, precision if precision in ("fp32", "tf32") else "tf32")
+    return LeafEvaluator(model, obs, policy, value, precision=lib_prec, use_graph=use_graph, channels_last=channels_last)

@@ -96,14 +96,20 @@ class NNetWrapper:
     """Inference half of alphazero/NNetWrapper.py (process / predict); training
     stays with the reference wrapper."""
 
-    def __init__(self, game_cls=None, args=None, nnet=None, cuda=None, fused=False):
+    def __init__(self, game_cls=None, args=None, nnet=None, cuda=None, fused=False, precision=None):
         self.game_cls, self.args = game_cls, args
         self.nnet = nnet if nnet is not None else ResNet.for_game(game_cls, args)
         self.cuda = torch.cuda.is_available() if cuda is None else cuda
         if self.cuda:
             self.nnet.cuda()
-        self.fused = fused          # evaluate with the fused bf16 kernels (csrc/azb_resnet_tc.cu / azb_resnet.cu) when supported
+        # fused: evaluate with the hand-written tcgen05 kernels (csrc/azb_resnet_g.cu) when they cover the network, at
+        # `precision` (azb200.nn_tc: default "bf16x2", within 1e-5 of this module in fp32; "fp16" / "bf16" are opt-in)
+        self.fused, self.precision = fused, precision
         self._fused_eval = {}
+
+    def fused_supported(self):
+        from . import nn_tc
+        return bool(self.fused) and self.cuda and nn_tc.supported(self.nnet)
 
     def _process_fused(self, batch):
         n = batch.shape[0]
@@ -112,18 +118,18 @@ class NNetWrapper:
         key = (n, batch.data_ptr() if not batch.is_cuda else 0)
         ev = self._fused_eval.get(key)
         if ev is None:
-            from .fused_nn import FusedResNetEvaluator
+            from .nn_tc import TensorCoreEvaluator
             dev = next(self.nnet.parameters()).device
             obs = torch.empty((n,) + tuple(batch.shape[1:]), device=dev)
-            ev = FusedResNetEvaluator(self.nnet, obs, torch.empty(n, self.nnet.action_size, device=dev),
-                                      torch.empty(n, 3, device=dev))
+            ev = TensorCoreEvaluator(self.nnet, obs, torch.empty(n, self.nnet.action_size, device=dev),
+                                     torch.empty(n, 3, device=dev), precision=self.precision)
             self._fused_eval[key] = ev
         upload(ev.obs, batch)
         ev()
         return ev.policy, ev.value
 
     def process(self, batch):
-        if self.fused and self.cuda:
+        if self.fused_supported():
             return self._process_fused(batch)
         batch = batch.type(torch.FloatTensor) if not batch.is_cuda else batch.float()
         if self.cuda and not batch.is_cuda:

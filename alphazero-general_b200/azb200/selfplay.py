@@ -291,45 +291,39 @@ class DeviceSelfPlay:
     ``nn_stream``; with cohorts == 2 the two halves of the games alternate so
     that tree work of one half overlaps inference of the other."""
 
-    def __init__(self, engine, nnet, cohorts=1, precision="tf32", use_graph=True, channels_last=False, fused=False,
+    def __init__(self, engine, nnet, cohorts=1, precision=None, use_graph=True, channels_last=False, fused=None,
                  split=None, round_graph=None, skip_terminal=True):
+        """precision: operand precision of the leaf evaluator, see azb200.nn_tc.make_evaluator -- "bf16x2" (default:
+        hand-written tcgen05 kernels, within 1e-5 of the reference's fp32 module), "fp16", "bf16" (opt-in performance
+        modes), "fp32" / "tf32" / "cudnn-bf16" (PyTorch / cuDNN).  fused: None = the hand-written kernels whenever they
+        cover the network and the precision; False = cuDNN; "tc-r1" / "mma" = the round-1 bf16-only kernels."""
         assert cohorts in (1, 2)
+        from . import nn_tc
         self.engine = engine
         self.cohorts = cohorts
         B = engine.B
+        if fused is False and (precision is None or precision in nn_tc.PRECISIONS):
+            precision = {None: "tf32", "bf16": "cudnn-bf16"}.get(precision, "tf32")
+        precision = precision or nn_tc.DEFAULT_PRECISION
+        kernel = fused if fused in ("tc-r1", "mma") else None
+        hand = kernel is not None or (precision in nn_tc.PRECISIONS and nn_tc.supported(nnet))
         if cohorts == 2 and split is None:
             split = B // 2
-            if fused:
-                # the fused evaluators run one CTA of `nb` boards per SM: cut the batch at a whole number of
-                # waves so that two launches cost the same number of waves as one
-                import torch as _t
-                from .fused_nn import boards_per_cta
-                nb = boards_per_cta(nnet, None if fused is True else fused)
-                sms = _t.cuda.get_device_properties(engine.obs.device).multi_processor_count
-                waves = -(-(-(-B // nb)) // sms)
-                split = min(B - nb, max(nb, ((waves + 1) // 2) * sms * nb))
         bounds = [0, B] if cohorts == 1 else [0, split, B]
         self.ranges = [(bounds[i], bounds[i + 1] - bounds[i]) for i in range(cohorts)]
-        from .nnet import LeafEvaluator
-        if fused:
-            # hand-written fused ResNet kernel: tcgen05 / TMEM (csrc/azb_resnet_tc.cu) where it applies, else the
-            # mma.sync one (csrc/azb_resnet.cu); fused="tc" / "mma" forces one
-            from .fused_nn import FusedResNetEvaluator, supported_tc
-            kern = None if fused is True else fused
-            if (kern or ("tc" if supported_tc(nnet) else "mma")) == "tc" and skip_terminal and cohorts == 1:
-                # compact evaluation: only the leaves that need the network (the reference evaluates terminal leaves
-                # too and discards the answers, SelfPlayAgent.pyx:116-123 / MCTS.pyx:234-235)
-                self.evals = [FusedResNetEvaluator(nnet, engine.obs, engine.policy, engine.value, kernel="tc",
-                                                   rows=engine.nn_rows, count=engine.nn_count_ptr, max_batch=c)
-                              for f, c in self.ranges]
-            else:
-                self.evals = [FusedResNetEvaluator(nnet, engine.obs[f:f + c], engine.policy[f:f + c], engine.value[f:f + c],
-                                                   kernel=kern)
-                              for f, c in self.ranges]
-        else:
-            self.evals = [LeafEvaluator(nnet, engine.obs[f:f + c], engine.policy[f:f + c], engine.value[f:f + c],
-                                        precision=precision, use_graph=use_graph, channels_last=channels_last)
+        if hand and kernel != "mma" and skip_terminal and cohorts == 1:
+            # compact evaluation: only the leaves that need the network (the reference evaluates terminal leaves
+            # too and discards the answers, SelfPlayAgent.pyx:116-123 / MCTS.pyx:234-235)
+            self.evals = [nn_tc.make_evaluator(nnet, engine.obs, engine.policy, engine.value, precision=precision, kernel=kernel,
+                                               rows=engine.nn_rows, count=engine.nn_count_ptr, max_batch=c)
                           for f, c in self.ranges]
+        else:
+            self.evals = [nn_tc.make_evaluator(nnet, engine.obs[f:f + c], engine.policy[f:f + c], engine.value[f:f + c],
+                                               precision=precision, kernel=kernel, use_graph=use_graph,
+                                               channels_last=channels_last)
+                          for f, c in self.ranges]
+        self.precision = getattr(self.evals[0], "precision", precision)
+        fused = hand
         dev = engine.obs.device
         self.tree_stream = torch.cuda.Stream(device=dev)
         self.nn_stream = torch.cuda.Stream(device=dev)

@@ -54,16 +54,21 @@ def parse():
     ap.add_argument("--games", type=int, default=8192)
     ap.add_argument("--sims", type=int, default=100)
     ap.add_argument("--net", default="default", choices=["default", "connect4_train", "brandubh_train"])
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default=None, choices=["bf16x2", "fp16", "bf16", "fp32", "tf32", "cudnn-bf16"],
+                    help="operand precision of the leaf evaluator (accumulation is fp32): bf16x2 = hi+lo bf16 operands, within 1e-5 "
+                         "of the fp32 module (default of --nn tc); fp16 / bf16 = one-pass modes of the same kernels; fp32 / tf32 / "
+                         "cudnn-bf16 = PyTorch/cuDNN (--nn cudnn; default tf32, the reference's own arithmetic)")
     ap.add_argument("--cohorts", type=int, default=1)
     ap.add_argument("--split", type=int, default=0, help="games in the first cohort (0 = automatic)")
-    ap.add_argument("--nn", default="fused", choices=["cudnn", "fused", "fused_mma"],
-                    help="leaf evaluator: PyTorch/cuDNN CUDA graph, the fused bf16 tcgen05/TMEM kernel, or the fused mma.sync kernel")
+    ap.add_argument("--nn", default="tc", choices=["tc", "tc-r1", "mma", "cudnn", "fused", "fused_mma"],
+                    help="leaf evaluator: tc = hand-written tcgen05/TMEM kernels (csrc/azb_resnet_g.cu, every shipped geometry up to 64 "
+                         "channels); tc-r1 / mma = the round-1 bf16-only kernels (6x7, 32 channels); cudnn = PyTorch/cuDNN CUDA graph")
     ap.add_argument("--lanes", type=int, default=0, help="threads per game (0 = library default)")
     ap.add_argument("--nchw", action="store_true", help="keep the ResNet in NCHW (default: channels_last)")
     ap.add_argument("--preroll", type=int, default=48, help="cheap tree-only rounds that de-synchronise the games")
     ap.add_argument("--tree-only", action="store_true", help="warmup mode (constant NN outputs), one fused kernel per round")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--sustain-seconds", type=float, default=5.0, help="extra sustained leg of the device-resident step (0 = off)")
     ap.add_argument("--e2e-agents", type=int, default=4, help="reference `workers`: agents sharing the GPU in the e2e leg")
     ap.add_argument("--e2e-mode", default="inline", choices=["inline", "threads"],
                     help="inline: one host thread runs the Coach loop over the agents (generateBatch -> process -> "
@@ -348,13 +353,28 @@ def main():
     netargs = {"default": aznet.DEFAULT_NET_ARGS, "connect4_train": aznet.CONNECT4_TRAIN_NET_ARGS,
                "brandubh_train": aznet.BRANDUBH_TRAIN_NET_ARGS}[a.net]
     model = aznet.ResNet(OBS, A, 3, **netargs).to(dev).eval()
-    if a.net != "default" or tafl:
-        a.nn = "cudnn"                      # the fused kernel covers the 32-channel DEFAULT_ARGS net on 6x7 boards
-        a.no_e2e = True if tafl else a.no_e2e
+    from azb200 import nn_tc
+    a.nn = {"fused": "tc", "fused_mma": "mma"}.get(a.nn, a.nn)
+    if a.nn == "tc" and not nn_tc.supported(model):
+        a.nn = "cudnn"                      # the hand-written kernels cover up to 64 channels; the 128-channel net stays on cuDNN
+    if tafl:
+        a.no_e2e = True                     # the host-tensor agent legs below are written for Connect4 shapes
+    if a.nn == "cudnn":
+        a.precision = a.precision if a.precision in ("fp32", "tf32", "cudnn-bf16") else "tf32"
+    elif a.nn == "tc":
+        a.precision = a.precision if a.precision in nn_tc.PRECISIONS else nn_tc.DEFAULT_PRECISION
+    else:
+        a.precision = "bf16"
     drv = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision, channels_last=not a.nchw,
-                         fused={"fused": True, "fused_mma": "mma", "cudnn": False}[a.nn],
+                         fused={"tc": None, "tc-r1": "tc-r1", "mma": "mma", "cudnn": False}[a.nn],
                          round_graph=False if a.no_round_graph else None, split=a.split or None,
                          skip_terminal=not a.eval_terminal)
+    compact = a.nn in ("tc", "tc-r1") and not a.eval_terminal and a.cohorts == 1
+    nn_kernel = {"tc": "k_trunk_tc + k_head_tc (tcgen05/TMEM, csrc/azb_resnet_g.cu)", "tc-r1": "k_resnet_tc (tcgen05/TMEM, round 1)",
+                 "mma": "k_resnet_fused (mma.sync)"}.get(a.nn, "cuDNN " + a.precision)
+    # what the arithmetic is: operand type of the convolutions / head GEMM + accumulator type
+    dtype = {"bf16x2": "bf16x2-split operands (16 significant bits) + f32 accumulate", "fp16": "f16 operands + f32 accumulate",
+             "bf16": "bf16 operands + f32 accumulate", "cudnn-bf16": "bf16 (autocast)", "tf32": "tf32", "fp32": "f32"}[a.precision]
 
     sel_events, nn_events = [], []
 
@@ -516,13 +536,12 @@ def main():
     if nn_events:
         nn_ms, nn_n, nn_dropped, nn_mean_all = launch_times(nn_events)
         nn_pct = launch_times.last_percentiles
-        compact = a.nn == "fused" and not a.eval_terminal and a.cohorts == 1
         rows = (roof_sims - ((r1["terminal_leaves"] - r0["terminal_leaves"]) if compact else 0)) * (nn_n / float(len(nn_events)))
         fl = model_flops(model, OBS)
         tf = fl * rows / (nn_ms / 1000.0) / 1e12
         sustained = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1388.0)))
         roof_nn = {"bound": "tensor", "achieved": tf, "peak": sustained, "unit": "TFLOP/s", "frac": tf / sustained, "traffic": None,
-                   "kernel": {"fused": "k_resnet_tc (tcgen05/TMEM)", "fused_mma": "k_resnet_fused (mma.sync)"}.get(a.nn, "cuDNN " + a.precision),
+                   "kernel": nn_kernel, "precision": a.precision,
                    "launches": nn_n, "avg_launch_us": 1000.0 * nn_ms / nn_n, "flops_per_eval": fl,
                    "rows_per_launch": rows / nn_n, "evals_per_s": rows / (nn_ms / 1000.0),
                    "launches_set_aside": nn_dropped, "mean_launch_us_untrimmed": nn_mean_all, "launch_us_p10_p50_p90": nn_pct,
@@ -540,27 +559,87 @@ def main():
         except Exception:
             pass
 
-    # secondary: the same step with the PyTorch/cuDNN TF32 evaluator (the reference's default numerics)
-    alt = None
-    if a.nn != "cudnn" and not a.tree_only and not a.no_alt:
-        model.to(memory_format=torch.channels_last)
-        drv2 = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision="tf32", channels_last=True, fused=False)
-        for _ in range(2):
-            drv2.run_round(sims); clear_samples()
+    def timed_rounds(driver, steps, warm=2):
+        for _ in range(warm):
+            driver.run_round(sims); clear_samples()
         s0 = eng.stats()["sims"]
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for _ in range(3):
-            drv2.run_round(sims); clear_samples()
+        for _ in range(steps):
+            driver.run_round(sims); clear_samples()
         f1.record()
         barrier()
         tt = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
         nn_ = torch.tensor([eng.stats()["sims"] - s0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(nn_, op=dist.ReduceOp.SUM)
-        alt = {"nn": "cudnn (CUDA graph, channels_last)", "dtype": "tf32", "value": float(nn_.item()) / (float(tt.item()) / 1000.0),
-               "unit": UNIT, "steps": 3}
+        return float(nn_.item()) / (float(tt.item()) / 1000.0), float(tt.item())
+
+    # measured error of the evaluator the timed steps used, on leaf observations of this very run, against the PyTorch
+    # module in strict fp32 (NNetWrapper.process, the oracle for this floating-point kernel)
+    nn_error = None
+    if not a.tree_only:
+        try:
+            n_chk = min(B, 2048)
+            o = eng.obs[:n_chk].clone()
+            pol_c, val_c = torch.zeros(n_chk, A, device=dev), torch.zeros(n_chk, 3, device=dev)
+            ev_c = nn_tc.make_evaluator(model, o, pol_c, val_c, precision=a.precision,
+                                        kernel=a.nn if a.nn in ("tc-r1", "mma") else None, channels_last=not a.nchw)
+            ev_c()
+            old_flags = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+            with torch.no_grad():
+                lp, lv = model(o)
+            torch.backends.cudnn.allow_tf32 = True
+            with torch.no_grad():
+                lp_t, lv_t = model(o)
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_flags
+            torch.cuda.synchronize()
+            err = lambda p_, v_: max((p_ - lp.exp()).abs().max().item(), (v_ - lv.exp()).abs().max().item())
+            nn_error = {"boards": n_chk, "max_abs_error_vs_f32_module": err(pol_c, val_c),
+                        "cudnn_tf32_max_abs_error_vs_f32_module": err(lp_t.exp(), lv_t.exp()),
+                        "note": "probabilities (policy and value) on leaf observations of this run; the second figure is what the "
+                                "reference's own default arithmetic (PyTorch cuDNN TF32 convolutions) does on the same boards"}
+            del ev_c
+        except Exception as ex:
+            nn_error = {"error": repr(ex)}
+
+    # sustained leg: the same device-resident step for >= --sustain-seconds with its own clock record
+    sustained_leg = None
+    if a.sustain_seconds > 0 and not a.tree_only:
+        n_sus = max(a.steps, int(a.sustain_seconds * 1000.0 / max(ms_max / a.steps, 1e-3)) + 1)
+        clocks2 = ClockSampler(local)
+        if rank == 0:
+            clocks2.start(); clocks2.t_warm = time.time(); clocks2.mark()
+        v_sus, ms_sus = timed_rounds(drv, n_sus, warm=0)
+        sustained_leg = {"value": v_sus, "unit": UNIT, "steps": n_sus, "seconds": ms_sus / 1000.0,
+                         "clocks": clocks2.stop() if rank == 0 else None}
+
+    # secondary legs, same step: the PyTorch/cuDNN TF32 evaluator (the reference's own default arithmetic) and the other
+    # operand precisions of the hand-written kernels
+    alt, alt_prec = None, None
+    if a.nn != "cudnn" and not a.tree_only and not a.no_alt:
+        if a.nn == "tc":
+            alt_prec = {}
+            for prec in ("bf16x2", "fp16", "bf16"):
+                if prec == a.precision:
+                    continue
+                d3 = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=prec, skip_terminal=not a.eval_terminal)
+                v3, _ = timed_rounds(d3, 5)
+                alt_prec[prec] = {"value": v3, "unit": UNIT, "steps": 5}
+                del d3
+            try:
+                d3 = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision="bf16", fused="tc-r1", skip_terminal=not a.eval_terminal)
+                v3, _ = timed_rounds(d3, 5)
+                alt_prec["bf16 (round-1 kernel k_resnet_tc)"] = {"value": v3, "unit": UNIT, "steps": 5}
+                del d3
+            except (NotImplementedError, RuntimeError):
+                pass
+        model.to(memory_format=torch.channels_last)
+        drv2 = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision="tf32", channels_last=True, fused=False)
+        v2, _ = timed_rounds(drv2, 3)
+        alt = {"nn": "cudnn (CUDA graph, channels_last)", "dtype": "tf32", "value": v2, "unit": UNIT, "steps": 3}
 
     # e2e: reference-facing SelfPlayAgent surface with host tensors
     e2e = None
@@ -569,12 +648,19 @@ def main():
 
     # e2e_coach: the call a user of the drop-in Coach makes (GpuSelfPlayMixin.processSelfPlayBatches)
     e2e_coach = None
-    if not a.no_e2e and not a.tree_only and a.game == "connect4" and a.net == "default" and world == 1:
-        # (N = 1 only: a secondary leg with its own collectives is not worth a rank-asymmetric failure in a scaling run)
+    if not a.no_e2e and not a.tree_only and a.game == "connect4" and a.net == "default":
+        # every N: the local part may fail without touching a collective; the reduction below always runs on every rank
         try:
             e2e_coach = run_e2e_coach(a, model, dev, local, rank, world)
         except Exception as ex:          # a secondary number must never take the bench down
-            e2e_coach = {"value": None, "error": repr(ex)}
+            e2e_coach = {"value": None, "error": repr(ex), "seconds": float("nan"), "sims": 0.0}
+        if world > 1:
+            tq = torch.tensor([e2e_coach["seconds"]], device=dev, dtype=torch.float64)
+            nq = torch.tensor([e2e_coach["sims"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(tq, op=dist.ReduceOp.MAX); dist.all_reduce(nq, op=dist.ReduceOp.SUM)
+            if "error" not in e2e_coach:
+                e2e_coach.update(value=float(nq.item()) / float(tq.item()), seconds=float(tq.item()), sims=float(nq.item()),
+                                 ranks=world)
 
     if world > 1:
         clear_samples()
@@ -587,17 +673,18 @@ def main():
             "metric": METRIC if (a.game == "connect4" and B == 8192) else f"self-play MCTS simulations/sec ({B} {a.game} games)",
             "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if a.nn != "cudnn" else ("f32" if a.precision == "fp32" else a.precision), "data": "synthetic",
+            "dtype": dtype, "data": "synthetic",
             "config": {"workload": f"{a.game} {B} games/GPU x {sims} sims/move, DEFAULT_ARGS MCTS (cpuct 1.25, fpu 0.2, "
                                    f"root noise 0.1 + temp 1.1), net={a.net} ResNet random-init, "
                                    f"{'tree-only warmup mode' if a.tree_only else 'NN in the loop'}",
-                       "games_per_gpu": B, "sims_per_move": sims, "net": a.net, "nn": a.nn, "nn_precision": "bf16" if a.nn != "cudnn" else a.precision,
+                       "games_per_gpu": B, "sims_per_move": sims, "net": a.net, "nn": a.nn, "nn_kernel": nn_kernel, "nn_precision": a.precision,
                        "cohorts": a.cohorts, "round_graph": bool(drv.round_graph),
-                       "nn_rows": "non-terminal leaves only" if (a.nn == "fused" and not a.eval_terminal and a.cohorts == 1) else "every leaf", "channels_last": not a.nchw, "lanes_per_game": a.lanes or 8, "rng": "philox", "parallelism": f"games x{world} (no data-path collective)",
+                       "nn_rows": "non-terminal leaves only" if compact else "every leaf", "channels_last": not a.nchw, "lanes_per_game": a.lanes or 8, "rng": "philox", "parallelism": f"games x{world} (no data-path collective)",
                        "l2": "node pool %.1f GB per GPU > 126 MB L2; no flush" % (st1["pool_bytes"] / 1e9),
                        "preroll_rounds": a.preroll},
             "clocks": clk, "gpu_launches": drv.launches - launches0,
             "roofline": roof, "roofline_nn": roof_nn, "cpu_baseline": cpu_base, "e2e": e2e, "e2e_coach": e2e_coach, "alt_nn": alt,
+            "alt_precisions": alt_prec, "nn_error": nn_error, "sustained": sustained_leg,
             "tree_stats": {"sims": dsims, "mean_depth": dD / max(dsims, 1), "mean_children_scanned": dC / max(dsims, 1),
                            "games_finished": st1["results"] - st0["results"], "peak_nodes_per_game": st1["peak_nodes"],
                            "terminal_leaf_fraction": (st1["terminal_leaves"] - st0["terminal_leaves"]) / max(dsims, 1)},
@@ -661,8 +748,6 @@ def run_e2e_coach(a, model, dev, local, rank, world):
     eng = SelfPlayEngine(**engine_kwargs_from_args(Connect4, args, B, device=local, rng="philox", seed=1, game_id_base=rank * B))
     run_selfplay_iteration(Connect4, net, args, device=local, seed=1, engine=eng)   # warm-up: a previous iteration of the same size
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     t0 = time.perf_counter()
     sd = net.state_dict()
     for k, v in host_weights.items():                                    # H2D: this iteration's network
@@ -671,13 +756,9 @@ def run_e2e_coach(a, model, dev, local, rank, world):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     eng.close()
-    t = torch.tensor([dt], device=dev, dtype=torch.float64)
-    n = torch.tensor([float(res.sims)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(n, op=dist.ReduceOp.SUM)
     h2d = sum(v.numel() * v.element_size() for v in host_weights.values())
     d2h = sum(x.numel() * x.element_size() for x in (res.data, res.policy, res.value)) + res.result_turns.nbytes + res.result_winstates.nbytes
-    return {"value": float(n.item()) / float(t.item()), "unit": UNIT, "seconds": float(t.item()), "games": int(len(res.result_turns)),
+    return {"value": float(res.sims) / dt, "unit": UNIT, "seconds": dt, "sims": float(res.sims), "games": int(len(res.result_turns)),
             "examples": int(res.data.shape[0]), "h2d_bytes": int(h2d), "d2h_bytes": int(d2h),
             "api": "azb200.coach.run_selfplay_iteration (the body of GpuSelfPlayMixin.processSelfPlayBatches): network weights from "
                    "pinned host memory, gamesPerIteration = 2 x games, examples and results returned in host memory; wall clock"}
@@ -727,7 +808,7 @@ def run_e2e(a, eng, model, dev, world):
         vts.append(torch.zeros(Bw, 3).pin_memory()); evs.append(threading.Event())
         agents.append(SelfPlayAgent(i, _Game, ready, evs[i], bts[i], pts[i], vts[i], file_queue, _Sink(), completed, played,
                                     stop, pause, args, engine=e, stream_ordered=not a.e2e_sync))
-    wrap = NNetWrapper(nnet=model, cuda=True, fused=(a.nn != "cudnn"))
+    wrap = NNetWrapper(nnet=model, cuda=True, fused=(a.nn != "cudnn"), precision=a.precision if a.nn == "tc" else None)
     old_tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = a.precision != "fp32"
     srv = torch.cuda.Stream(device=dev)

@@ -9,10 +9,13 @@ from azb200 import _capi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
-    text = open(os.path.join(ROOT, "include", "azb200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(azb_[a-z0-9_]+)\s*\(", text)))
+def _declared(headers=("azb200.h",)):
+    names = set()
+    for h in headers:
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(azb_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_header_symbols_are_exported():
@@ -28,14 +31,20 @@ def test_nn_header_symbols_are_exported():
     text = open(os.path.join(ROOT, "include", "azb200_nn.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     names = sorted(set(re.findall(r"\b(azb_[a-z0-9_]+)\s*\(", text)))
-    assert {"azb_nn_forward", "azb_nn_forward_tc", "azb_nn_forward_tc_debug", "azb_upload_pinned"} <= set(names)
+    assert {"azb_nn_forward", "azb_nn_forward_tc", "azb_nn_forward_tc_debug", "azb_upload_pinned", "azb_nng_forward",
+            "azb_nng_layout"} <= set(names)
     lib = ctypes.CDLL(_capi.LIB_PATH)
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, f"libazb200.so lacks {missing}"
 
 
 def test_binding_table_matches_header():
-    assert sorted(_capi.SYMBOLS) == _declared()
+    """every symbol of both headers is bound in ONE table (no ad-hoc restype / argtypes elsewhere)"""
+    assert sorted(_capi.SYMBOLS) == _declared(("azb200.h", "azb200_nn.h"))
+    pkg = os.path.join(ROOT, "alphazero-general_b200", "azb200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py") and f != "_capi.py":
+            assert ".argtypes" not in open(os.path.join(pkg, f)).read(), f
 
 
 def test_library_loads_and_reports_abi():
