@@ -2,7 +2,9 @@
 // helpers whose rounding must match the reference bit for bit.
 //
 // Layout in HBM (one engine = B game slots, NPG node entries per slot):
-//   node pool, two parallel arrays, entry index = slot * NPG + local id
+//   node pool, two parallel arrays, entry index = slot * NPG + local id; a slot's NPG entries are two halves and the
+//     live tree is a dense prefix of one of them: re-rooting (playMoves) copies the kept subtree breadth-first into the
+//     other half, so the discarded siblings never accumulate and the working set stays compact
 //     hot  (16 B)  n int32, q float, p float, child0 int32     -- what the PUCT
 //                  scan reads for every sibling (Node.n/.q/.p, MCTS.pyx:53-56)
 //                  plus the link to the node's own children
@@ -51,7 +53,7 @@ struct __align__(8) NodeCold { float v; uint32_t meta; };
 struct __align__(16) SlotHead {
     GState st;                                   // 32 B
     int root; int root_n; float root_v; int root_child0;
-    uint32_t root_meta; int alloc; int pad0; int pad1;
+    uint32_t root_meta; int alloc; int root_rec /* 1: the root has a pool record (it was a child once) */; int pad1;
 };
 
 // what select leaves for expand/backup (MCTS._curnode / len(_path))
@@ -77,7 +79,7 @@ struct Counters {
 };
 
 struct DevView {
-    int B, npg;
+    int B, npg, half;   // npg = 2 * half entries per slot: two halves, the live tree occupies a prefix of one (re-root compaction)
     // node pool
     NodeHot *hot; NodeCold *cold;
     // per slot

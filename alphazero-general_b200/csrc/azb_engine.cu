@@ -202,15 +202,22 @@ extern "C" int azb_create(const azb_config *cfg, azb_engine **out)
     const int B = cfg->num_games;
     d.B = B;
     int sims = cfg->max_sims_per_move > 0 ? cfg->max_sims_per_move : 100;
-    long long npg = cfg->max_nodes_per_game > 0 ? cfg->max_nodes_per_game
-                                                : 1 + (long long)gd.max_turns * sims * gd.maxc;
-    if (cfg->max_nodes_per_game == 0 && cfg->game != AZB_GAME_CONNECT4) {
-        // tafl: children per expansion average ~35 (max 96); bound the default pool
-        long long cap = 1 + (long long)gd.max_turns * sims * 40;
-        if (npg > cap) npg = cap;
+    // Capacity of the LIVE tree of one game (entries of one half of the slot's arena; re-rooting compacts the kept
+    // subtree into the other half, azb_kernels.cuh compact_subtree).  The live tree holds at most one block of children
+    // per simulation that went through the current root, i.e. <= root.n * maxc entries; root.n grows by `sims` per move
+    // and shrinks to the played child's share at every re-root.  Default: room for 8 moves' worth of simulations at the
+    // typical fan-out (tafl: ~35 of at most 96), never more than the whole-game bound.  Exhaustion is reported
+    // (AZB_ERR_POOL_EXHAUSTED), never overrun.
+    const long long whole_game = 1 + (long long)gd.max_turns * sims * gd.maxc;
+    long long live = cfg->max_nodes_per_game;
+    if (live <= 0) {
+        live = 1 + 8LL * sims * (gd.maxc < 40 ? gd.maxc : 40) + gd.maxc;
+        if (live > whole_game) live = whole_game;
     }
-    if (npg < 2 + gd.maxc || npg > 0x7fffffffLL) { delete e; return fail(AZB_ERR_BAD_CONFIG, "max_nodes_per_game %lld", npg); }
+    if (live < 2 + gd.maxc || 2 * live > 0x7fffffffLL) { delete e; return fail(AZB_ERR_BAD_CONFIG, "max_nodes_per_game %lld", live); }
+    const long long npg = 2 * live;
     d.npg = (int)npg;
+    d.half = (int)live;
     const size_t N = (size_t)B * (size_t)npg;
     int rc = 0;
 #define A_(x) do { if (!rc) rc = (x); } while (0)
@@ -587,7 +594,7 @@ extern "C" int azb_tree_dump(azb_engine *e, int32_t slot, double *rows, int64_t 
     CK(cudaStreamSynchronize(s));
     SlotHead hd;
     CK(cudaMemcpy(&hd, e->d.head + slot, sizeof(SlotHead), cudaMemcpyDeviceToHost));
-    const int used = hd.alloc, root = hd.root;
+    const int used = hd.alloc, root = hd.root;      // entries [0, alloc) cover the live half (and, in the upper half, stale ones below it)
     const size_t nb = (size_t)slot * (size_t)e->d.npg;
     std::vector<NodeHot> hot(used); std::vector<NodeCold> cold(used);
     CK(cudaMemcpy(hot.data(), e->d.hot + nb, sizeof(NodeHot) * used, cudaMemcpyDeviceToHost));
@@ -595,7 +602,9 @@ extern "C" int azb_tree_dump(azb_engine *e, int32_t slot, double *rows, int64_t 
     // while a node is the root its live fields are in the slot header
     hot[root].n = hd.root_n; hot[root].child0 = hd.root_child0; cold[root].v = hd.root_v;
     cold[root].meta = (cold[root].meta & 1023u) | (hd.root_meta & ~1023u);
-    if (hd.root == 0) { cold[root].meta = hd.root_meta; hot[root].q = 0.0f; hot[root].p = 0.0f; }   // fresh root: no pool record
+    if (!hd.root_rec) {
+        cold[root].meta = hd.root_meta; hot[root].q = 0.0f; hot[root].p = 0.0f;                       // fresh root: no pool record
+    }
     std::vector<int> n(used), c0(used); std::vector<float> q(used), p(used), v(used); std::vector<uint32_t> m(used);
     for (int i = 0; i < used; i++) {
         n[i] = hot[i].n; c0[i] = hot[i].child0; q[i] = hot[i].q; p[i] = hot[i].p; v[i] = cold[i].v; m[i] = cold[i].meta;
@@ -636,7 +645,8 @@ extern "C" int azb_stats_get(azb_engine *e, azb_stats *out, void *stream)
         out->sims += (int64_t)ss[i].sims; out->sum_depth += (int64_t)ss[i].sum_depth;
         out->sum_children += (int64_t)ss[i].sum_children; out->nodes_created += (int64_t)ss[i].nodes_created;
         out->terminal_leaves += (int64_t)ss[i].terminal_leaves; out->moves += (int64_t)ss[i].moves;
-        const int pk = ss[i].peak_nodes > hd[i].alloc ? ss[i].peak_nodes : hd[i].alloc;
+        const int used = hd[i].alloc - (hd[i].root >= e->d.half ? e->d.half : 0);
+        const int pk = ss[i].peak_nodes > used ? ss[i].peak_nodes : used;
         if (pk > out->peak_nodes) out->peak_nodes = pk;
     }
     out->games_played = c.games_played; out->results = c.results; out->samples = c.samples_total;

@@ -408,7 +408,7 @@ __device__ __forceinline__ void select_game(const DevView &d, int g, bool active
         bool store = false;
         if (expd && !term) {
             base = H.alloc;
-            if (base + C > d.npg) { if (lane == 0) atomicOr(d.err, ERRB_POOL); base = -1; }
+            if (base + C > (H.root >= d.half ? d.npg : d.half)) { if (lane == 0) atomicOr(d.err, ERRB_POOL); base = -1; }
             else { store = true; nc = C; }
         }
         int cpos[IT], cact[IT];
@@ -678,7 +678,75 @@ __device__ __forceinline__ void tree_reset(SlotHead &H)
 {
     H.root = 0; H.root_n = 0; H.root_v = 0.0f; H.root_child0 = -1;
     H.root_meta = meta_pack(META_ACTION_NONE, 0u, 0u, 0u);
-    H.alloc = 1;
+    H.alloc = 1; H.root_rec = 0;
+}
+
+// ------------------------------------------------------------------------------
+// Re-root compaction.  A slot's arena is two halves of d.half entries; after MCTS.update_root (MCTS.pyx:185-195) the
+// kept subtree is copied breadth-first into the other half -- the C children of a node stay one contiguous block in
+// the reference's list order, so the scan is unchanged -- and the discarded siblings' subtrees (which the reference frees
+// by refcount) are left behind: the live tree is always one dense prefix [base, base + live) of a half.
+// Every lane of the warp calls this; `on` = this group compacts.  The new root is node `src_root` of the current half;
+// its record is copied to entry 0 of the other half.  A batch of up to L copied nodes is expanded per step: lane j reads
+// node head+j (its child0 still names the OLD block), an exclusive scan of the child counts places the new blocks, then
+// the group copies block after block (16 B + 8 B per child, coalesced).  Returns the new live size; H.root /
+// H.root_child0 / H.alloc are updated on every lane of the group.
+// ------------------------------------------------------------------------------
+template <class G>
+__device__ __forceinline__ int compact_subtree(const DevView &d, size_t nb, SlotHead &H, bool on, int lane)
+{
+    constexpr int L = G::LANES;
+    const int dst = H.root >= d.half ? 0 : d.half;          // the half the tree moves to
+    NodeHot *hot = d.hot + nb;
+    NodeCold *cold = d.cold + nb;
+    if (on && lane == 0) {                                   // the root's own record (q, p, action of the played child)
+        NodeHot h = load_hot(hot + H.root);
+        h.child0 = H.root_child0;
+        *reinterpret_cast<int4 *>(hot + dst) = make_int4(h.n, __float_as_int(h.q), __float_as_int(h.p), h.child0);
+        NodeCold c = load_cold(cold + H.root);
+        c.meta = H.root_meta;
+        *reinterpret_cast<int2 *>(cold + dst) = make_int2(__float_as_int(c.v), (int)c.meta);
+    }
+    __syncwarp();
+    int head = 0, tail = on ? 1 : 0;
+    while (__any_sync(FULL, head < tail)) {
+        const int i = head + lane;
+        int c0 = -1, C = 0;
+        if (i < tail) {
+            c0 = hot[dst + i].child0;
+            C = c0 >= 0 ? meta_nc(cold[dst + i].meta) : 0;
+        }
+        // exclusive scan of C over the group's lanes
+        int off = C;
+#pragma unroll
+        for (int o = 1; o < L; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, off, o, L);
+            if (lane >= o) off += v;
+        }
+        const int total = __shfl_sync(FULL, off, L - 1, L);
+        off -= C;
+        if (i < tail && C > 0) hot[dst + i].child0 = dst + tail + off;
+        const int nbatch = min(L, tail - head);
+        for (int j = 0; j < L; j++) {
+            if (!__any_sync(FULL, j < nbatch)) break;
+            const int sc0 = __shfl_sync(FULL, c0, j, L), sC = __shfl_sync(FULL, C, j, L), so = __shfl_sync(FULL, off, j, L);
+            if (j < nbatch) {
+                for (int k = lane; k < sC; k += L) {
+                    *reinterpret_cast<int4 *>(hot + dst + tail + so + k) = *reinterpret_cast<const int4 *>(hot + sc0 + k);
+                    *reinterpret_cast<int2 *>(cold + dst + tail + so + k) = *reinterpret_cast<const int2 *>(cold + sc0 + k);
+                }
+            }
+        }
+        head += nbatch > 0 ? nbatch : 0;
+        tail += total;
+        __syncwarp();
+    }
+    if (on) {
+        H.root_child0 = hot[dst].child0;
+        H.root = dst;
+        H.alloc = dst + tail;
+    }
+    return tail;
 }
 
 // is `action` one of the C valid moves listed by G::list_valid (every lane answers)
@@ -792,6 +860,7 @@ __device__ __forceinline__ int play_move_game(const DevView &d, int g, bool acti
         if (lane == 0) store_head(d.head + g, H);
         on = false;
     }
+    bool compact = false;
     if (on && lane == 0) {
         if (fresh) {
             tree_reset(H);
@@ -800,23 +869,36 @@ __device__ __forceinline__ int play_move_game(const DevView &d, int g, bool acti
             const int nr = H.root_child0 + found;
             const NodeHot h = load_hot(d.hot + nb + nr);
             const NodeCold c = load_cold(d.cold + nb + nr);
-            H.root = nr; H.root_n = h.n; H.root_v = c.v; H.root_child0 = h.child0; H.root_meta = c.meta;
+            H.root = nr; H.root_n = h.n; H.root_v = c.v; H.root_child0 = h.child0; H.root_meta = c.meta; H.root_rec = 1;
+            compact = true;
         }
         G::play(st, action);
         const int e = G::win_code(st);
         st.flags &= 0xff;
-        if (e != 0) { st.flags |= GF_FINISHED; d.fin_code[g] = e; }
+        if (e != 0) { st.flags |= GF_FINISHED; d.fin_code[g] = e; compact = false; }      // the tree is dropped with the game
         H.st = st;
         d.last_action[g] = action;
         if (forced < 0) reinterpret_cast<unsigned *>(d.stats + g)[5] += 1u;     // moves
         if (d.reset_threshold && st.turns >= d.next_reset[g]) {
-            int *pk = reinterpret_cast<int *>(d.stats + g) + 6;
-            if (H.alloc > *pk) *pk = H.alloc;
             tree_reset(H);
             d.next_reset[g] = st.turns + d.reset_threshold;
+            compact = false;
         }
-        store_head(d.head + g, H);
     }
+    // peak of the live tree (entries in use in the current half), sampled before the tree shrinks
+    if (on && lane == 0) {
+        const int used = H.alloc - (H.root >= d.half ? d.half : 0);
+        int *pk = reinterpret_cast<int *>(d.stats + g) + 6;
+        if (!fresh && used > *pk) *pk = used;
+    }
+    compact = group_bcast<L>((int)compact, 0) != 0;
+    if (__any_sync(FULL, compact)) {
+        H.root = group_bcast<L>(H.root, 0);
+        H.root_child0 = group_bcast<L>(H.root_child0, 0);
+        H.root_meta = group_bcast<L>(H.root_meta, 0);
+        compact_subtree<G>(d, nb, H, compact, lane);
+    }
+    if (on && lane == 0) store_head(d.head + g, H);
     __syncwarp();
     return on ? action : G::A;
 }
@@ -1031,7 +1113,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_emit(DevView d)
     }
     if (lane == 0) {
         int *pk = reinterpret_cast<int *>(d.stats + g) + 6;
-        if (H.alloc > *pk) *pk = H.alloc;
+        const int used = H.alloc - (H.root >= d.half ? d.half : 0);
+        if (used > *pk) *pk = used;
         G::init(H.st);
         tree_reset(H);
         store_head(d.head + g, H);
@@ -1108,7 +1191,7 @@ __global__ void k_init_slots(DevView d, const uint32_t *mt_seeds)
     SlotHead H;
     G::init(H.st);
     tree_reset(H);
-    H.pad0 = H.pad1 = 0;
+    H.root_rec = H.pad1 = 0;
     store_head(d.head + g, H);
     LeafInfo li; li.leaf = -1; li.depth = 0; li.child0 = -1; li.meta = 0u;
     d.leafinfo[g] = li;

@@ -347,7 +347,7 @@ def main():
         game=a.game, num_games=B, device=local, rng="philox", seed=0, game_id_base=rank * B,
         cpuct=1.25, fpu_reduction=0.2, root_noise_frac=0.1, root_policy_temp=1.1, add_root_noise=True,
         add_root_temp=True, symmetric_samples=True, games_per_iteration=0, max_sims_per_move=sims,
-        max_nodes_per_game=(120000 if tafl else 0), sample_capacity=(600000 if tafl else 0),
+        max_nodes_per_game=0, sample_capacity=(600000 if tafl else 0),
         temps=temp_table(default_temp_scaling, 1, None if tafl else 42), lanes_per_game=a.lanes)
     torch.manual_seed(0)
     netargs = {"default": aznet.DEFAULT_NET_ARGS, "connect4_train": aznet.CONNECT4_TRAIN_NET_ARGS,

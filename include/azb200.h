@@ -65,7 +65,9 @@ typedef struct azb_config {
     int32_t mcts_reset_threshold; /* args.mctsResetThreshold (0 = None)                    */
     int32_t max_sims_per_move;    /* largest numMCTSSims/numFastSims/numWarmupSims used;   */
                                   /* sizes the per-slot node pool when max_nodes_per_game=0*/
-    int32_t max_nodes_per_game;   /* node-pool entries per slot (0 = derive)               */
+    int32_t max_nodes_per_game;   /* capacity of one game's LIVE tree in nodes (0 = derive: 8 moves' worth of      */
+                                  /* simulations); the slot's arena is twice that -- re-rooting copies the kept      */
+                                  /* subtree into the other half, discarded siblings never accumulate                */
     int32_t temp_table_len;       /* entries of temp_table (0 = constant 1.0)              */
     int32_t lanes_per_game;       /* threads cooperating on one game: 0 = default, Connect4 */
                                   /* accepts 8, 16, 32 (tuning knob, results are identical) */
