@@ -89,7 +89,11 @@ def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup
     for every game, play the moves.  Returns a SelfPlayResult (host tensors; CUDA
     tensors that never left the device with ``device_samples``)."""
     g = lambda k, d=None: (args[k] if k in args else d)
-    B = int(g("process_batch_size", 256))
+    # the reference runs `workers` agents of process_batch_size games each at once (Coach.py:294-323): one engine holds
+    # them all (never more slots than games the iteration asks for)
+    B = int(g("process_batch_size", 256)) * max(1, int(g("workers", 1) or 1))
+    if g("gamesPerIteration"):
+        B = max(1, min(B, int(g("gamesPerIteration"))))
     own_engine = engine is None
     if own_engine:
         engine = SelfPlayEngine(**engine_kwargs_from_args(game_cls, args, B, device=device, rng="philox", seed=seed,
@@ -199,6 +203,18 @@ class ExampleQueue:
         row, self.row = self.row, 0
         blocks[0] = tuple(t[row:] for t in blocks[0])
         return tuple(torch.cat([b[i] for b in blocks]) for i in range(3))
+
+
+def game_with_defaults(game_cls):
+    """A Game plugin that does not derive from GameState (brandubh's fastafl.Game) lacks the defaults of
+    alphazero/Game.py:55-63 that Coach.__init__ (Coach.py:161) and SelfPlayAgent.playMoves (SelfPlayAgent.pyx:157)
+    call: max_turns() -> None, has_draw() -> True.  Returns the class itself or a subclass that supplies them (the
+    device rules follow the plugin's module, so the subclass keeps them)."""
+    missing = {k: staticmethod(v) for k, v in (("max_turns", lambda: None), ("has_draw", lambda: True))
+               if not hasattr(game_cls, k)}
+    if not missing:
+        return game_cls
+    return type(game_cls.__name__, (game_cls,), dict(missing, __module__=game_cls.__module__))
 
 
 class GpuSelfPlayMixin:
