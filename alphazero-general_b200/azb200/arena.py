@@ -33,7 +33,8 @@ def arena_engine(game_cls, args, num_games, **over):
     kw = engine_kwargs_from_args(game_cls, args, 2 * num_games, **over)
     kw.update(arena=True, add_root_noise=False, add_root_temp=False,
               temps=np.full(1, float(args["arenaTemp"] if "arenaTemp" in args else 0.25), dtype=np.float64))
-    kw["max_sims_per_move"] = max(int(args["numMCTSSims"] if "numMCTSSims" in args else 100), 1)
+    kw["max_sims_per_move"] = max(int(args["numMCTSSims"] if "numMCTSSims" in args else 100),
+                                  int(args["numFastSims"] if "numFastSims" in args else 0), 1)
     return SelfPlayEngine(**kw)
 
 
@@ -52,11 +53,16 @@ class _Round:
         return [rows[model == m] for m in range(len(self.p2i))]
 
 
-def play_games(engine, models, player_to_index=(0, 1), sims=None, stop_event=None, progress=None, round_graph=True):
+def play_games(engine, models, player_to_index=(0, 1), sims=None, stop_event=None, progress=None, round_graph=True,
+               fast_sims=None, prob_fast=0.0, coin=None):
     """Arena.play_games on the device: `models[m].process(batch) -> (pi, v)` (NNetWrapper surface), model
     `player_to_index[p]` moves for env player p.  Plays until the engine's games_per_iteration quota is reached.
+    prob_fast / fast_sims: the arena-mode agent of the reference draws the fast-move coin per move-round as well
+    (SelfPlayAgent.pyx:84-86: numFastSims simulations when it comes up); coin = RandomState it is drawn from.
     -> (wins per model index, draws, mean turns, simulations run)."""
-    sims = int(sims or 100)
+    sims_full = int(sims or 100)
+    fast_sims = int(fast_sims or sims_full)
+    coin = coin or np.random.RandomState(0)
     rnd = _Round(engine, player_to_index)
     wins, draws, turns = [0] * len(models), 0, []
     quota = engine.quota
@@ -68,14 +74,14 @@ def play_games(engine, models, player_to_index=(0, 1), sims=None, stop_event=Non
     # ... and then a whole move-round (sims x (select, model 0, model 1, expand/backup) + playMoves) is ONE CUDA graph:
     # every launch argument is constant (row lists and counters live on the device), so after one eager round the
     # graph is captured and replayed per move -- same kernels, same order, same results (tests/test_arena.py)
-    graph, rounds = None, 0
+    graphs, rounds = {}, 0
     use_graph = round_graph and evals is not None
     gstream = torch.cuda.Stream(device=engine.obs.device) if use_graph else None
 
     side = torch.cuda.Stream(device=engine.obs.device) if evals is not None else None
     e_fork, e_join = torch.cuda.Event(), torch.cuda.Event()
 
-    def fused_round(stream=None):
+    def fused_round(sims, stream=None):
         stream = stream or torch.cuda.current_stream()
         engine.select(stream=stream)
         for s in range(sims):
@@ -95,13 +101,15 @@ def play_games(engine, models, player_to_index=(0, 1), sims=None, stop_event=Non
     stamps = []
     while engine.games_played() < quota and not (stop_event is not None and stop_event.is_set()):
         stamps.append(time.time())
+        sims = fast_sims if (prob_fast > 0.0 and coin.random_sample() < prob_fast) else sims_full
+        graph = graphs.get(sims)
         if evals is not None:
             if use_graph and graph is None and rounds >= 1:
                 # not the torch.cuda.graph context manager: it runs gc.collect() and torch.cuda.empty_cache() first
                 # (hundreds of ms right after a training phase); nothing here allocates through torch
                 from .nnet import capture_graph
                 gstream.wait_stream(torch.cuda.current_stream())
-                graph = capture_graph(lambda: fused_round(gstream), gstream)
+                graph = graphs[sims] = capture_graph(lambda: fused_round(sims, gstream), gstream)
             if graph is not None:
                 cur = torch.cuda.current_stream()
                 gstream.wait_stream(cur)
@@ -109,7 +117,7 @@ def play_games(engine, models, player_to_index=(0, 1), sims=None, stop_event=Non
                     graph.replay()
                 cur.wait_stream(gstream)
             else:
-                fused_round()
+                fused_round(sims)
             rounds += 1
         else:
             for _ in range(sims):
@@ -185,7 +193,9 @@ class ArenaAgent(threading.Thread):
         try:
             with torch.cuda.stream(torch.cuda.Stream(device=self.engine.obs.device)):
                 while not self.stop_event.is_set() and self.games_played.value < self.args.gamesPerIteration:
-                    for _ in range(self.args.numMCTSSims):
+                    # the arena-mode agent draws the fast-move coin as well (SelfPlayAgent.pyx:84-86)
+                    fast = self._coin() < (self.args["probFastSim"] if "probFastSim" in self.args else 0.0)
+                    for _ in range(self.args.numFastSims if fast else self.args.numMCTSSims):
                         if self.stop_event.is_set(): break
                         self.generateBatch()
                         if self.stop_event.is_set(): break
@@ -197,6 +207,11 @@ class ArenaAgent(threading.Thread):
         except Exception:
             import traceback
             print(traceback.format_exc())
+
+    def _coin(self):
+        """np.random.random_sample() of SelfPlayAgent.run, from the agent's own stream (the games' streams live on the
+        device, one per slot)."""
+        return float(self._rs.random_sample())
 
     def generateBatch(self):
         while self.pause_event.is_set():

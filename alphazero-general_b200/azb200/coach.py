@@ -119,8 +119,9 @@ def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup
     while engine.games_played() < quota and not (stop_event is not None and stop_event.is_set()):
         round_times.append(time.time())
         fast = bool(rs.random_sample() < g("probFastSim", 0.0))
+        # sims = numFastSims if fast else (numMCTSSims if not warmup else numWarmupSims)      (SelfPlayAgent.pyx:85-86)
         if warmup:
-            engine.warmup_sims(int(g("numWarmupSims", 5)))
+            engine.warmup_sims(int(g("numFastSims", 20)) if fast else int(g("numWarmupSims", 5)))
             engine.play_moves(fast)
         else:
             drv.run_round(int(g("numFastSims", 20)) if fast else int(g("numMCTSSims", 100)), fast)

@@ -140,7 +140,8 @@ class GpuCoach:
             rec = dict(iteration=it)
             warmup = it <= a.numWarmupIters or self.self_play_iter == 0          # Coach.py:232-238
             t0 = time.time()
-            sp_args = dict(a, gamesPerIteration=a.gamesPerIteration // self.world)
+            from .distributed import shard_games
+            sp_args = dict(a, gamesPerIteration=shard_games(int(a.gamesPerIteration), self.rank, self.world)[1])
             if self._sp_engine is None:                                          # one node pool for all iterations
                 self._sp_engine = SelfPlayEngine(**engine_kwargs_from_args(
                     self.game_cls, sp_args, int(a.process_batch_size), device=self.device, rng="philox", seed=self.seed,
@@ -152,6 +153,13 @@ class GpuCoach:
             if self.world > 1:
                 from .distributed import gather_examples_to_rank0
                 obs, pi, z = gather_examples_to_rank0(obs, pi, z)
+            if self.world > 1:                          # every rank must be in the same mode (the gating decision is broadcast)
+                flags = [None] * self.world
+                torch.distributed.all_gather_object(flags, bool(warmup))
+                rec["warmup_by_rank"] = flags
+                tot = torch.tensor([float(res.sims)], device=torch.device("cuda", self.device), dtype=torch.float64)
+                torch.distributed.all_reduce(tot)
+                rec["sims_all_ranks"] = float(tot.item())
             rec.update(selfplay_seconds=time.time() - t0, selfplay_loop_seconds=res.seconds, sims=res.sims, warmup=warmup,
                        selfplay_rounds=int(len(res.last_round_seconds)), slowest_round_seconds=float(np.max(res.last_round_seconds, initial=0.0)),
                        samples=int(obs.shape[0]) if self.rank == 0 else 0, game_results=res.game_results())
@@ -178,9 +186,19 @@ class GpuCoach:
                 rec.update(train_steps=steps, train_seconds=time.time() - t0, window=used)
                 if a.compareWithPast and (it - 1) % a.pastCompareFreq == 0:
                     rec.update(self.compare_to_past(it))
+            if not a.model_gating and self.rank == 0:
+                # Coach.processSelfPlayBatches plays with train_net when gating is off (Coach.py:338): keep the network
+                # self-play uses in step with it after every training phase
+                self.self_play_net.nnet.load_state_dict(self.train_net.nnet.state_dict())
+                self._fresh(self.self_play_net)
             if self.world > 1:                                                # everybody self-plays with rank 0's decision
                 for p in list(self.self_play_net.nnet.parameters()) + list(self.self_play_net.nnet.buffers()):
                     torch.distributed.broadcast(p.data, 0)
+                # ... and knows it: self_play_iter decides warm-up mode on every rank (Coach.py:232-238)
+                t = torch.tensor([self.self_play_iter, self.gating_counter], device=torch.device("cuda", self.device),
+                                 dtype=torch.int64)
+                torch.distributed.broadcast(t, 0)
+                self.self_play_iter, self.gating_counter = int(t[0].item()), int(t[1].item())
                 self._fresh(self.self_play_net)
             self.history.append(rec)
         return self.history
@@ -188,19 +206,33 @@ class GpuCoach:
     def compare_to_past(self, model_iter):
         """Coach.compareToPast (Coach.py:528-570): new net (model 0) against the self-play net, gating."""
         a = self.args
-        eng = arena_engine(self.game_cls, dict(a, gamesPerIteration=a.arenaCompare), min(a.arenaCompare, 4096), device=self.device,
-                           rng="philox", seed=self.seed + 7 * model_iter)
+        # The reference's Arena starts `workers` agents, each with its own shuffle of the sides (SelfPlayAgent.pyx:44-46),
+        # so the new network moves first in some games and second in others.  One engine = one side assignment: play the
+        # match as two halves with opposite assignments (which half gets the extra game of an odd match is drawn).
         rs = np.random.RandomState(self.seed + model_iter)
-        p2i = [0, 1]
-        rs.shuffle(p2i)                                                       # SelfPlayAgent.pyx:44-46
+        first = [0, 1]
+        rs.shuffle(first)
+        n_a = (a.arenaCompare + 1) // 2
+        halves = [(tuple(first), n_a), (tuple(first[::-1]), a.arenaCompare - n_a)]
         t0 = time.time()
-        wins, draws, mean_turns, sims = play_games(eng, [self.train_net, self.self_play_net], tuple(p2i), sims=a.numMCTSSims)
+        wins, draws, sims, turns_sum, t_setup, rounds, slowest = [0, 0], 0, 0, 0.0, 0.0, 0, 0.0
+        for k, (p2i, games) in enumerate(halves):
+            if games <= 0:
+                continue
+            eng = arena_engine(self.game_cls, dict(a, gamesPerIteration=games), min(games, 4096), device=self.device,
+                               rng="philox", seed=self.seed + 7 * model_iter + k)
+            w, d, mean_turns, ns = play_games(eng, [self.train_net, self.self_play_net], p2i, sims=a.numMCTSSims,
+                                              fast_sims=a.numFastSims, prob_fast=a.probFastSim, coin=rs)
+            eng.close()
+            wins = [wins[0] + w[0], wins[1] + w[1]]
+            draws, sims, turns_sum = draws + d, sims + ns, turns_sum + mean_turns * games
+            t_setup += play_games.setup_seconds
+            rounds += int(len(play_games.last_round_seconds))
+            slowest = max(slowest, float(np.max(play_games.last_round_seconds, initial=0.0)))
         t_play = time.time() - t0
-        eng.close()
         winrate = winrate_of_first(wins, draws, a.use_draws_for_winrate)
-        out = dict(arena_wins=wins, arena_draws=draws, arena_winrate=winrate, arena_seconds=time.time() - t0, arena_play_seconds=t_play, arena_setup_seconds=play_games.setup_seconds, arena_sims=sims,
-                   arena_rounds=int(len(play_games.last_round_seconds)),
-                   arena_slowest_round_seconds=float(np.max(play_games.last_round_seconds, initial=0.0)))
+        out = dict(arena_wins=wins, arena_draws=draws, arena_winrate=winrate, arena_seconds=time.time() - t0, arena_play_seconds=t_play, arena_setup_seconds=t_setup, arena_sims=sims,
+                   arena_rounds=rounds, arena_slowest_round_seconds=slowest, arena_sides=[h[0] for h in halves])
         if a.model_gating and winrate < a.min_next_model_winrate and (a.max_gating_iters is None or self.gating_counter < a.max_gating_iters):
             self.gating_counter += 1
             out["accepted"] = False

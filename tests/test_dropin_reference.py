@@ -140,6 +140,9 @@ def test_real_arena_play_games_with_the_import_swap_equals_the_reference_agent(t
             super().__init__(id, game_cls, *a, engine=eng, **kw)
             self.player_to_index = list(p2i)
             made.append(self)
+
+        def _coin(self):
+            return 1.0                                                      # fed, as the reference's
     monkeypatch.setattr(arena_mod, "SelfPlayAgent", SwappedAgent)           # from azb200.arena import ArenaAgent as SelfPlayAgent
     our_arena = arena_mod.Arena(players, Game, use_batched_mcts=True, args=args)
     our_out = our_arena.play_games(N)
