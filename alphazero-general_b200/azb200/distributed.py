@@ -120,6 +120,70 @@ def train_steps_sharded(net, optimizer, loader, steps, value_loss_weight, device
     return (float(acc[0]) / n, float(acc[1]) / n) if n else (0.0, 0.0)
 
 
+def train_steps_local_windows(net, optimizer, window, iteration, args, value_loss_weight, device, group=None,
+                              sync_bn_stats=True, bn_eval=False):
+    """Data-parallel training without moving the examples (DDP NNetWrapper.train): every rank keeps the
+    examples of its OWN games in its own SampleWindow (nothing is gathered to rank 0), draws train_batch_size / world
+    rows per step from it and the gradients are averaged over the ranks -- the standard data-parallel estimator of the
+    same loss (NNetWrapper.py:234-238) over the union of the shards.  The step count follows Coach.train's rule
+    (Coach.py:452-478) on the GLOBAL sample counts.  Parameters stay identical on all ranks.
+    -> (mean policy loss, mean value loss, steps, global samples in the window)."""
+    from .samples import WindowLoader, loss_pi, loss_v
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    g = lambda k, d: (args[k] if k in args else d)
+    its = window.window(iteration, args)
+    sizes = torch.tensor([int(window.iters[i][0].shape[0]) for i in its] + [len(its)], device=device, dtype=torch.int64)
+    n_its = torch.tensor([len(its)], device=device, dtype=torch.int64)
+    dist.all_reduce(n_its, op=dist.ReduceOp.MIN, group=group)
+    if int(n_its.item()) != len(its):
+        raise RuntimeError("ranks disagree on the iterations in their sample windows")
+    dist.all_reduce(sizes, op=dist.ReduceOp.SUM, group=group)
+    gsz = sizes[:-1].tolist()
+    bs = int(g("train_batch_size", 1024))
+    if not g("autoTrainSteps", True):
+        steps = int(g("train_steps_per_iteration", 64))
+    else:
+        steps = ((sum(gsz) // len(gsz)) if g("averageTrainSteps", False) else gsz[-1]) // bs if gsz else 0
+    local_bs = shard_games(bs, rank, world)[1]
+    params = [p for p in net.parameters() if p.requires_grad]
+    net.train(not bn_eval)
+    loader = WindowLoader(window.tensors(its), max(local_bs, 1)) if its else None
+    it = None
+    acc = torch.zeros(3, device=device, dtype=torch.float64)
+    for _ in range(steps):
+        try:
+            batch = next(it) if it is not None else None
+        except StopIteration:
+            batch = None
+        if batch is None:
+            it = iter(loader)
+            batch = next(it)
+        boards, pis, vs = batch
+        optimizer.zero_grad()
+        out_pi, out_v = net(boards)
+        l_pi, l_v = loss_pi(pis, out_pi), loss_v(vs, out_v, value_loss_weight)
+        (l_pi + l_v).backward()
+        rows = float(boards.shape[0])
+        stat = torch.stack([l_pi.detach() * rows, l_v.detach() * rows, torch.tensor(rows, device=device)])
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params] + [stat])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)               # one bucket: the net is < 25 MB
+        off = 0
+        for p in params:
+            k = p.numel()
+            p.grad = (flat[off:off + k] / world).view_as(p).clone()
+            off += k
+        optimizer.step()
+        acc += flat[off:off + 3].double()
+    if sync_bn_stats and world > 1:
+        for name, buf in net.named_buffers():
+            if buf.dtype.is_floating_point:
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+                buf /= world
+    net.eval()
+    n = float(acc[2])
+    return ((float(acc[0]) / n, float(acc[1]) / n) if n else (0.0, 0.0)) + (steps, sum(gsz))
+
+
 def _bcast_int(v, device, group=None):
     t = torch.tensor([int(v)], dtype=torch.int64, device=device)
     dist.broadcast(t, 0, group=group)

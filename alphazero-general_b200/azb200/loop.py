@@ -150,9 +150,13 @@ class GpuCoach:
                                          device=self.device, seed=self.seed + 1000 * it + self.rank, warmup=warmup,
                                          engine=self._sp_engine, device_samples=True)
             obs, pi, z = res.data, res.policy, res.value                        # CUDA tensors, never copied to the host
-            if self.world > 1:
+            local_windows = self.world > 1 and a.ddp_train == "local"           # every rank keeps its own examples
+            if self.world > 1 and not local_windows:
                 from .distributed import gather_examples_to_rank0
+                t_g = time.time()
                 obs, pi, z = gather_examples_to_rank0(obs, pi, z)
+                torch.cuda.synchronize()
+                rec["gather_seconds"] = time.time() - t_g
             if self.world > 1:                          # every rank must be in the same mode (the gating decision is broadcast)
                 flags = [None] * self.world
                 torch.distributed.all_gather_object(flags, bool(warmup))
@@ -164,13 +168,23 @@ class GpuCoach:
                        selfplay_rounds=int(len(res.last_round_seconds)), slowest_round_seconds=float(np.max(res.last_round_seconds, initial=0.0)),
                        samples=int(obs.shape[0]) if self.rank == 0 else 0, game_results=res.game_results())
             loader, steps, used = None, 0, []
-            if self.rank == 0:
+            if self.rank == 0 or local_windows:
                 self.window.add_iteration(it, obs, pi, z)
                 self.window.evict_before(it - a.maxTrainHistoryWindow)
-                loader, used = self.window.loader(it, a)
-                steps = self.window.train_steps(used, a)
+                if local_windows:
+                    used = self.window.window(it, a)
+                else:
+                    loader, used = self.window.loader(it, a)
+                    steps = self.window.train_steps(used, a)
             t0 = time.time()
-            if self.world > 1 and a.ddp_train:
+            if local_windows:
+                from .distributed import train_steps_local_windows
+                lp, lv, steps, gsamples = train_steps_local_windows(self.train_net.nnet, self.optimizer, self.window, it, a,
+                                                                    a.value_loss_weight, torch.device("cuda", self.device))
+                losses = (lp, lv)
+                rec["samples_all_ranks"] = gsamples
+                self._fresh(self.train_net)
+            elif self.world > 1 and a.ddp_train:
                 # every rank trains: rank 0 draws the batches from its window, the rows of each batch are split
                 # over the ranks, gradients summed (azb200.distributed.train_steps_sharded)
                 from .distributed import train_steps_sharded

@@ -82,7 +82,7 @@ class SelfPlayAgent(threading.Thread):
                  stream_ordered=False, step_graphs=None):
         super().__init__(daemon=True)
         if _is_arena:
-            raise NotImplementedError("arena mode is served by the reference agent (SURVEY 8f-1)")
+            raise NotImplementedError("arena mode: use azb200.arena.ArenaAgent (same constructor; Arena.pyx:253-259)")
         self.id = id
         self.game_cls = game_cls
         self.ready_queue, self.batch_ready = ready_queue, batch_ready
@@ -208,6 +208,42 @@ class SelfPlayAgent(threading.Thread):
         if not self._await_answers():
             return
         self._g_last.replay()
+
+    def round_with_server(self, server, sims):
+        """One move-round (`sims` x generateBatch -> NN server -> processBatch) as ONE replayed CUDA graph on this
+        agent's stream, the body of the NN server (Coach.py:337-342: process(batch_tensor), copies into policy_tensor /
+        value_tensor) captured inside it.  Every batch still travels through the pinned HOST tensors in both directions
+        -- observations device -> batch_tensor -> device, answers device -> policy / value tensors -> device -- but the
+        host issues one launch per agent and round instead of ~5 per agent and simulation: with the per-step graphs the
+        issuing Python thread is busy 100 % of the time and bounds the protocol (profiles/r2_e2e_scaling.md).
+        playMoves stays with the caller."""
+        key = int(sims)
+        graphs = self.__dict__.setdefault("_round_graphs", {})
+        g = graphs.get(key)
+        if g is None:
+            eng = self.engine
+
+            def whole_round():
+                eng.select(stream=self.stream)
+                self.batch_tensor.copy_(eng.obs, non_blocking=True)
+                for s_ in range(key):
+                    server._body(self)                              # upload batch_tensor, network, answers -> host tensors
+                    self._upload_answers()
+                    eng.expand_backup(stream=self.stream)
+                    if s_ + 1 < key:
+                        eng.select(stream=self.stream)
+                        self.batch_tensor.copy_(eng.obs, non_blocking=True)
+            with torch.cuda.stream(self.stream):
+                if not graphs.get("warm"):
+                    server._body(self)                              # lazy one-time setup of the evaluator: not capturable
+                    graphs["warm"] = True
+                    self.stream.synchronize()
+                g = graphs[key] = self._capture(whole_round)
+        with torch.cuda.stream(self.stream):
+            g.replay()
+        self.batches += key
+        self.d2h_bytes += key * self.batch_tensor.numel() * 4
+        self.h2d_bytes += key * (self.policy_tensor.numel() + self.value_tensor.numel()) * 4
 
     def _prepare_graphs(self):
         eng = self.engine

@@ -265,7 +265,8 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     uint32_t *cnts = tmem_slot + 4;
 
     enum { BAR_PFULL = 0, BAR_PEMPTY = BAR_PFULL + C::NRING, BAR_READY = BAR_PEMPTY + C::NRING,
-           BAR_WFULL = BAR_READY + C::TILES, BAR_WEMPTY = BAR_WFULL + C::NSLOT, NBARS = BAR_WEMPTY + C::NSLOT };
+           BAR_WFULL = BAR_READY + C::TILES, BAR_WEMPTY = BAR_WFULL + C::NSLOT, BAR_TURN = BAR_WEMPTY + C::NSLOT,
+           NBARS = BAR_TURN + 3 };
     static_assert(NBARS <= 40, "barrier storage");
 
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -285,8 +286,13 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
             for (int i = 0; i < C::NRING; i++) { mbar_init(BAR(BAR_PFULL + i), 1); mbar_init(BAR(BAR_PEMPTY + i), C::GW); }
             for (int i = 0; i < C::TILES; i++) mbar_init(BAR(BAR_READY + i), C::GW);
             for (int i = 0; i < C::NSLOT; i++) { mbar_init(BAR(BAR_WFULL + i), 1); mbar_init(BAR(BAR_WEMPTY + i), (uint32_t)nissue); }
+            // the MMAs of a tile enter the tensor pipe back to back and in tile order: issuer w waits for TURN[w], which the
+            // issuer of the previous tile arrives on (an mbarrier wait parks the thread; a polled shared-memory word takes
+            // wavefronts of the shared-memory pipe away from the MMA operand reads the kernel is bound by)
+            for (int i = 0; i < 3; i++) mbar_init(BAR(BAR_TURN + i), 1);
             cnts[0] = 0u;
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+            mbar_arrive(BAR(BAR_TURN));                       // tile 0 may go
         }
         __syncwarp();
         tmem_alloc<512>(smem_u32(tmem_slot));
@@ -338,12 +344,12 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     fence_proxy_async();
     __syncthreads();
 
-    const uint32_t turn_s = smem_u32(cnts);
     const int nslabs = 1 + (layers - 1) * C::SLABS;
     if (warp < 3) {
         // ---- MMA issuers: warp k feeds the tiles g = k, k + nissue, ... (g = layer * tiles + tile) ---------------
         if (warp < nissue && elect_one_sync()) {
-            int l = warp / tiles, t = warp - l * tiles, seen = 0;
+            int l = warp / tiles, t = warp - l * tiles, seen = 0, turn = 0;
+            const uint32_t my_turn = BAR(BAR_TURN + warp), next_turn = BAR(BAR_TURN + (warp + 1 == nissue ? 0 : warp + 1));
 #pragma unroll 1
             for (int g = warp; g < total; g += nissue) {
                 const int slot = g % C::NRING, use = g / C::NRING;
@@ -351,7 +357,8 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
                 if (l > 0) mbar_wait(BAR(BAR_READY + t), (uint32_t)((l - 1) & 1));         // my tile's previous epilogue
                 if (use > 0) mbar_wait(BAR(BAR_PEMPTY + slot), (uint32_t)((use - 1) & 1));  // ring slot drained
                 tc_fence_after();
-                turn_wait(turn_s, (uint32_t)g);
+                mbar_wait(my_turn, (uint32_t)(turn & 1));
+                turn++;
                 const int s0 = l == 0 ? 0 : 1 + (l - 1) * C::SLABS, ns = l == 0 ? 1 : C::SLABS;
                 const bool my_last = t + nissue >= tiles;          // my last tile of this layer: release its slabs
 #pragma unroll 1
@@ -362,7 +369,7 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
                     if (my_last) umma_commit(BAR(BAR_WEMPTY + ws));
                 }
                 umma_commit(BAR(BAR_PFULL + slot));
-                turn_store(turn_s, (uint32_t)(g + 1));
+                mbar_arrive_relaxed(next_turn);
                 t += nissue;
                 while (t >= tiles) { t -= tiles; l++; }
             }

@@ -18,6 +18,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
+// arrive without release semantics: orders nothing but the barrier itself (a releasing arrive by the MMA-issuing
+// thread would wait for its asynchronous MMAs to retire)
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");

@@ -74,6 +74,9 @@ def parse():
                     help="inline: one host thread runs the Coach loop over the agents (generateBatch -> process -> "
                          "processBatch, every call asynchronous and stream-ordered); threads: agents are threads, ready queue")
     ap.add_argument("--e2e-eager", action="store_true", help="inline e2e leg without the agents' captured step graphs")
+    ap.add_argument("--e2e-step-graphs", action="store_true",
+                    help="inline e2e leg with three step graphs per agent and simulation (round 1) instead of one graph per agent "
+                         "and move-round with the server body inside")
     ap.add_argument("--e2e-item-queue", action="store_true",
                     help="e2e leg: the agents put one queue item per example (reference file_queue protocol) instead of blocks")
     ap.add_argument("--e2e-sync", action="store_true",
@@ -928,9 +931,20 @@ def run_e2e_inline(a, eng, agents, server, evs, ready, dev, world, Bw, old_tf32)
             with torch.cuda.stream(ag.stream):
                 ag.playMoves()
 
+    def one_round_fused():
+        # one graph per agent and move-round, the NN server's body captured inside (SelfPlayAgent.round_with_server):
+        # the same copies through the same pinned host tensors, one host launch per agent and round
+        for ag in agents:
+            ag.round_with_server(server, a.sims)
+        for ag in agents:
+            with torch.cuda.stream(ag.stream):
+                ag.playMoves()
+
     one_round()                                           # eager: one-time kernel / evaluator setup
+    while not ready.empty():
+        ready.get_nowait()
     if not a.e2e_eager:
-        one_round = one_round_graphed
+        one_round = one_round_graphed if a.e2e_step_graphs else one_round_fused
     one_round(); one_round()
     if world > 1:
         dist.barrier()
@@ -938,11 +952,14 @@ def run_e2e_inline(a, eng, agents, server, evs, ready, dev, world, Bw, old_tf32)
     for ag in agents:
         ag.h2d_bytes = ag.d2h_bytes = 0
     n0 = sum(ag.batches for ag in agents)
+    cpu0 = os.times()
     t0 = time.perf_counter()
     for _ in range(a.e2e_steps):
         one_round()
+    t_issue = time.perf_counter() - t0                 # the host thread is done issuing; the GPU may still be working
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    cpu1 = os.times()
     n1 = sum(ag.batches for ag in agents)
     torch.backends.cudnn.allow_tf32 = old_tf32
     t = torch.tensor([dt], device=dev, dtype=torch.float64)
@@ -958,8 +975,16 @@ def run_e2e_inline(a, eng, agents, server, evs, ready, dev, world, Bw, old_tf32)
             "h2d_bytes_per_step": int(a.sims * obs_b + sum(ag.h2d_bytes for ag in agents) / steps),
             "d2h_bytes_per_step": int(a.sims * pv_b + sum(ag.d2h_bytes for ag in agents) / steps),
             "steps": steps, "agents": W, "games_per_agent": Bw,
+            # limiter diagnosis (this rank): share of the timed wall clock the issuing host thread was busy issuing, CPU
+            # seconds of the process per wall second, and PCIe traffic each way
+            "host_issue_fraction": t_issue / dt, "host_cpu_cores_busy": ((cpu1.user - cpu0.user) + (cpu1.system - cpu0.system)) / dt,
+            "pcie_gbs_h2d": (a.sims * obs_b + sum(ag.h2d_bytes for ag in agents) / steps) * steps / dt / 1e9,
+            "pcie_gbs_d2h": (a.sims * pv_b + sum(ag.d2h_bytes for ag in agents) / steps) * steps / dt / 1e9,
+            "seconds": dt,
             "file_queue": "one item per example" if a.e2e_item_queue else "azb200.coach.ExampleQueue (one block per move-round, every example kept)",
             "host_tensor_protocol": "stream-ordered (CUDA events)",
+            "issue": ("eager launches" if a.e2e_eager else "three step graphs per agent and simulation" if a.e2e_step_graphs
+                      else "one CUDA graph per agent and move-round, NN-server body inside (SelfPlayAgent.round_with_server)"),
             "api": "Coach.processSelfPlayBatches data flow driven by one host thread: azb200.selfplay.SelfPlayAgent."
                    "generateBatch -> HostBatchServer.serve (NNetWrapper.process on the pinned host batch tensor) -> "
                    "processBatch, playMoves; every batch crosses PCIe in both directions"}

@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--sims", type=int, default=100)
     ap.add_argument("--arena", type=int, default=128)
     ap.add_argument("--graph-train", action="store_true", help="replay the training step as a CUDA graph (3.3 vs 4 ms per step)")
-    ap.add_argument("--ddp-train", action="store_true", help="N > 1: every rank trains on its slice of each batch")
+    ap.add_argument("--ddp-train", nargs="?", const=True, default=False, help="N > 1: every rank trains; `--ddp-train local` = per-rank window shards (no example gather), bare flag = rank 0 draws and broadcasts each batch")
     a = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
