@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libazb200.so")
 
 ABI_VERSION = 1
-GAME_CONNECT4, GAME_BRANDUBH = 0, 1
+GAME_CONNECT4, GAME_BRANDUBH, GAME_HNEFATAFL = 0, 1, 2
 RNG_MT19937, RNG_PHILOX = 0, 1
 
 STATUS_NAMES = {

@@ -12,7 +12,7 @@ import numpy as np
 from . import _capi
 from ._capi import AzbConfig, AzbStats, check
 
-GAMES = {"connect4": _capi.GAME_CONNECT4, "brandubh": _capi.GAME_BRANDUBH}
+GAMES = {"connect4": _capi.GAME_CONNECT4, "brandubh": _capi.GAME_BRANDUBH, "hnefatafl": _capi.GAME_HNEFATAFL}
 
 
 def default_temp_scaling(cur_temp, turns, const_max_turns):

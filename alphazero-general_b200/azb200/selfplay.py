@@ -36,6 +36,8 @@ def game_name(game_cls):
             return "connect4"
         if "brandubh" in m:
             return "brandubh"
+        if "hnefatafl" in m and m.endswith("fastafl"):           # alphazero/envs/hnefatafl/fastafl.pyx, the 11x11 game
+            return "hnefatafl"
     raise NotImplementedError(f"no device rules for game plugin {game_cls!r} (module {mod})")
 
 

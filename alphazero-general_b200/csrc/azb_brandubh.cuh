@@ -29,6 +29,9 @@ struct Brandubh {
     static constexpr int MAX_TURNS = 100;  // DRAW_MOVE_COUNT
     static constexpr int MAXD = 104;
     static constexpr int NSYM = 8;
+    using State = GState;
+    static constexpr int CTA = 128;        // threads per CTA of the tree kernels
+    static constexpr int TYPC = 40;        // typical children per expansion (measured mean ~33)
     static constexpr int LANES = 32;
     static constexpr bool LANE_IS_ACTION = false;
     static constexpr unsigned long long BOARD = (1ULL << 49) - 1ULL;

@@ -24,15 +24,17 @@
 namespace azb {
 
 // ---- node meta word --------------------------------------------------------
-constexpr uint32_t META_ACTION_NONE = 1023u;
+// action:12 (hnefatafl has 2420 actions) | nchild:8 | e:2 | player:1
+constexpr uint32_t META_ACTION_MASK = 4095u;
+constexpr uint32_t META_ACTION_NONE = 4095u;
 __host__ __device__ __forceinline__ uint32_t meta_pack(uint32_t a, uint32_t nc, uint32_t e, uint32_t pl)
 {
-    return (a & 1023u) | ((nc & 255u) << 10) | ((e & 3u) << 18) | ((pl & 1u) << 20);
+    return (a & META_ACTION_MASK) | ((nc & 255u) << 12) | ((e & 3u) << 20) | ((pl & 1u) << 22);
 }
-__host__ __device__ __forceinline__ int meta_action(uint32_t m) { return (int)(m & 1023u); }
-__host__ __device__ __forceinline__ int meta_nc(uint32_t m) { return (int)((m >> 10) & 255u); }
-__host__ __device__ __forceinline__ int meta_e(uint32_t m) { return (int)((m >> 18) & 3u); }
-__host__ __device__ __forceinline__ int meta_player(uint32_t m) { return (int)((m >> 20) & 1u); }
+__host__ __device__ __forceinline__ int meta_action(uint32_t m) { return (int)(m & META_ACTION_MASK); }
+__host__ __device__ __forceinline__ int meta_nc(uint32_t m) { return (int)((m >> 12) & 255u); }
+__host__ __device__ __forceinline__ int meta_e(uint32_t m) { return (int)((m >> 20) & 3u); }
+__host__ __device__ __forceinline__ int meta_player(uint32_t m) { return (int)((m >> 22) & 1u); }
 
 // ---- packed game state (32 B) ------------------------------------------------
 struct __align__(16) GState {
@@ -48,13 +50,16 @@ constexpr int GF_DEAD = 0x200;       // finished beyond the games_played quota: 
 struct __align__(16) NodeHot { int n; float q; float p; int child0; };
 struct __align__(8) NodeCold { float v; uint32_t meta; };
 
-// 64-byte slot header.  While a node is the root its n / v / child0 / meta live
-// here (the pool record of a re-rooted child is copied in by play_moves).
-struct __align__(16) SlotHead {
-    GState st;                                   // 32 B
+// Slot header: the game's packed state (G::State: 32 B for Connect4 / brandubh -> a 64-byte header; 64 B for the
+// 121-cell hnefatafl boards -> 96 B) followed by 32 B of root fields.  While a node is the root its n / v / child0 /
+// meta live here (the pool record of a re-rooted child is copied in by play_moves).
+template <class S>
+struct __align__(16) SlotHeadT {
+    S st;
     int root; int root_n; float root_v; int root_child0;
     uint32_t root_meta; int alloc; int root_rec /* 1: the root has a pool record (it was a child once) */; int pad1;
 };
+using SlotHead = SlotHeadT<GState>;
 
 // what select leaves for expand/backup (MCTS._curnode / len(_path))
 struct __align__(16) LeafInfo { int leaf; int depth; int child0; uint32_t meta; };
@@ -83,9 +88,11 @@ struct DevView {
     // node pool
     NodeHot *hot; NodeCold *cold;
     // per slot
-    SlotHead *head; LeafInfo *leafinfo; int *path;
+    void *head;                        // SlotHeadT<G::State>[B]
+    LeafInfo *leafinfo; int *path;
     uint32_t *mt; unsigned long long *ctr;
-    GState *hist_state; float *hist_pi; int *hist_len; int hist_cap;
+    void *hist_state;                  // G::State[B][hist_cap]
+    float *hist_pi; int *hist_len; int hist_cap;
     int *next_reset; int *noise_event; int *last_action; int *fin_code;
     long long *emit_off;
     SlotStats *stats;

@@ -24,6 +24,9 @@ struct Connect4T {
     static constexpr int MAX_TURNS = 42;   // Game.max_turns()
     static constexpr int MAXD = 44;        // path buffer entries per slot
     static constexpr int NSYM = 2;         // symmetries(): identity, mirror
+    using State = GState;
+    static constexpr int CTA = 128;        // threads per CTA of the tree kernels
+    static constexpr int TYPC = 7;         // typical children per expansion (sizes the default live-tree capacity)
     static constexpr int LANES = LANES_;   // threads cooperating on one game (8, 16 or 32)
     static constexpr bool LANE_IS_ACTION = true;   // A <= LANES: lane a can own the child of action a
     static constexpr unsigned long long TOP = 0x0810204081020ULL;  // bits col*7+5

@@ -6,6 +6,7 @@
 #include "azb_connect4.cuh"
 #ifdef AZB_HAVE_BRANDUBH
 #include "azb_brandubh.cuh"
+#include "azb_hnefatafl_game.cuh"
 #endif
 #include "azb_kernels.cuh"
 
@@ -41,12 +42,32 @@ static int fail(int code, const char *fmt, ...)
 
 struct GameDims {
     int A, obs_c, obs_h, obs_w, cells, maxc, max_turns, maxd, nsym, lanes;
+    int state_bytes, head_bytes, turns_off;      // layout of SlotHeadT<G::State> for the host-side readers
+    int typc;                                    // typical children per expansion
 };
 
 template <class G>
 static GameDims dims_of()
 {
-    return GameDims{G::A, G::OBS_C, G::H, G::W, G::CELLS, G::MAXC, G::MAX_TURNS, G::MAXD, G::NSYM, G::LANES};
+    using S = typename G::State;
+    S probe;
+    const int turns_off = (int)(reinterpret_cast<const char *>(&probe.turns) - reinterpret_cast<const char *>(&probe));
+    return GameDims{G::A, G::OBS_C, G::H, G::W, G::CELLS, G::MAXC, G::MAX_TURNS, G::MAXD, G::NSYM, G::LANES,
+                    (int)sizeof(S), (int)sizeof(SlotHeadT<S>), turns_off, G::TYPC};
+}
+
+// the game-independent part of a slot header, as the host reads it
+struct HeadView {
+    int turns, flags, root, root_n; float root_v; int root_child0; uint32_t root_meta; int alloc, root_rec;
+};
+static HeadView head_view(const GameDims &gd, const unsigned char *raw)
+{
+    HeadView h;
+    memcpy(&h.turns, raw + gd.turns_off, 4); memcpy(&h.flags, raw + gd.turns_off + 4, 4);
+    const unsigned char *r = raw + gd.state_bytes;
+    memcpy(&h.root, r, 4); memcpy(&h.root_n, r + 4, 4); memcpy(&h.root_v, r + 8, 4); memcpy(&h.root_child0, r + 12, 4);
+    memcpy(&h.root_meta, r + 16, 4); memcpy(&h.alloc, r + 20, 4); memcpy(&h.root_rec, r + 24, 4);
+    return h;
 }
 
 struct azb_engine {
@@ -80,7 +101,7 @@ static int dev_alloc(azb_engine *e, T **p, size_t count, bool zero = true)
 
 
 template <class G>
-static inline int grid_for(int games) { return (games * G::LANES + CTA_THREADS - 1) / CTA_THREADS; }
+static inline int grid_for(int games) { return (games * G::LANES + G::CTA - 1) / G::CTA; }
 
 // launchers (one per kernel) so that the game dispatch is a plain if/else
 template <class G> static void l_init(azb_engine *e, const uint32_t *seeds_dev, cudaStream_t s)
@@ -89,22 +110,22 @@ template <class G> static void l_init(azb_engine *e, const uint32_t *seeds_dev, 
 }
 template <class G> static void l_select(azb_engine *e, int first, int count, cudaStream_t s)
 {
-    k_select<G><<<grid_for<G>(count), CTA_THREADS, 0, s>>>(e->d, first, count);
+    k_select<G><<<grid_for<G>(count), G::CTA, 0, s>>>(e->d, first, count);
 }
 template <class G> static void l_expand(azb_engine *e, int first, int count, const float *pol, const float *val, cudaStream_t s)
 {
-    k_expand_backup<G><<<grid_for<G>(count), CTA_THREADS, 0, s>>>(e->d, first, count, pol, val);
+    k_expand_backup<G><<<grid_for<G>(count), G::CTA, 0, s>>>(e->d, first, count, pol, val);
 }
 template <class G> static void l_expand_select(azb_engine *e, int first, int count, const float *pol, const float *val, cudaStream_t s)
 {
-    k_expand_select<G><<<grid_for<G>(count), CTA_THREADS, 0, s>>>(e->d, first, count, pol, val);
+    k_expand_select<G><<<grid_for<G>(count), G::CTA, 0, s>>>(e->d, first, count, pol, val);
 }
 template <class G> static void l_play(azb_engine *e, int fast, cudaStream_t s)
 {
-    if (e->d.arena) k_play_moves_arena<G><<<grid_for<G>(e->d.B / 2), CTA_THREADS, 0, s>>>(e->d);
-    else k_play_moves<G><<<grid_for<G>(e->d.B), CTA_THREADS, 0, s>>>(e->d, fast);
+    if (e->d.arena) k_play_moves_arena<G><<<grid_for<G>(e->d.B / 2), G::CTA, 0, s>>>(e->d);
+    else k_play_moves<G><<<grid_for<G>(e->d.B), G::CTA, 0, s>>>(e->d, fast);
     k_finalize<G><<<1, 1024, 0, s>>>(e->d);
-    k_emit<G><<<grid_for<G>(e->d.B), CTA_THREADS, 0, s>>>(e->d);
+    k_emit<G><<<grid_for<G>(e->d.B), G::CTA, 0, s>>>(e->d);
 }
 template <class G> static void l_arena_players(azb_engine *e, int *out, cudaStream_t s)
 {
@@ -116,11 +137,11 @@ template <class G> static void l_set_state(azb_engine *e, int slot, const signed
 }
 template <class G> static void l_force_move(azb_engine *e, int slot, int action, cudaStream_t s)
 {
-    k_force_move<G><<<1, CTA_THREADS, 0, s>>>(e->d, slot, action);
+    k_force_move<G><<<1, G::CTA, 0, s>>>(e->d, slot, action);
 }
 template <class G> static void l_warmup(azb_engine *e, int sims, cudaStream_t s)
 {
-    k_warmup_sims<G><<<grid_for<G>(e->d.B), CTA_THREADS, 0, s>>>(e->d, sims);
+    k_warmup_sims<G><<<grid_for<G>(e->d.B), G::CTA, 0, s>>>(e->d, sims);
 }
 template <class G> static void l_counts(azb_engine *e, cudaStream_t s)
 {
@@ -136,7 +157,8 @@ template <class G> static void l_boards(azb_engine *e, cudaStream_t s)
         else if ((e)->lanes == 16) fn<Connect4T<16>>(__VA_ARGS__); \
         else fn<Connect4T<8>>(__VA_ARGS__); } while (0)
 #ifdef AZB_HAVE_BRANDUBH
-#define DISPATCH(e, fn, ...) do { if ((e)->cfg.game == AZB_GAME_CONNECT4) DISPATCH_C4(e, fn, __VA_ARGS__); else fn<Brandubh>(__VA_ARGS__); } while (0)
+#define DISPATCH(e, fn, ...) do { if ((e)->cfg.game == AZB_GAME_CONNECT4) DISPATCH_C4(e, fn, __VA_ARGS__); \
+        else if ((e)->cfg.game == AZB_GAME_HNEFATAFL) fn<HnefataflG>(__VA_ARGS__); else fn<Brandubh>(__VA_ARGS__); } while (0)
 #else
 #define DISPATCH(e, fn, ...) DISPATCH_C4(e, fn, __VA_ARGS__)
 #endif
@@ -176,6 +198,7 @@ extern "C" int azb_create(const azb_config *cfg, azb_engine **out)
     if (cfg->game == AZB_GAME_CONNECT4) gd = dims_of<Connect4>();
 #ifdef AZB_HAVE_BRANDUBH
     else if (cfg->game == AZB_GAME_BRANDUBH) gd = dims_of<Brandubh>();
+    else if (cfg->game == AZB_GAME_HNEFATAFL) gd = dims_of<HnefataflG>();
 #endif
     else return fail(AZB_ERR_BAD_CONFIG, "unknown game %d", cfg->game);
     if (cfg->temp_table_len < 0 || (cfg->temp_table_len > 0 && !cfg->temp_table))
@@ -206,12 +229,12 @@ extern "C" int azb_create(const azb_config *cfg, azb_engine **out)
     // subtree into the other half, azb_kernels.cuh compact_subtree).  The live tree holds at most one block of children
     // per simulation that went through the current root, i.e. <= root.n * maxc entries; root.n grows by `sims` per move
     // and shrinks to the played child's share at every re-root.  Default: room for 8 moves' worth of simulations at the
-    // typical fan-out (tafl: ~35 of at most 96), never more than the whole-game bound.  Exhaustion is reported
+    // game's typical fan-out (G::TYPC; brandubh ~35 of at most 96), never more than the whole-game bound.  Exhaustion is reported
     // (AZB_ERR_POOL_EXHAUSTED), never overrun.
     const long long whole_game = 1 + (long long)gd.max_turns * sims * gd.maxc;
     long long live = cfg->max_nodes_per_game;
     if (live <= 0) {
-        live = 1 + 8LL * sims * (gd.maxc < 40 ? gd.maxc : 40) + gd.maxc;
+        live = 1 + 8LL * sims * gd.typc + gd.maxc;
         if (live > whole_game) live = whole_game;
     }
     if (live < 2 + gd.maxc || 2 * live > 0x7fffffffLL) { delete e; return fail(AZB_ERR_BAD_CONFIG, "max_nodes_per_game %lld", live); }
@@ -224,12 +247,13 @@ extern "C" int azb_create(const azb_config *cfg, azb_engine **out)
     // +128 entries: the speculative sibling-block prefetch may read past a slot's last block
     A_(dev_alloc(e, &d.hot, N + 128, false)); A_(dev_alloc(e, &d.cold, N + 128, false));
     e->pool_bytes = e->device_bytes;
-    A_(dev_alloc(e, &d.head, B)); A_(dev_alloc(e, &d.leafinfo, B));
+    { unsigned char *hp = nullptr; A_(dev_alloc(e, &hp, (size_t)B * gd.head_bytes)); d.head = hp; }
+    A_(dev_alloc(e, &d.leafinfo, B));
     A_(dev_alloc(e, &d.path, (size_t)B * gd.maxd));
     if (cfg->rng_mode == AZB_RNG_MT19937) A_(dev_alloc(e, &d.mt, (size_t)B * 625));
     A_(dev_alloc(e, &d.ctr, B));
     d.hist_cap = gd.max_turns;
-    A_(dev_alloc(e, &d.hist_state, (size_t)B * d.hist_cap));
+    { unsigned char *hs = nullptr; A_(dev_alloc(e, &hs, (size_t)B * d.hist_cap * gd.state_bytes)); d.hist_state = hs; }
     A_(dev_alloc(e, &d.hist_pi, (size_t)B * d.hist_cap * gd.A));
     A_(dev_alloc(e, &d.hist_len, B)); A_(dev_alloc(e, &d.next_reset, B)); A_(dev_alloc(e, &d.noise_event, B));
     A_(dev_alloc(e, &d.last_action, B)); A_(dev_alloc(e, &d.fin_code, B));
@@ -564,13 +588,14 @@ extern "C" int azb_game_info(azb_engine *e, int32_t *last_action, int32_t *turns
     cudaStream_t s = (cudaStream_t)stream;
     const int B = e->d.B;
     if (last_action) CK(cudaMemcpyAsync(last_action, e->d.last_action, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, s));
-    std::vector<SlotHead> hd;
+    std::vector<unsigned char> hd;
+    const size_t hb = (size_t)e->gd.head_bytes;
     if (turns) {
-        hd.resize(B);
-        CK(cudaMemcpyAsync(hd.data(), e->d.head, sizeof(SlotHead) * (size_t)B, cudaMemcpyDeviceToHost, s));
+        hd.resize(hb * (size_t)B);
+        CK(cudaMemcpyAsync(hd.data(), e->d.head, hb * (size_t)B, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(s));
-    if (turns) for (int i = 0; i < B; i++) turns[i] = hd[i].st.turns;
+    if (turns) for (int i = 0; i < B; i++) turns[i] = head_view(e->gd, hd.data() + hb * (size_t)i).turns;
     return AZB_OK;
 }
 
@@ -592,8 +617,9 @@ extern "C" int azb_tree_dump(azb_engine *e, int32_t slot, double *rows, int64_t 
     if (slot < 0 || slot >= e->d.B) return fail(AZB_ERR_BAD_ARGUMENT, "slot %d", slot);
     cudaStream_t s = (cudaStream_t)stream;
     CK(cudaStreamSynchronize(s));
-    SlotHead hd;
-    CK(cudaMemcpy(&hd, e->d.head + slot, sizeof(SlotHead), cudaMemcpyDeviceToHost));
+    std::vector<unsigned char> hraw((size_t)e->gd.head_bytes);
+    CK(cudaMemcpy(hraw.data(), (const unsigned char *)e->d.head + (size_t)slot * e->gd.head_bytes, hraw.size(), cudaMemcpyDeviceToHost));
+    const HeadView hd = head_view(e->gd, hraw.data());
     const int used = hd.alloc, root = hd.root;      // entries [0, alloc) cover the live half (and, in the upper half, stale ones below it)
     const size_t nb = (size_t)slot * (size_t)e->d.npg;
     std::vector<NodeHot> hot(used); std::vector<NodeCold> cold(used);
@@ -601,7 +627,7 @@ extern "C" int azb_tree_dump(azb_engine *e, int32_t slot, double *rows, int64_t 
     CK(cudaMemcpy(cold.data(), e->d.cold + nb, sizeof(NodeCold) * used, cudaMemcpyDeviceToHost));
     // while a node is the root its live fields are in the slot header
     hot[root].n = hd.root_n; hot[root].child0 = hd.root_child0; cold[root].v = hd.root_v;
-    cold[root].meta = (cold[root].meta & 1023u) | (hd.root_meta & ~1023u);
+    cold[root].meta = (cold[root].meta & META_ACTION_MASK) | (hd.root_meta & ~META_ACTION_MASK);
     if (!hd.root_rec) {
         cold[root].meta = hd.root_meta; hot[root].q = 0.0f; hot[root].p = 0.0f;                       // fresh root: no pool record
     }
@@ -638,14 +664,16 @@ extern "C" int azb_stats_get(azb_engine *e, azb_stats *out, void *stream)
     CK(cudaMemcpyAsync(ss.data(), e->d.stats, sizeof(SlotStats) * (size_t)B, cudaMemcpyDeviceToHost, s));
     TRY(read_counters(e, &c, s));
     memset(out, 0, sizeof(*out));
-    std::vector<SlotHead> hd(B);
-    CK(cudaMemcpyAsync(hd.data(), e->d.head, sizeof(SlotHead) * (size_t)B, cudaMemcpyDeviceToHost, s));
+    const size_t hb = (size_t)e->gd.head_bytes;
+    std::vector<unsigned char> hraw(hb * (size_t)B);
+    CK(cudaMemcpyAsync(hraw.data(), e->d.head, hb * (size_t)B, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     for (int i = 0; i < B; i++) {
         out->sims += (int64_t)ss[i].sims; out->sum_depth += (int64_t)ss[i].sum_depth;
         out->sum_children += (int64_t)ss[i].sum_children; out->nodes_created += (int64_t)ss[i].nodes_created;
         out->terminal_leaves += (int64_t)ss[i].terminal_leaves; out->moves += (int64_t)ss[i].moves;
-        const int used = hd[i].alloc - (hd[i].root >= e->d.half ? e->d.half : 0);
+        const HeadView hv = head_view(e->gd, hraw.data() + hb * (size_t)i);
+        const int used = hv.alloc - (hv.root >= e->d.half ? e->d.half : 0);
         const int pk = ss[i].peak_nodes > used ? ss[i].peak_nodes : used;
         if (pk > out->peak_nodes) out->peak_nodes = pk;
     }

@@ -21,7 +21,7 @@
 
 namespace azb {
 
-constexpr int CTA_THREADS = 128;
+constexpr int CTA_THREADS = 128;       // default threads per CTA (G::CTA: games with large per-group scratch use fewer)
 constexpr unsigned FULL = 0xffffffffu;
 
 template <class G>
@@ -44,25 +44,39 @@ __device__ __forceinline__ unsigned group_ballot(bool p, int sub)
 template <int L, class T>
 __device__ __forceinline__ T group_bcast(T v, int src) { return __shfl_sync(FULL, v, src, L); }
 
-__device__ __forceinline__ SlotHead load_head(const SlotHead *p)
+template <class G> using HeadOf = SlotHeadT<typename G::State>;
+template <class G>
+__device__ __forceinline__ HeadOf<G> *head_at(const DevView &d, int g) { return reinterpret_cast<HeadOf<G> *>(d.head) + g; }
+template <class G>
+__device__ __forceinline__ typename G::State *hist_at(const DevView &d, size_t i) { return reinterpret_cast<typename G::State *>(d.hist_state) + i; }
+
+template <class H>
+__device__ __forceinline__ H load_head(const H *p)
 {
-    SlotHead h;
+    static_assert(sizeof(H) % 16 == 0, "slot header is copied in 16-byte pieces");
+    H h;
     const int4 *s = reinterpret_cast<const int4 *>(p);
     int4 *dst = reinterpret_cast<int4 *>(&h);
-    dst[0] = s[0]; dst[1] = s[1]; dst[2] = s[2]; dst[3] = s[3];
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(H) / 16); i++) dst[i] = s[i];
     return h;
 }
-__device__ __forceinline__ void store_head_tail(SlotHead *p, const SlotHead &h)
+// the 32 bytes of root fields behind the game state
+template <class H>
+__device__ __forceinline__ void store_head_tail(H *p, const H &h)
 {
+    constexpr int N = (int)(sizeof(H) / 16);
     int4 *dst = reinterpret_cast<int4 *>(p);
     const int4 *s = reinterpret_cast<const int4 *>(&h);
-    dst[2] = s[2]; dst[3] = s[3];
+    dst[N - 2] = s[N - 2]; dst[N - 1] = s[N - 1];
 }
-__device__ __forceinline__ void store_head(SlotHead *p, const SlotHead &h)
+template <class H>
+__device__ __forceinline__ void store_head(H *p, const H &h)
 {
     int4 *dst = reinterpret_cast<int4 *>(p);
     const int4 *s = reinterpret_cast<const int4 *>(&h);
-    dst[0] = s[0]; dst[1] = s[1]; dst[2] = s[2]; dst[3] = s[3];
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(H) / 16); i++) dst[i] = s[i];
 }
 __device__ __forceinline__ NodeHot load_hot(const NodeHot *p)
 {
@@ -139,6 +153,25 @@ __device__ __forceinline__ float np_sum_588_warp(const float *a, int lane)
     return __shfl_sync(FULL, f_add(t0, t1), 0);
 }
 
+// n = 2420 (hnefatafl): the recursion is a perfect binary tree of depth 5 whose 32 leaves have 72, 80 or 84 elements
+// (azb_hnefatafl.cuh np2420_leaf): lane b sums leaf b with the leaf loop, the tree is five xor-shuffle steps
+// (level 0 joins neighbouring leaves first; a + b is commutative, only the tree shape matters).
+__device__ __forceinline__ float np_sum_2420_warp(const float *a, int lane)
+{
+    int off = 0, n = 2420;
+#pragma unroll
+    for (int level = 4; level >= 0; level--) {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        if ((lane >> level) & 1) { off += n2; n -= n2; }
+        else n = n2;
+    }
+    float r = np_leaf_sum(a + off, n);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) r = f_add(r, __shfl_xor_sync(FULL, r, o));
+    return r;
+}
+
 template <class G>
 __device__ __forceinline__ float np_sum_group(const float *vec, int lane)
 {
@@ -148,6 +181,8 @@ __device__ __forceinline__ float np_sum_group(const float *vec, int lane)
         r = np_leaf_sum(vec, G::A);          // every lane, broadcast reads
     } else if (G::A == 588 && G::LANES == 32) {
         r = np_sum_588_warp(vec, lane);
+    } else if (G::A == 2420 && G::LANES == 32) {
+        r = np_sum_2420_warp(vec, lane);
     } else {
         r = 0.0f;
         if (lane == 0) r = np_sum_serial(vec, G::A);
@@ -312,10 +347,10 @@ __device__ __forceinline__ void select_game(const DevView &d, int g, bool active
     constexpr bool SPEC = (G::MAXC <= L);       // small fan-out: prefetch the next sibling block speculatively
     const size_t nb = (size_t)g * (size_t)d.npg;
     const bool in_range = active;               // out-of-range groups alias slot `first`: they must not write
-    SlotHead H = load_head(d.head + g);
+    HeadOf<G> H = load_head(head_at<G>(d, g));
     if (H.st.flags & (GF_FINISHED | GF_DEAD)) active = false;
     if (d.arena && ((g ^ H.st.turns) & 1)) active = false;      // arena: only the tree of the player to move searches
-    GState st = H.st;
+    typename G::State st = H.st;
     int *path = d.path + (size_t)g * G::MAXD;
     int cur = H.root, cn = H.root_n, cch = H.root_child0;
     float cv = H.root_v;
@@ -450,7 +485,7 @@ __device__ __forceinline__ void select_game(const DevView &d, int g, bool active
         li.leaf = active ? cur : -1; li.depth = depth; li.child0 = cch; li.meta = cmeta;
         *reinterpret_cast<int4 *>(d.leafinfo + g) = *reinterpret_cast<const int4 *>(&li);
         if (active) {
-            if (head_dirty) store_head_tail(d.head + g, H);
+            if (head_dirty) store_head_tail(head_at<G>(d, g), H);
             uint4 *sp = reinterpret_cast<uint4 *>(d.stats + g);
             uint4 s = *sp;
             s.x += (unsigned)depth; s.y += (unsigned)sumc; s.z += (unsigned)nodes_new; s.w += (meta_e(cmeta) != 0) ? 1u : 0u;
@@ -516,7 +551,7 @@ __device__ __forceinline__ void expand_backup_game(const DevView &d, int g, bool
     constexpr int IT = (G::MAXC + L - 1) / L;
     const size_t nb = (size_t)g * (size_t)d.npg;
     const int4 li4 = *reinterpret_cast<const int4 *>(d.leafinfo + g);
-    const int4 hr = reinterpret_cast<const int4 *>(d.head + g)[2];       // root, root_n, root_v, root_child0
+    const int4 hr = reinterpret_cast<const int4 *>(head_at<G>(d, g))[sizeof(typename G::State) / 16];   // root, root_n, root_v, root_child0
     const int leaf = li4.x, depth = li4.y, base = li4.z;
     const uint32_t lmeta = (uint32_t)li4.w;
     const bool on = active && leaf >= 0;
@@ -647,7 +682,7 @@ __device__ __forceinline__ void expand_backup_game(const DevView &d, int g, bool
             *reinterpret_cast<int2 *>(hp) = make_int2(nn + 1, __float_as_int(qn));
         }
         if (lane == 0) {
-            d.head[g].root_n = hr.y + 1;
+            head_at<G>(d, g)->root_n = hr.y + 1;
             reinterpret_cast<unsigned *>(d.stats + g)[4] += 1u;     // sims
         }
     }
@@ -674,7 +709,8 @@ __device__ __forceinline__ void probs_group(const DevView &d, const float *count
     __syncwarp();
 }
 
-__device__ __forceinline__ void tree_reset(SlotHead &H)
+template <class H_>
+__device__ __forceinline__ void tree_reset(H_ &H)
 {
     H.root = 0; H.root_n = 0; H.root_v = 0.0f; H.root_child0 = -1;
     H.root_meta = meta_pack(META_ACTION_NONE, 0u, 0u, 0u);
@@ -693,7 +729,7 @@ __device__ __forceinline__ void tree_reset(SlotHead &H)
 // H.root_child0 / H.alloc are updated on every lane of the group.
 // ------------------------------------------------------------------------------
 template <class G>
-__device__ __forceinline__ int compact_subtree(const DevView &d, size_t nb, SlotHead &H, bool on, int lane)
+__device__ __forceinline__ int compact_subtree(const DevView &d, size_t nb, HeadOf<G> &H, bool on, int lane)
 {
     constexpr int L = G::LANES;
     const int dst = H.root >= d.half ? 0 : d.half;          // the half the tree moves to
@@ -771,9 +807,9 @@ __device__ __forceinline__ int play_move_game(const DevView &d, int g, bool acti
     constexpr int L = G::LANES;
     constexpr int IT = (G::MAXC + L - 1) / L;
     const size_t nb = (size_t)g * (size_t)d.npg;
-    SlotHead H = load_head(d.head + g);
+    HeadOf<G> H = load_head(head_at<G>(d, g));
     bool on = active && !(H.st.flags & (GF_FINISHED | GF_DEAD));
-    GState st = H.st;
+    typename G::State st = H.st;
     const int C = on ? meta_nc(H.root_meta) : 0;
     const size_t cb = nb + (size_t)(H.root_child0 < 0 ? 0 : H.root_child0);
     // MCTS.counts
@@ -843,7 +879,7 @@ __device__ __forceinline__ int play_move_game(const DevView &d, int g, bool acti
             if (hl < d.hist_cap) {
                 float *hp = d.hist_pi + ((size_t)g * d.hist_cap + hl) * G::A;
                 for (int a = lane; a < G::A; a += L) hp[a] = sm.vec2[a];
-                if (lane == 0) { d.hist_state[(size_t)g * d.hist_cap + hl] = st; d.hist_len[g] = hl + 1; }
+                if (lane == 0) { *hist_at<G>(d, (size_t)g * d.hist_cap + hl) = st; d.hist_len[g] = hl + 1; }
             } else if (lane == 0) atomicOr(d.err, ERRB_SAMPLES);
         }
     }
@@ -857,7 +893,7 @@ __device__ __forceinline__ int play_move_game(const DevView &d, int g, bool acti
     if (on && found < 0) {
         if (lane == 0) atomicOr(d.err, ERRB_ACTION);
         H.st.flags |= GF_DEAD;
-        if (lane == 0) store_head(d.head + g, H);
+        if (lane == 0) store_head(head_at<G>(d, g), H);
         on = false;
     }
     bool compact = false;
@@ -898,7 +934,7 @@ __device__ __forceinline__ int play_move_game(const DevView &d, int g, bool acti
         H.root_meta = group_bcast<L>(H.root_meta, 0);
         compact_subtree<G>(d, nb, H, compact, lane);
     }
-    if (on && lane == 0) store_head(d.head + g, H);
+    if (on && lane == 0) store_head(head_at<G>(d, g), H);
     __syncwarp();
     return on ? action : G::A;
 }
@@ -921,9 +957,9 @@ __device__ __forceinline__ bool group_setup(int first, int count, int &g, bool &
 }
 
 template <class G>
-__global__ void __launch_bounds__(CTA_THREADS) k_select(DevView d, int first, int count)
+__global__ void __launch_bounds__(G::CTA) k_select(DevView d, int first, int count)
 {
-    __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
+    __shared__ GroupSmem<G> sm[G::CTA / G::LANES];
     int g, lane, sub, gi; bool active;
     if (blockIdx.x == 0 && threadIdx.x == 0) { d.nn_count[2 * (d.nn_par ^ 1)] = 0; d.nn_count[2 * (d.nn_par ^ 1) + 1] = 0; }   // consumed
     if (!group_setup<G>(first, count, g, active, lane, sub, gi)) return;
@@ -931,9 +967,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_select(DevView d, int first, in
 }
 
 template <class G>
-__global__ void __launch_bounds__(CTA_THREADS) k_expand_backup(DevView d, int first, int count, const float *policy, const float *value)
+__global__ void __launch_bounds__(G::CTA) k_expand_backup(DevView d, int first, int count, const float *policy, const float *value)
 {
-    __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
+    __shared__ GroupSmem<G> sm[G::CTA / G::LANES];
     int g, lane, sub, gi; bool active;
     if (!group_setup<G>(first, count, g, active, lane, sub, gi)) return;
     if (G::A > G::LANES) { for (int a = lane; a < G::A; a += G::LANES) sm[gi].vec[a] = 0.0f; __syncwarp(); }
@@ -943,9 +979,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_expand_backup(DevView d, int fi
 // processBatch of simulation s fused with generateBatch of simulation s+1 for the same slots: one launch instead of
 // two between two network evaluations, and the slot's header / leaf record stay in cache
 template <class G>
-__global__ void __launch_bounds__(CTA_THREADS) k_expand_select(DevView d, int first, int count, const float *policy, const float *value)
+__global__ void __launch_bounds__(G::CTA) k_expand_select(DevView d, int first, int count, const float *policy, const float *value)
 {
-    __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
+    __shared__ GroupSmem<G> sm[G::CTA / G::LANES];
     int g, lane, sub, gi; bool active;
     if (blockIdx.x == 0 && threadIdx.x == 0) { d.nn_count[2 * (d.nn_par ^ 1)] = 0; d.nn_count[2 * (d.nn_par ^ 1) + 1] = 0; }   // consumed
     if (!group_setup<G>(first, count, g, active, lane, sub, gi)) return;
@@ -957,9 +993,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_expand_select(DevView d, int fi
 
 // `sims` simulations per game with constant NN outputs, no NN round trip
 template <class G>
-__global__ void __launch_bounds__(CTA_THREADS) k_warmup_sims(DevView d, int sims)
+__global__ void __launch_bounds__(G::CTA) k_warmup_sims(DevView d, int sims)
 {
-    __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
+    __shared__ GroupSmem<G> sm[G::CTA / G::LANES];
     int g, lane, sub, gi; bool active;
     if (!group_setup<G>(0, d.B, g, active, lane, sub, gi)) return;
     if (G::A > G::LANES) { for (int a = lane; a < G::A; a += G::LANES) sm[gi].vec[a] = 0.0f; __syncwarp(); }
@@ -970,9 +1006,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_warmup_sims(DevView d, int sims
 }
 
 template <class G>
-__global__ void __launch_bounds__(CTA_THREADS) k_play_moves(DevView d, int fast)
+__global__ void __launch_bounds__(G::CTA) k_play_moves(DevView d, int fast)
 {
-    __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
+    __shared__ GroupSmem<G> sm[G::CTA / G::LANES];
     int g, lane, sub, gi; bool active;
     if (!group_setup<G>(0, d.B, g, active, lane, sub, gi)) return;
     play_move_game<G>(d, g, active, fast, lane, sub, sm[gi]);
@@ -982,12 +1018,12 @@ __global__ void __launch_bounds__(CTA_THREADS) k_play_moves(DevView d, int fast)
 // ([mcts.update_root(game, action) for mcts in self.mcts[i]], SelfPlayAgent.pyx:167-168 -- the searching tree's
 // update never draws, so the order of the two updates does not matter for the game's RNG stream).
 template <class G>
-__global__ void __launch_bounds__(CTA_THREADS) k_play_moves_arena(DevView d)
+__global__ void __launch_bounds__(G::CTA) k_play_moves_arena(DevView d)
 {
-    __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
+    __shared__ GroupSmem<G> sm[G::CTA / G::LANES];
     int g, lane, sub, gi; bool active;
     if (!group_setup<G>(0, d.B / 2, g, active, lane, sub, gi)) return;
-    const int mover = d.head[2 * g].st.turns & 1;
+    const int mover = head_at<G>(d, 2 * g)->st.turns & 1;
     const int action = play_move_game<G>(d, 2 * g + mover, active, 1, lane, sub, sm[gi]);
     play_move_game<G>(d, 2 * g + (mover ^ 1), active && action < G::A, 1, lane, sub, sm[gi], action < G::A ? action : 0);
 }
@@ -1012,7 +1048,7 @@ __global__ void __launch_bounds__(1024) k_finalize(DevView d)
     for (int g0 = 0; g0 < d.B; g0 += 1024) {
         const int g = g0 + tid;
         int flags = 0, turns = 0;
-        if (g < d.B) { flags = d.head[g].st.flags; turns = d.head[g].st.turns; }
+        if (g < d.B) { flags = head_at<G>(d, g)->st.flags; turns = head_at<G>(d, g)->st.turns; }
         const int fin = ((flags & GF_FINISHED) && !(d.arena && (g & 1))) ? 1 : 0;     // arena: a game is two slots
         s_scan[tid] = fin;
         __syncthreads();
@@ -1076,17 +1112,17 @@ __global__ void __launch_bounds__(1024) k_finalize(DevView d)
 
 // Sample emission with symmetries and game/tree restart for the finished games.
 template <class G>
-__global__ void __launch_bounds__(CTA_THREADS) k_emit(DevView d)
+__global__ void __launch_bounds__(G::CTA) k_emit(DevView d)
 {
     constexpr int L = G::LANES;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int g = tid / L, lane = threadIdx.x % L;
     if (g >= d.B) return;
-    SlotHead H = load_head(d.head + g);
+    HeadOf<G> H = load_head(head_at<G>(d, g));
     if (!(H.st.flags & GF_FINISHED)) return;
     const long long off = d.emit_off[g];
     if (off == -1) {                    // beyond the quota: the game stays finished
-        if (lane == 0) { H.st.flags = (H.st.flags & ~GF_FINISHED) | GF_DEAD; store_head(d.head + g, H); }
+        if (lane == 0) { H.st.flags = (H.st.flags & ~GF_FINISHED) | GF_DEAD; store_head(head_at<G>(d, g), H); }
         return;
     }
     const int code = d.fin_code[g];
@@ -1094,11 +1130,11 @@ __global__ void __launch_bounds__(CTA_THREADS) k_emit(DevView d)
     const int per = d.symmetric ? G::NSYM : 1;
     if (off >= 0) {
         for (int h = 0; h < hl; h++) {
-            const GState hs = d.hist_state[(size_t)g * d.hist_cap + h];
+            const typename G::State hs = *hist_at<G>(d, (size_t)g * d.hist_cap + h);
             const float *hp = d.hist_pi + ((size_t)g * d.hist_cap + h) * G::A;
             for (int k = 0; k < per; k++) {
                 const long long si = off + (long long)h * per + k;
-                const GState ss = d.symmetric ? G::symmetry(hs, k) : hs;
+                const typename G::State ss = d.symmetric ? G::symmetry(hs, k) : hs;
                 G::write_obs(ss, d.s_obs + (size_t)si * G::OBS, lane);
                 float *pp = d.s_pi + (size_t)si * G::A;
                 for (int a = lane; a < G::A; a += L) pp[d.symmetric ? G::sym_action(k, a) : a] = hp[a];
@@ -1117,7 +1153,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_emit(DevView d)
         if (used > *pk) *pk = used;
         G::init(H.st);
         tree_reset(H);
-        store_head(d.head + g, H);
+        store_head(head_at<G>(d, g), H);
         d.hist_len[g] = 0;
         d.fin_code[g] = 0;
     }
@@ -1130,7 +1166,7 @@ __global__ void k_root_counts(DevView d, int *out)
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= d.B) return;
     const size_t nb = (size_t)g * (size_t)d.npg;
-    const SlotHead H = load_head(d.head + g);
+    const HeadOf<G> H = load_head(head_at<G>(d, g));
     const int C = meta_nc(H.root_meta);
     const size_t cb = nb + (size_t)(H.root_child0 < 0 ? 0 : H.root_child0);
     for (int a = 0; a < G::A; a++) out[(size_t)g * G::A + a] = 0;
@@ -1142,10 +1178,10 @@ template <class G>
 __global__ void k_set_state(DevView d, int g, const signed char *cells, int turns)
 {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    SlotHead H = load_head(d.head + g);
+    HeadOf<G> H = load_head(head_at<G>(d, g));
     G::from_cells(H.st, cells, turns);
     tree_reset(H);
-    store_head(d.head + g, H);
+    store_head(head_at<G>(d, g), H);
     LeafInfo li; li.leaf = -1; li.depth = 0; li.child0 = -1; li.meta = 0u;
     d.leafinfo[g] = li;
     d.hist_len[g] = 0; d.next_reset[g] = 0; d.noise_event[g] = 0; d.last_action[g] = -1; d.fin_code[g] = 0; d.emit_off[g] = -1;
@@ -1155,9 +1191,9 @@ __global__ void k_set_state(DevView d, int g, const signed char *cells, int turn
 // move decided by the caller; an unexpanded root draws the shuffle of its children first.  No terminal handling:
 // a finished game just stops being searched until the slot is set to a new position.
 template <class G>
-__global__ void __launch_bounds__(CTA_THREADS) k_force_move(DevView d, int g0, int action)
+__global__ void __launch_bounds__(G::CTA) k_force_move(DevView d, int g0, int action)
 {
-    __shared__ GroupSmem<G> sm[CTA_THREADS / G::LANES];
+    __shared__ GroupSmem<G> sm[G::CTA / G::LANES];
     int g, lane, sub, gi; bool active;
     if (!group_setup<G>(g0, 1, g, active, lane, sub, gi)) return;
     play_move_game<G>(d, g, active, 1, lane, sub, sm[gi], action);
@@ -1169,7 +1205,7 @@ __global__ void k_arena_players(DevView d, int *out)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= d.B) return;
-    const GState st = d.head[g].st;
+    const typename G::State st = head_at<G>(d, g)->st;
     const bool live = !(st.flags & (GF_FINISHED | GF_DEAD));
     out[g] = (live && !((g ^ st.turns) & 1)) ? (g & 1) : -1;
 }
@@ -1179,7 +1215,7 @@ __global__ void k_boards(DevView d, int8_t *out)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= d.B) return;
-    const GState st = d.head[g].st;
+    const typename G::State st = head_at<G>(d, g)->st;
     for (int i = 0; i < G::CELLS; i++) out[(size_t)g * G::CELLS + i] = (int8_t)G::cell_code(st, i);
 }
 
@@ -1188,11 +1224,11 @@ __global__ void k_init_slots(DevView d, const uint32_t *mt_seeds)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= d.B) return;
-    SlotHead H;
+    HeadOf<G> H;
     G::init(H.st);
     tree_reset(H);
     H.root_rec = H.pad1 = 0;
-    store_head(d.head + g, H);
+    store_head(head_at<G>(d, g), H);
     LeafInfo li; li.leaf = -1; li.depth = 0; li.child0 = -1; li.meta = 0u;
     d.leafinfo[g] = li;
     d.hist_len[g] = 0; d.next_reset[g] = 0; d.noise_event[g] = 0; d.last_action[g] = -1;

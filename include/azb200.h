@@ -44,7 +44,7 @@ typedef enum azb_status {
     AZB_ERR_NOISE_UNDERRUN = -8   /* fed root-noise table exhausted                       */
 } azb_status;
 
-enum { AZB_GAME_CONNECT4 = 0, AZB_GAME_BRANDUBH = 1 };
+enum { AZB_GAME_CONNECT4 = 0, AZB_GAME_BRANDUBH = 1, AZB_GAME_HNEFATAFL = 2 /* 11x11, alphazero/envs/hnefatafl/fastafl.pyx */ };
 /* AZB_RNG_MT19937: per-slot numpy-legacy MT19937 streams with numpy's shuffle /
  * choice consumption -> bit-equal to an unmodified reference agent seeded with
  * np.random.seed(mt_seeds[i]).  AZB_RNG_PHILOX: counter-based Philox4x32-10

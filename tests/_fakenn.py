@@ -17,9 +17,12 @@ class FakeNN:
         h = np.tanh(np.stack([r @ self.w1 for r in x]))      # row-wise: independent of batch size
         lp = np.stack([r @ self.wp for r in h])
         lv = np.stack([r @ self.wv for r in h])
-        p = np.exp(lp - lp.max(1, keepdims=True)); p /= p.sum(1, keepdims=True)
-        v = np.exp(lv - lv.max(1, keepdims=True)); v /= v.sum(1, keepdims=True)
-        return p.astype(np.float32), v.astype(np.float32)
+        # importing the compiled reference switches NumPy to np.seterr(all='raise') (MCTS.pyx:23); a probability that is
+        # subnormal or zero in float32 is a perfectly good network answer
+        with np.errstate(under="ignore"):
+            p = np.exp(lp - lp.max(1, keepdims=True)); p /= p.sum(1, keepdims=True)
+            v = np.exp(lv - lv.max(1, keepdims=True)); v /= v.sum(1, keepdims=True)
+            return p.astype(np.float32), v.astype(np.float32)
 
 
 def warmup_outputs(batch, action_size):

@@ -11,13 +11,13 @@ from _lockstep import run_trace
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GAME_IDS = {"connect4": _orc.GAME_CONNECT4, "brandubh": _orc.GAME_BRANDUBH, "hnefatafl": _orc.GAME_HNEFATAFL}
 DIMS = {"connect4": (4 * 6 * 7, 7, 42), "brandubh": (5 * 7 * 7, 588, None), "hnefatafl": (5 * 11 * 11, 2420, None)}
-ENGINE_GAMES = ("connect4", "brandubh")      # what libazb200.so serves; hnefatafl fixtures wait for the engine
+ENGINE_GAMES = ("connect4", "brandubh", "hnefatafl")      # what libazb200.so serves
 
 
 def cases(arena=False, engine=False):
     names = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and (f[:-4].endswith("_arena") == arena))
     if engine:
-        names = [n for n in names if not n.startswith("hnefatafl")]
+        names = [n for n in names if any(n.startswith(g if g != "brandubh" else "tafl") or n.startswith(g[:2]) for g in ENGINE_GAMES)]
     return names
 
 

@@ -43,7 +43,7 @@ def _args(coach_mod, tmp, **over):
     return base
 
 
-@pytest.mark.parametrize("game", ["connect4", "brandubh"])
+@pytest.mark.parametrize("game", ["connect4", "brandubh", "hnefatafl"])
 def test_real_coach_learns_with_the_engine_as_its_self_play_phase(game, tmp_path, monkeypatch):
     coach_mod = _ref()
     from alphazero.NNetWrapper import NNetWrapper
@@ -52,11 +52,20 @@ def test_real_coach_learns_with_the_engine_as_its_self_play_phase(game, tmp_path
     if game == "connect4":
         from alphazero.envs.connect4.connect4 import Game
         obs, A = (4, 6, 7), 7
-    else:
+    elif game == "brandubh":
         from alphazero.envs.brandubh.fastafl import Game
         Game = game_with_defaults(Game)             # the plugin lacks GameState's max_turns / has_draw (Coach.py:161)
         obs, A = (5, 7, 7), 588
+    else:
+        from alphazero.envs.hnefatafl.fastafl import Game
+        Game = game_with_defaults(Game)
+        obs, A = (5, 11, 11), 2420
     args = _args(coach_mod, tmp_path)
+    games = 128
+    if game == "hnefatafl":      # 11x11 games last hundreds of plies and an example is 12 KB: a small iteration, no symmetries
+        games = 12
+        args.update(workers=1, process_batch_size=12, gamesPerIteration=12, symmetricSamples=False, numMCTSSims=8, numFastSims=3,
+                    arenaCompare=2, arena_batch_size=1)
 
     class C(GpuSelfPlayMixin, coach_mod.Coach):
         pass
@@ -75,7 +84,7 @@ def test_real_coach_learns_with_the_engine_as_its_self_play_phase(game, tmp_path
     c.learn()                                        # the reference's loop, unmodified
 
     assert [s[:2] for s in seen] == [(1, True), (2, False)]        # warm-up iteration, then the network in the loop
-    assert all(s[2] == 128 and s[3] > 128 * 5 and s[4] is ExampleQueue for s in seen)
+    assert all(s[2] == games and s[3] > games * 5 and s[4] is ExampleQueue for s in seen)
     assert c.self_play_iter >= 1 and c.model_iter == 3
     for it in (1, 2):
         base = os.path.join(args.data, "dropin", f"iteration-{it:04d}")

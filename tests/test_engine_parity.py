@@ -159,7 +159,7 @@ def test_brandubh_root_noise_deep_search():
 
 
 @pytest.mark.parametrize("game,rng,p2i,reset", [("connect4", "mt19937", [0, 1], None), ("connect4", "philox", [1, 0], 5),
-                                                ("brandubh", "philox", [0, 1], None)])
+                                                ("brandubh", "philox", [0, 1], None), ("hnefatafl", "mt19937", [1, 0], None)])
 def test_arena_mode_equals_oracle(game, rng, p2i, reset):
     """SelfPlayAgent(_is_arena=True) on the engine (azb_config.arena): visit counts of the searching tree, sampled
     actions, leaf observations, results and the quota, bit-equal to the oracle's arena mode (itself pinned against the
@@ -168,11 +168,12 @@ def test_arena_mode_equals_oracle(game, rng, p2i, reset):
     from _fakenn import ArenaNN
     c4 = game == "connect4"
     B, sims, quota = (6, 9, 14) if c4 else (3, 6, 1 << 40)
-    obs_n, A = (4 * 6 * 7, 7) if c4 else (5 * 7 * 7, 588)
+    obs_n, A = (4 * 6 * 7, 7) if c4 else (5 * 11 * 11, 2420) if game == "hnefatafl" else (5 * 7 * 7, 588)
+    gid = {"connect4": _orc.GAME_CONNECT4, "brandubh": _orc.GAME_BRANDUBH, "hnefatafl": _orc.GAME_HNEFATAFL}[game]
     seeds = list(range(31, 31 + B))
     nets = [FakeNN(obs_n, A, seed=70, sharp=3.0 if c4 else 1.0), FakeNN(obs_n, A, seed=71, sharp=3.0 if c4 else 1.0)]
     kw = dict(mt_seeds=seeds) if rng == "mt19937" else dict(seed=9)
-    orc = _orc.OracleAgent(_orc.GAME_CONNECT4 if c4 else _orc.GAME_BRANDUBH, B, arena=True, arena_temp=0.25,
+    orc = _orc.OracleAgent(gid, B, arena=True, arena_temp=0.25,
                            rng_mode=_orc.RNG_MT19937 if rng == "mt19937" else _orc.RNG_PHILOX, player_to_index=p2i,
                            mcts_reset_threshold=reset or 0, games_per_iteration=quota, **kw)
     eng = ArenaEngineAgent(game, B, rng=rng, arena_temp=0.25, player_to_index=p2i, mcts_reset_threshold=reset,
@@ -235,3 +236,53 @@ def test_select_lists_the_leaves_that_need_the_network():
     st = e.stats()
     assert total_listed == (st["sims"] - before["sims"]) - (st["terminal_leaves"] - before["terminal_leaves"])
     assert st["terminal_leaves"] > 0
+
+
+# ---- hnefatafl 11x11: 128-bit bitboards, 2420 actions ----------------------------------------------------
+def _hnef_pair(B, rng, noise=None, arena=False, **kw):
+    from _engine_agent import ArenaEngineAgent, EngineAgent
+    okw = {k: v for k, v in kw.items() if k not in ("max_sims_per_move", "max_nodes_per_game")}
+    mk = ArenaEngineAgent if arena else EngineAgent
+    if rng == "mt19937":
+        seeds = list(range(300, 300 + B))
+        orc = _orc.OracleAgent(_orc.GAME_HNEFATAFL, B, rng_mode=_orc.RNG_MT19937, mt_seeds=seeds, arena=arena, **okw)
+        eng = mk("hnefatafl", B, rng="mt19937", mt_seeds=seeds, **kw)
+    else:
+        orc = _orc.OracleAgent(_orc.GAME_HNEFATAFL, B, rng_mode=_orc.RNG_PHILOX, seed=11, game_id_base=5, arena=arena, **okw)
+        eng = mk("hnefatafl", B, rng="philox", seed=11, game_id_base=5, **kw)
+    if noise is not None:
+        orc.set_root_noise(noise)
+        eng.set_root_noise(noise)
+    return orc, eng
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rng", ["mt19937", "philox"])
+@pytest.mark.parametrize("mode", ["warmup", "nn"])
+def test_hnefatafl_selfplay_bit_exact(rng, mode):
+    """Engine == oracle (pinned to the compiled reference's hnefatafl env, tests/test_hnefatafl_rules.py): visit counts,
+    actions, turns, leaf observations, the 8-fold symmetric samples with the 2420-entry permutation, results,
+    statistics and boards -- games end (king's-side wins) inside the run."""
+    B, rounds, sims = 4, 90, 12
+    nn = FakeNN(5 * 11 * 11, 2420, seed=31, sharp=1.0) if mode == "nn" else None
+    orc, eng = _hnef_pair(B, rng, temps=TAFL_TEMPS, add_root_temp=True, max_sims_per_move=sims)
+    to = run_trace(orc, nn, rounds, sims, keep_obs=True)
+    te = run_trace(eng, nn, rounds, sims, keep_obs=True)
+    assert_traces_equal(to, te, f"hnefatafl {rng}/{mode}")
+    assert_queues_equal(orc, eng, f"hnefatafl {rng}/{mode}")
+    so, se = orc.stats(), eng.stats()
+    for k in ("sims", "sum_depth", "sum_children", "nodes_created", "terminal_leaves", "games_played",
+              "results", "samples", "moves"):
+        assert so[k] == se[k], (k, so[k], se[k])
+    assert np.array_equal(orc.boards(), eng.boards())
+
+
+@pytest.mark.gpu
+def test_hnefatafl_root_noise_deep_search():
+    B, rounds, sims = 2, 6, 120
+    noise = np.random.RandomState(9).dirichlet([10.83 / 116] * 256, size=(B, 4)).astype(np.float32)
+    nn = FakeNN(5 * 11 * 11, 2420, seed=32, sharp=2.0)
+    orc, eng = _hnef_pair(B, "mt19937", noise=noise, temps=TAFL_TEMPS, add_root_temp=True, add_root_noise=True,
+                          max_sims_per_move=sims)
+    assert_traces_equal(run_trace(orc, nn, rounds, sims), run_trace(eng, nn, rounds, sims), "hnefatafl noise")
+    assert np.array_equal(orc.boards(), eng.boards())
