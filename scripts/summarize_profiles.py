@@ -5,7 +5,13 @@ import collections, csv, json, os, subprocess, sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "gpurun_out", "final"); OUT = os.path.join(ROOT, "profiles")
-KEYS = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread', 'gpu__time_duration.sum',
+KEYS = ['lts__t_sectors_srcunit_tex_op_read.sum', 'lts__t_sectors_srcunit_tex_op_write.sum', 'lts__t_sectors_srcunit_tex_lookup_hit.sum',
+        'lts__t_sectors_srcunit_tex_lookup_miss.sum', 'lts__t_sectors_op_read.sum', 'lts__t_sectors_op_write.sum', 'lts__t_bytes.sum',
+        'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum',
+        'l1tex__data_pipe_tc_wavefronts_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum', 'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_tensor.sum',
+        'Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread', 'gpu__time_duration.sum',
         'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
         'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
@@ -16,7 +22,7 @@ def to_bytes(v, unit):
     m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     return float(v.replace(",", "")) * m.get(unit, 1)
 traffic = {}
-for k in ("select", "expand", "expand_select", "resnet", "warmup"):
+for k in ("select", "expand", "expand_select", "resnet", "warmup", "trunk", "head", "play"):
     rep = os.path.join(SRC, f"prof_{k}.ncu-rep")
     if not os.path.exists(rep): continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
