@@ -352,6 +352,9 @@ __device__ __forceinline__ void select_game(const DevView &d, int g, bool active
     if (d.arena && ((g ^ H.st.turns) & 1)) active = false;      // arena: only the tree of the player to move searches
     typename G::State st = H.st;
     int *path = d.path + (size_t)g * G::MAXD;
+    // this game's statistics row is updated at the very end: fetch it now, under the descent
+    uint4 stat_row = make_uint4(0u, 0u, 0u, 0u);
+    if (lane == 0 && in_range) stat_row = *reinterpret_cast<const uint4 *>(d.stats + g);
     int cur = H.root, cn = H.root_n, cch = H.root_child0;
     float cv = H.root_v;
     uint32_t cmeta = H.root_meta;
@@ -471,13 +474,24 @@ __device__ __forceinline__ void select_game(const DevView &d, int g, bool active
     }
     if (WRITE_OBS) {
         if (active) G::write_obs(st, d.obs + (size_t)g * G::OBS, lane);
-        // the leaves the network has to evaluate: a terminal leaf's value is its win state (MCTS.pyx:234-235)
-        if (active && in_range && lane == 0 && meta_e(cmeta) == 0) {
-            // arena: one list per model (the model of env player p is p ^ arena_swap), each at most B / 2 long
-            const int m = d.arena ? ((g & 1) ^ d.arena_swap) : 0;
-            const unsigned cap = d.arena ? (unsigned)(d.B / 2) : (unsigned)d.B;
-            const unsigned idx = (unsigned)atomicAdd(d.nn_count + 2 * d.nn_par + m, 1);
-            if (idx < cap) d.nn_rows[(size_t)m * cap + idx] = g;
+        // the leaves the network has to evaluate: a terminal leaf's value is its win state (MCTS.pyx:234-235).  One
+        // atomic per warp and model, not per game: 8192 adds to one counter were a quarter of this kernel's stall samples
+        // arena: one list per model (the model of env player p is p ^ arena_swap), each at most B / 2 long
+        const bool want = active && in_range && lane == 0 && meta_e(cmeta) == 0;
+        const int m = d.arena ? ((g & 1) ^ d.arena_swap) : 0;
+        const unsigned cap = d.arena ? (unsigned)(d.B / 2) : (unsigned)d.B;
+        const unsigned wl = threadIdx.x & 31u;
+        for (int mm = 0; mm < (d.arena ? 2 : 1); mm++) {
+            const unsigned bal = __ballot_sync(FULL, want && m == mm);
+            if (bal == 0u) continue;
+            const unsigned leader = (unsigned)__ffs((int)bal) - 1u;
+            unsigned base = 0u;
+            if (wl == leader) base = (unsigned)atomicAdd(d.nn_count + 2 * d.nn_par + mm, (int)__popc(bal));
+            base = __shfl_sync(FULL, base, (int)leader);
+            if (want && m == mm) {
+                const unsigned idx = base + (unsigned)__popc(bal & ((1u << wl) - 1u));
+                if (idx < cap) d.nn_rows[(size_t)mm * cap + idx] = g;
+            }
         }
     }
     if (lane == 0 && in_range) {
@@ -486,10 +500,9 @@ __device__ __forceinline__ void select_game(const DevView &d, int g, bool active
         *reinterpret_cast<int4 *>(d.leafinfo + g) = *reinterpret_cast<const int4 *>(&li);
         if (active) {
             if (head_dirty) store_head_tail(head_at<G>(d, g), H);
-            uint4 *sp = reinterpret_cast<uint4 *>(d.stats + g);
-            uint4 s = *sp;
+            uint4 s = stat_row;
             s.x += (unsigned)depth; s.y += (unsigned)sumc; s.z += (unsigned)nodes_new; s.w += (meta_e(cmeta) != 0) ? 1u : 0u;
-            *sp = s;
+            *reinterpret_cast<uint4 *>(d.stats + g) = s;
         }
     }
     __syncwarp();

@@ -554,11 +554,15 @@ def main():
     if roof is not None and os.path.exists(traffic_file):
         try:
             roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
-            roof["traffic_note"] = ("ncu dram read+write per launch (profiles/select_traffic.json). `achieved` counts only the PUCT scan "
-                                    "(16 B header + 12 B per scanned child, SURVEY 8d); the same launch also expands the leaf (24 B per "
-                                    "new child record), writes the leaf observation (obs floats x 4 B per game), the path and the slot "
-                                    "header: whole-simulation algorithmic traffic is ~1.5 KB per Connect4 simulation = ~12 MB per launch "
-                                    "of 8192 games, so the measured traffic is not re-reads of the scan")
+            roof["traffic_note"] = (
+                "ncu dram read+write per k_select launch with caches flushed before the launch (profiles/r2_ncu_select_summary.csv): "
+                "6.45 MB read + 0.2 MB written.  Cold, every L2 read sector misses (lts__t_sectors_srcunit_tex_op_read = 200 k sectors = "
+                "6.4 MB): sibling blocks 3.3 MB (7 x 16 B hot records = 112 B, of which 12 B per child are the scan's N/Q/P, spread over "
+                "4-5 32-byte sectors per level), the chosen child's 8-byte cold record per level 0.7 MB (one sector each), the speculative "
+                "next-block prefetch ~1 MB, slot header 0.5 MB, RNG counter and statistics rows 0.5 MB -- sector granularity around 8-16 B "
+                "records, not re-reads.  Writes are 13.8 MB of L2 write sectors (leaf observations 5.5 MB, new child records, path, leaf "
+                "record, header), almost none of which reach DRAM inside the launch.  `achieved` counts only the PUCT scan (16 B header + "
+                "12 B per scanned child, SURVEY 8d)")
         except Exception:
             pass
 
