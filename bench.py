@@ -561,8 +561,10 @@ def main():
                 "4-5 32-byte sectors per level), the chosen child's 8-byte cold record per level 0.7 MB (one sector each), the speculative "
                 "next-block prefetch ~1 MB, slot header 0.5 MB, RNG counter and statistics rows 0.5 MB -- sector granularity around 8-16 B "
                 "records, not re-reads.  Writes are 13.8 MB of L2 write sectors (leaf observations 5.5 MB, new child records, path, leaf "
-                "record, header), almost none of which reach DRAM inside the launch.  `achieved` counts only the PUCT scan (16 B header + "
-                "12 B per scanned child, SURVEY 8d)")
+                "record, header), almost none of which reach DRAM inside the launch.  In the loop (same counters with --cache-control none, "
+                "profiles/r2_select_insitu_cache.csv) the launch reads 8.9 MB from DRAM and evicts 9.0 MB: the evaluator's traffic between two "
+                "selects leaves none of the ~300 MB of live tree records in the 126 MB L2, every tree access is a DRAM access (17 % of the "
+                "HBM peak in real bytes).  `achieved` counts only the PUCT scan (16 B header + 12 B per scanned child, SURVEY 8d)")
         except Exception:
             pass
 
