@@ -1,11 +1,13 @@
 """TensorCoreEvaluator -- the reference ResNet (alphazero/NNetArchitecture.py:69-120, evaluated by
 NNetWrapper.process, alphazero/NNetWrapper.py:225-232) on the tcgen05 tensor cores for every shipped
-geometry (boards up to 7x7, 32 / 64 trunk channels, any action size): csrc/azb_resnet_g.cu behind
+geometry (boards up to 7x7, 32 / 64 / 128 trunk channels, any action size): csrc/azb_resnet_g.cu behind
 azb_nng_forward (include/azb200_nn.h).
 
 precision (operands of the convolutions and of the head GEMM; accumulation is fp32 throughout):
   "bf16x2"  default -- every operand as hi + lo bf16 (16 significant bits; TF32, the reference's cuDNN
             default, has 11), three MMAs per K step: probabilities within 1e-5 of the fp32 module
+  "fp16x2"  the same three products on hi + lo fp16 pairs (22 significant bits for |v| >= 0.03, saturation at 65504):
+            default of the 128-channel network (default_precision)
   "fp16"    one pass, 11 significant bits (TF32's), activations saturate at 65504
   "bf16"    one pass, 8 significant bits
 Host-side folding (BN into the convolutions, the affine heads into one matrix) is fused_nn._folded,
@@ -17,8 +19,18 @@ import torch
 from . import _capi
 from .fused_nn import _folded
 
-PRECISIONS = {"bf16": 0, "fp16": 1, "bf16x2": 2}
+PRECISIONS = {"bf16": 0, "fp16": 1, "bf16x2": 2, "fp16x2": 3}
 DEFAULT_PRECISION = "bf16x2"
+SPLIT = ("bf16x2", "fp16x2")
+
+
+def default_precision(model=None):
+    """The precision product paths use when none is given: the one that keeps probabilities within 1e-5 of the fp32
+    module with margin -- bf16x2, and fp16x2 for the 128-channel network (measured: bf16x2 1.07e-5 against the exact
+    network with x8-sharpened heads, tests/test_nn_tc.py)."""
+    if model is not None and model.conv1.out_channels == 128:
+        return "fp16x2"
+    return DEFAULT_PRECISION
 
 
 class _NNGNet(C.Structure):
@@ -32,8 +44,8 @@ class _NNGNet(C.Structure):
 def supported(model):
     """Geometry azb_nng_forward covers."""
     ch = model.conv1.out_channels
-    return (ch in (32, 64) and 1 <= model.board_x <= 7 and 1 <= model.board_y <= 7 and model.channels <= 8
-            and len(model.resnet) <= 6)
+    return (ch in (32, 64, 128) and 1 <= model.board_x <= 7 and 1 <= model.board_y <= 7 and model.channels <= 8
+            and len(model.resnet) <= (8 if ch == 128 else 6))
 
 
 def head_tiles(nout):
@@ -45,8 +57,9 @@ def head_tiles(nout):
 
 def _split(w64, precision):
     """float64 tensor -> list of operand parts in the kernel's element type."""
-    if precision == "fp16":
-        return [w64.clamp(-65504.0, 65504.0).to(torch.float16)]
+    if precision in ("fp16", "fp16x2"):
+        hi = w64.clamp(-65504.0, 65504.0).to(torch.float16)
+        return [hi] if precision == "fp16" else [hi, (w64 - hi.double()).to(torch.float16)]
     hi = w64.to(torch.bfloat16)
     if precision == "bf16":
         return [hi]
@@ -59,7 +72,8 @@ def layout(channels, precision):
     rc = lib.azb_nng_layout(channels, PRECISIONS[precision], out)
     if rc != 0:
         raise NotImplementedError(f"tcgen05 evaluator: {channels} channels / {precision} not supported")
-    return dict(parts=out[0], dys=out[1], slab_bytes=out[2], boards_per_cta=out[3], head_kgran=out[4], max_depth=out[5])
+    return dict(parts=out[0], dys=out[1], slab_bytes=out[2], boards_per_cta=out[3], head_kgran=out[4], max_depth=out[5],
+                layer_slabs=out[6], stem_slabs=out[7])
 
 
 @torch.no_grad()
@@ -68,30 +82,51 @@ def fold_g(model, precision=DEFAULT_PRECISION, lay=None):
     f = _folded(model)
     ch, depth, cin, H, W = f["channels"], f["depth"], f["in_channels"], f["board_h"], f["board_w"]
     if lay is None:       # the library's constants, restated (tests compare them with azb_nng_layout)
-        parts = 2 if precision == "bf16x2" else 1
-        dys = 3 if ch == 32 else 1
-        lay = dict(parts=parts, dys=dys, slab_bytes=parts * dys * (ch // 8) * 3 * ch * 16, head_kgran=4)
+        parts = 2 if precision in SPLIT else 1
+        if ch == 128:
+            lay = dict(parts=parts, dys=0, slab_bytes=parts * 4 * ch * 16, head_kgran=4, layer_slabs=36, stem_slabs=3)
+        else:
+            dys = 3 if ch == 32 else 1
+            lay = dict(parts=parts, dys=dys, slab_bytes=parts * dys * (ch // 8) * 3 * ch * 16, head_kgran=4,
+                       layer_slabs=3 // dys, stem_slabs=1)
     parts, dys, c8, nacc = lay["parts"], lay["dys"], ch // 8, 3 * ch
     slab_elems = lay["slab_bytes"] // 2
     L = 1 + 2 * depth
-    slabs_per_layer = 3 // dys
-    nslabs = 1 + (L - 1) * slabs_per_layer
-    edt = torch.float16 if precision == "fp16" else torch.bfloat16
+    slabs_per_layer = lay["layer_slabs"]
+    nslabs = lay["stem_slabs"] + (L - 1) * slabs_per_layer
+    edt = torch.float16 if precision in ("fp16", "fp16x2") else torch.bfloat16
     wtrunk = torch.zeros(nslabs, slab_elems, dtype=edt)
-    # stem slab: [part][4 K chunks: dy = -1, 0, +1, zero][dx*ch + cout][8 cin]
-    w0 = torch.zeros(4, nacc, 8, dtype=torch.float64)
-    w0[:3, :, :cin] = f["convs"][0].view(ch, 3, 3, cin).permute(1, 2, 0, 3).reshape(3, nacc, cin)
-    stem_part = 4 * nacc * 8
-    for p, t in enumerate(_split(w0, precision)):
-        wtrunk[0, p * stem_part:(p + 1) * stem_part] = t.reshape(-1)
-    # trunk slabs: [part][dy in slab][cin/8][dx*ch + cout][8 cin]
-    slab_part = dys * c8 * nacc * 8
-    for l in range(1, L):
-        w = f["convs"][l].view(ch, 3, 3, c8, 8).permute(1, 3, 2, 0, 4).reshape(3, c8, nacc, 8)    # [dy][cin/8][dx*ch+cout][8]
-        for j in range(slabs_per_layer):
-            s = 1 + (l - 1) * slabs_per_layer + j
-            for p, t in enumerate(_split(w[j * dys:(j + 1) * dys], precision)):
-                wtrunk[s, p * slab_part:(p + 1) * slab_part] = t.reshape(-1)
+    if dys == 0:
+        # k_trunk_wide: every tap is its own MMA.  Stem slab j (dx = j - 1): [part][4 K chunks: dy = -1, 0, zero, +1][cout][8 cin];
+        # trunk slab (tap = 3 (dy+1) + (dx+1), kq): [part][4 K chunks = cin/8 in 4 kq .. 4 kq + 3][cout][8 cin]
+        slab_part = 4 * ch * 8
+        w0 = torch.zeros(3, 4, ch, 8, dtype=torch.float64)                                 # [dx][chunk][cout][cin]
+        ws = f["convs"][0].view(ch, 3, 3, cin).permute(2, 1, 0, 3)                         # [dx][dy][cout][cin]
+        w0[:, 0, :, :cin], w0[:, 1, :, :cin], w0[:, 3, :, :cin] = ws[:, 0], ws[:, 1], ws[:, 2]
+        for j in range(3):
+            for p, t in enumerate(_split(w0[j], precision)):
+                wtrunk[j, p * slab_part:(p + 1) * slab_part] = t.reshape(-1)
+        for l in range(1, L):
+            w = f["convs"][l].view(ch, 9, c8 // 4, 4, 8).permute(1, 2, 3, 0, 4)             # [tap][kq][chunk][cout][8]
+            w = w.reshape(slabs_per_layer, slab_part)
+            s0 = 3 + (l - 1) * slabs_per_layer
+            for p, t in enumerate(_split(w, precision)):
+                wtrunk[s0:s0 + slabs_per_layer, p * slab_part:(p + 1) * slab_part] = t
+    else:
+        # stem slab: [part][4 K chunks: dy = -1, 0, +1, zero][dx*ch + cout][8 cin]
+        w0 = torch.zeros(4, nacc, 8, dtype=torch.float64)
+        w0[:3, :, :cin] = f["convs"][0].view(ch, 3, 3, cin).permute(1, 2, 0, 3).reshape(3, nacc, cin)
+        stem_part = 4 * nacc * 8
+        for p, t in enumerate(_split(w0, precision)):
+            wtrunk[0, p * stem_part:(p + 1) * stem_part] = t.reshape(-1)
+        # trunk slabs: [part][dy in slab][cin/8][dx*ch + cout][8 cin]
+        slab_part = dys * c8 * nacc * 8
+        for l in range(1, L):
+            w = f["convs"][l].view(ch, 3, 3, c8, 8).permute(1, 3, 2, 0, 4).reshape(3, c8, nacc, 8)    # [dy][cin/8][dx*ch+cout][8]
+            for j in range(slabs_per_layer):
+                s = 1 + (l - 1) * slabs_per_layer + j
+                for p, t in enumerate(_split(w[j * dys:(j + 1) * dys], precision)):
+                    wtrunk[s, p * slab_part:(p + 1) * slab_part] = t.reshape(-1)
     # heads: [part][n tile][K chunk = pos*c8 + ch/8][row in tile][8]
     whead, bias = f["whead"], f["bhead"]                                   # [nout, pos, ch], [nout]
     nout = whead.shape[0]
@@ -115,11 +150,11 @@ class TensorCoreEvaluator:
     int32; count a tensor or a callable returning the device address of the counter)."""
 
     def __init__(self, model, obs, policy, value, precision=None, rows=None, count=None, max_batch=None):
-        precision = precision or DEFAULT_PRECISION
+        precision = precision or default_precision(model)
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
         if not supported(model):
-            raise NotImplementedError("tcgen05 evaluator: boards up to 7x7, 32 or 64 channels, <= 8 planes, depth <= 6")
+            raise NotImplementedError("tcgen05 evaluator: boards up to 7x7, 32 / 64 / 128 channels, <= 8 planes, depth <= 6 (8 at 128)")
         self.precision, self.kernel = precision, "tcg"
         self.lib = _capi.load()
         dev = obs.device
@@ -178,7 +213,7 @@ def make_evaluator(model, obs, policy, value, precision=None, kernel=None, rows=
       "fp32" / "tf32" / "cudnn-bf16"         PyTorch / cuDNN (azb200.nnet.LeafEvaluator; strict fp32 = the parity oracle)
     A geometry the hand-written kernels do not cover falls back to cuDNN TF32 -- the reference's own arithmetic -- never
     to a narrower type."""
-    precision = precision or DEFAULT_PRECISION
+    precision = precision or default_precision(model)
     if kernel in ("tc-r1", "mma"):
         from .fused_nn import FusedResNetEvaluator
         if precision != "bf16":

@@ -342,7 +342,7 @@ class DeviceSelfPlay:
         B = engine.B
         if fused is False and (precision is None or precision in nn_tc.PRECISIONS):
             precision = {None: "tf32", "bf16": "cudnn-bf16"}.get(precision, "tf32")
-        precision = precision or nn_tc.DEFAULT_PRECISION
+        precision = precision or nn_tc.default_precision(nnet)
         kernel = fused if fused in ("tc-r1", "mma") else None
         hand = kernel is not None or (precision in nn_tc.PRECISIONS and nn_tc.supported(nnet))
         if cohorts == 2 and split is None:

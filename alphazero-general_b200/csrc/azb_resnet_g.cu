@@ -5,8 +5,11 @@
 // Precision.  PREC_BF16X2 (the default) keeps every convolution / head operand as a pair of bf16 values hi + lo
 // (16 significant bits; TF32, what the reference gets from cuDNN, has 11) and evaluates a.w as
 // a_hi.w_hi + a_hi.w_lo + a_lo.w_hi with fp32 accumulation in TMEM: three tcgen05.mma per K step, probabilities within
-// 1e-5 of the fp32 module (tests/test_nn_tc.py states and checks the bound).  PREC_F16 (one pass, 11-bit significand =
-// TF32's) and PREC_BF16 (one pass, 8 bits) are opt-in performance modes.
+// 1e-5 of the fp32 module (tests/test_nn_tc.py states and checks the bound).  PREC_F16X2 is the same scheme with fp16
+// pairs (22 significant bits while the low part stays a normal fp16 number, i.e. for |v| >= 0.03; below that the absolute
+// error is the subnormal spacing 6e-8; |v| saturates at 65504): the default of the 128-channel network, whose 17 layers of
+// K = 1152 leave bf16x2 at 1.07e-5 with sharpened heads.  PREC_F16 (one pass, 11-bit significand = TF32's) and PREC_BF16
+// (one pass, 8 bits) are opt-in performance modes.
 //
 // Trunk kernel (k_trunk_tc).  A board is an 8 x 8 frame of positions (live H x W corner, the rest zero): one zero
 // column and >= one zero row per board are all the padding a 3x3 convolution needs, a tap (dy, dx) is a shift of
@@ -36,12 +39,14 @@ namespace g {
 using namespace azbtc;
 
 constexpr int MAXD = 6, MAXL = 1 + 2 * MAXD;
+__host__ __device__ constexpr bool prec_split(int prec) { return prec == AZB_NN_BF16X2 || prec == AZB_NN_F16X2; }   // operands as hi + lo
+__host__ __device__ constexpr bool prec_f16(int prec) { return prec == AZB_NN_F16 || prec == AZB_NN_F16X2; }        // element type fp16
 
 template <int CH_, int TILES_, int PREC_, int NGROUPS_, int DYS_, int NSLOT_>
 struct TrunkCfg {
     static constexpr int CH = CH_, TILES = TILES_, PREC = PREC_, NGROUPS = NGROUPS_, DYS = DYS_, NSLOT = NSLOT_;
-    static constexpr int PARTS = PREC == AZB_NN_BF16X2 ? 2 : 1;
-    static constexpr bool F16 = PREC == AZB_NN_F16;
+    static constexpr int PARTS = prec_split(PREC) ? 2 : 1;
+    static constexpr bool F16 = prec_f16(PREC);
     static constexpr int C8 = CH / 8, KST = CH / 16;
     static constexpr int ROWS = TILES * 128, PADR = 16, FROWS = ROWS + 2 * PADR;
     static constexpr int PLANE = FROWS * 16, FPART = C8 * PLANE, FRAME = PARTS * FPART;
@@ -84,8 +89,12 @@ __device__ __forceinline__ void store_operand(const float2 (&r)[8], unsigned cha
     uint32_t o[8], o2[8];
 #pragma unroll
     for (int c = 0; c < 8; c++) {
-        if (C::PREC == AZB_NN_F16) {
+        if (C::F16) {
             o[c] = f16x2_sat(r[c]);
+            if (C::PARTS == 2) {
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&o[c]));
+                o2[c] = f16x2_sat(make_float2(__fsub_rn(r[c].x, hf.x), __fsub_rn(r[c].y, hf.y)));
+            }
         } else {
             const __nv_bfloat162 h = __float22bfloat162_rn(r[c]);
             o[c] = bf2_bits(h);
@@ -99,8 +108,12 @@ __device__ __forceinline__ void store_operand(const float2 (&r)[8], unsigned cha
 #pragma unroll
         for (int c = 0; c < 8; c++) {
             float2 v;
-            if (C::PREC == AZB_NN_F16) {
+            if (C::F16) {
                 v = __half22float2(*reinterpret_cast<__half2 *>(&o[c]));
+                if (C::PARTS == 2) {
+                    const float2 w = __half22float2(*reinterpret_cast<__half2 *>(&o2[c]));
+                    v.x += w.x; v.y += w.y;
+                }
             } else {
                 v = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&o[c]));
                 if (C::PARTS == 2) {
@@ -120,6 +133,52 @@ __device__ __forceinline__ void store_operand(const float2 (&r)[8], unsigned cha
             *reinterpret_cast<uint4 *>(dst + part_stride + chunk_stride) = make_uint4(o2[4], o2[5], o2[6], o2[7]);
         }
     }
+}
+
+// The part of an epilogue that follows the accumulator gather: r = the convolution output of this thread's row for 16
+// channels, xv = the residual stream's 16 values (EPI_CONV2 only; rewritten for stem / conv2).
+template <class C, int EPI, bool DBG>
+__device__ __forceinline__ void epilogue_finish(float2 (&r)[8], uint32_t (&xv)[16], uint32_t t_x, unsigned char *dst, size_t part_stride,
+                                                size_t chunk_stride, const float *bias, const float *nsc, const float *nsh, bool live,
+                                                float *dump_row)
+{
+    if (EPI != EPI_CONV2) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float4 b4 = reinterpret_cast<const float4 *>(bias)[c];
+            r[2 * c] = __fadd2_rn(r[2 * c], make_float2(b4.x, b4.y));
+            r[2 * c + 1] = __fadd2_rn(r[2 * c + 1], make_float2(b4.z, b4.w));
+        }
+    }
+    if (EPI == EPI_STEM) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            r[c].x = fmaxf(r[c].x, 0.0f); r[c].y = fmaxf(r[c].y, 0.0f);
+            xv[2 * c] = __float_as_uint(r[c].x); xv[2 * c + 1] = __float_as_uint(r[c].y);
+        }
+        tmem_st16(t_x, xv);
+    } else if (EPI == EPI_CONV2) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            r[c] = __fadd2_rn(r[c], f2(xv[2 * c], xv[2 * c + 1]));
+            xv[2 * c] = __float_as_uint(r[c].x); xv[2 * c + 1] = __float_as_uint(r[c].y);
+        }
+        tmem_st16(t_x, xv);
+    }
+    if (EPI == EPI_CONV1 || nsc != nullptr) {
+        if (EPI != EPI_CONV1) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float4 s4 = reinterpret_cast<const float4 *>(nsc)[c], h4 = reinterpret_cast<const float4 *>(nsh)[c];
+                r[2 * c] = __ffma2_rn(r[2 * c], make_float2(s4.x, s4.y), make_float2(h4.x, h4.y));
+                r[2 * c + 1] = __ffma2_rn(r[2 * c + 1], make_float2(s4.z, s4.w), make_float2(h4.z, h4.w));
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) { r[c].x = fmaxf(r[c].x, 0.0f); r[c].y = fmaxf(r[c].y, 0.0f); }
+    }
+    store_operand<C>(r, dst, part_stride, chunk_stride, live, DBG ? dump_row : nullptr);
+    if (EPI != EPI_CONV1) tmem_st_wait();
 }
 
 // Epilogue of one tile for 16 of its channels: this thread owns tile row q*32 + lane (= its TMEM lane) and the channels
@@ -159,43 +218,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_p, uint32_t t_x, unsign
         }
         r[c] = __fadd2_rn(__fadd2_rn(up, f2(p0[2 * c], p0[2 * c + 1])), dn);
     }
-    if (EPI != EPI_CONV2) {
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const float4 b4 = reinterpret_cast<const float4 *>(bias)[c];
-            r[2 * c] = __fadd2_rn(r[2 * c], make_float2(b4.x, b4.y));
-            r[2 * c + 1] = __fadd2_rn(r[2 * c + 1], make_float2(b4.z, b4.w));
-        }
-    }
-    if (EPI == EPI_STEM) {
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            r[c].x = fmaxf(r[c].x, 0.0f); r[c].y = fmaxf(r[c].y, 0.0f);
-            xv[2 * c] = __float_as_uint(r[c].x); xv[2 * c + 1] = __float_as_uint(r[c].y);
-        }
-        tmem_st16(t_x, xv);
-    } else if (EPI == EPI_CONV2) {
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            r[c] = __fadd2_rn(r[c], f2(xv[2 * c], xv[2 * c + 1]));
-            xv[2 * c] = __float_as_uint(r[c].x); xv[2 * c + 1] = __float_as_uint(r[c].y);
-        }
-        tmem_st16(t_x, xv);
-    }
-    if (EPI == EPI_CONV1 || nsc != nullptr) {
-        if (EPI != EPI_CONV1) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const float4 s4 = reinterpret_cast<const float4 *>(nsc)[c], h4 = reinterpret_cast<const float4 *>(nsh)[c];
-                r[2 * c] = __ffma2_rn(r[2 * c], make_float2(s4.x, s4.y), make_float2(h4.x, h4.y));
-                r[2 * c + 1] = __ffma2_rn(r[2 * c + 1], make_float2(s4.z, s4.w), make_float2(h4.z, h4.w));
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 8; c++) { r[c].x = fmaxf(r[c].x, 0.0f); r[c].y = fmaxf(r[c].y, 0.0f); }
-    }
-    store_operand<C>(r, dst, part_stride, chunk_stride, live, DBG ? dump_row : nullptr);
-    if (EPI != EPI_CONV1) tmem_st_wait();
+    epilogue_finish<C, EPI, DBG>(r, xv, t_x, dst, part_stride, chunk_stride, bias, nsc, nsh, live, dump_row);
 }
 
 // MMAs of one (tile, slab).  Trunk slab: [part][dy in slab][K chunk][NACC][8]; per 16-channel K step the passes
@@ -328,8 +351,10 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
         uint32_t o[4], o2[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (C::PREC == AZB_NN_F16) {
+            if (C::F16) {
                 o[k] = f16x2_sat(c[k]);
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&o[k]));
+                o2[k] = f16x2_sat(make_float2(c[k].x - hf.x, c[k].y - hf.y));
             } else {
                 const __nv_bfloat162 h = __float22bfloat162_rn(c[k]);
                 o[k] = bf2_bits(h);
@@ -445,6 +470,255 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
 #undef BAR
 }
 
+// ---- 128-channel trunk (connect4/train.py:44-49: 128 channels x 8 blocks) ---------------------------------------------
+// One layer of split operands is 590 KB -- it cannot stay in shared memory, and N = 3 CH = 384 exceeds an MMA's N -- so
+// this kernel differs from k_trunk_tc in two places.  (1) Every tap is its own MMA: a K-major no-swizzle descriptor may
+// start at any 16-byte row (measured on the B200, scripts/umma_shift_probe.cu / umma_shift_timing.cu: exact, and an
+// M = 128, N = 128, K = 16 MMA takes 64 cycles = its math floor whatever the shift), so tap (dy, dx) is `start address +=
+// 16 (8 dy + dx)`, N = CH = 128, and the epilogue needs no rotations.  (2) Weights stream through a ring of 16 KB slabs
+// ((tap, 32 input channels): [part][4 K chunks][128 cout][8 cin]) and the MMAs run slab-major: the CTA's two tiles (four
+// boards; tensor memory = 2 x (128 residual + 128 accumulator columns)) consume a slab one after the other, so a layer's
+// weights cross L2 -> shared memory once per four boards.  One issuing thread, one producer, one epilogue group of eight
+// warps per tile (TMEM lane quadrant x half of the channels, four 16-channel groups each).
+template <int PREC_>
+struct WideCfg {
+    static constexpr int CH = 128, TILES = 2, PREC = PREC_, MAXDEPTH = 8, MAXLAYERS = 1 + 2 * MAXDEPTH;
+    static constexpr int PARTS = prec_split(PREC) ? 2 : 1;
+    static constexpr bool F16 = prec_f16(PREC);
+    static constexpr int C8 = CH / 8;
+    static constexpr int ROWS = TILES * 128, PADR = 16, FROWS = ROWS + 2 * PADR;
+    static constexpr int PLANE = FROWS * 16, FPART = C8 * PLANE, FRAME = PARTS * FPART;
+    static constexpr int WCHUNK = CH * 16;                              // one 8-channel K chunk of the B operand
+    static constexpr int SLAB_PART = 4 * WCHUNK, SLAB = PARTS * SLAB_PART;
+    static constexpr int KQ = C8 / 4, LSLABS = 9 * KQ, STEM_SLABS = 3;  // slabs per tap / per trunk layer / of the stem
+    static constexpr int NSLOT = PARTS == 2 ? 4 : 8;
+    static constexpr int CGW = 2, CGI = CH / 16 / CGW;                  // warps per lane quadrant, channel groups per warp
+    static constexpr int GW = 4 * CGW, EPI_WARP0 = 4;
+    static constexpr int WARPS = EPI_WARP0 + TILES * GW, THREADS = WARPS * 32;
+    static constexpr uint32_t COL_X = 0, COL_P = TILES * CH;
+    static constexpr int PRM_FLOATS = MAXLAYERS * CH + 2 * MAXDEPTH * CH;
+    static constexpr size_t SMEM = (size_t)FRAME + (size_t)NSLOT * SLAB + (size_t)PRM_FLOATS * 4 + 24 * 8 + 64;
+    static constexpr uint32_t IDESC = umma_idesc(CH, F16);
+    static_assert(COL_P + TILES * CH <= 512, "tensor memory budget");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    static_assert(PADR >= 9 + 1, "taps reach 9 frame rows beyond a tile");
+};
+
+// epilogue of one tile row for 16 channels, accumulator = the finished convolution (same cases as epilogue_tile)
+template <class C, int EPI, bool DBG>
+__device__ __forceinline__ void epilogue_direct(uint32_t t_p, uint32_t t_x, unsigned char *dst, size_t part_stride, size_t chunk_stride,
+                                                const float *bias, const float *nsc, const float *nsh, bool live, float *dump_row)
+{
+    uint32_t p0[16], xv[16];
+    tmem_ld16(t_p, p0);
+    if (EPI == EPI_CONV2) tmem_ld16(t_x, xv);
+    tmem_ld_wait();
+    float2 r[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) r[c] = f2(p0[2 * c], p0[2 * c + 1]);
+    epilogue_finish<C, EPI, DBG>(r, xv, t_x, dst, part_stride, chunk_stride, bias, nsc, nsh, live, dump_row);
+}
+
+template <class C, bool DBG>
+__global__ void __launch_bounds__(C::THREADS, 1)
+k_trunk_wide(const float *__restrict__ obs, int B, int in_ch, int H, int W, int depth, const unsigned char *__restrict__ wtrunk,
+             const float *__restrict__ cbias, const float *__restrict__ bn_scale, const float *__restrict__ bn_shift,
+             unsigned char *__restrict__ gact, int MT, int KC, float *__restrict__ dump, int dump_layer,
+             const int *__restrict__ rows, const int *__restrict__ count_ptr, int sms)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *frame = smem;
+    unsigned char *wb = frame + C::FRAME;                                       // weight slab ring
+    float *prm = reinterpret_cast<float *>(wb + (size_t)C::NSLOT * C::SLAB);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(prm + C::PRM_FLOATS);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
+
+    enum { BAR_PFULL = 0, BAR_READY = BAR_PFULL + C::TILES, BAR_WFULL = BAR_READY + C::TILES, BAR_WEMPTY = BAR_WFULL + C::NSLOT,
+           NBARS = BAR_WEMPTY + C::NSLOT };
+    static_assert(NBARS <= 24, "barrier storage");
+
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    if (rows != nullptr) B = *count_ptr;                 // compact mode: the batch size lives in device memory
+    const TileShare sh = tile_share(B, C::TILES, sms);
+    if ((int)blockIdx.x >= sh.nct) return;
+    const int tiles = sh.base + ((int)blockIdx.x < sh.extra ? 1 : 0);
+    const int tile0 = (int)blockIdx.x * sh.base + ((int)blockIdx.x < sh.extra ? (int)blockIdx.x : sh.extra);
+    const int board0 = 2 * tile0;
+    const int layers = 1 + 2 * depth;
+    const uint32_t bar0 = smem_u32(bars), frame_s = smem_u32(frame), wb_s = smem_u32(wb);
+#define BAR(i) (bar0 + 8u * (uint32_t)(i))
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < C::TILES; i++) { mbar_init(BAR(BAR_PFULL + i), 1); mbar_init(BAR(BAR_READY + i), C::GW); }
+            for (int i = 0; i < C::NSLOT; i++) { mbar_init(BAR(BAR_WFULL + i), 1); mbar_init(BAR(BAR_WEMPTY + i), 1); }
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncwarp();
+        tmem_alloc<512>(smem_u32(tmem_slot));
+    }
+    {   // zero the frame (padding rows / columns must read as zero), stage the per-channel parameters
+        uint4 *z = reinterpret_cast<uint4 *>(frame);
+        for (int i = tid; i < C::FRAME / 16; i += C::THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < layers * C::CH; i += C::THREADS) prm[i] = cbias[i];
+        for (int i = tid; i < depth * C::CH; i += C::THREADS) {
+            prm[C::MAXLAYERS * C::CH + i] = bn_scale[i];
+            prm[C::MAXLAYERS * C::CH + C::MAXDEPTH * C::CH + i] = bn_shift[i];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const float *s_bias = prm, *s_sc = prm + C::MAXLAYERS * C::CH, *s_sh = prm + C::MAXLAYERS * C::CH + C::MAXDEPTH * C::CH;
+
+    // observation -> chunk plane 0 (channels >= in_ch stay zero)
+    const int HW = H * W;
+    for (int i = tid; i < tiles * 2 * HW; i += C::THREADS) {
+        const int bl = i / HW, pos = i - bl * HW, y = pos / W, xx = pos - y * W;
+        int gb = board0 + bl;
+        const bool have = gb < B;
+        if (have && rows != nullptr) gb = rows[gb];
+        float2 c[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            c[k].x = (have && 2 * k < in_ch) ? obs[((size_t)gb * in_ch + 2 * k) * HW + pos] : 0.0f;
+            c[k].y = (have && 2 * k + 1 < in_ch) ? obs[((size_t)gb * in_ch + 2 * k + 1) * HW + pos] : 0.0f;
+        }
+        uint32_t o[4], o2[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (C::F16) {
+                o[k] = f16x2_sat(c[k]);
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&o[k]));
+                o2[k] = f16x2_sat(make_float2(c[k].x - hf.x, c[k].y - hf.y));
+            } else {
+                const __nv_bfloat162 h = __float22bfloat162_rn(c[k]);
+                o[k] = bf2_bits(h);
+                const float2 hf = __bfloat1622float2(h);
+                o2[k] = bf2_bits(__float22bfloat162_rn(make_float2(c[k].x - hf.x, c[k].y - hf.y)));
+            }
+        }
+        unsigned char *d = frame + (size_t)(C::PADR + bl * 64 + y * 8 + xx) * 16;
+        *reinterpret_cast<uint4 *>(d) = make_uint4(o[0], o[1], o[2], o[3]);
+        if (C::PARTS == 2) *reinterpret_cast<uint4 *>(d + C::FPART) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    const int nslabs = C::STEM_SLABS + (layers - 1) * C::LSLABS;
+    constexpr int NPASS = C::PARTS == 2 ? 3 : 1;
+    if (warp == 0) {
+        // ---- MMA issuer: layer by layer, slab by slab, tile by tile ------------------------------------------------------
+        if (elect_one_sync()) {
+            int s = 0;
+#pragma unroll 1
+            for (int l = 0; l < layers; l++) {
+                const int ns = l == 0 ? C::STEM_SLABS : C::LSLABS;
+#pragma unroll 1
+                for (int j = 0; j < ns; j++, s++) {
+                    const int ws = s % C::NSLOT;
+                    mbar_wait(BAR(BAR_WFULL + ws), (uint32_t)((s / C::NSLOT) & 1));
+                    tc_fence_after();
+                    const uint32_t w_s = wb_s + (uint32_t)(ws * C::SLAB);
+                    // stem slab j: dx = j - 1, K chunks (dy=-1, dy=0, zero, dy=+1) of chunk plane 0: two K steps whose second
+                    // chunk is the first one 8 rows further.  Trunk slab j: tap j / KQ, input channels 32 (j % KQ) ..
+                    const int tap = j / C::KQ, kq = j - tap * C::KQ;
+                    const int shift = l == 0 ? (j - 1) : (8 * (tap / 3 - 1) + (tap % 3 - 1));          // frame rows
+#pragma unroll 1
+                    for (int t = 0; t < tiles; t++) {
+                        if (j == 0 && l > 0) { mbar_wait(BAR(BAR_READY + t), (uint32_t)((l - 1) & 1)); tc_fence_after(); }
+                        const uint32_t d_tmem = tmem_base + C::COL_P + (uint32_t)(C::CH * t);
+                        const uint32_t row0 = frame_s + (uint32_t)((C::PADR + 128 * t + shift) * 16);
+#pragma unroll
+                        for (int kk = 0; kk < 2; kk++) {
+#pragma unroll
+                            for (int pass = 0; pass < NPASS; pass++) {
+                                const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
+                                uint64_t ad;
+                                if (l == 0) ad = umma_desc(row0 + (uint32_t)(pa * C::FPART) + (uint32_t)((kk == 0 ? -8 : 0) * 16), 128u, 128u);
+                                else ad = umma_desc(row0 + (uint32_t)(pa * C::FPART + (4 * kq + 2 * kk) * C::PLANE), (uint32_t)C::PLANE, 128u);
+                                const uint64_t bd = umma_desc(w_s + (uint32_t)(pb * C::SLAB_PART + 2 * kk * C::WCHUNK), (uint32_t)C::WCHUNK, 128u);
+                                umma_f16(d_tmem, ad, bd, C::IDESC, (j > 0 || kk > 0 || pass > 0) ? 1u : 0u);
+                            }
+                        }
+                    }
+                    umma_commit(BAR(BAR_WEMPTY + ws));
+                }
+                for (int t = 0; t < tiles; t++) umma_commit(BAR(BAR_PFULL + t));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3) {
+        // ---- weight producer ------------------------------------------------------------------------------------
+        if (elect_one_sync()) {
+#pragma unroll 1
+            for (int s = 0; s < nslabs; s++) {
+                const int ws = s % C::NSLOT, use = s / C::NSLOT;
+                if (use > 0) mbar_wait(BAR(BAR_WEMPTY + ws), (uint32_t)((use - 1) & 1));
+                mbar_expect_tx(BAR(BAR_WFULL + ws), (uint32_t)C::SLAB);
+                bulk_g2s(wb_s + (uint32_t)(ws * C::SLAB), wtrunk + (size_t)s * C::SLAB, (uint32_t)C::SLAB, BAR(BAR_WFULL + ws));
+            }
+        }
+        __syncwarp();
+    } else if (warp >= C::EPI_WARP0) {
+        // ---- epilogue group t: tile t of every layer --------------------------------------------------------------------
+        const int e = warp - C::EPI_WARP0, t = e / C::GW, within = e % C::GW, q = warp & 3, cgw = within >> 2;
+        if (t < tiles) {
+            const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+            const int r0 = q * 32 + lane, fy = (r0 & 63) >> 3, fx = r0 & 7;
+            const int brd = board0 + 2 * t + (r0 >> 6);                     // (compact) board index of this row
+            const bool live = fx < W && fy < H && brd < B;
+            const int pos = fy * W + fx;
+#pragma unroll 1
+            for (int l = 0; l < layers; l++) {
+                const bool is_c1 = (l & 1) == 1, last = l + 1 == layers;
+                if (within == 0) mbar_wait<32>(BAR(BAR_PFULL + t), (uint32_t)(l & 1));
+                asm volatile("bar.sync %0, %1;\n" ::"r"(1 + t), "r"(C::GW * 32) : "memory");
+                tc_fence_after();
+#pragma unroll 1
+                for (int i = 0; i < C::CGI; i++) {
+                    const int cg = cgw * C::CGI + i, ho = 16 * cg;
+                    const uint32_t t_p = tmem_base + lane_off + C::COL_P + (uint32_t)(C::CH * t + ho);
+                    const uint32_t t_x = tmem_base + lane_off + C::COL_X + (uint32_t)(C::CH * t + ho);
+                    unsigned char *dst;
+                    size_t part_stride, chunk_stride;
+                    if (last) {     // head GEMM A operand: [part][M tile of 128 boards][K chunk = pos * C8 + c][board][16 B]
+                        chunk_stride = (size_t)128 * 16;
+                        part_stride = (size_t)MT * KC * chunk_stride;
+                        dst = gact + ((size_t)(brd >> 7) * KC + (size_t)(pos * C::C8 + 2 * cg)) * chunk_stride + (size_t)(brd & 127) * 16;
+                    } else {
+                        chunk_stride = C::PLANE;
+                        part_stride = C::FPART;
+                        dst = frame + (size_t)(2 * cg) * C::PLANE + (size_t)(C::PADR + 128 * t + r0) * 16;
+                    }
+                    float *dmp = nullptr;
+                    if (DBG && dump != nullptr && l == dump_layer && brd < B) dmp = dump + ((size_t)brd * 64 + (r0 & 63)) * C::CH + ho;
+                    if (l == 0) {
+                        epilogue_direct<C, EPI_STEM, DBG>(t_p, t_x, dst, part_stride, chunk_stride, s_bias + ho, depth > 0 ? s_sc + ho : nullptr,
+                                                          s_sh + ho, live, dmp);
+                    } else if (is_c1) {
+                        epilogue_direct<C, EPI_CONV1, DBG>(t_p, t_x, dst, part_stride, chunk_stride, s_bias + l * C::CH + ho, nullptr, nullptr,
+                                                           live, dmp);
+                    } else {
+                        const int nblk = l >> 1;                      // the block that consumes x next
+                        epilogue_direct<C, EPI_CONV2, DBG>(t_p, t_x, dst, part_stride, chunk_stride, nullptr,
+                                                           last ? nullptr : s_sc + nblk * C::CH + ho, s_sh + nblk * C::CH + ho, live, dmp);
+                    }
+                }
+                tc_fence_before();                // accumulator and residual accesses are complete (wait::ld / wait::st inside)
+                fence_proxy_async();              // the next layer's MMAs read these rows through the async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(BAR_READY + t));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+#undef BAR
+}
+
 // ---- heads ---------------------------------------------------------------------------------------------------------
 constexpr int HSTAGES = 4, HKC = 4;                        // K chunks (of 8) per pipeline stage
 constexpr int HTHREADS = 192;
@@ -455,8 +729,8 @@ k_head_tc(const unsigned char *__restrict__ gact, const unsigned char *__restric
           float *__restrict__ logits, float *__restrict__ policy, float *__restrict__ value, int B, const int *__restrict__ rows,
           const int *__restrict__ count_ptr, int MT, int KC, int NT, int ntiles, int nout_pad, int A, uint32_t tmem_cols)
 {
-    constexpr int PARTS = PREC == AZB_NN_BF16X2 ? 2 : 1;
-    constexpr bool F16 = PREC == AZB_NN_F16;
+    constexpr int PARTS = prec_split(PREC) ? 2 : 1;
+    constexpr bool F16 = prec_f16(PREC);
     extern __shared__ __align__(128) unsigned char smem[];
     const int a_part = HKC * 128 * 16, b_part = HKC * NT * 16, stage_bytes = PARTS * (a_part + b_part);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + (size_t)HSTAGES * stage_bytes);
@@ -615,8 +889,8 @@ k_softmax(const float *__restrict__ logits, float *__restrict__ policy, float *_
 //                          CH  TILES PREC NGROUPS DYS NSLOT
 // 32 channels: two epilogue groups keep up with the MMAs of a tile (measured 191.9 us with two, 195.6 us with three for
 // 6960 boards in split mode; 121.3 vs 124.8 us in bf16) and leave the registers of eight warps unused
-template <int PREC> using Cfg32 = TrunkCfg<32, 7, PREC, 2, 3, PREC == AZB_NN_BF16X2 ? 2 : 3>;
-template <int PREC> using Cfg64 = TrunkCfg<64, 2, PREC, 1, 1, PREC == AZB_NN_BF16X2 ? 3 : 6>;
+template <int PREC> using Cfg32 = TrunkCfg<32, 7, PREC, 2, 3, prec_split(PREC) ? 2 : 3>;
+template <int PREC> using Cfg64 = TrunkCfg<64, 2, PREC, 1, 1, prec_split(PREC) ? 3 : 6>;
 
 
 int sm_count()
@@ -659,10 +933,38 @@ int launch_trunk(const azb_nng_net *n, const float *obs, int batch, const int *r
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+template <class C>
+int launch_wide(const azb_nng_net *n, const float *obs, int batch, const int *rows, const int *count, cudaStream_t s, float *dump,
+                int dump_layer)
+{
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_trunk_wide<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(k_trunk_wide<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess)
+            return -2;
+        configured = true;
+    }
+    const int sms = sm_count();
+    if (sms <= 0) return -2;
+    const int grid = tile_share(batch, C::TILES, sms).nct;      // compact mode: upper bound, surplus CTAs exit at once
+    const int MT = (n->max_boards + 127) / 128;
+    if (dump != nullptr)
+        k_trunk_wide<C, true><<<grid, C::THREADS, C::SMEM, s>>>(obs, batch, n->in_channels, n->board_h, n->board_w, n->depth,
+                                                               reinterpret_cast<const unsigned char *>(n->wtrunk), n->cbias, n->bn_scale,
+                                                               n->bn_shift, reinterpret_cast<unsigned char *>(n->gact), MT, n->head_kc, dump,
+                                                               dump_layer, rows, count, sms);
+    else
+        k_trunk_wide<C, false><<<grid, C::THREADS, C::SMEM, s>>>(obs, batch, n->in_channels, n->board_h, n->board_w, n->depth,
+                                                                reinterpret_cast<const unsigned char *>(n->wtrunk), n->cbias, n->bn_scale,
+                                                                n->bn_shift, reinterpret_cast<unsigned char *>(n->gact), MT, n->head_kc,
+                                                                nullptr, -1, rows, count, sms);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 template <int PREC>
 int launch_head(const azb_nng_net *n, float *policy, float *value, int batch, const int *rows, const int *count, cudaStream_t s)
 {
-    constexpr int PARTS = PREC == AZB_NN_BF16X2 ? 2 : 1;
+    constexpr int PARTS = prec_split(PREC) ? 2 : 1;
     const int NT = n->head_nt, ntiles = n->head_ntiles, nout_pad = NT * ntiles;
     const size_t smem = (size_t)HSTAGES * PARTS * (HKC * 128 * 16 + HKC * NT * 16) + (2 * HSTAGES + 1) * 8 + 64;
     static size_t configured = 0;
@@ -691,7 +993,8 @@ int forward_prec(const azb_nng_net *n, const float *obs, float *policy, float *v
 {
     int rc;
     if (n->channels == 32) rc = launch_trunk<Cfg32<PREC>>(n, obs, batch, rows, count, s, dump, dump_layer);
-    else rc = launch_trunk<Cfg64<PREC>>(n, obs, batch, rows, count, s, dump, dump_layer);
+    else if (n->channels == 64) rc = launch_trunk<Cfg64<PREC>>(n, obs, batch, rows, count, s, dump, dump_layer);
+    else rc = launch_wide<WideCfg<PREC>>(n, obs, batch, rows, count, s, dump, dump_layer);
     if (rc != 0) return rc;
     return launch_head<PREC>(n, policy, value, batch, rows, count, s);
 }
@@ -700,8 +1003,9 @@ int forward(const azb_nng_net *n, const float *obs, float *policy, float *value,
             float *dump, int dump_layer)
 {
     if (!n || !obs || !policy || !value || batch <= 0 || (rows != nullptr) != (count != nullptr)) return -7;
-    if ((n->channels != 32 && n->channels != 64) || n->board_h < 1 || n->board_h > 7 || n->board_w < 1 || n->board_w > 7 ||
-        n->in_channels < 1 || n->in_channels > 8 || n->depth < 0 || n->depth > MAXD || n->action_size < 1 || batch > n->max_boards ||
+    if ((n->channels != 32 && n->channels != 64 && n->channels != 128) || n->board_h < 1 || n->board_h > 7 || n->board_w < 1 ||
+        n->board_w > 7 || n->in_channels < 1 || n->in_channels > 8 || n->depth < 0 ||
+        n->depth > (n->channels == 128 ? WideCfg<AZB_NN_BF16>::MAXDEPTH : MAXD) || n->action_size < 1 || batch > n->max_boards ||
         n->head_nt % 16 != 0 || n->head_nt < 16 || n->head_nt > 256 || n->head_ntiles < 1 || n->head_kc % HKC != 0 ||
         n->head_kc < n->board_h * n->board_w * (n->channels / 8) || n->head_nt * n->head_ntiles < n->action_size + 3 ||
         !n->wtrunk || !n->cbias || !n->bn_scale || !n->bn_shift || !n->whead || !n->bhead || !n->gact ||
@@ -712,6 +1016,7 @@ int forward(const azb_nng_net *n, const float *obs, float *policy, float *value,
     case AZB_NN_BF16: return forward_prec<AZB_NN_BF16>(n, obs, policy, value, batch, rows, count, s, dump, dump_layer);
     case AZB_NN_F16: return forward_prec<AZB_NN_F16>(n, obs, policy, value, batch, rows, count, s, dump, dump_layer);
     case AZB_NN_BF16X2: return forward_prec<AZB_NN_BF16X2>(n, obs, policy, value, batch, rows, count, s, dump, dump_layer);
+    case AZB_NN_F16X2: return forward_prec<AZB_NN_F16X2>(n, obs, policy, value, batch, rows, count, s, dump, dump_layer);
     default: return -1;
     }
 }
@@ -721,8 +1026,20 @@ int forward(const azb_nng_net *n, const float *obs, float *policy, float *value,
 
 extern "C" int azb_nng_layout(int32_t channels, int32_t precision, int32_t *out)
 {
-    if (!out || (channels != 32 && channels != 64) || precision < AZB_NN_BF16 || precision > AZB_NN_BF16X2) return -1;
-    const int parts = precision == AZB_NN_BF16X2 ? 2 : 1;
+    if (!out || (channels != 32 && channels != 64 && channels != 128) || precision < AZB_NN_BF16 || precision > AZB_NN_F16X2) return -1;
+    const int parts = g::prec_split(precision) ? 2 : 1;
+    if (channels == 128) {                                  /* k_trunk_wide: one slab = (tap, 32 input channels) */
+        using W = g::WideCfg<AZB_NN_BF16>;
+        out[0] = parts;
+        out[1] = 0;                                         /* per-tap slabs */
+        out[2] = parts * W::SLAB_PART;
+        out[3] = 2 * W::TILES;
+        out[4] = g::HKC;
+        out[5] = W::MAXDEPTH;
+        out[6] = W::LSLABS;
+        out[7] = W::STEM_SLABS;
+        return 0;
+    }
     const int dys = channels == 32 ? 3 : 1, tiles = channels == 32 ? 7 : 2;
     out[0] = parts;
     out[1] = dys;                                           /* vertical taps per weight slab */
@@ -730,6 +1047,8 @@ extern "C" int azb_nng_layout(int32_t channels, int32_t precision, int32_t *out)
     out[3] = 2 * tiles;                                     /* boards per CTA */
     out[4] = g::HKC;                                        /* head K chunks per stage: head_kc is a multiple */
     out[5] = g::MAXD;
+    out[6] = 3 / dys;                                       /* weight slabs per trunk layer */
+    out[7] = 1;                                             /* weight slabs of the stem */
     return 0;
 }
 

@@ -54,14 +54,14 @@ def parse():
     ap.add_argument("--games", type=int, default=8192)
     ap.add_argument("--sims", type=int, default=100)
     ap.add_argument("--net", default="default", choices=["default", "connect4_train", "brandubh_train"])
-    ap.add_argument("--precision", default=None, choices=["bf16x2", "fp16", "bf16", "fp32", "tf32", "cudnn-bf16"],
+    ap.add_argument("--precision", default=None, choices=["bf16x2", "fp16x2", "fp16", "bf16", "fp32", "tf32", "cudnn-bf16"],
                     help="operand precision of the leaf evaluator (accumulation is fp32): bf16x2 = hi+lo bf16 operands, within 1e-5 "
                          "of the fp32 module (default of --nn tc); fp16 / bf16 = one-pass modes of the same kernels; fp32 / tf32 / "
                          "cudnn-bf16 = PyTorch/cuDNN (--nn cudnn; default tf32, the reference's own arithmetic)")
     ap.add_argument("--cohorts", type=int, default=1)
     ap.add_argument("--split", type=int, default=0, help="games in the first cohort (0 = automatic)")
     ap.add_argument("--nn", default="tc", choices=["tc", "tc-r1", "mma", "cudnn", "fused", "fused_mma"],
-                    help="leaf evaluator: tc = hand-written tcgen05/TMEM kernels (csrc/azb_resnet_g.cu, every shipped geometry up to 64 "
+                    help="leaf evaluator: tc = hand-written tcgen05/TMEM kernels (csrc/azb_resnet_g.cu, every shipped geometry: 32 / 64 / 128 "
                          "channels); tc-r1 / mma = the round-1 bf16-only kernels (6x7, 32 channels); cudnn = PyTorch/cuDNN CUDA graph")
     ap.add_argument("--lanes", type=int, default=0, help="threads per game (0 = library default)")
     ap.add_argument("--nchw", action="store_true", help="keep the ResNet in NCHW (default: channels_last)")
@@ -359,13 +359,13 @@ def main():
     from azb200 import nn_tc
     a.nn = {"fused": "tc", "fused_mma": "mma"}.get(a.nn, a.nn)
     if a.nn == "tc" and not nn_tc.supported(model):
-        a.nn = "cudnn"                      # the hand-written kernels cover up to 64 channels; the 128-channel net stays on cuDNN
+        a.nn = "cudnn"                      # a geometry the hand-written kernels do not cover (boards > 7x7)
     if tafl:
         a.no_e2e = True                     # the host-tensor agent legs below are written for Connect4 shapes
     if a.nn == "cudnn":
         a.precision = a.precision if a.precision in ("fp32", "tf32", "cudnn-bf16") else "tf32"
     elif a.nn == "tc":
-        a.precision = a.precision if a.precision in nn_tc.PRECISIONS else nn_tc.DEFAULT_PRECISION
+        a.precision = a.precision if a.precision in nn_tc.PRECISIONS else nn_tc.default_precision(model)
     else:
         a.precision = "bf16"
     drv = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision, channels_last=not a.nchw,
@@ -373,10 +373,11 @@ def main():
                          round_graph=False if a.no_round_graph else None, split=a.split or None,
                          skip_terminal=not a.eval_terminal)
     compact = a.nn in ("tc", "tc-r1") and not a.eval_terminal and a.cohorts == 1
-    nn_kernel = {"tc": "k_trunk_tc + k_head_tc (tcgen05/TMEM, csrc/azb_resnet_g.cu)", "tc-r1": "k_resnet_tc (tcgen05/TMEM, round 1)",
+    nn_kernel = {"tc": ("k_trunk_wide" if netargs["num_channels"] == 128 else "k_trunk_tc") + " + k_head_tc (tcgen05/TMEM, csrc/azb_resnet_g.cu)", "tc-r1": "k_resnet_tc (tcgen05/TMEM, round 1)",
                  "mma": "k_resnet_fused (mma.sync)"}.get(a.nn, "cuDNN " + a.precision)
     # what the arithmetic is: operand type of the convolutions / head GEMM + accumulator type
-    dtype = {"bf16x2": "bf16x2-split operands (16 significant bits) + f32 accumulate", "fp16": "f16 operands + f32 accumulate",
+    dtype = {"bf16x2": "bf16x2-split operands (16 significant bits) + f32 accumulate",
+             "fp16x2": "f16x2-split operands (22 significant bits) + f32 accumulate", "fp16": "f16 operands + f32 accumulate",
              "bf16": "bf16 operands + f32 accumulate", "cudnn-bf16": "bf16 (autocast)", "tf32": "tf32", "fp32": "f32"}[a.precision]
 
     sel_events, nn_events = [], []
@@ -631,7 +632,7 @@ def main():
     if a.nn != "cudnn" and not a.tree_only and not a.no_alt:
         if a.nn == "tc":
             alt_prec = {}
-            for prec in ("bf16x2", "fp16", "bf16"):
+            for prec in ("bf16x2", "fp16x2", "fp16", "bf16"):
                 if prec == a.precision:
                     continue
                 d3 = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=prec, skip_terminal=not a.eval_terminal)

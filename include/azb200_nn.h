@@ -61,15 +61,19 @@ int azb_nn_tc_layer_bytes(void);
 int azb_nn_tc_head_row_stride(void);
 int azb_nn_tc_boards_per_cta(void);
 int azb_nn_tc_frame_rows_per_board(void);
-/* ---- generic tcgen05 evaluator (csrc/azb_resnet_g.cu): boards up to 7x7, 32 or 64 trunk channels, any action
+/* ---- generic tcgen05 evaluator (csrc/azb_resnet_g.cu): boards up to 7x7, 32 / 64 / 128 trunk channels, any action
  * size, at the reference's numerics.  Replaces NNetWrapper.process (alphazero/NNetWrapper.py:225-232) for the ResNet of
  * alphazero/NNetArchitecture.py:69-120 with the presets of Coach.py:103-116 (32 ch), envs/hnefatafl/train_brandubh.py:50-55
- * (64 ch, 7x7, 588 actions).  Operand precision of the convolutions and the head GEMM (accumulation is always fp32):
+ * (64 ch, 7x7, 588 actions), envs/connect4/train.py:44-49 (128 ch x 8 blocks).  Operand precision of the convolutions and the head GEMM (accumulation is always fp32):
  *   AZB_NN_BF16X2  every operand as hi + lo bf16 (16 significant bits; TF32 -- what cuDNN gives the reference -- has
  *                  11), a.w = a_hi.w_hi + a_hi.w_lo + a_lo.w_hi: probabilities within 1e-5 of the fp32 module.  Default.
+ *   AZB_NN_F16X2   every operand as hi + lo fp16, same three products: 22 significant bits for |v| >= 0.03 (below, the
+ *                  low part is a subnormal fp16: absolute error 6e-8), |v| saturates at 65504.  Default of the
+ *                  128-channel network (envs/connect4/train.py:44-49), where 17 layers of K = 1152 leave BF16X2 at the
+ *                  edge of 1e-5.
  *   AZB_NN_F16     fp16 operands (11 significant bits = TF32's), one pass; activations saturate at 65504.
  *   AZB_NN_BF16    bf16 operands (8 bits), one pass.                                                              */
-enum { AZB_NN_BF16 = 0, AZB_NN_F16 = 1, AZB_NN_BF16X2 = 2 };
+enum { AZB_NN_BF16 = 0, AZB_NN_F16 = 1, AZB_NN_BF16X2 = 2, AZB_NN_F16X2 = 3 };
 
 typedef struct azb_nng_net {
     int32_t channels, depth, in_channels, board_h, board_w, action_size;
@@ -79,9 +83,12 @@ typedef struct azb_nng_net {
     int32_t head_ntiles;    /* head_nt * head_ntiles >= action_size + 3                                       */
     int32_t head_kc;        /* head K in 8-element chunks, >= H*W*channels/8, multiple of layout[4]           */
     int32_t reserved;
-    const void *wtrunk;     /* device, slab stream: slab s at s * layout[2] bytes; slab 0 = stem               */
+    const void *wtrunk;     /* device, slab stream: slab s at s * layout[2] bytes.  32 / 64 channels: slab 0 = stem    */
                             /*   [part][4 K chunks: dy=-1,0,+1,zero][3*channels][8 cin], the others, layer by     */
-                            /*   layer, [part][dy in slab][cin/8][dx*channels + cout][8 cin]; part = hi, lo        */
+                            /*   layer, [part][dy in slab][cin/8][dx*channels + cout][8 cin]; part = hi, lo.       */
+                            /*   128 channels: stem slabs dx = -1, 0, +1 as [part][4 K chunks: dy=-1,0,zero,+1]    */
+                            /*   [cout][8 cin], then per layer 36 slabs (tap = 3(dy+1)+(dx+1), kq):                */
+                            /*   [part][4 K chunks = cin/8 in 4kq..4kq+3][cout][8 cin]                             */
     const float *cbias;     /* device f32 [1+2*depth][channels] (folded BN shift; 0 for conv2)                 */
     const float *bn_scale;  /* device f32 [max(depth,1)][channels]: BN1 of every block                         */
     const float *bn_shift;
@@ -93,8 +100,9 @@ typedef struct azb_nng_net {
                             /*   fit one 16-wide tile                                                            */
 } azb_nng_net;
 
-/* out[0] = operand parts, out[1] = vertical taps per weight slab, out[2] = slab bytes, out[3] = boards per CTA,
- * out[4] = head K-chunk granularity, out[5] = max depth.  -1: unsupported channels / precision. */
+/* out[0..7] = operand parts, vertical taps per weight slab (0: the 128-channel kernel, one slab per tap and 32 input
+ * channels), slab bytes, boards per CTA, head K-chunk granularity, max depth, weight slabs per trunk layer, weight slabs
+ * of the stem.  -1: unsupported channels / precision. */
 int azb_nng_layout(int32_t channels, int32_t precision, int32_t *out);
 /* obs f32 [batch, C, H, W] -> policy f32 [batch, A], value f32 [batch, 3] (probabilities).  rows / count (both or
  * neither): compact evaluation of boards rows[0 .. *count) as azb_nn_forward_tc_rows, batch = upper bound.

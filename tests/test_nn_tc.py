@@ -5,7 +5,8 @@ azb200.nnet, state_dict-compatible, checked equal to the reference's own module 
 strict fp32 (no TF32), i.e. NNetWrapper.process (NNetWrapper.py:225-232).
 
 Stated tolerances on probabilities (absolute):
-  bf16x2  1e-5   the north star's bound -- the default precision of every product path
+  bf16x2  1e-5   the north star's bound -- the default precision of every product path (32 / 64 channels)
+  fp16x2  1e-5   the same, default for the 128-channel network
   fp16    max(2 x the error of cuDNN's TF32 evaluation of the same boards, 1e-4): TF32-class (11-bit significand)
   bf16    3e-2   performance mode
 CPU half: the folded operand layouts, decoded again, reproduce the module in float64."""
@@ -22,6 +23,9 @@ GEOMS = {
     "brandubh": dict(obs=(5, 7, 7), A=588, args=aznet.BRANDUBH_TRAIN_NET_ARGS),
     "brandubh32": dict(obs=(5, 7, 7), A=588, args=aznet.DEFAULT_NET_ARGS),
     "connect4_64": dict(obs=(4, 6, 7), A=7, args=aznet.BRANDUBH_TRAIN_NET_ARGS),
+    # envs/connect4/train.py:44-49 (128 channels x 8 blocks): k_trunk_wide; the same trunk on a 7x7 board with 588 actions
+    "connect4_train": dict(obs=(4, 6, 7), A=7, args=aznet.CONNECT4_TRAIN_NET_ARGS),
+    "brandubh128": dict(obs=(5, 7, 7), A=588, args=aznet.CONNECT4_TRAIN_NET_ARGS),
 }
 
 
@@ -67,8 +71,8 @@ def _want(m, obs):
     return lp.exp(), lv.exp()
 
 
-@pytest.mark.parametrize("geom", ["connect4", "brandubh"])
-@pytest.mark.parametrize("precision", ["bf16x2", "fp16"])
+@pytest.mark.parametrize("geom", ["connect4", "brandubh", "connect4_train"])
+@pytest.mark.parametrize("precision", ["bf16x2", "fp16x2", "fp16"])
 def test_folded_operand_layouts_reproduce_the_module(geom, precision):
     """Decode wtrunk / whead exactly as the kernel addresses them and evaluate in float64."""
     m = _model(geom)
@@ -79,13 +83,29 @@ def test_folded_operand_layouts_reproduce_the_module(geom, precision):
     parts, dys, c8, nacc = lay["parts"], lay["dys"], ch // 8, 3 * ch
     wt = f["wtrunk"].double()
 
+    def wide_stem_w():                                  # k_trunk_wide: slab j = dx, K chunks (dy=-1, dy=0, zero, dy=+1)
+        sp = 4 * ch * 8
+        w = torch.stack([sum(wt[j, p * sp:(p + 1) * sp] for p in range(parts)).view(4, ch, 8) for j in range(3)])
+        assert bool((w[:, 2] == 0).all())
+        return w[:, [0, 1, 3]][..., :cin].permute(2, 3, 1, 0)                             # [dx][dy][cout][cin] -> [cout][cin][dy][dx]
+
+    def wide_layer_w(l):                                # slab (tap, kq): [4 K chunks][cout][8]
+        sp = 4 * ch * 8
+        s0 = 3 + (l - 1) * 36
+        w = sum(wt[s0:s0 + 36, p * sp:(p + 1) * sp] for p in range(parts)).view(3, 3, c8 // 4, 4, ch, 8)
+        return w.permute(4, 2, 3, 5, 0, 1).reshape(ch, ch, 3, 3)                          # [cout][cin][dy][dx]
+
     def stem_w():
+        if dys == 0:
+            return wide_stem_w()
         sp = 4 * nacc * 8
         w = sum(wt[0, p * sp:(p + 1) * sp] for p in range(parts)).view(4, 3, ch, 8)       # [dy][dx][cout][cin]
         assert bool((w[3] == 0).all())
         return w[:3, :, :, :cin].permute(2, 3, 0, 1)                                      # [cout][cin][dy][dx]
 
     def layer_w(l):
+        if dys == 0:
+            return wide_layer_w(l)
         sp = dys * c8 * nacc * 8
         per = 3 // dys
         rows = []
@@ -95,7 +115,7 @@ def test_folded_operand_layouts_reproduce_the_module(geom, precision):
         w = torch.cat(rows, 0)                                                            # [dy][cin/8][dx][cout][8]
         return w.permute(3, 1, 4, 0, 2).reshape(ch, ch, 3, 3)
 
-    x = _obs(geom, 8).double()
+    x = _obs(geom, 4 if ch == 128 else 8).double()
     b = lambda v: v.double().view(1, -1, 1, 1)
     t = torch.relu(F.conv2d(x, stem_w(), padding=1) + b(f["cbias"][0]))
     for i in range(depth):
@@ -113,13 +133,13 @@ def test_folded_operand_layouts_reproduce_the_module(geom, precision):
         lp, lv = m.double()(x)
     want = torch.cat([lp.exp(), lv.exp()], 1)
     # only the rounding of the weights to 16 (bf16x2) / 11 (fp16) significant bits separates the two
-    tol = 2e-6 if precision == "bf16x2" else 2e-4
+    tol = 2e-4 if precision == "fp16" else 2e-6
     assert (got - want).abs().max().item() < tol
     assert bool((wh[A + 3:] == 0).all())
 
 
 def _tol(precision, m, obs, want):
-    if precision == "bf16x2":
+    if precision in ("bf16x2", "fp16x2"):
         return 1e-5
     if precision == "bf16":
         return 3e-2
@@ -146,8 +166,8 @@ def _run(geom, batch, precision, sharpen=1.0, depth=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("geom", ["connect4", "brandubh", "brandubh32", "connect4_64"])
-@pytest.mark.parametrize("precision", ["bf16x2", "fp16", "bf16"])
+@pytest.mark.parametrize("geom", ["connect4", "brandubh", "brandubh32", "connect4_64", "connect4_train", "brandubh128"])
+@pytest.mark.parametrize("precision", ["bf16x2", "fp16x2", "fp16", "bf16"])
 @pytest.mark.parametrize("batch", [6, 1000])
 def test_evaluator_matches_the_fp32_module(geom, precision, batch):
     m, obs, pol, val, _ = _run(geom, batch, precision)
@@ -161,12 +181,12 @@ def test_evaluator_matches_the_fp32_module(geom, precision, batch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("geom,batch", [("connect4", 8192), ("brandubh", 4096)])
+@pytest.mark.parametrize("geom,batch", [("connect4", 8192), ("brandubh", 4096), ("connect4_train", 8192)])
 def test_default_precision_at_baseline_sizes_and_peaked_outputs(geom, batch):
     """BASELINE batch sizes, heads sharpened x8 so that the probabilities are peaked like a trained network's:
     the default precision stays within 1e-5 of the fp32 module."""
     m, obs, pol, val, ev = _run(geom, batch, None, sharpen=8.0)
-    assert ev.precision == "bf16x2"
+    assert ev.precision == ("fp16x2" if geom == "connect4_train" else "bf16x2")
     want = _want(m, obs)
     assert want[0].max().item() > 2.0 / GEOMS[geom]["A"]            # visibly non-uniform
     ep, evl = (pol - want[0]).abs().max().item(), (val - want[1]).abs().max().item()
@@ -174,8 +194,28 @@ def test_default_precision_at_baseline_sizes_and_peaked_outputs(geom, batch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("geom", ["connect4", "brandubh"])
-@pytest.mark.parametrize("depth", [0, 1, 4])
+def test_wide_network_precisions_against_the_exact_network():
+    """Why the 128-channel network defaults to fp16x2: 17 layers of K = 1152 with x8-sharpened heads, every split
+    precision against the module in float64 (the exact network) next to the fp32 module's own distance to it."""
+    dev = torch.device("cuda")
+    batch, errs = 2048, {}
+    for prec in ("fp16x2", "bf16x2"):
+        m, obs, pol, val, _ = _run("connect4_train", batch, prec, sharpen=8.0)
+        want = _want(m, obs)
+        with torch.no_grad():
+            lp, lv = m.double()(obs.double())
+        exact = (lp.exp(), lv.exp())
+        errs[prec] = max((pol.double() - exact[0]).abs().max().item(), (val.double() - exact[1]).abs().max().item())
+        errs["fp32 module"] = max((want[0].double() - exact[0]).abs().max().item(), (want[1].double() - exact[1]).abs().max().item())
+    print("connect4_train x8-sharpened, max |dp| against float64:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["fp16x2"] < 1e-5, errs                 # measured 7.7e-6 (what is left is the accumulation itself)
+    assert errs["bf16x2"] < 3e-5, errs                 # measured 1.07e-5: at the edge, hence not this network's default
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom,depth", [("connect4", 0), ("connect4", 1), ("connect4", 4), ("brandubh", 0), ("brandubh", 1),
+                                        ("brandubh", 4), ("connect4_train", 0), ("connect4_train", 1), ("connect4_train", 8),
+                                        ("brandubh128", 2)])
 def test_layer_by_layer(geom, depth):
     """Every epilogue (stem, conv1, conv2 of each block) against the fp32 activations of the module; reports all layers."""
     dev = torch.device("cuda")
@@ -205,7 +245,7 @@ def test_layer_by_layer(geom, depth):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("geom,batch,keep", [("connect4", 8192, 0.85), ("connect4", 1000, 0.5), ("brandubh", 300, 0.7),
-                                             ("connect4", 40, 0.0)])
+                                             ("connect4", 40, 0.0), ("connect4_train", 1000, 0.6)])
 def test_compact_rows_equal_dense(geom, batch, keep):
     """rows / count: the listed rows get bit-identical answers to the dense evaluation, the others are left untouched;
     the row count is read from device memory."""
