@@ -36,7 +36,7 @@ def default_precision(model=None):
 class _NNGNet(C.Structure):
     _fields_ = [("channels", C.c_int32), ("depth", C.c_int32), ("in_channels", C.c_int32), ("board_h", C.c_int32),
                 ("board_w", C.c_int32), ("action_size", C.c_int32), ("precision", C.c_int32), ("max_boards", C.c_int32),
-                ("head_nt", C.c_int32), ("head_ntiles", C.c_int32), ("head_kc", C.c_int32), ("reserved", C.c_int32),
+                ("head_nt", C.c_int32), ("head_ntiles", C.c_int32), ("head_kc", C.c_int32), ("flags", C.c_int32),
                 ("wtrunk", C.c_void_p), ("cbias", C.c_void_p), ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
                 ("whead", C.c_void_p), ("bhead", C.c_void_p), ("gact", C.c_void_p), ("logits", C.c_void_p)]
 
@@ -76,9 +76,20 @@ def layout(channels, precision):
                 layer_slabs=out[6], stem_slabs=out[7])
 
 
+NNG_PAIR = 1      # azb_nng_net.flags: CTA pairs (tcgen05 cta_group::2), include/azb200_nn.h
+
+
+def pair_default(channels):
+    """CTA pairs are the default for the 32 / 64-channel trunk kernel (AZB_NN_PAIR=0 switches them off)."""
+    import os
+    return channels in (32, 64) and os.environ.get("AZB_NN_PAIR", "1") != "0"
+
+
 @torch.no_grad()
-def fold_g(model, precision=DEFAULT_PRECISION, lay=None):
-    """-> dict of CPU tensors in the layouts of azb_nng_net (include/azb200_nn.h)."""
+def fold_g(model, precision=DEFAULT_PRECISION, lay=None, pair=False):
+    """-> dict of CPU tensors in the layouts of azb_nng_net (include/azb200_nn.h).  pair: the trunk weights in the
+    AZB_NNG_PAIR layout (every slab as two halves, CTA rank r holding the N rows [r * 3 ch / 2, (r + 1) * 3 ch / 2) of
+    every K chunk)."""
     f = _folded(model)
     ch, depth, cin, H, W = f["channels"], f["depth"], f["in_channels"], f["board_h"], f["board_w"]
     if lay is None:       # the library's constants, restated (tests compare them with azb_nng_layout)
@@ -127,6 +138,19 @@ def fold_g(model, precision=DEFAULT_PRECISION, lay=None):
                 s = 1 + (l - 1) * slabs_per_layer + j
                 for p, t in enumerate(_split(w[j * dys:(j + 1) * dys], precision)):
                     wtrunk[s, p * slab_part:(p + 1) * slab_part] = t.reshape(-1)
+    if pair:
+        assert dys != 0, "CTA pairs: 32 / 64 channels"
+        nb = nacc // 2
+        wp = torch.zeros(nslabs, 2, slab_elems // 2, dtype=edt)
+        sp = 4 * nacc * 8
+        for p in range(parts):                                             # stem: [part][4 K chunks][rows][8]
+            src = wtrunk[0, p * sp:(p + 1) * sp].view(4, nacc, 8)
+            for r in range(2):
+                wp[0, r, p * (sp // 2):(p + 1) * (sp // 2)] = src[:, r * nb:(r + 1) * nb].reshape(-1)
+        body = wtrunk[1:].view(nslabs - 1, parts * dys * c8, nacc, 8)       # [slab][part x dy x K chunk][rows][8]
+        for r in range(2):
+            wp[1:, r] = body[:, :, r * nb:(r + 1) * nb].reshape(nslabs - 1, -1)
+        wtrunk = wp.view(nslabs, slab_elems)
     # heads: [part][n tile][K chunk = pos*c8 + ch/8][row in tile][8]
     whead, bias = f["whead"], f["bhead"]                                   # [nout, pos, ch], [nout]
     nout = whead.shape[0]
@@ -149,7 +173,7 @@ class TensorCoreEvaluator:
     ``policy`` / ``value`` (engine-owned device rows).  rows / count: compact evaluation of rows[0 .. count) (device
     int32; count a tensor or a callable returning the device address of the counter)."""
 
-    def __init__(self, model, obs, policy, value, precision=None, rows=None, count=None, max_batch=None):
+    def __init__(self, model, obs, policy, value, precision=None, rows=None, count=None, max_batch=None, pair=None):
         precision = precision or default_precision(model)
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
@@ -160,7 +184,8 @@ class TensorCoreEvaluator:
         dev = obs.device
         ch = model.conv1.out_channels
         self.layout = layout(ch, precision)
-        f = fold_g(model, precision, self.layout)
+        self.pair = pair_default(ch) if pair is None else bool(pair) and ch in (32, 64)
+        f = fold_g(model, precision, self.layout, pair=self.pair)
         self.t = {k: v.to(dev).contiguous() for k, v in f.items() if torch.is_tensor(v)}
         assert obs.is_contiguous() and policy.is_contiguous() and value.is_contiguous()
         assert obs.dtype == policy.dtype == value.dtype == torch.float32
@@ -174,7 +199,8 @@ class TensorCoreEvaluator:
         fused_softmax = f["head_ntiles"] == 1 and f["head_nt"] == 16
         self.logits = None if fused_softmax else torch.zeros(self.max_batch, nout_pad, device=dev)
         self.net = _NNGNet(f["channels"], f["depth"], f["in_channels"], f["board_h"], f["board_w"], f["action_size"],
-                           PRECISIONS[precision], self.max_batch, f["head_nt"], f["head_ntiles"], f["head_kc"], 0,
+                           PRECISIONS[precision], self.max_batch, f["head_nt"], f["head_ntiles"], f["head_kc"],
+                           NNG_PAIR if self.pair else 0,
                            *(self.t[k].data_ptr() for k in ("wtrunk", "cbias", "bn_scale", "bn_shift", "whead", "bhead")),
                            self.gact.data_ptr(), self.logits.data_ptr() if self.logits is not None else None)
         self.rows, self.count = rows, count

@@ -31,6 +31,8 @@
 // (azb200/fused_nn.py): logits[B, A+3] = act[B, H W CH] . Wh^T + b as a tcgen05 GEMM with M = 128 boards per CTA,
 // bulk-copy staged operands (4-stage ring), same split arithmetic; softmax in fp32 (in the epilogue when all outputs fit
 // one N tile, else k_softmax over the logits).
+#include <cstdio>
+#include <cstdlib>
 #include "azb_tc_ptx.cuh"
 #include "../../include/azb200_nn.h"
 
@@ -42,15 +44,19 @@ constexpr int MAXD = 6, MAXL = 1 + 2 * MAXD;
 __host__ __device__ constexpr bool prec_split(int prec) { return prec == AZB_NN_BF16X2 || prec == AZB_NN_F16X2; }   // operands as hi + lo
 __host__ __device__ constexpr bool prec_f16(int prec) { return prec == AZB_NN_F16 || prec == AZB_NN_F16X2; }        // element type fp16
 
-template <int CH_, int TILES_, int PREC_, int NGROUPS_, int DYS_, int NSLOT_>
+template <int CH_, int TILES_, int PREC_, int NGROUPS_, int DYS_, int NSLOT_, bool PAIR_ = false>
 struct TrunkCfg {
     static constexpr int CH = CH_, TILES = TILES_, PREC = PREC_, NGROUPS = NGROUPS_, DYS = DYS_, NSLOT = NSLOT_;
+    // PAIR: two CTAs of a cluster run their tiles in lockstep as ONE M = 256 MMA stream (cta_group::2) issued by the
+    // leader; each CTA stages only half of the N rows of every weight chunk (NB), which takes the B operand's share of
+    // the shared-memory wavefronts per MMA from 3 CH / 4 to 3 CH / 8 -- the pipe both trunk configurations are bound by
+    static constexpr bool PAIR = PAIR_;
     static constexpr int PARTS = prec_split(PREC) ? 2 : 1;
     static constexpr bool F16 = prec_f16(PREC);
     static constexpr int C8 = CH / 8, KST = CH / 16;
     static constexpr int ROWS = TILES * 128, PADR = 16, FROWS = ROWS + 2 * PADR;
     static constexpr int PLANE = FROWS * 16, FPART = C8 * PLANE, FRAME = PARTS * FPART;
-    static constexpr int NACC = 3 * CH, WCHUNK = NACC * 16;
+    static constexpr int NACC = 3 * CH, NB = PAIR ? NACC / 2 : NACC, WCHUNK = NB * 16;       // B rows staged by this CTA
     static constexpr int SLABS = 3 / DYS;                               // weight slabs per trunk layer
     static constexpr int SLAB_PART = DYS * C8 * WCHUNK, SLAB = PARTS * SLAB_PART;
     static constexpr int STEM_PART = 4 * WCHUNK;                        // stem slab: [part][4 K chunks][NACC][8]
@@ -62,8 +68,9 @@ struct TrunkCfg {
     static constexpr uint32_t COL_X = 0, COL_P = TILES * CH;
     static constexpr int PRM_FLOATS = MAXL * CH + 2 * MAXD * CH;
     static constexpr size_t SMEM = (size_t)FRAME + (size_t)NSLOT * SLAB + (size_t)PRM_FLOATS * 4 + 40 * 8 + 64;
-    static constexpr uint32_t IDESC = umma_idesc(NACC, F16);
+    static constexpr uint32_t IDESC = umma_idesc(NACC, F16, PAIR ? 256 : 128);
     static_assert(3 % DYS == 0 && STEM_PART <= SLAB_PART && NSLOT >= SLABS, "slab geometry");
+    static_assert(!PAIR || NACC % 16 == 0, "an M = 256 MMA needs N % 16 == 0");
     static_assert(NRING >= 2 && COL_P + NRING * NACC <= 512, "tensor memory budget");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static_assert(NACC <= 256 && NACC % 16 == 0 && WARPS <= 32, "shape limits");
@@ -137,7 +144,7 @@ __device__ __forceinline__ void store_operand(const float2 (&r)[8], unsigned cha
 
 // The part of an epilogue that follows the accumulator gather: r = the convolution output of this thread's row for 16
 // channels, xv = the residual stream's 16 values (EPI_CONV2 only; rewritten for stem / conv2).
-template <class C, int EPI, bool DBG>
+template <class C, int EPI, bool DBG, bool WAIT_ST = true>
 __device__ __forceinline__ void epilogue_finish(float2 (&r)[8], uint32_t (&xv)[16], uint32_t t_x, unsigned char *dst, size_t part_stride,
                                                 size_t chunk_stride, const float *bias, const float *nsc, const float *nsh, bool live,
                                                 float *dump_row)
@@ -178,7 +185,7 @@ __device__ __forceinline__ void epilogue_finish(float2 (&r)[8], uint32_t (&xv)[1
         for (int c = 0; c < 8; c++) { r[c].x = fmaxf(r[c].x, 0.0f); r[c].y = fmaxf(r[c].y, 0.0f); }
     }
     store_operand<C>(r, dst, part_stride, chunk_stride, live, DBG ? dump_row : nullptr);
-    if (EPI != EPI_CONV1) tmem_st_wait();
+    if (WAIT_ST && EPI != EPI_CONV1) tmem_st_wait();
 }
 
 // Epilogue of one tile for 16 of its channels: this thread owns tile row q*32 + lane (= its TMEM lane) and the channels
@@ -199,7 +206,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_p, uint32_t t_x, unsign
     tmem_ld_wait();
     tc_fence_before();                    // the accumulator is in registers: hand the ring slot back to the MMA warps
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_pempty);
+    if (lane == 0) { if (C::PAIR) mbar_arrive_cluster(bar_pempty); else mbar_arrive(bar_pempty); }
     const int src_up = (lane + 31) & 31, src_dn = (lane + 1) & 31;
     float2 r[8];
 #pragma unroll
@@ -236,7 +243,8 @@ __device__ __forceinline__ void issue_slab(uint32_t frame_s, uint32_t w_s, uint3
                 const int pa = pass == 2 ? 1 : 0, pb = pass == 1 ? 1 : 0;
                 const uint64_t ad = umma_desc(row0 + (uint32_t)(pa * C::FPART + (2 * s - 1) * 128), 128u, 128u);
                 const uint64_t bd = umma_desc(w_s + (uint32_t)(pb * C::STEM_PART + 2 * s * C::WCHUNK), (uint32_t)C::WCHUNK, 128u);
-                umma_f16(d_tmem, ad, bd, C::IDESC, (s > 0 || pass > 0) ? 1u : 0u);
+                if (C::PAIR) umma_f16_pair(d_tmem, ad, bd, C::IDESC, (s > 0 || pass > 0) ? 1u : 0u);
+                else umma_f16(d_tmem, ad, bd, C::IDESC, (s > 0 || pass > 0) ? 1u : 0u);
             }
         }
     } else {
@@ -251,7 +259,8 @@ __device__ __forceinline__ void issue_slab(uint32_t frame_s, uint32_t w_s, uint3
                     const uint64_t ad = umma_desc(row0 + (uint32_t)(pa * C::FPART + 2 * ks * C::PLANE + dy * 128), (uint32_t)C::PLANE, 128u);
                     const uint64_t bd = umma_desc(w_s + (uint32_t)(pb * C::SLAB_PART + (dl * C::C8 + 2 * ks) * C::WCHUNK),
                                                   (uint32_t)C::WCHUNK, 128u);
-                    umma_f16(d_tmem, ad, bd, C::IDESC, (j > 0 || dl > 0 || ks > 0 || pass > 0) ? 1u : 0u);
+                    if (C::PAIR) umma_f16_pair(d_tmem, ad, bd, C::IDESC, (j > 0 || dl > 0 || ks > 0 || pass > 0) ? 1u : 0u);
+                    else umma_f16(d_tmem, ad, bd, C::IDESC, (j > 0 || dl > 0 || ks > 0 || pass > 0) ? 1u : 0u);
                 }
             }
         }
@@ -287,18 +296,24 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 40);
     uint32_t *cnts = tmem_slot + 4;
 
+    // pair mode: PEMPTY / READY / TURN / WFULLP are the LEADER's (rank 0; both CTAs' epilogue warps arrive there, the
+    // peer's weight relay arrives on WFULLP); PFULL / WEMPTY exist in both CTAs and are signalled by multicast commits
     enum { BAR_PFULL = 0, BAR_PEMPTY = BAR_PFULL + C::NRING, BAR_READY = BAR_PEMPTY + C::NRING,
            BAR_WFULL = BAR_READY + C::TILES, BAR_WEMPTY = BAR_WFULL + C::NSLOT, BAR_TURN = BAR_WEMPTY + C::NSLOT,
-           NBARS = BAR_TURN + 3 };
+           BAR_WFULLP = BAR_TURN + 3, NBARS = BAR_WFULLP + C::NSLOT };
     static_assert(NBARS <= 40, "barrier storage");
 
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     if (rows != nullptr) B = *count_ptr;                 // compact mode: the batch size lives in device memory
-    const TileShare sh = tile_share(B, C::TILES, sms);
-    if ((int)blockIdx.x >= sh.nct) return;
-    const int tiles = sh.base + ((int)blockIdx.x < sh.extra ? 1 : 0);
-    const int tile0 = (int)blockIdx.x * sh.base + ((int)blockIdx.x < sh.extra ? (int)blockIdx.x : sh.extra);
-    const int board0 = 2 * tile0;
+    // tile (two boards) t of this CTA is global tile tbase + tstride * t.  Pair mode deals PAIRS of tiles to pairs of CTAs
+    // (the two CTAs of a cluster run the same number of tiles in lockstep): the CTA of rank r takes the r-th of every pair
+    const uint32_t rank = C::PAIR ? cluster_ctarank() : 0u;
+    const int unit = C::PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const TileShare sh = tile_share(C::PAIR ? (B + 1) / 2 : B, C::TILES, C::PAIR ? sms / 2 : sms);
+    if (unit >= sh.nct) return;                          // the whole cluster leaves
+    const int tiles = sh.base + (unit < sh.extra ? 1 : 0);
+    const int unit0 = unit * sh.base + (unit < sh.extra ? unit : sh.extra);
+    const int tbase = C::PAIR ? 2 * unit0 + (int)rank : unit0, tstride = C::PAIR ? 2 : 1;
     const int layers = 1 + 2 * depth, total = layers * tiles;
     const int nissue = tiles < C::NISSUE ? tiles : C::NISSUE;
     const uint32_t bar0 = smem_u32(bars), frame_s = smem_u32(frame), wb_s = smem_u32(wb);
@@ -306,9 +321,12 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int i = 0; i < C::NRING; i++) { mbar_init(BAR(BAR_PFULL + i), 1); mbar_init(BAR(BAR_PEMPTY + i), C::GW); }
-            for (int i = 0; i < C::TILES; i++) mbar_init(BAR(BAR_READY + i), C::GW);
-            for (int i = 0; i < C::NSLOT; i++) { mbar_init(BAR(BAR_WFULL + i), 1); mbar_init(BAR(BAR_WEMPTY + i), (uint32_t)nissue); }
+            constexpr uint32_t EW = C::PAIR ? 2 * C::GW : C::GW;      // epilogue warps arriving on a leader barrier
+            for (int i = 0; i < C::NRING; i++) { mbar_init(BAR(BAR_PFULL + i), 1); mbar_init(BAR(BAR_PEMPTY + i), EW); }
+            for (int i = 0; i < C::TILES; i++) mbar_init(BAR(BAR_READY + i), EW);
+            for (int i = 0; i < C::NSLOT; i++) {
+                mbar_init(BAR(BAR_WFULL + i), 1); mbar_init(BAR(BAR_WEMPTY + i), (uint32_t)nissue); mbar_init(BAR(BAR_WFULLP + i), 1);
+            }
             // the MMAs of a tile enter the tensor pipe back to back and in tile order: issuer w waits for TURN[w], which the
             // issuer of the previous tile arrives on (an mbarrier wait parks the thread; a polled shared-memory word takes
             // wavefronts of the shared-memory pipe away from the MMA operand reads the kernel is bound by)
@@ -318,7 +336,7 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
             mbar_arrive(BAR(BAR_TURN));                       // tile 0 may go
         }
         __syncwarp();
-        tmem_alloc<512>(smem_u32(tmem_slot));
+        if (C::PAIR) tmem_alloc_pair<512>(smem_u32(tmem_slot)); else tmem_alloc<512>(smem_u32(tmem_slot));
     }
     {   // zero the frame (padding rows / columns must read as zero), stage the per-channel parameters
         uint4 *z = reinterpret_cast<uint4 *>(frame);
@@ -331,15 +349,18 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     }
     tc_fence_before();
     __syncthreads();
+    if (C::PAIR) cluster_sync_all();                     // the peer's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t lead0 = C::PAIR ? map_to_rank(bar0, 0u) : bar0;      // the leader's barrier block
+#define LBAR(i) (lead0 + 8u * (uint32_t)(i))
     const float *s_bias = prm, *s_sc = prm + MAXL * C::CH, *s_sh = prm + MAXL * C::CH + MAXD * C::CH;
 
     // observation -> chunk plane 0 (channels >= in_ch stay zero)
     const int HW = H * W;
     for (int i = tid; i < tiles * 2 * HW; i += C::THREADS) {
         const int bl = i / HW, pos = i - bl * HW, y = pos / W, xx = pos - y * W;
-        int gb = board0 + bl;
+        int gb = 2 * (tbase + tstride * (bl >> 1)) + (bl & 1);
         const bool have = gb < B;
         if (have && rows != nullptr) gb = rows[gb];
         float2 c[4];
@@ -372,15 +393,20 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     const int nslabs = 1 + (layers - 1) * C::SLABS;
     if (warp < 3) {
         // ---- MMA issuers: warp k feeds the tiles g = k, k + nissue, ... (g = layer * tiles + tile) ---------------
-        if (warp < nissue && elect_one_sync()) {
+        if (warp < nissue && rank == 0 && elect_one_sync()) {
             int l = warp / tiles, t = warp - l * tiles, seen = 0, turn = 0;
             const uint32_t my_turn = BAR(BAR_TURN + warp), next_turn = BAR(BAR_TURN + (warp + 1 == nissue ? 0 : warp + 1));
 #pragma unroll 1
             for (int g = warp; g < total; g += nissue) {
                 const int slot = g % C::NRING, use = g / C::NRING;
                 const uint32_t d_tmem = tmem_base + C::COL_P + (uint32_t)(slot * C::NACC);
-                if (l > 0) mbar_wait(BAR(BAR_READY + t), (uint32_t)((l - 1) & 1));         // my tile's previous epilogue
-                if (use > 0) mbar_wait(BAR(BAR_PEMPTY + slot), (uint32_t)((use - 1) & 1));  // ring slot drained
+                if (C::PAIR) {
+                    if (l > 0) mbar_wait_cluster(BAR(BAR_READY + t), (uint32_t)((l - 1) & 1));
+                    if (use > 0) mbar_wait_cluster(BAR(BAR_PEMPTY + slot), (uint32_t)((use - 1) & 1));
+                } else {
+                    if (l > 0) mbar_wait(BAR(BAR_READY + t), (uint32_t)((l - 1) & 1));         // my tile's previous epilogue
+                    if (use > 0) mbar_wait(BAR(BAR_PEMPTY + slot), (uint32_t)((use - 1) & 1));  // ring slot drained
+                }
                 tc_fence_after();
                 mbar_wait(my_turn, (uint32_t)(turn & 1));
                 turn++;
@@ -389,27 +415,43 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
 #pragma unroll 1
                 for (int j = 0; j < ns; j++) {
                     const int s = s0 + j, ws = s % C::NSLOT;
-                    if (s >= seen) { mbar_wait(BAR(BAR_WFULL + ws), (uint32_t)((s / C::NSLOT) & 1)); seen = s + 1; tc_fence_after(); }
+                    if (s >= seen) {
+                        mbar_wait(BAR(BAR_WFULL + ws), (uint32_t)((s / C::NSLOT) & 1));
+                        if (C::PAIR) mbar_wait_cluster(BAR(BAR_WFULLP + ws), (uint32_t)((s / C::NSLOT) & 1));   // the peer's half
+                        seen = s + 1;
+                        tc_fence_after();
+                    }
                     issue_slab<C>(frame_s, wb_s + (uint32_t)(ws * C::SLAB), d_tmem, t, l, j);
-                    if (my_last) umma_commit(BAR(BAR_WEMPTY + ws));
+                    if (my_last) { if (C::PAIR) umma_commit_pair(BAR(BAR_WEMPTY + ws)); else umma_commit(BAR(BAR_WEMPTY + ws)); }
                 }
-                umma_commit(BAR(BAR_PFULL + slot));
+                if (C::PAIR) umma_commit_pair(BAR(BAR_PFULL + slot)); else umma_commit(BAR(BAR_PFULL + slot));
                 mbar_arrive_relaxed(next_turn);
                 t += nissue;
                 while (t >= tiles) { t -= tiles; l++; }
             }
         }
+        // ---- peer CTA of a pair: tell the leader when MY half of a weight slab has landed ------------------------------
+        if (C::PAIR && warp == 0 && rank == 1 && elect_one_sync()) {
+#pragma unroll 1
+            for (int s = 0; s < nslabs; s++) {
+                const int ws = s % C::NSLOT;
+                mbar_wait(BAR(BAR_WFULL + ws), (uint32_t)((s / C::NSLOT) & 1));
+                mbar_arrive_cluster(LBAR(BAR_WFULLP + ws));
+            }
+        }
         __syncwarp();
     } else if (warp == 3) {
-        // ---- weight producer ------------------------------------------------------------------------------------
+        // ---- weight producer (pair mode: each CTA streams its own half of every slab: [slab][rank][...]) --------------
         if (elect_one_sync()) {
+            const unsigned char *wsrc = wtrunk + (C::PAIR ? (size_t)rank * C::SLAB : 0);
+            const size_t wstride = C::PAIR ? 2 * (size_t)C::SLAB : (size_t)C::SLAB;
 #pragma unroll 1
             for (int s = 0; s < nslabs; s++) {
                 const int ws = s % C::NSLOT, use = s / C::NSLOT;
                 if (use > 0) mbar_wait(BAR(BAR_WEMPTY + ws), (uint32_t)((use - 1) & 1));
                 const uint32_t bytes = s == 0 ? (uint32_t)(C::PARTS * C::STEM_PART) : (uint32_t)C::SLAB;
                 mbar_expect_tx(BAR(BAR_WFULL + ws), bytes);
-                bulk_g2s(wb_s + (uint32_t)(ws * C::SLAB), wtrunk + (size_t)s * C::SLAB, bytes, BAR(BAR_WFULL + ws));
+                bulk_g2s(wb_s + (uint32_t)(ws * C::SLAB), wsrc + (size_t)s * wstride, bytes, BAR(BAR_WFULL + ws));
             }
         }
         __syncwarp();
@@ -427,7 +469,7 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
             const bool is_c1 = (l & 1) == 1, last = l + 1 == layers;
             const uint32_t t_p = tmem_base + lane_off + C::COL_P + (uint32_t)(slot * C::NACC + 16 * cg);
             const uint32_t t_x = tmem_base + lane_off + C::COL_X + (uint32_t)(C::CH * t + 16 * cg);
-            const int brd = board0 + 2 * t + (r0 >> 6);                 // (compact) board index of this row
+            const int brd = 2 * (tbase + tstride * t) + (r0 >> 6);       // (compact) board index of this row
             const bool live = live_pos && brd < B;
             unsigned char *dst;
             size_t part_stride, chunk_stride;
@@ -448,26 +490,28 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
             const int ho = 16 * cg;
             if (l == 0) {
                 epilogue_tile<C, EPI_STEM, DBG>(t_p, t_x, dst, part_stride, chunk_stride, s_bias + ho, depth > 0 ? s_sc + ho : nullptr,
-                                                s_sh + ho, live, lane, BAR(BAR_PEMPTY + slot), dmp);
+                                                s_sh + ho, live, lane, LBAR(BAR_PEMPTY + slot), dmp);
             } else if (is_c1) {
                 epilogue_tile<C, EPI_CONV1, DBG>(t_p, t_x, dst, part_stride, chunk_stride, s_bias + l * C::CH + ho, nullptr, nullptr, live,
-                                                 lane, BAR(BAR_PEMPTY + slot), dmp);
+                                                 lane, LBAR(BAR_PEMPTY + slot), dmp);
             } else {
                 const int nblk = l >> 1;                      // the block that consumes x next
                 epilogue_tile<C, EPI_CONV2, DBG>(t_p, t_x, dst, part_stride, chunk_stride, nullptr, last ? nullptr : s_sc + nblk * C::CH + ho,
-                                                 s_sh + nblk * C::CH + ho, live, lane, BAR(BAR_PEMPTY + slot), dmp);
+                                                 s_sh + nblk * C::CH + ho, live, lane, LBAR(BAR_PEMPTY + slot), dmp);
             }
             fence_proxy_async();              // the next layer's MMAs read these rows through the async proxy
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(BAR_READY + t));
+            if (lane == 0) { if (C::PAIR) mbar_arrive_cluster(LBAR(BAR_READY + t)); else mbar_arrive(BAR(BAR_READY + t)); }
             t += C::NGROUPS;
             while (t >= tiles) { t -= tiles; l++; }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<512>(tmem_base);
+    if (C::PAIR) cluster_sync_all();                     // the leader's MMAs read the peer's shared memory until the very end
+    if (warp == 0) { if (C::PAIR) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base); }
 #undef BAR
+#undef LBAR
 }
 
 // ---- 128-channel trunk (connect4/train.py:44-49: 128 channels x 8 blocks) ---------------------------------------------
@@ -504,19 +548,31 @@ struct WideCfg {
     static_assert(PADR >= 9 + 1, "taps reach 9 frame rows beyond a tile");
 };
 
-// epilogue of one tile row for 16 channels, accumulator = the finished convolution (same cases as epilogue_tile)
+// Epilogue of one tile row for this warp's CGI 16-channel groups, accumulator = the finished convolution (same cases as
+// epilogue_tile).  The tensor-memory loads of group i + 1 are in flight while group i is processed, and the residual
+// stores are waited for once at the end: between two layers the tensor pipe idles for exactly this function.
 template <class C, int EPI, bool DBG>
-__device__ __forceinline__ void epilogue_direct(uint32_t t_p, uint32_t t_x, unsigned char *dst, size_t part_stride, size_t chunk_stride,
-                                                const float *bias, const float *nsc, const float *nsh, bool live, float *dump_row)
+__device__ __forceinline__ void epilogue_wide_row(uint32_t t_p, uint32_t t_x, unsigned char *dst, size_t part_stride, size_t chunk_stride,
+                                                  const float *bias, const float *nsc, const float *nsh, bool live, float *dump_row)
 {
-    uint32_t p0[16], xv[16];
-    tmem_ld16(t_p, p0);
-    if (EPI == EPI_CONV2) tmem_ld16(t_x, xv);
-    tmem_ld_wait();
-    float2 r[8];
+    uint32_t acc[2][16], xv[2][16];
+    tmem_ld16(t_p, acc[0]);
+    if (EPI == EPI_CONV2) tmem_ld16(t_x, xv[0]);
 #pragma unroll
-    for (int c = 0; c < 8; c++) r[c] = f2(p0[2 * c], p0[2 * c + 1]);
-    epilogue_finish<C, EPI, DBG>(r, xv, t_x, dst, part_stride, chunk_stride, bias, nsc, nsh, live, dump_row);
+    for (int i = 0; i < C::CGI; i++) {
+        tmem_ld_wait();
+        if (i + 1 < C::CGI) {
+            tmem_ld16(t_p + (uint32_t)(16 * (i + 1)), acc[(i + 1) & 1]);
+            if (EPI == EPI_CONV2) tmem_ld16(t_x + (uint32_t)(16 * (i + 1)), xv[(i + 1) & 1]);
+        }
+        float2 r[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) r[c] = f2(acc[i & 1][2 * c], acc[i & 1][2 * c + 1]);
+        epilogue_finish<C, EPI, DBG, false>(r, xv[i & 1], t_x + (uint32_t)(16 * i), dst + (size_t)(2 * i) * chunk_stride, part_stride, chunk_stride,
+                                            bias != nullptr ? bias + 16 * i : nullptr, nsc != nullptr ? nsc + 16 * i : nullptr, nsh + 16 * i, live,
+                                            DBG && dump_row != nullptr ? dump_row + 16 * i : nullptr);
+    }
+    if (EPI != EPI_CONV1) tmem_st_wait();
 }
 
 template <class C, bool DBG>
@@ -676,9 +732,8 @@ k_trunk_wide(const float *__restrict__ obs, int B, int in_ch, int H, int W, int 
                 if (within == 0) mbar_wait<32>(BAR(BAR_PFULL + t), (uint32_t)(l & 1));
                 asm volatile("bar.sync %0, %1;\n" ::"r"(1 + t), "r"(C::GW * 32) : "memory");
                 tc_fence_after();
-#pragma unroll 1
-                for (int i = 0; i < C::CGI; i++) {
-                    const int cg = cgw * C::CGI + i, ho = 16 * cg;
+                {
+                    const int cg = cgw * C::CGI, ho = 16 * cg;       // this warp's first channel group
                     const uint32_t t_p = tmem_base + lane_off + C::COL_P + (uint32_t)(C::CH * t + ho);
                     const uint32_t t_x = tmem_base + lane_off + C::COL_X + (uint32_t)(C::CH * t + ho);
                     unsigned char *dst;
@@ -695,15 +750,15 @@ k_trunk_wide(const float *__restrict__ obs, int B, int in_ch, int H, int W, int 
                     float *dmp = nullptr;
                     if (DBG && dump != nullptr && l == dump_layer && brd < B) dmp = dump + ((size_t)brd * 64 + (r0 & 63)) * C::CH + ho;
                     if (l == 0) {
-                        epilogue_direct<C, EPI_STEM, DBG>(t_p, t_x, dst, part_stride, chunk_stride, s_bias + ho, depth > 0 ? s_sc + ho : nullptr,
-                                                          s_sh + ho, live, dmp);
+                        epilogue_wide_row<C, EPI_STEM, DBG>(t_p, t_x, dst, part_stride, chunk_stride, s_bias + ho, depth > 0 ? s_sc + ho : nullptr,
+                                                            s_sh + ho, live, dmp);
                     } else if (is_c1) {
-                        epilogue_direct<C, EPI_CONV1, DBG>(t_p, t_x, dst, part_stride, chunk_stride, s_bias + l * C::CH + ho, nullptr, nullptr,
-                                                           live, dmp);
+                        epilogue_wide_row<C, EPI_CONV1, DBG>(t_p, t_x, dst, part_stride, chunk_stride, s_bias + l * C::CH + ho, nullptr, s_sh + ho,
+                                                             live, dmp);
                     } else {
                         const int nblk = l >> 1;                      // the block that consumes x next
-                        epilogue_direct<C, EPI_CONV2, DBG>(t_p, t_x, dst, part_stride, chunk_stride, nullptr,
-                                                           last ? nullptr : s_sc + nblk * C::CH + ho, s_sh + nblk * C::CH + ho, live, dmp);
+                        epilogue_wide_row<C, EPI_CONV2, DBG>(t_p, t_x, dst, part_stride, chunk_stride, nullptr,
+                                                             last ? nullptr : s_sc + nblk * C::CH + ho, s_sh + nblk * C::CH + ho, live, dmp);
                     }
                 }
                 tc_fence_before();                // accumulator and residual accesses are complete (wait::ld / wait::st inside)
@@ -720,22 +775,24 @@ k_trunk_wide(const float *__restrict__ obs, int B, int in_ch, int H, int W, int 
 }
 
 // ---- heads ---------------------------------------------------------------------------------------------------------
-constexpr int HSTAGES = 4, HKC = 4;                        // K chunks (of 8) per pipeline stage
+constexpr int HMAXST = 12, HKC = 4;                        // deepest operand ring; K chunks (of 8) per pipeline stage
 constexpr int HTHREADS = 192;
 
 template <int PREC>
 __global__ void __launch_bounds__(HTHREADS, 1)
 k_head_tc(const unsigned char *__restrict__ gact, const unsigned char *__restrict__ whead, const float *__restrict__ bhead,
           float *__restrict__ logits, float *__restrict__ policy, float *__restrict__ value, int B, const int *__restrict__ rows,
-          const int *__restrict__ count_ptr, int MT, int KC, int NT, int ntiles, int nout_pad, int A, uint32_t tmem_cols)
+          const int *__restrict__ count_ptr, int MT, int KC, int NT, int ntiles, int nout_pad, int A, uint32_t tmem_cols, int HSTAGES)
 {
     constexpr int PARTS = prec_split(PREC) ? 2 : 1;
     constexpr bool F16 = prec_f16(PREC);
     extern __shared__ __align__(128) unsigned char smem[];
     const int a_part = HKC * 128 * 16, b_part = HKC * NT * 16, stage_bytes = PARTS * (a_part + b_part);
+    // HSTAGES stages in flight: with 55 CTAs for 6960 boards the kernel is bound by the latency of its own operand stream
+    // (4 stages = 66 KB in flight per SM: 18 us; 12 stages: the HBM time of the 37 MB it reads)
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + (size_t)HSTAGES * stage_bytes);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * HSTAGES + 1);
-    enum { BAR_FULL = 0, BAR_EMPTY = HSTAGES, BAR_DONE = 2 * HSTAGES };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * HMAXST + 1);
+    enum { BAR_FULL = 0, BAR_EMPTY = HMAXST, BAR_DONE = 2 * HMAXST };
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int mt = blockIdx.x, nt = blockIdx.y;
     if (rows != nullptr) B = *count_ptr;
@@ -891,6 +948,9 @@ k_softmax(const float *__restrict__ logits, float *__restrict__ policy, float *_
 // 6960 boards in split mode; 121.3 vs 124.8 us in bf16) and leave the registers of eight warps unused
 template <int PREC> using Cfg32 = TrunkCfg<32, 7, PREC, 2, 3, prec_split(PREC) ? 2 : 3>;
 template <int PREC> using Cfg64 = TrunkCfg<64, 2, PREC, 1, 1, prec_split(PREC) ? 3 : 6>;
+// CTA pairs (AZB_NNG_PAIR): half of every weight slab per CTA, so the ring holds more of them
+template <int PREC> using Cfg32P = TrunkCfg<32, 7, PREC, 2, 3, prec_split(PREC) ? 3 : 4, true>;
+template <int PREC> using Cfg64P = TrunkCfg<64, 2, PREC, 1, 1, 6, true>;
 
 
 int sm_count()
@@ -905,6 +965,24 @@ int sm_count()
     return sms;
 }
 
+template <class K, class... Args>
+int launch_maybe_pair(K kernel, bool pair, int grid, int threads, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pair ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...) == cudaSuccess ? 0 : -2;
+}
+
 template <class C>
 int launch_trunk(const azb_nng_net *n, const float *obs, int batch, const int *rows, const int *count, cudaStream_t s, float *dump,
                  int dump_layer)
@@ -916,21 +994,40 @@ int launch_trunk(const azb_nng_net *n, const float *obs, int batch, const int *r
             return -2;
         configured = true;
     }
-    const int sms = sm_count();
+    int sms = sm_count();
     if (sms <= 0) return -2;
-    const int grid = tile_share(batch, C::TILES, sms).nct;      // compact mode: upper bound, surplus CTAs exit at once
+    if (C::PAIR) {
+        // tiles are dealt in whole waves of resident CTA pairs: ask how many clusters of two fit (a GPC with an odd number of
+        // usable SMs leaves one unpaired)
+        static int pairs = 0;
+        if (pairs == 0) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(sms & ~1));
+            cfg.blockDim = dim3((unsigned)C::THREADS);
+            cfg.dynamicSmemBytes = C::SMEM;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, k_trunk_tc<C, false>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = sms / 2; }
+            pairs = n < sms / 2 ? n : sms / 2;
+            if (getenv("AZB_NN_VERBOSE")) fprintf(stderr, "azb_nng: %d resident CTA pairs (cudaOccupancyMaxActiveClusters %d, %d SMs)\n", pairs, n, sms);
+        }
+        sms = 2 * pairs;
+    }
+    // compact mode: upper bound, surplus CTAs exit at once.  Pair mode: pairs of tiles over pairs of CTAs
+    const int grid = C::PAIR ? 2 * tile_share((batch + 1) / 2, C::TILES, sms / 2).nct : tile_share(batch, C::TILES, sms).nct;
     const int MT = (n->max_boards + 127) / 128;
+    const unsigned char *wt = reinterpret_cast<const unsigned char *>(n->wtrunk);
+    unsigned char *gact = reinterpret_cast<unsigned char *>(n->gact);
     if (dump != nullptr)
-        k_trunk_tc<C, true><<<grid, C::THREADS, C::SMEM, s>>>(obs, batch, n->in_channels, n->board_h, n->board_w, n->depth,
-                                                             reinterpret_cast<const unsigned char *>(n->wtrunk), n->cbias, n->bn_scale,
-                                                             n->bn_shift, reinterpret_cast<unsigned char *>(n->gact), MT, n->head_kc, dump,
-                                                             dump_layer, rows, count, sms);
-    else
-        k_trunk_tc<C, false><<<grid, C::THREADS, C::SMEM, s>>>(obs, batch, n->in_channels, n->board_h, n->board_w, n->depth,
-                                                              reinterpret_cast<const unsigned char *>(n->wtrunk), n->cbias, n->bn_scale,
-                                                              n->bn_shift, reinterpret_cast<unsigned char *>(n->gact), MT, n->head_kc, nullptr,
-                                                              -1, rows, count, sms);
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+        return launch_maybe_pair(k_trunk_tc<C, true>, C::PAIR, grid, C::THREADS, C::SMEM, s, obs, batch, (int)n->in_channels, (int)n->board_h,
+                                 (int)n->board_w, (int)n->depth, wt, n->cbias, n->bn_scale, n->bn_shift, gact, MT, (int)n->head_kc, dump,
+                                 dump_layer, rows, count, sms);
+    return launch_maybe_pair(k_trunk_tc<C, false>, C::PAIR, grid, C::THREADS, C::SMEM, s, obs, batch, (int)n->in_channels, (int)n->board_h,
+                             (int)n->board_w, (int)n->depth, wt, n->cbias, n->bn_scale, n->bn_shift, gact, MT, (int)n->head_kc,
+                             (float *)nullptr, -1, rows, count, sms);
 }
 
 template <class C>
@@ -966,7 +1063,12 @@ int launch_head(const azb_nng_net *n, float *policy, float *value, int batch, co
 {
     constexpr int PARTS = prec_split(PREC) ? 2 : 1;
     const int NT = n->head_nt, ntiles = n->head_ntiles, nout_pad = NT * ntiles;
-    const size_t smem = (size_t)HSTAGES * PARTS * (HKC * 128 * 16 + HKC * NT * 16) + (2 * HSTAGES + 1) * 8 + 64;
+    const size_t stage = (size_t)PARTS * (HKC * 128 * 16 + HKC * NT * 16), fixed = (2 * HMAXST + 1) * 8 + 64;
+    int stages = (int)((220 * 1024 - fixed) / stage);
+    stages = stages > HMAXST ? HMAXST : stages;
+    if (stages > n->head_kc / HKC) stages = n->head_kc / HKC;
+    if (stages < 2) return -1;
+    const size_t smem = (size_t)stages * stage + fixed;
     static size_t configured = 0;
     if (smem > configured) {
         if (cudaFuncSetAttribute(k_head_tc<PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
@@ -978,7 +1080,7 @@ int launch_head(const azb_nng_net *n, float *policy, float *value, int batch, co
     k_head_tc<PREC><<<dim3(mtiles, ntiles), HTHREADS, smem, s>>>(reinterpret_cast<const unsigned char *>(n->gact),
                                                                  reinterpret_cast<const unsigned char *>(n->whead), n->bhead, n->logits, policy,
                                                                  value, batch, rows, count, MT, n->head_kc, NT, ntiles, nout_pad, n->action_size,
-                                                                 cols);
+                                                                 cols, stages);
     if (cudaGetLastError() != cudaSuccess) return -2;
     if (!(ntiles == 1 && NT == 16)) {
         k_softmax<<<(batch + 7) / 8, 256, 0, s>>>(n->logits, policy, value, batch, rows, count, nout_pad, n->action_size);
@@ -992,8 +1094,11 @@ int forward_prec(const azb_nng_net *n, const float *obs, float *policy, float *v
                  cudaStream_t s, float *dump, int dump_layer)
 {
     int rc;
-    if (n->channels == 32) rc = launch_trunk<Cfg32<PREC>>(n, obs, batch, rows, count, s, dump, dump_layer);
-    else if (n->channels == 64) rc = launch_trunk<Cfg64<PREC>>(n, obs, batch, rows, count, s, dump, dump_layer);
+    const bool pair = (n->flags & AZB_NNG_PAIR) != 0;
+    if (n->channels == 32) rc = pair ? launch_trunk<Cfg32P<PREC>>(n, obs, batch, rows, count, s, dump, dump_layer)
+                                     : launch_trunk<Cfg32<PREC>>(n, obs, batch, rows, count, s, dump, dump_layer);
+    else if (n->channels == 64) rc = pair ? launch_trunk<Cfg64P<PREC>>(n, obs, batch, rows, count, s, dump, dump_layer)
+                                          : launch_trunk<Cfg64<PREC>>(n, obs, batch, rows, count, s, dump, dump_layer);
     else rc = launch_wide<WideCfg<PREC>>(n, obs, batch, rows, count, s, dump, dump_layer);
     if (rc != 0) return rc;
     return launch_head<PREC>(n, policy, value, batch, rows, count, s);

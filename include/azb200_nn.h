@@ -75,6 +75,10 @@ int azb_nn_tc_frame_rows_per_board(void);
  *   AZB_NN_BF16    bf16 operands (8 bits), one pass.                                                              */
 enum { AZB_NN_BF16 = 0, AZB_NN_F16 = 1, AZB_NN_BF16X2 = 2, AZB_NN_F16X2 = 3 };
 
+/* azb_nng_net.flags.  AZB_NNG_PAIR: the 32 / 64-channel trunk runs as clusters of two CTAs whose tiles advance in
+ * lockstep as one M = 256 MMA stream (tcgen05 cta_group::2), each CTA staging half of the N rows of every weight chunk. */
+enum { AZB_NNG_PAIR = 1 };
+
 typedef struct azb_nng_net {
     int32_t channels, depth, in_channels, board_h, board_w, action_size;
     int32_t precision;      /* AZB_NN_*                                                                       */
@@ -82,13 +86,15 @@ typedef struct azb_nng_net {
     int32_t head_nt;        /* head GEMM N tile (multiple of 16, <= 256)                                      */
     int32_t head_ntiles;    /* head_nt * head_ntiles >= action_size + 3                                       */
     int32_t head_kc;        /* head K in 8-element chunks, >= H*W*channels/8, multiple of layout[4]           */
-    int32_t reserved;
+    int32_t flags;          /* AZB_NNG_PAIR: wtrunk is laid out for CTA pairs (32 / 64 channels), see wtrunk            */
     const void *wtrunk;     /* device, slab stream: slab s at s * layout[2] bytes.  32 / 64 channels: slab 0 = stem    */
                             /*   [part][4 K chunks: dy=-1,0,+1,zero][3*channels][8 cin], the others, layer by     */
                             /*   layer, [part][dy in slab][cin/8][dx*channels + cout][8 cin]; part = hi, lo.       */
                             /*   128 channels: stem slabs dx = -1, 0, +1 as [part][4 K chunks: dy=-1,0,zero,+1]    */
                             /*   [cout][8 cin], then per layer 36 slabs (tap = 3(dy+1)+(dx+1), kq):                */
                             /*   [part][4 K chunks = cin/8 in 4kq..4kq+3][cout][8 cin]                             */
+                            /*   AZB_NNG_PAIR: slab s of CTA rank r at (2 s + r) * layout[2] / 2 bytes, same layouts   */
+                            /*   with the N rows [r * 3 channels / 2, (r + 1) * 3 channels / 2) of every K chunk      */
     const float *cbias;     /* device f32 [1+2*depth][channels] (folded BN shift; 0 for conv2)                 */
     const float *bn_scale;  /* device f32 [max(depth,1)][channels]: BN1 of every block                         */
     const float *bn_shift;

@@ -153,13 +153,13 @@ def _tol(precision, m, obs, want):
     return max(2 * err, 1e-4)
 
 
-def _run(geom, batch, precision, sharpen=1.0, depth=None):
+def _run(geom, batch, precision, sharpen=1.0, depth=None, pair=None):
     dev = torch.device("cuda")
     m = _model(geom, depth=depth, sharpen=sharpen).to(dev)
     obs = _obs(geom, batch).to(dev)
     A = GEOMS[geom]["A"]
     pol = torch.zeros(batch, A, device=dev); val = torch.zeros(batch, 3, device=dev)
-    ev = nn_tc.TensorCoreEvaluator(m, obs, pol, val, precision=precision)
+    ev = nn_tc.TensorCoreEvaluator(m, obs, pol, val, precision=precision, pair=pair)
     ev()
     torch.cuda.synchronize()
     return m, obs, pol, val, ev
@@ -265,3 +265,18 @@ def test_compact_rows_equal_dense(geom, batch, keep):
     mask[torch.from_numpy(sel).long().to(dev)] = True
     assert torch.equal(pol2[mask], pol[mask]) and torch.equal(val2[mask], val[mask])
     assert bool((pol2[~mask] == -1).all()) and bool((val2[~mask] == -1).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", ["connect4", "brandubh", "brandubh32", "connect4_64"])
+@pytest.mark.parametrize("precision", ["bf16x2", "fp16x2", "fp16"])
+@pytest.mark.parametrize("batch", [1, 2, 3, 6, 29, 1000, 4133])
+def test_cta_pairs_equal_single_ctas_bit_for_bit(geom, precision, batch):
+    """AZB_NNG_PAIR (two CTAs in lockstep, one M = 256 MMA stream, half of the weight rows staged per CTA) changes where
+    the operands come from, not the arithmetic: policy and value are bit-identical to the single-CTA kernel -- for batch
+    sizes that leave the peer CTA's tile half empty or empty, too."""
+    m, obs, pol, val, ev = _run(geom, batch, precision, pair=True)
+    assert ev.pair
+    m2, obs2, pol2, val2, ev2 = _run(geom, batch, precision, pair=False)
+    assert not ev2.pair
+    assert torch.equal(pol, pol2) and torch.equal(val, val2)
