@@ -147,9 +147,10 @@ def fold_g(model, precision=DEFAULT_PRECISION, lay=None, pair=False):
             src = wtrunk[0, p * sp:(p + 1) * sp].view(4, nacc, 8)
             for r in range(2):
                 wp[0, r, p * (sp // 2):(p + 1) * (sp // 2)] = src[:, r * nb:(r + 1) * nb].reshape(-1)
-        body = wtrunk[1:].view(nslabs - 1, parts * dys * c8, nacc, 8)       # [slab][part x dy x K chunk][rows][8]
-        for r in range(2):
-            wp[1:, r] = body[:, :, r * nb:(r + 1) * nb].reshape(nslabs - 1, -1)
+        if nslabs > 1:
+            body = wtrunk[1:].view(nslabs - 1, parts * dys * c8, nacc, 8)   # [slab][part x dy x K chunk][rows][8]
+            for r in range(2):
+                wp[1:, r] = body[:, :, r * nb:(r + 1) * nb].reshape(nslabs - 1, slab_elems // 2)
         wtrunk = wp.view(nslabs, slab_elems)
     # heads: [part][n tile][K chunk = pos*c8 + ch/8][row in tile][8]
     whead, bias = f["whead"], f["bhead"]                                   # [nout, pos, ch], [nout]

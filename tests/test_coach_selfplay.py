@@ -45,7 +45,7 @@ def test_warmup_iteration_matches_oracle_and_writes_reference_files(tmp_path):
     rs = np.random.RandomState(9)
     while orc.stats()["games_played"] < 100:
         fast = bool(rs.random_sample() < 0.6)
-        for _ in range(12):                      # warmup iterations always run numWarmupSims (SelfPlayAgent.pyx:85-86)
+        for _ in range(4 if fast else 12):       # numFastSims if fast else numWarmupSims (SelfPlayAgent.pyx:85-86)
             orc.generateBatch(); orc.processBatch(*warmup_outputs(64, 7))
         orc.playMoves(fast)
     o, pi, z, _ = orc.samples()

@@ -138,6 +138,30 @@ def test_folded_operand_layouts_reproduce_the_module(geom, precision):
     assert bool((wh[A + 3:] == 0).all())
 
 
+@pytest.mark.parametrize("geom,depth", [("connect4", 4), ("brandubh", 4), ("connect4", 0), ("connect4_64", 1)])
+def test_pair_layout_is_the_single_cta_layout_split_by_rows(geom, depth):
+    """AZB_NNG_PAIR: slab s of CTA rank r holds the N rows [r * 3 ch / 2, (r + 1) * 3 ch / 2) of every K chunk of slab s."""
+    m = _model(geom, depth=depth)
+    one, two = nn_tc.fold_g(m, "bf16x2"), nn_tc.fold_g(m, "bf16x2", pair=True)
+    ch, parts = one["channels"], one["parts"]
+    nacc, nb, c8 = 3 * ch, 3 * ch // 2, ch // 8
+    dys = 3 if ch == 32 else 1
+    a, b = one["wtrunk"], two["wtrunk"]
+    assert a.shape == b.shape and a.dtype == b.dtype
+    sp = 4 * nacc * 8                                                    # stem part
+    for p in range(parts):
+        full = a[0, p * sp:(p + 1) * sp].view(4, nacc, 8)
+        for r in range(2):
+            half = b[0].view(2, -1)[r, p * (sp // 2):(p + 1) * (sp // 2)].view(4, nb, 8)
+            assert torch.equal(half, full[:, r * nb:(r + 1) * nb])
+    for s in range(1, a.shape[0]):
+        full = a[s].view(parts * dys * c8, nacc, 8)
+        for r in range(2):
+            assert torch.equal(b[s].view(2, parts * dys * c8, nb, 8)[r], full[:, r * nb:(r + 1) * nb])
+    for k in ("whead", "bhead", "cbias", "bn_scale", "bn_shift"):
+        assert torch.equal(one[k], two[k])
+
+
 def _tol(precision, m, obs, want):
     if precision in ("bf16x2", "fp16x2"):
         return 1e-5
