@@ -96,6 +96,8 @@ SYMBOLS = {
     "azb_nng_layout": (C.c_int, [_i32, _i32, _vp]),
     "azb_nng_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "azb_nng_forward_debug": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32]),
+    "azb_nng_trace": (C.c_int, [_vp, _i32]),
+    "azb_nng_cta_trace": (C.c_int, [_vp, _i32]),
 }
 
 _lib = None

@@ -38,7 +38,8 @@ class _NNGNet(C.Structure):
                 ("board_w", C.c_int32), ("action_size", C.c_int32), ("precision", C.c_int32), ("max_boards", C.c_int32),
                 ("head_nt", C.c_int32), ("head_ntiles", C.c_int32), ("head_kc", C.c_int32), ("flags", C.c_int32),
                 ("wtrunk", C.c_void_p), ("cbias", C.c_void_p), ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
-                ("whead", C.c_void_p), ("bhead", C.c_void_p), ("gact", C.c_void_p), ("logits", C.c_void_p)]
+                ("whead", C.c_void_p), ("bhead", C.c_void_p), ("gact", C.c_void_p), ("logits", C.c_void_p),
+                ("h_params", C.c_void_p)]
 
 
 def supported(model):
@@ -188,6 +189,8 @@ class TensorCoreEvaluator:
         self.pair = pair_default(ch) if pair is None else bool(pair) and ch in (32, 64)
         f = fold_g(model, precision, self.layout, pair=self.pair)
         self.t = {k: v.to(dev).contiguous() for k, v in f.items() if torch.is_tensor(v)}
+        # host copy of the per-channel parameters: a kernel argument of the 32 / 64-channel trunk (azb_nng_net.h_params)
+        self.h_params = torch.cat([f["cbias"].reshape(-1), f["bn_scale"].reshape(-1), f["bn_shift"].reshape(-1)]).float().contiguous()
         assert obs.is_contiguous() and policy.is_contiguous() and value.is_contiguous()
         assert obs.dtype == policy.dtype == value.dtype == torch.float32
         self.obs, self.policy, self.value = obs, policy, value
@@ -203,7 +206,8 @@ class TensorCoreEvaluator:
                            PRECISIONS[precision], self.max_batch, f["head_nt"], f["head_ntiles"], f["head_kc"],
                            NNG_PAIR if self.pair else 0,
                            *(self.t[k].data_ptr() for k in ("wtrunk", "cbias", "bn_scale", "bn_shift", "whead", "bhead")),
-                           self.gact.data_ptr(), self.logits.data_ptr() if self.logits is not None else None)
+                           self.gact.data_ptr(), self.logits.data_ptr() if self.logits is not None else None,
+                           self.h_params.data_ptr())
         self.rows, self.count = rows, count
         if rows is not None:
             assert count is not None and rows.dtype == torch.int32

@@ -33,6 +33,7 @@
 // one N tile, else k_softmax over the logits).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include "azb_tc_ptx.cuh"
 #include "../../include/azb200_nn.h"
 
@@ -67,7 +68,7 @@ struct TrunkCfg {
     static constexpr int WARPS = EPI_WARP0 + NGROUPS * GW, THREADS = WARPS * 32;
     static constexpr uint32_t COL_X = 0, COL_P = TILES * CH;
     static constexpr int PRM_FLOATS = MAXL * CH + 2 * MAXD * CH;
-    static constexpr size_t SMEM = (size_t)FRAME + (size_t)NSLOT * SLAB + (size_t)PRM_FLOATS * 4 + 40 * 8 + 64;
+    static constexpr size_t SMEM = (size_t)FRAME + (size_t)NSLOT * SLAB + 40 * 8 + 64;
     static constexpr uint32_t IDESC = umma_idesc(NACC, F16, PAIR ? 256 : 128);
     static_assert(3 % DYS == 0 && STEM_PART <= SLAB_PART && NSLOT >= SLABS, "slab geometry");
     static_assert(!PAIR || NACC % 16 == 0, "an M = 256 MMA needs N % 16 == 0");
@@ -77,6 +78,14 @@ struct TrunkCfg {
 };
 
 enum { EPI_STEM = 0, EPI_CONV1 = 1, EPI_CONV2 = 2 };
+
+// DBG kernels only (azb_nng_forward_debug): clock64 of CTA 0's pipeline events per (layer, tile) -- [0] the tile's MMAs start
+// to issue, [1] they are committed, [2] its epilogue sees the accumulator, [3] the epilogue hands the tile on
+__device__ long long g_trace[4 * 256];
+// DBG kernels only: (SM id, %globaltimer at entry, at exit) of every CTA with blockIdx.x < 2048
+__device__ long long g_cta_trace[3 * 2048];
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t)); return t; }
+__device__ __forceinline__ int sm_id() { int v; asm volatile("mov.u32 %0, %%smid;\n" : "=r"(v)); return v; }
 
 __device__ __forceinline__ float2 f2(uint32_t lo, uint32_t hi) { return make_float2(__uint_as_float(lo), __uint_as_float(hi)); }
 __device__ __forceinline__ uint32_t bf2_bits(__nv_bfloat162 h) { return *reinterpret_cast<uint32_t *>(&h); }
@@ -142,17 +151,40 @@ __device__ __forceinline__ void store_operand(const float2 (&r)[8], unsigned cha
     }
 }
 
+// Per-channel parameters of the epilogues (folded-BN bias of stem / conv1, BN1 scale and shift of every block).  The
+// 32 / 64-channel kernel takes them BY VALUE as a kernel argument (constant bank): ncu's per-instruction accounting showed
+// the float4 parameter loads from shared memory (12 LDS.128 per warp, tile and layer, two wavefronts each) to be 22 % of the
+// LSU wavefronts on the very pipe the MMA operand reads saturate; LDC goes through the constant cache instead.
+template <int CH>
+struct NetParams {
+    float bias[MAXL * CH], sc[MAXD * CH], sh[MAXD * CH];
+};
+template <int CH>
+struct ConstPrm {                              // view of a __grid_constant__ NetParams
+    const NetParams<CH> &p;
+    __device__ __forceinline__ float4 bias(int off, int c) const { return make_float4(p.bias[off + 4 * c], p.bias[off + 4 * c + 1], p.bias[off + 4 * c + 2], p.bias[off + 4 * c + 3]); }
+    __device__ __forceinline__ float4 scale(int off, int c) const { return make_float4(p.sc[off + 4 * c], p.sc[off + 4 * c + 1], p.sc[off + 4 * c + 2], p.sc[off + 4 * c + 3]); }
+    __device__ __forceinline__ float4 shift(int off, int c) const { return make_float4(p.sh[off + 4 * c], p.sh[off + 4 * c + 1], p.sh[off + 4 * c + 2], p.sh[off + 4 * c + 3]); }
+};
+struct SmemPrm {                               // the three arrays staged in shared memory (128-channel kernel)
+    const float *b, *s, *h;
+    __device__ __forceinline__ float4 bias(int off, int c) const { return reinterpret_cast<const float4 *>(b + off)[c]; }
+    __device__ __forceinline__ float4 scale(int off, int c) const { return reinterpret_cast<const float4 *>(s + off)[c]; }
+    __device__ __forceinline__ float4 shift(int off, int c) const { return reinterpret_cast<const float4 *>(h + off)[c]; }
+};
+
 // The part of an epilogue that follows the accumulator gather: r = the convolution output of this thread's row for 16
 // channels, xv = the residual stream's 16 values (EPI_CONV2 only; rewritten for stem / conv2).
-template <class C, int EPI, bool DBG, bool WAIT_ST = true>
+// boff: offset of this thread's 16 bias values (stem / conv1); soff: of its 16 BN1 scale / shift values, < 0: no BN + ReLU
+// after the residual update (the last block hands x itself to the heads; depth 0: the stem does)
+template <class C, int EPI, bool DBG, bool WAIT_ST = true, class PV>
 __device__ __forceinline__ void epilogue_finish(float2 (&r)[8], uint32_t (&xv)[16], uint32_t t_x, unsigned char *dst, size_t part_stride,
-                                                size_t chunk_stride, const float *bias, const float *nsc, const float *nsh, bool live,
-                                                float *dump_row)
+                                                size_t chunk_stride, const PV &pv, int boff, int soff, bool live, float *dump_row)
 {
     if (EPI != EPI_CONV2) {
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const float4 b4 = reinterpret_cast<const float4 *>(bias)[c];
+            const float4 b4 = pv.bias(boff, c);
             r[2 * c] = __fadd2_rn(r[2 * c], make_float2(b4.x, b4.y));
             r[2 * c + 1] = __fadd2_rn(r[2 * c + 1], make_float2(b4.z, b4.w));
         }
@@ -172,11 +204,11 @@ __device__ __forceinline__ void epilogue_finish(float2 (&r)[8], uint32_t (&xv)[1
         }
         tmem_st16(t_x, xv);
     }
-    if (EPI == EPI_CONV1 || nsc != nullptr) {
+    if (EPI == EPI_CONV1 || soff >= 0) {
         if (EPI != EPI_CONV1) {
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                const float4 s4 = reinterpret_cast<const float4 *>(nsc)[c], h4 = reinterpret_cast<const float4 *>(nsh)[c];
+                const float4 s4 = pv.scale(soff, c), h4 = pv.shift(soff, c);
                 r[2 * c] = __ffma2_rn(r[2 * c], make_float2(s4.x, s4.y), make_float2(h4.x, h4.y));
                 r[2 * c + 1] = __ffma2_rn(r[2 * c + 1], make_float2(s4.z, s4.w), make_float2(h4.z, h4.w));
             }
@@ -193,10 +225,9 @@ __device__ __forceinline__ void epilogue_finish(float2 (&r)[8], uint32_t (&xv)[1
 //   stem : x = relu(D + bias) -> TMEM;  a = relu(bn1_0(x))      (depth 0: a = x)
 //   conv1: b = relu(D + bias)                                   (BN2 folded into conv1)
 //   conv2: x += D -> TMEM;  a = relu(bn1_next(x))               (last block: a = x, the head input)
-template <class C, int EPI, bool DBG>
+template <class C, int EPI, bool DBG, class PV>
 __device__ __forceinline__ void epilogue_tile(uint32_t t_p, uint32_t t_x, unsigned char *dst, size_t part_stride, size_t chunk_stride,
-                                              const float *bias, const float *nsc, const float *nsh, bool live, int lane,
-                                              uint32_t bar_pempty, float *dump_row)
+                                              const PV &pv, int boff, int soff, bool live, int lane, uint32_t bar_pempty, float *dump_row)
 {
     uint32_t pm[16], p0[16], pp[16], xv[16];
     tmem_ld16(t_p, pm);
@@ -225,7 +256,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_p, uint32_t t_x, unsign
         }
         r[c] = __fadd2_rn(__fadd2_rn(up, f2(p0[2 * c], p0[2 * c + 1])), dn);
     }
-    epilogue_finish<C, EPI, DBG>(r, xv, t_x, dst, part_stride, chunk_stride, bias, nsc, nsh, live, dump_row);
+    epilogue_finish<C, EPI, DBG>(r, xv, t_x, dst, part_stride, chunk_stride, pv, boff, soff, live, dump_row);
 }
 
 // MMAs of one (tile, slab).  Trunk slab: [part][dy in slab][K chunk][NACC][8]; per 16-channel K step the passes
@@ -284,15 +315,13 @@ __host__ __device__ inline TileShare tile_share(int boards, int tiles_per_cta, i
 template <class C, bool DBG>
 __global__ void __launch_bounds__(C::THREADS, 1)
 k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int depth, const unsigned char *__restrict__ wtrunk,
-           const float *__restrict__ cbias, const float *__restrict__ bn_scale, const float *__restrict__ bn_shift,
-           unsigned char *__restrict__ gact, int MT, int KC, float *__restrict__ dump, int dump_layer,
+           const __grid_constant__ NetParams<C::CH> P, unsigned char *__restrict__ gact, int MT, int KC, float *__restrict__ dump, int dump_layer,
            const int *__restrict__ rows, const int *__restrict__ count_ptr, int sms)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *frame = smem;
     unsigned char *wb = frame + C::FRAME;                                       // weight slab ring
-    float *prm = reinterpret_cast<float *>(wb + (size_t)C::NSLOT * C::SLAB);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(prm + C::PRM_FLOATS);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(wb + (size_t)C::NSLOT * C::SLAB);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 40);
     uint32_t *cnts = tmem_slot + 4;
 
@@ -301,10 +330,19 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     enum { BAR_PFULL = 0, BAR_PEMPTY = BAR_PFULL + C::NRING, BAR_READY = BAR_PEMPTY + C::NRING,
            BAR_WFULL = BAR_READY + C::TILES, BAR_WEMPTY = BAR_WFULL + C::NSLOT, BAR_TURN = BAR_WEMPTY + C::NSLOT,
            BAR_WFULLP = BAR_TURN + 3, NBARS = BAR_WFULLP + C::NSLOT };
-    static_assert(NBARS <= 40, "barrier storage");
+    static_assert(NBARS <= 32, "one barrier per lane of warp 0");
 
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-    if (rows != nullptr) B = *count_ptr;                 // compact mode: the batch size lives in device memory
+    if (DBG && blockIdx.x == 0 && tid == 0) g_trace[1000] = clock64();          // CTA entry
+    if (DBG && tid == 0 && blockIdx.x < 2048) { g_cta_trace[3 * blockIdx.x] = sm_id(); g_cta_trace[3 * blockIdx.x + 1] = global_ns(); }
+    int count_now = B;
+    if (rows != nullptr) count_now = *count_ptr;         // compact mode: the batch size lives in device memory
+    {   // zero the frame (padding rows / columns must read as zero) while that load is in flight
+        uint4 *z = reinterpret_cast<uint4 *>(frame);
+        for (int i = tid; i < C::FRAME / 16; i += C::THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    B = count_now;
+    if (DBG && blockIdx.x == 0 && tid == 0) g_trace[1008] = clock64();
     // tile (two boards) t of this CTA is global tile tbase + tstride * t.  Pair mode deals PAIRS of tiles to pairs of CTAs
     // (the two CTAs of a cluster run the same number of tiles in lockstep): the CTA of rank r takes the r-th of every pair
     const uint32_t rank = C::PAIR ? cluster_ctarank() : 0u;
@@ -319,56 +357,75 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     const uint32_t bar0 = smem_u32(bars), frame_s = smem_u32(frame), wb_s = smem_u32(wb);
 #define BAR(i) (bar0 + 8u * (uint32_t)(i))
 
+    // The CTA's set-up was 11 % of its life (scripts/nn_trace.py: 8.1 k of 72 k cycles from entry to the first MMA), so
+    // its latencies overlap (6.1 k now): the frame is zeroed under the load of the batch size, warp 0 initialises one barrier
+    // per lane, requests the first weight slabs and allocates tensor memory while the other warps fetch the observations
+    // into registers; the cluster barrier that publishes the barriers to the peer is arrived on (relaxed: the mbarrier-init
+    // fence is the release) before the observations are converted and waited for after.
+    const int nslabs = 1 + (layers - 1) * C::SLABS;
+    const unsigned char *wsrc = wtrunk + (C::PAIR ? (size_t)rank * C::SLAB : 0);
+    const size_t wstride = C::PAIR ? 2 * (size_t)C::SLAB : (size_t)C::SLAB;
+    const int early = nslabs < C::NSLOT ? nslabs : C::NSLOT;                 // weight slabs requested before the roles start
     if (warp == 0) {
-        if (lane == 0) {
+        if (lane < NBARS) {
             constexpr uint32_t EW = C::PAIR ? 2 * C::GW : C::GW;      // epilogue warps arriving on a leader barrier
-            for (int i = 0; i < C::NRING; i++) { mbar_init(BAR(BAR_PFULL + i), 1); mbar_init(BAR(BAR_PEMPTY + i), EW); }
-            for (int i = 0; i < C::TILES; i++) mbar_init(BAR(BAR_READY + i), EW);
-            for (int i = 0; i < C::NSLOT; i++) {
-                mbar_init(BAR(BAR_WFULL + i), 1); mbar_init(BAR(BAR_WEMPTY + i), (uint32_t)nissue); mbar_init(BAR(BAR_WFULLP + i), 1);
-            }
             // the MMAs of a tile enter the tensor pipe back to back and in tile order: issuer w waits for TURN[w], which the
             // issuer of the previous tile arrives on (an mbarrier wait parks the thread; a polled shared-memory word takes
             // wavefronts of the shared-memory pipe away from the MMA operand reads the kernel is bound by)
-            for (int i = 0; i < 3; i++) mbar_init(BAR(BAR_TURN + i), 1);
+            const uint32_t cnt = (lane >= BAR_PEMPTY && lane < BAR_WFULL) ? EW : (lane >= BAR_WEMPTY && lane < BAR_TURN) ? (uint32_t)nissue : 1u;
+            mbar_init(BAR(lane), cnt);
+        }
+        if (DBG && blockIdx.x == 0 && lane == 0) g_trace[1009] = clock64();
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        __syncwarp();
+        if (DBG && blockIdx.x == 0 && lane == 0) g_trace[1010] = clock64();
+        if (lane == 0) {
             cnts[0] = 0u;
-            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-            mbar_arrive(BAR(BAR_TURN));                       // tile 0 may go
+            mbar_arrive(BAR(BAR_TURN));                        // tile 0 may go
+            // the first weight slabs: their barriers are this CTA's own, nothing else has to be ready
+            for (int s = 0; s < early; s++) {
+                const uint32_t bytes = s == 0 ? (uint32_t)(C::PARTS * C::STEM_PART) : (uint32_t)C::SLAB;
+                mbar_expect_tx(BAR(BAR_WFULL + s), bytes);
+                bulk_g2s(wb_s + (uint32_t)(s * C::SLAB), wsrc + (size_t)s * wstride, bytes, BAR(BAR_WFULL + s));
+            }
         }
         __syncwarp();
+        if (DBG && blockIdx.x == 0 && lane == 0) g_trace[1004] = clock64();
         if (C::PAIR) tmem_alloc_pair<512>(smem_u32(tmem_slot)); else tmem_alloc<512>(smem_u32(tmem_slot));
+        if (DBG && blockIdx.x == 0 && lane == 0) g_trace[1005] = clock64();
     }
-    {   // zero the frame (padding rows / columns must read as zero), stage the per-channel parameters
-        uint4 *z = reinterpret_cast<uint4 *>(frame);
-        for (int i = tid; i < C::FRAME / 16; i += C::THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
-        for (int i = tid; i < layers * C::CH; i += C::THREADS) prm[i] = cbias[i];
-        for (int i = tid; i < depth * C::CH; i += C::THREADS) {
-            prm[MAXL * C::CH + i] = bn_scale[i];
-            prm[MAXL * C::CH + MAXD * C::CH + i] = bn_shift[i];
+    const int HW = H * W, n_obs = tiles * 2 * HW;
+    float2 oc[4];
+    bool o_have = false;
+    int o_row = 0;
+    if (tid < n_obs) {
+        const int bl = tid / HW, pos = tid - bl * HW, y = pos / W, xx = pos - y * W;
+        int gb = 2 * (tbase + tstride * (bl >> 1)) + (bl & 1);
+        o_have = gb < B;
+        if (o_have && rows != nullptr) gb = rows[gb];
+        o_row = C::PADR + bl * 64 + y * 8 + xx;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            oc[k].x = (o_have && 2 * k < in_ch) ? obs[((size_t)gb * in_ch + 2 * k) * HW + pos] : 0.0f;
+            oc[k].y = (o_have && 2 * k + 1 < in_ch) ? obs[((size_t)gb * in_ch + 2 * k + 1) * HW + pos] : 0.0f;
         }
     }
     tc_fence_before();
+    if (DBG && blockIdx.x == 0 && tid == 64) g_trace[1006] = clock64();         // a warp that only zeroed the frame is done
     __syncthreads();
-    if (C::PAIR) cluster_sync_all();                     // the peer's barriers exist before anything arrives on them
+    if (DBG && blockIdx.x == 0 && tid == 0) g_trace[1007] = clock64();
+    // the peer's barriers must exist before anything arrives on them: arrive on the cluster barrier now, wait for it only
+    // when the roles start (1.4 k cycles that the observation staging hides)
+    if (C::PAIR) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n" ::: "memory");   // fence.mbarrier_init above is the release
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (DBG && blockIdx.x == 0 && tid == 0) g_trace[1001] = clock64();          // barriers, tensor memory, zeroed frame, parameters
     const uint32_t lead0 = C::PAIR ? map_to_rank(bar0, 0u) : bar0;      // the leader's barrier block
 #define LBAR(i) (lead0 + 8u * (uint32_t)(i))
-    const float *s_bias = prm, *s_sc = prm + MAXL * C::CH, *s_sh = prm + MAXL * C::CH + MAXD * C::CH;
+    const ConstPrm<C::CH> pv{P};
 
     // observation -> chunk plane 0 (channels >= in_ch stay zero)
-    const int HW = H * W;
-    for (int i = tid; i < tiles * 2 * HW; i += C::THREADS) {
-        const int bl = i / HW, pos = i - bl * HW, y = pos / W, xx = pos - y * W;
-        int gb = 2 * (tbase + tstride * (bl >> 1)) + (bl & 1);
-        const bool have = gb < B;
-        if (have && rows != nullptr) gb = rows[gb];
-        float2 c[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            c[k].x = (have && 2 * k < in_ch) ? obs[((size_t)gb * in_ch + 2 * k) * HW + pos] : 0.0f;
-            c[k].y = (have && 2 * k + 1 < in_ch) ? obs[((size_t)gb * in_ch + 2 * k + 1) * HW + pos] : 0.0f;
-        }
+    auto stage_obs = [&](const float2 (&c)[4], int frow) {
         uint32_t o[4], o2[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -383,14 +440,29 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
                 o2[k] = bf2_bits(__float22bfloat162_rn(make_float2(c[k].x - hf.x, c[k].y - hf.y)));
             }
         }
-        unsigned char *d = frame + (size_t)(C::PADR + bl * 64 + y * 8 + xx) * 16;
+        unsigned char *d = frame + (size_t)frow * 16;
         *reinterpret_cast<uint4 *>(d) = make_uint4(o[0], o[1], o[2], o[3]);
         if (C::PARTS == 2) *reinterpret_cast<uint4 *>(d + C::FPART) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+    };
+    if (tid < n_obs) stage_obs(oc, o_row);
+    for (int i = tid + C::THREADS; i < n_obs; i += C::THREADS) {          // more positions than threads (7 tiles of 7x7 boards)
+        const int bl = i / HW, pos = i - bl * HW, y = pos / W, xx = pos - y * W;
+        int gb = 2 * (tbase + tstride * (bl >> 1)) + (bl & 1);
+        const bool have = gb < B;
+        if (have && rows != nullptr) gb = rows[gb];
+        float2 c[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            c[k].x = (have && 2 * k < in_ch) ? obs[((size_t)gb * in_ch + 2 * k) * HW + pos] : 0.0f;
+            c[k].y = (have && 2 * k + 1 < in_ch) ? obs[((size_t)gb * in_ch + 2 * k + 1) * HW + pos] : 0.0f;
+        }
+        stage_obs(c, C::PADR + bl * 64 + y * 8 + xx);
     }
     fence_proxy_async();
     __syncthreads();
+    if (C::PAIR) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    if (DBG && blockIdx.x == 0 && tid == 0) g_trace[1002] = clock64();          // observations in the frame
 
-    const int nslabs = 1 + (layers - 1) * C::SLABS;
     if (warp < 3) {
         // ---- MMA issuers: warp k feeds the tiles g = k, k + nissue, ... (g = layer * tiles + tile) ---------------
         if (warp < nissue && rank == 0 && elect_one_sync()) {
@@ -410,6 +482,7 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
                 tc_fence_after();
                 mbar_wait(my_turn, (uint32_t)(turn & 1));
                 turn++;
+                if (DBG && blockIdx.x == 0 && g < 256) g_trace[4 * g] = clock64();
                 const int s0 = l == 0 ? 0 : 1 + (l - 1) * C::SLABS, ns = l == 0 ? 1 : C::SLABS;
                 const bool my_last = t + nissue >= tiles;          // my last tile of this layer: release its slabs
 #pragma unroll 1
@@ -425,6 +498,7 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
                     if (my_last) { if (C::PAIR) umma_commit_pair(BAR(BAR_WEMPTY + ws)); else umma_commit(BAR(BAR_WEMPTY + ws)); }
                 }
                 if (C::PAIR) umma_commit_pair(BAR(BAR_PFULL + slot)); else umma_commit(BAR(BAR_PFULL + slot));
+                if (DBG && blockIdx.x == 0 && g < 256) g_trace[4 * g + 1] = clock64();
                 mbar_arrive_relaxed(next_turn);
                 t += nissue;
                 while (t >= tiles) { t -= tiles; l++; }
@@ -443,10 +517,8 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     } else if (warp == 3) {
         // ---- weight producer (pair mode: each CTA streams its own half of every slab: [slab][rank][...]) --------------
         if (elect_one_sync()) {
-            const unsigned char *wsrc = wtrunk + (C::PAIR ? (size_t)rank * C::SLAB : 0);
-            const size_t wstride = C::PAIR ? 2 * (size_t)C::SLAB : (size_t)C::SLAB;
 #pragma unroll 1
-            for (int s = 0; s < nslabs; s++) {
+            for (int s = early; s < nslabs; s++) {
                 const int ws = s % C::NSLOT, use = s / C::NSLOT;
                 if (use > 0) mbar_wait(BAR(BAR_WEMPTY + ws), (uint32_t)((use - 1) & 1));
                 const uint32_t bytes = s == 0 ? (uint32_t)(C::PARTS * C::STEM_PART) : (uint32_t)C::SLAB;
@@ -487,21 +559,23 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
             if (within == 0) mbar_wait<32>(BAR(BAR_PFULL + slot), (uint32_t)(use & 1));
             asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "r"(C::GW * 32) : "memory");
             tc_fence_after();
+            if (DBG && blockIdx.x == 0 && within == 0 && lane == 0 && g < 256) g_trace[4 * g + 2] = clock64();
             const int ho = 16 * cg;
             if (l == 0) {
-                epilogue_tile<C, EPI_STEM, DBG>(t_p, t_x, dst, part_stride, chunk_stride, s_bias + ho, depth > 0 ? s_sc + ho : nullptr,
-                                                s_sh + ho, live, lane, LBAR(BAR_PEMPTY + slot), dmp);
+                epilogue_tile<C, EPI_STEM, DBG>(t_p, t_x, dst, part_stride, chunk_stride, pv, ho, depth > 0 ? ho : -1, live, lane,
+                                                LBAR(BAR_PEMPTY + slot), dmp);
             } else if (is_c1) {
-                epilogue_tile<C, EPI_CONV1, DBG>(t_p, t_x, dst, part_stride, chunk_stride, s_bias + l * C::CH + ho, nullptr, nullptr, live,
-                                                 lane, LBAR(BAR_PEMPTY + slot), dmp);
+                epilogue_tile<C, EPI_CONV1, DBG>(t_p, t_x, dst, part_stride, chunk_stride, pv, l * C::CH + ho, -1, live, lane,
+                                                 LBAR(BAR_PEMPTY + slot), dmp);
             } else {
                 const int nblk = l >> 1;                      // the block that consumes x next
-                epilogue_tile<C, EPI_CONV2, DBG>(t_p, t_x, dst, part_stride, chunk_stride, nullptr, last ? nullptr : s_sc + nblk * C::CH + ho,
-                                                 s_sh + nblk * C::CH + ho, live, lane, LBAR(BAR_PEMPTY + slot), dmp);
+                epilogue_tile<C, EPI_CONV2, DBG>(t_p, t_x, dst, part_stride, chunk_stride, pv, 0, last ? -1 : nblk * C::CH + ho, live, lane,
+                                                 LBAR(BAR_PEMPTY + slot), dmp);
             }
             fence_proxy_async();              // the next layer's MMAs read these rows through the async proxy
             __syncwarp();
             if (lane == 0) { if (C::PAIR) mbar_arrive_cluster(LBAR(BAR_READY + t)); else mbar_arrive(BAR(BAR_READY + t)); }
+            if (DBG && blockIdx.x == 0 && within == 0 && lane == 0 && g < 256) g_trace[4 * g + 3] = clock64();
             t += C::NGROUPS;
             while (t >= tiles) { t -= tiles; l++; }
         }
@@ -510,6 +584,8 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     __syncthreads();
     if (C::PAIR) cluster_sync_all();                     // the leader's MMAs read the peer's shared memory until the very end
     if (warp == 0) { if (C::PAIR) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base); }
+    if (DBG && blockIdx.x == 0 && tid == 0) g_trace[1003] = clock64();          // CTA exit
+    if (DBG && tid == 0 && blockIdx.x < 2048) g_cta_trace[3 * blockIdx.x + 2] = global_ns();
 #undef BAR
 #undef LBAR
 }
@@ -553,7 +629,7 @@ struct WideCfg {
 // stores are waited for once at the end: between two layers the tensor pipe idles for exactly this function.
 template <class C, int EPI, bool DBG>
 __device__ __forceinline__ void epilogue_wide_row(uint32_t t_p, uint32_t t_x, unsigned char *dst, size_t part_stride, size_t chunk_stride,
-                                                  const float *bias, const float *nsc, const float *nsh, bool live, float *dump_row)
+                                                  const SmemPrm &pv, int boff, int soff, bool live, float *dump_row)
 {
     uint32_t acc[2][16], xv[2][16];
     tmem_ld16(t_p, acc[0]);
@@ -569,7 +645,7 @@ __device__ __forceinline__ void epilogue_wide_row(uint32_t t_p, uint32_t t_x, un
 #pragma unroll
         for (int c = 0; c < 8; c++) r[c] = f2(acc[i & 1][2 * c], acc[i & 1][2 * c + 1]);
         epilogue_finish<C, EPI, DBG, false>(r, xv[i & 1], t_x + (uint32_t)(16 * i), dst + (size_t)(2 * i) * chunk_stride, part_stride, chunk_stride,
-                                            bias != nullptr ? bias + 16 * i : nullptr, nsc != nullptr ? nsc + 16 * i : nullptr, nsh + 16 * i, live,
+                                            pv, boff + 16 * i, soff >= 0 ? soff + 16 * i : -1, live,
                                             DBG && dump_row != nullptr ? dump_row + 16 * i : nullptr);
     }
     if (EPI != EPI_CONV1) tmem_st_wait();
@@ -749,16 +825,15 @@ k_trunk_wide(const float *__restrict__ obs, int B, int in_ch, int H, int W, int 
                     }
                     float *dmp = nullptr;
                     if (DBG && dump != nullptr && l == dump_layer && brd < B) dmp = dump + ((size_t)brd * 64 + (r0 & 63)) * C::CH + ho;
+                    const SmemPrm pv{s_bias, s_sc, s_sh};
                     if (l == 0) {
-                        epilogue_wide_row<C, EPI_STEM, DBG>(t_p, t_x, dst, part_stride, chunk_stride, s_bias + ho, depth > 0 ? s_sc + ho : nullptr,
-                                                            s_sh + ho, live, dmp);
+                        epilogue_wide_row<C, EPI_STEM, DBG>(t_p, t_x, dst, part_stride, chunk_stride, pv, ho, depth > 0 ? ho : -1, live, dmp);
                     } else if (is_c1) {
-                        epilogue_wide_row<C, EPI_CONV1, DBG>(t_p, t_x, dst, part_stride, chunk_stride, s_bias + l * C::CH + ho, nullptr, s_sh + ho,
-                                                             live, dmp);
+                        epilogue_wide_row<C, EPI_CONV1, DBG>(t_p, t_x, dst, part_stride, chunk_stride, pv, l * C::CH + ho, -1, live, dmp);
                     } else {
                         const int nblk = l >> 1;                      // the block that consumes x next
-                        epilogue_wide_row<C, EPI_CONV2, DBG>(t_p, t_x, dst, part_stride, chunk_stride, nullptr,
-                                                             last ? nullptr : s_sc + nblk * C::CH + ho, s_sh + nblk * C::CH + ho, live, dmp);
+                        epilogue_wide_row<C, EPI_CONV2, DBG>(t_p, t_x, dst, part_stride, chunk_stride, pv, 0, last ? -1 : nblk * C::CH + ho, live,
+                                                             dmp);
                     }
                 }
                 tc_fence_before();                // accumulator and residual accesses are complete (wait::ld / wait::st inside)
@@ -949,7 +1024,7 @@ k_softmax(const float *__restrict__ logits, float *__restrict__ policy, float *_
 template <int PREC> using Cfg32 = TrunkCfg<32, 7, PREC, 2, 3, prec_split(PREC) ? 2 : 3>;
 template <int PREC> using Cfg64 = TrunkCfg<64, 2, PREC, 1, 1, prec_split(PREC) ? 3 : 6>;
 // CTA pairs (AZB_NNG_PAIR): half of every weight slab per CTA, so the ring holds more of them
-template <int PREC> using Cfg32P = TrunkCfg<32, 7, PREC, 2, 3, prec_split(PREC) ? 3 : 4, true>;
+template <int PREC> using Cfg32P = TrunkCfg<32, 7, PREC, 3, 3, prec_split(PREC) ? 3 : 4, true>;
 template <int PREC> using Cfg64P = TrunkCfg<64, 2, PREC, 1, 1, 6, true>;
 
 
@@ -1021,13 +1096,17 @@ int launch_trunk(const azb_nng_net *n, const float *obs, int batch, const int *r
     const int MT = (n->max_boards + 127) / 128;
     const unsigned char *wt = reinterpret_cast<const unsigned char *>(n->wtrunk);
     unsigned char *gact = reinterpret_cast<unsigned char *>(n->gact);
+    // per-channel parameters by value (constant bank): h_params = host copy of [cbias | bn_scale | bn_shift]
+    NetParams<C::CH> P = {};
+    const int L = 1 + 2 * n->depth, D1 = n->depth > 0 ? n->depth : 1;
+    memcpy(P.bias, n->h_params, sizeof(float) * (size_t)L * C::CH);
+    memcpy(P.sc, n->h_params + (size_t)L * C::CH, sizeof(float) * (size_t)D1 * C::CH);
+    memcpy(P.sh, n->h_params + (size_t)(L + D1) * C::CH, sizeof(float) * (size_t)D1 * C::CH);
     if (dump != nullptr)
         return launch_maybe_pair(k_trunk_tc<C, true>, C::PAIR, grid, C::THREADS, C::SMEM, s, obs, batch, (int)n->in_channels, (int)n->board_h,
-                                 (int)n->board_w, (int)n->depth, wt, n->cbias, n->bn_scale, n->bn_shift, gact, MT, (int)n->head_kc, dump,
-                                 dump_layer, rows, count, sms);
+                                 (int)n->board_w, (int)n->depth, wt, P, gact, MT, (int)n->head_kc, dump, dump_layer, rows, count, sms);
     return launch_maybe_pair(k_trunk_tc<C, false>, C::PAIR, grid, C::THREADS, C::SMEM, s, obs, batch, (int)n->in_channels, (int)n->board_h,
-                             (int)n->board_w, (int)n->depth, wt, n->cbias, n->bn_scale, n->bn_shift, gact, MT, (int)n->head_kc,
-                             (float *)nullptr, -1, rows, count, sms);
+                             (int)n->board_w, (int)n->depth, wt, P, gact, MT, (int)n->head_kc, (float *)nullptr, -1, rows, count, sms);
 }
 
 template <class C>
@@ -1114,6 +1193,7 @@ int forward(const azb_nng_net *n, const float *obs, float *policy, float *value,
         n->head_nt % 16 != 0 || n->head_nt < 16 || n->head_nt > 256 || n->head_ntiles < 1 || n->head_kc % HKC != 0 ||
         n->head_kc < n->board_h * n->board_w * (n->channels / 8) || n->head_nt * n->head_ntiles < n->action_size + 3 ||
         !n->wtrunk || !n->cbias || !n->bn_scale || !n->bn_shift || !n->whead || !n->bhead || !n->gact ||
+        (n->channels != 128 && !n->h_params) ||
         (!(n->head_ntiles == 1 && n->head_nt == 16) && !n->logits))
         return -1;
     cudaStream_t s = (cudaStream_t)stream;
@@ -1161,6 +1241,20 @@ extern "C" int azb_nng_forward(const azb_nng_net *net, const float *obs, float *
                                const int32_t *count, void *stream)
 {
     return g::forward(net, obs, policy, value, batch, rows, count, stream, nullptr, -1);
+}
+
+/* test / tuning hook: the pipeline trace of the last debug forward (see g_trace), n <= 1024 values */
+extern "C" int azb_nng_trace(long long *out, int32_t n)
+{
+    if (!out || n < 0 || n > 4 * 256) return -7;
+    return cudaMemcpyFromSymbol(out, g::g_trace, (size_t)n * sizeof(long long)) == cudaSuccess ? 0 : -2;
+}
+
+/* tuning hook: (SM id, globaltimer ns at entry, at exit) of the first n <= 2048 CTAs of the last debug forward */
+extern "C" int azb_nng_cta_trace(long long *out, int32_t n)
+{
+    if (!out || n < 0 || n > 2048) return -7;
+    return cudaMemcpyFromSymbol(out, g::g_cta_trace, (size_t)n * 3 * sizeof(long long)) == cudaSuccess ? 0 : -2;
 }
 
 extern "C" int azb_nng_forward_debug(const azb_nng_net *net, const float *obs, float *policy, float *value, int32_t batch, void *stream,

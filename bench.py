@@ -551,6 +551,20 @@ def main():
                    "launches_set_aside": nn_dropped, "mean_launch_us_untrimmed": nn_mean_all, "launch_us_p10_p50_p90": nn_pct,
                    "peak_source": ("measured sustained bf16" if "bf16_tflops_sustained" in peaks else "fallback"),
                    "note": "useful flops of the network (2 x multiply-adds of its convolutions and linear layers), not issued MMA flops"}
+        if a.nn == "tc":
+            # what the tensor pipe actually executes: M = 128 x N x K = 16 MMAs over 8x8 board frames (64 rows per board for
+            # H x W live positions), three per K step at a split precision; trunk only (the head GEMM is < 2 %)
+            ch, dep = netargs["num_channels"], netargs["depth"]
+            passes = 3 if a.precision in nn_tc.SPLIT else 1
+            if ch == 128:
+                mmas, n_mma = (3 * 2 + 2 * dep * 36 * 2) * passes, 128
+            else:
+                mmas, n_mma = (2 + 2 * dep * 3 * (ch // 16)) * passes, 3 * ch
+            issued = (rows / nn_n / 2.0) * mmas * 2.0 * 128 * n_mma * 16 / (nn_ms / nn_n / 1000.0) / 1e12
+            roof_nn["issued_mma"] = {"tflops": issued, "frac_of_sustained_peak": issued / sustained, "mma_per_tile": mmas, "mma_n": n_mma,
+                                     "note": "issued tensor-core flops of the trunk kernel (frames of 64 rows per board, "
+                                             f"{passes} MMA(s) per K step) over the same time: the split precision and the frame padding "
+                                             "are what separate it from the useful-flop figure"}
     traffic_file = os.path.join(ROOT, "profiles", "select_traffic.json")
     if roof is not None and os.path.exists(traffic_file):
         try:

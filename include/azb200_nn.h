@@ -104,6 +104,9 @@ typedef struct azb_nng_net {
     void *gact;             /* scratch, device: parts * ceil(max_boards/128) * head_kc * 2048 bytes             */
     float *logits;          /* scratch, device f32 [max_boards][head_nt*head_ntiles]; may be NULL when all outputs */
                             /*   fit one 16-wide tile                                                            */
+    const float *h_params;  /* HOST copy of [cbias | bn_scale | bn_shift] (same shapes, concatenated): the 32 / 64-   */
+                            /*   channel kernel takes them by value as a kernel argument (constant bank) -- read at  */
+                            /*   every azb_nng_forward call; required for 32 / 64 channels, unused for 128           */
 } azb_nng_net;
 
 /* out[0..7] = operand parts, vertical taps per weight slab (0: the 128-channel kernel, one slab per tap and 32 input
@@ -119,6 +122,12 @@ int azb_nng_forward(const azb_nng_net *net, const float *obs, float *policy, flo
  * included) to dump f32 [batch][64 frame rows][channels] (padding rows zero) */
 int azb_nng_forward_debug(const azb_nng_net *net, const float *obs, float *policy, float *value, int32_t batch, void *stream,
                           float *dump, int32_t dump_layer);
+
+/* tuning hook: clock64 stamps of CTA 0's pipeline in the last azb_nng_forward_debug call, four per (layer, tile) in issue
+ * order: MMAs start to issue, MMAs committed, epilogue sees the accumulator, epilogue hands the tile on.  n <= 1024. */
+int azb_nng_trace(long long *out, int32_t n);
+/* tuning hook: (SM id, %globaltimer at entry, at exit) of the first n <= 2048 CTAs of the last azb_nng_forward_debug call */
+int azb_nng_cta_trace(long long *out, int32_t n);
 
 /* Upload of a caller-owned PINNED host tensor (the batch_tensor / policy_tensor / value_tensor of the reference's
  * SelfPlayAgent protocol, SelfPlayAgent.pyx:14-16; NNetWrapper.process does `batch.cuda()`, NNetWrapper.py:227) by a
