@@ -45,7 +45,7 @@ constexpr int MAXD = 6, MAXL = 1 + 2 * MAXD;
 __host__ __device__ constexpr bool prec_split(int prec) { return prec == AZB_NN_BF16X2 || prec == AZB_NN_F16X2; }   // operands as hi + lo
 __host__ __device__ constexpr bool prec_f16(int prec) { return prec == AZB_NN_F16 || prec == AZB_NN_F16X2; }        // element type fp16
 
-template <int CH_, int TILES_, int PREC_, int NGROUPS_, int DYS_, int NSLOT_, bool PAIR_ = false>
+template <int CH_, int TILES_, int PREC_, int NGROUPS_, int DYS_, int NSLOT_, bool PAIR_ = false, int NISSUE_ = 0>
 struct TrunkCfg {
     static constexpr int CH = CH_, TILES = TILES_, PREC = PREC_, NGROUPS = NGROUPS_, DYS = DYS_, NSLOT = NSLOT_;
     // PAIR: two CTAs of a cluster run their tiles in lockstep as ONE M = 256 MMA stream (cta_group::2) issued by the
@@ -62,7 +62,7 @@ struct TrunkCfg {
     static constexpr int SLAB_PART = DYS * C8 * WCHUNK, SLAB = PARTS * SLAB_PART;
     static constexpr int STEM_PART = 4 * WCHUNK;                        // stem slab: [part][4 K chunks][NACC][8]
     static constexpr int NRING = (512 - TILES * CH) / NACC >= 3 ? 3 : (512 - TILES * CH) / NACC;
-    static constexpr int NISSUE = TILES < 3 ? TILES : 3;
+    static constexpr int NISSUE = NISSUE_ > 0 ? NISSUE_ : (TILES < 3 ? TILES : 3);      // MMA-issuing threads
     static constexpr int GW = 4 * (CH / 16);                            // warps of one epilogue group
     static constexpr int EPI_WARP0 = 4;                                 // warps 0..2 issue, warp 3 produces
     static constexpr int WARPS = EPI_WARP0 + NGROUPS * GW, THREADS = WARPS * 32;
@@ -262,11 +262,15 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_p, uint32_t t_x, unsign
 // MMAs of one (tile, slab).  Trunk slab: [part][dy in slab][K chunk][NACC][8]; per 16-channel K step the passes
 // hi.hi (+ hi.lo + lo.hi when the operands are split).  Stem slab: [part][4 K chunks][NACC][8], two K steps over chunk
 // plane 0: (dy=-1, dy=0) and (dy=+1, zero weights) -- the second K chunk of a step is the first one 8 rows further.
+// turn_bar != 0: the barrier the NEXT tile's issuer waits on; it is arrived on before this slab's last vertical tap, so that
+// that thread's wake-up (~300 cycles, measured as the gap between two tiles' MMAs) passes under the MMAs still to issue.
+// The two tiles' MMAs may interleave in the pipe for a few instructions; they touch different accumulators.
 template <class C>
-__device__ __forceinline__ void issue_slab(uint32_t frame_s, uint32_t w_s, uint32_t d_tmem, int t, int layer, int j)
+__device__ __forceinline__ void issue_slab(uint32_t frame_s, uint32_t w_s, uint32_t d_tmem, int t, int layer, int j, uint32_t turn_bar = 0u)
 {
     const uint32_t row0 = frame_s + (uint32_t)((C::PADR + 128 * t) * 16);
     if (layer == 0) {
+        if (turn_bar != 0u) mbar_arrive_relaxed(turn_bar);
 #pragma unroll
         for (int s = 0; s < 2; s++) {
 #pragma unroll
@@ -282,6 +286,7 @@ __device__ __forceinline__ void issue_slab(uint32_t frame_s, uint32_t w_s, uint3
 #pragma unroll
         for (int dl = 0; dl < C::DYS; dl++) {
             const int dy = j * C::DYS + dl - 1;
+            if (turn_bar != 0u && dl == C::DYS - 1) mbar_arrive_relaxed(turn_bar);
 #pragma unroll
             for (int ks = 0; ks < C::KST; ks++) {
 #pragma unroll
@@ -480,7 +485,7 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
                     if (use > 0) mbar_wait(BAR(BAR_PEMPTY + slot), (uint32_t)((use - 1) & 1));  // ring slot drained
                 }
                 tc_fence_after();
-                mbar_wait(my_turn, (uint32_t)(turn & 1));
+                if (nissue > 1) mbar_wait(my_turn, (uint32_t)(turn & 1));          // a single issuer is in order by itself
                 turn++;
                 if (DBG && blockIdx.x == 0 && g < 256) g_trace[4 * g] = clock64();
                 const int s0 = l == 0 ? 0 : 1 + (l - 1) * C::SLABS, ns = l == 0 ? 1 : C::SLABS;
@@ -494,12 +499,11 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
                         seen = s + 1;
                         tc_fence_after();
                     }
-                    issue_slab<C>(frame_s, wb_s + (uint32_t)(ws * C::SLAB), d_tmem, t, l, j);
+                    issue_slab<C>(frame_s, wb_s + (uint32_t)(ws * C::SLAB), d_tmem, t, l, j, (nissue > 1 && j == ns - 1) ? next_turn : 0u);
                     if (my_last) { if (C::PAIR) umma_commit_pair(BAR(BAR_WEMPTY + ws)); else umma_commit(BAR(BAR_WEMPTY + ws)); }
                 }
                 if (C::PAIR) umma_commit_pair(BAR(BAR_PFULL + slot)); else umma_commit(BAR(BAR_PFULL + slot));
                 if (DBG && blockIdx.x == 0 && g < 256) g_trace[4 * g + 1] = clock64();
-                mbar_arrive_relaxed(next_turn);
                 t += nissue;
                 while (t >= tiles) { t -= tiles; l++; }
             }
