@@ -208,6 +208,7 @@ class TensorCoreEvaluator:
                            *(self.t[k].data_ptr() for k in ("wtrunk", "cbias", "bn_scale", "bn_shift", "whead", "bhead")),
                            self.gact.data_ptr(), self.logits.data_ptr() if self.logits is not None else None,
                            self.h_params.data_ptr())
+        self.kernels_per_call = 2 if fused_softmax else 3       # trunk + head (+ softmax over the logits)
         self.rows, self.count = rows, count
         if rows is not None:
             assert count is not None and rows.dtype == torch.int32

@@ -406,7 +406,9 @@ class DeviceSelfPlay:
                 with torch.cuda.stream(T):
                     g.replay()
                 cur.wait_stream(T)
-                self.launches += sims * 2 + 4
+                # kernels of this repository inside the graph: select, sims x (evaluator + expand/backup[+select]), playMoves
+                # (play, finalize, emit, emit_reset)
+                self.launches += sims * (getattr(self.evals[0], "kernels_per_call", 1) + 1) + 5
                 return
             self._eager_rounds += 1
         T.wait_stream(cur)
@@ -425,10 +427,10 @@ class DeviceSelfPlay:
             eng.expand_backup(f, c, stream=T)
         eng.play_moves(fast, stream=T)
         cur.wait_stream(T)
-        self.launches += sims * len(self.ranges) * 2 + 3
+        self.launches += sims * len(self.ranges) * (getattr(self.evals[0], "kernels_per_call", 1) + 2) + 4
 
     def run_round_warmup(self, sims, fast=False):
         """Tree-only round (numWarmupSims): one fused kernel + playMoves."""
         self.engine.warmup_sims(sims)
         self.engine.play_moves(fast)
-        self.launches += 4
+        self.launches += 5

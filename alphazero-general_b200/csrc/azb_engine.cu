@@ -125,7 +125,8 @@ template <class G> static void l_play(azb_engine *e, int fast, cudaStream_t s)
     if (e->d.arena) k_play_moves_arena<G><<<grid_for<G>(e->d.B / 2), G::CTA, 0, s>>>(e->d);
     else k_play_moves<G><<<grid_for<G>(e->d.B), G::CTA, 0, s>>>(e->d, fast);
     k_finalize<G><<<1, 1024, 0, s>>>(e->d);
-    k_emit<G><<<grid_for<G>(e->d.B), G::CTA, 0, s>>>(e->d);
+    k_emit<G><<<dim3(grid_for<G>(e->d.B), G::A >= 256 ? 16 : 2), G::CTA, 0, s>>>(e->d);
+    k_emit_reset<G><<<(e->d.B + 127) / 128, 128, 0, s>>>(e->d);
 }
 template <class G> static void l_arena_players(azb_engine *e, int *out, cudaStream_t s)
 {

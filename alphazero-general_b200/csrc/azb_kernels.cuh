@@ -1123,7 +1123,9 @@ __global__ void __launch_bounds__(1024) k_finalize(DevView d)
     }
 }
 
-// Sample emission with symmetries and game/tree restart for the finished games.
+// Sample emission with symmetries for the finished games: blockIdx.y = chunk of the game's history (a finished tafl game
+// is up to 100 positions x 8 symmetries x (980 B observation + 588-entry policy scatter): one group per game took 3.4 ms per
+// move-round of 4096 brandubh games, 3.7 % of the step).  Read-only on the game state; k_emit_reset restarts the games.
 template <class G>
 __global__ void __launch_bounds__(G::CTA) k_emit(DevView d)
 {
@@ -1131,45 +1133,52 @@ __global__ void __launch_bounds__(G::CTA) k_emit(DevView d)
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int g = tid / L, lane = threadIdx.x % L;
     if (g >= d.B) return;
-    HeadOf<G> H = load_head(head_at<G>(d, g));
-    if (!(H.st.flags & GF_FINISHED)) return;
+    if (!(head_at<G>(d, g)->st.flags & GF_FINISHED)) return;
     const long long off = d.emit_off[g];
-    if (off == -1) {                    // beyond the quota: the game stays finished
-        if (lane == 0) { H.st.flags = (H.st.flags & ~GF_FINISHED) | GF_DEAD; store_head(head_at<G>(d, g), H); }
-        return;
-    }
+    if (off < 0) return;                // beyond the quota (-1) or no samples wanted
     const int code = d.fin_code[g];
     const int hl = d.hist_len[g];
     const int per = d.symmetric ? G::NSYM : 1;
-    if (off >= 0) {
-        for (int h = 0; h < hl; h++) {
-            const typename G::State hs = *hist_at<G>(d, (size_t)g * d.hist_cap + h);
-            const float *hp = d.hist_pi + ((size_t)g * d.hist_cap + h) * G::A;
-            for (int k = 0; k < per; k++) {
-                const long long si = off + (long long)h * per + k;
-                const typename G::State ss = d.symmetric ? G::symmetry(hs, k) : hs;
-                G::write_obs(ss, d.s_obs + (size_t)si * G::OBS, lane);
-                float *pp = d.s_pi + (size_t)si * G::A;
-                for (int a = lane; a < G::A; a += L) pp[d.symmetric ? G::sym_action(k, a) : a] = hp[a];
-                if (lane == 0) {
-                    d.s_z[si * 3 + 0] = code == 1 ? 1.0f : 0.0f;
-                    d.s_z[si * 3 + 1] = code == 2 ? 1.0f : 0.0f;
-                    d.s_z[si * 3 + 2] = code == 3 ? 1.0f : 0.0f;
-                    d.s_slot[si] = g;
-                }
+    for (int h = (int)blockIdx.y; h < hl; h += (int)gridDim.y) {
+        const typename G::State hs = *hist_at<G>(d, (size_t)g * d.hist_cap + h);
+        const float *hp = d.hist_pi + ((size_t)g * d.hist_cap + h) * G::A;
+        for (int k = 0; k < per; k++) {
+            const long long si = off + (long long)h * per + k;
+            const typename G::State ss = d.symmetric ? G::symmetry(hs, k) : hs;
+            G::write_obs(ss, d.s_obs + (size_t)si * G::OBS, lane);
+            float *pp = d.s_pi + (size_t)si * G::A;
+            for (int a = lane; a < G::A; a += L) pp[d.symmetric ? G::sym_action(k, a) : a] = hp[a];
+            if (lane == 0) {
+                d.s_z[si * 3 + 0] = code == 1 ? 1.0f : 0.0f;
+                d.s_z[si * 3 + 1] = code == 2 ? 1.0f : 0.0f;
+                d.s_z[si * 3 + 2] = code == 3 ? 1.0f : 0.0f;
+                d.s_slot[si] = g;
             }
         }
     }
-    if (lane == 0) {
-        int *pk = reinterpret_cast<int *>(d.stats + g) + 6;
-        const int used = H.alloc - (H.root >= d.half ? d.half : 0);
-        if (used > *pk) *pk = used;
-        G::init(H.st);
-        tree_reset(H);
+}
+
+// game / tree restart of the finished games (after k_emit has read their histories)
+template <class G>
+__global__ void __launch_bounds__(128) k_emit_reset(DevView d)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= d.B) return;
+    HeadOf<G> H = load_head(head_at<G>(d, g));
+    if (!(H.st.flags & GF_FINISHED)) return;
+    if (d.emit_off[g] == -1) {          // beyond the quota: the game stays finished
+        H.st.flags = (H.st.flags & ~GF_FINISHED) | GF_DEAD;
         store_head(head_at<G>(d, g), H);
-        d.hist_len[g] = 0;
-        d.fin_code[g] = 0;
+        return;
     }
+    int *pk = reinterpret_cast<int *>(d.stats + g) + 6;
+    const int used = H.alloc - (H.root >= d.half ? d.half : 0);
+    if (used > *pk) *pk = used;
+    G::init(H.st);
+    tree_reset(H);
+    store_head(head_at<G>(d, g), H);
+    d.hist_len[g] = 0;
+    d.fin_code[g] = 0;
 }
 
 // MCTS.counts of every root (host introspection)
