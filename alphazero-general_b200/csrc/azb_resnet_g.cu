@@ -73,12 +73,11 @@ struct TrunkCfg {
     static_assert(3 % DYS == 0 && STEM_PART <= SLAB_PART && NSLOT >= SLABS, "slab geometry");
     static_assert(!PAIR || NACC % 16 == 0, "an M = 256 MMA needs N % 16 == 0");
     static_assert(NRING >= 2 && COL_P + NRING * NACC <= 512, "tensor memory budget");
-    // every barrier wait names a phase by its parity only, so a waiter must have seen the previous phase of the barrier it
-    // waits on: an issuer / an epilogue group has to meet the same ring slot every time (8 tiles of 32 channels = a ring of
-    // two under three issuers trapped in the bounded wait; with two issuers and two groups it runs, at 183.7 instead of
-    // 162.3 us per 6960 boards)
-    static_assert(NISSUE % NRING == 0 || NRING % NISSUE == 0 || TILES < NISSUE, "issuers must rotate through the accumulator ring in step");
-    static_assert(NGROUPS % NRING == 0 || NRING % NGROUPS == 0, "epilogue groups must rotate through the accumulator ring in step");
+    // Every barrier wait names a phase by its parity only, so when a waiter reaches a wait, all earlier phases of that barrier
+    // must be known to be complete.  The configurations below satisfy it (an issuer always meets the same ring slot, or the
+    // in-order MMA stream implies the phases a group skipped); 8 tiles of 32 channels = a ring of two under three issuers
+    // does not (issuer 0 would wait for the third drain of slot 0 having seen only the first) and trapped in the bounded
+    // wait; with two issuers and two groups it runs, at 183.7 instead of 162.3 us per 6960 boards.
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static_assert(NACC <= 256 && NACC % 16 == 0 && WARPS <= 32, "shape limits");
 };
