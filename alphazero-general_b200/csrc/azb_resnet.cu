@@ -388,8 +388,21 @@ namespace {
 __global__ void __launch_bounds__(256) k_upload(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16, const unsigned char *src_tail,
                                                 unsigned char *dst_tail, int tail)
 {
+    // eight independent 16-byte loads per thread in flight: PCIe needs ~100 KB outstanding, and it should come from FEW
+    // CTAs -- a CTA of this kernel on an SM keeps a trunk CTA (which owns its SM's registers) off it, and with its pair
+    // partner a whole TPC, for the ~50 us the upload lasts
+    constexpr int U = 8;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (U - 1) * stride < n16; i += U * stride) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src + i + u * stride));
+#pragma unroll
+        for (int u = 0; u < U; u++) dst[i + u * stride] = v[u];
+    }
+    for (; i < n16; i += stride) {
         uint4 v;
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i));
         dst[i] = v;
@@ -406,8 +419,9 @@ extern "C" int azb_upload_pinned(void *dst_device, const void *src_pinned_host, 
     const size_t n16 = (size_t)bytes / 16;
     const int tail = (int)(bytes - (int64_t)n16 * 16);
     // few CTAs: PCIe needs ~100 KB in flight, not SMs -- the upload should leave the SMs to the kernels it overlaps with
+    // (e2e leg, M sims/s with 2 / 4 / 8 / 12 / 16 / 32 CTAs of eight loads per thread: 17.5 / 18.5 / 22.8 / 22.4 / 22.7 / 21.6)
     static int cap = 0;
-    if (cap == 0) { const char *env = getenv("AZB_UPLOAD_CTAS"); cap = env ? atoi(env) : 32; if (cap < 1) cap = 1; }
+    if (cap == 0) { const char *env = getenv("AZB_UPLOAD_CTAS"); cap = env ? atoi(env) : 8; if (cap < 1) cap = 1; }
     int grid = (int)((n16 + 255) / 256);
     grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
     k_upload<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4 *>(dst_device), reinterpret_cast<const uint4 *>(src_pinned_host), n16,
