@@ -170,6 +170,10 @@ class SelfPlayAgent(threading.Thread):
         from .nnet import capture_graph
         return capture_graph(fn, self.stream)
 
+    def _download_batch(self):
+        from .nnet import download
+        download(self.batch_tensor, self.engine.obs)
+
     def _upload_answers(self):
         from .nnet import upload
         upload(self.engine.policy, self.policy_tensor)
@@ -227,14 +231,14 @@ class SelfPlayAgent(threading.Thread):
 
             def whole_round():
                 eng.select(stream=self.stream)
-                self.batch_tensor.copy_(eng.obs, non_blocking=True)
+                self._download_batch()
                 for s_ in range(key):
                     server._body(self)                              # upload batch_tensor, network, answers -> host tensors
                     self._upload_answers()
                     eng.expand_backup(stream=self.stream)
                     if s_ + 1 < key:
                         eng.select(stream=self.stream)
-                        self.batch_tensor.copy_(eng.obs, non_blocking=True)
+                        self._download_batch()
             with torch.cuda.stream(self.stream):
                 if not graphs.get("warm"):
                     server._body(self)                              # lazy one-time setup of the evaluator: not capturable
@@ -252,13 +256,13 @@ class SelfPlayAgent(threading.Thread):
 
         def first():
             eng.select(stream=self.stream)
-            self.batch_tensor.copy_(eng.obs, non_blocking=True)
+            self._download_batch()
 
         def mid():
             self._upload_answers()
             eng.expand_backup(stream=self.stream)
             eng.select(stream=self.stream)
-            self.batch_tensor.copy_(eng.obs, non_blocking=True)
+            self._download_batch()
 
         def last():
             self._upload_answers()
@@ -271,7 +275,7 @@ class SelfPlayAgent(threading.Thread):
         if self._is_warmup:
             return
         if self.stream_ordered:
-            self.batch_tensor.copy_(self.engine.obs, non_blocking=True)
+            self._download_batch()
             ev = torch.cuda.Event()
             ev.record()
             self.batch_event = ev

@@ -132,7 +132,9 @@ int azb_nng_cta_trace(long long *out, int32_t n);
 /* Upload of a caller-owned PINNED host tensor (the batch_tensor / policy_tensor / value_tensor of the reference's
  * SelfPlayAgent protocol, SelfPlayAgent.pyx:14-16; NNetWrapper.process does `batch.cuda()`, NNetWrapper.py:227) by a
  * kernel that reads the mapped host memory over PCIe -- a small cudaMemcpyAsync host->device pays ~190 us of DMA
- * start-up on this platform.  Both pointers 16-byte aligned.  Asynchronous on `stream`; status codes as above. */
+ * start-up on this platform.  The same kernel serves the other direction (dst = the pinned host tensor's device mapping,
+ * src = device memory: posted PCIe writes), which azb200.nnet.download uses for the batch / policy / value tensors the
+ * protocol returns to the host.  Both pointers 16-byte aligned.  Asynchronous on `stream`; status codes as above. */
 int azb_upload_pinned(void *dst_device, const void *src_pinned_host, int64_t bytes, void *stream);
 int azb_nn_weight_row_stride(void);
 int azb_nn_head_row_stride(void);
