@@ -94,6 +94,7 @@ SYMBOLS = {
     "azb_nn_boards_per_cta": (C.c_int, []),
     "azb_upload_pinned": (C.c_int, [_vp, _vp, _i64, _vp]),
     "azb_nng_layout": (C.c_int, [_i32, _i32, _vp]),
+    "azb_nng_tile_plan": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "azb_nng_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "azb_nng_forward_debug": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32]),
     "azb_nng_trace": (C.c_int, [_vp, _i32]),

@@ -78,6 +78,7 @@ def layout(channels, precision):
 
 
 NNG_PAIR = 1      # azb_nng_net.flags: CTA pairs (tcgen05 cta_group::2), include/azb200_nn.h
+NNG_PERSIST, NNG_ONE_ROUND = 2, 4     # one wave of persistent CTAs / whole waves of one-round CTAs (neither: kernel default)
 
 
 def pair_default(channels):
@@ -175,7 +176,8 @@ class TensorCoreEvaluator:
     ``policy`` / ``value`` (engine-owned device rows).  rows / count: compact evaluation of rows[0 .. count) (device
     int32; count a tensor or a callable returning the device address of the counter)."""
 
-    def __init__(self, model, obs, policy, value, precision=None, rows=None, count=None, max_batch=None, pair=None):
+    def __init__(self, model, obs, policy, value, precision=None, rows=None, count=None, max_batch=None, pair=None,
+                 persist=None):
         precision = precision or default_precision(model)
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
@@ -204,7 +206,7 @@ class TensorCoreEvaluator:
         self.logits = None if fused_softmax else torch.zeros(self.max_batch, nout_pad, device=dev)
         self.net = _NNGNet(f["channels"], f["depth"], f["in_channels"], f["board_h"], f["board_w"], f["action_size"],
                            PRECISIONS[precision], self.max_batch, f["head_nt"], f["head_ntiles"], f["head_kc"],
-                           NNG_PAIR if self.pair else 0,
+                           (NNG_PAIR if self.pair else 0) | (0 if persist is None else NNG_PERSIST if persist else NNG_ONE_ROUND),
                            *(self.t[k].data_ptr() for k in ("wtrunk", "cbias", "bn_scale", "bn_shift", "whead", "bhead")),
                            self.gact.data_ptr(), self.logits.data_ptr() if self.logits is not None else None,
                            self.h_params.data_ptr())

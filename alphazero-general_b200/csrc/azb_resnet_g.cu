@@ -322,11 +322,34 @@ __host__ __device__ inline TileShare tile_share(int boards, int tiles_per_cta, i
     return s;
 }
 
+// k_trunk_tc: how the tiles (pair mode: pairs of tiles) are dealt to units (CTAs, pair mode: CTA pairs).  persist: ONE wave
+// of resident units with equal shares, a unit running its share in `rounds` rounds of `tiles` tiles (the same for every
+// round: at most rounds - 1 empty tiles per unit).  Otherwise whole waves of units with one round each (tile_share).
+struct UnitShare { int units, n, first, rounds, tiles; };
+__host__ __device__ inline UnitShare unit_share(int boards, int tiles_per_cta, int sms, bool pair, bool persist, int unit)
+{
+    UnitShare u;
+    const int T2 = (boards + 1) / 2, items = pair ? (T2 + 1) / 2 : T2, resident = pair ? sms / 2 : sms;
+    if (persist) u.units = items < resident ? items : resident;
+    else {
+        const int waves = (items + tiles_per_cta * resident - 1) / (tiles_per_cta * resident);
+        u.units = waves * resident < items ? waves * resident : items;
+    }
+    u.n = 0; u.first = 0; u.rounds = 0; u.tiles = 0;
+    if (unit < 0 || unit >= u.units) return u;
+    const int base = items / u.units, extra = items % u.units;
+    u.n = base + (unit < extra ? 1 : 0);
+    u.first = unit * base + (unit < extra ? unit : extra);
+    u.rounds = (u.n + tiles_per_cta - 1) / tiles_per_cta;
+    u.tiles = (u.n + u.rounds - 1) / u.rounds;
+    return u;
+}
+
 template <class C, bool DBG>
 __global__ void __launch_bounds__(C::THREADS, 1)
 k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int depth, const unsigned char *__restrict__ wtrunk,
            const __grid_constant__ NetParams<C::CH> P, unsigned char *__restrict__ gact, int MT, int KC, float *__restrict__ dump, int dump_layer,
-           const int *__restrict__ rows, const int *__restrict__ count_ptr, int sms)
+           const int *__restrict__ rows, const int *__restrict__ count_ptr, int sms, int persist)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *frame = smem;
@@ -353,16 +376,23 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     }
     B = count_now;
     if (DBG && blockIdx.x == 0 && tid == 0) g_trace[1008] = clock64();
-    // tile (two boards) t of this CTA is global tile tbase + tstride * t.  Pair mode deals PAIRS of tiles to pairs of CTAs
-    // (the two CTAs of a cluster run the same number of tiles in lockstep): the CTA of rank r takes the r-th of every pair
+    // A unit (a CTA; pair mode: a CTA pair, the two CTAs of a cluster in lockstep, rank r taking the r-th tile of every pair
+    // of tiles) runs its share of the tiles in `rounds` rounds of `tiles` tiles each; round r, local tile t is the unit's
+    // tile k = r * tiles + t (beyond the share: an empty tile, computed on stale rows and never stored).  A round is nothing
+    // but `layers` more entries of the same (layer, tile) sequence: the last layer's epilogue of round r stages the
+    // observations of round r + 1 in the frame rows it has just finished reading.  persist: one wave of units and several
+    // rounds, so the set-up of a CTA (6 k cycles), its last-epilogue tail and the gap to the next CTA are paid once instead
+    // of once per 5-7 tiles; otherwise whole waves of units with one round each.
     const uint32_t rank = C::PAIR ? cluster_ctarank() : 0u;
     const int unit = C::PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const TileShare sh = tile_share(C::PAIR ? (B + 1) / 2 : B, C::TILES, C::PAIR ? sms / 2 : sms);
-    if (unit >= sh.nct) return;                          // the whole cluster leaves
-    const int tiles = sh.base + (unit < sh.extra ? 1 : 0);
-    const int unit0 = unit * sh.base + (unit < sh.extra ? unit : sh.extra);
-    const int tbase = C::PAIR ? 2 * unit0 + (int)rank : unit0, tstride = C::PAIR ? 2 : 1;
-    const int layers = 1 + 2 * depth, total = layers * tiles;
+    const UnitShare us = unit_share(B, C::TILES, sms, C::PAIR, persist != 0, unit);
+    if (us.n <= 0) return;                               // the whole cluster leaves
+    const int tiles = us.tiles, ktot = us.rounds * us.tiles;
+    // (compact) board index of half hb of the unit's tile k: b0 + KSTEP * k + hb; it exists if it is below blim
+    constexpr int KSTEP = C::PAIR ? 4 : 2;
+    const int b0 = C::PAIR ? 4 * us.first + 2 * (int)rank : 2 * us.first;
+    const int blim = B < b0 + KSTEP * us.n ? B : b0 + KSTEP * us.n;
+    const int layers = 1 + 2 * depth, total = us.rounds * layers * tiles;
     const int nissue = tiles < C::NISSUE ? tiles : C::NISSUE;
     const uint32_t bar0 = smem_u32(bars), frame_s = smem_u32(frame), wb_s = smem_u32(wb);
 #define BAR(i) (bar0 + 8u * (uint32_t)(i))
@@ -375,7 +405,8 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     const int nslabs = 1 + (layers - 1) * C::SLABS;
     const unsigned char *wsrc = wtrunk + (C::PAIR ? (size_t)rank * C::SLAB : 0);
     const size_t wstride = C::PAIR ? 2 * (size_t)C::SLAB : (size_t)C::SLAB;
-    const int early = nslabs < C::NSLOT ? nslabs : C::NSLOT;                 // weight slabs requested before the roles start
+    const int vslabs = us.rounds * nslabs;                                      // the slab stream repeats every round
+    const int early = vslabs < C::NSLOT ? vslabs : C::NSLOT;                 // weight slabs requested before the roles start
     if (warp == 0) {
         if (lane < NBARS) {
             constexpr uint32_t EW = C::PAIR ? 2 * C::GW : C::GW;      // epilogue warps arriving on a leader barrier
@@ -394,9 +425,10 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
             mbar_arrive(BAR(BAR_TURN));                        // tile 0 may go
             // the first weight slabs: their barriers are this CTA's own, nothing else has to be ready
             for (int s = 0; s < early; s++) {
-                const uint32_t bytes = s == 0 ? (uint32_t)(C::PARTS * C::STEM_PART) : (uint32_t)C::SLAB;
+                const int ss = s % nslabs;
+                const uint32_t bytes = ss == 0 ? (uint32_t)(C::PARTS * C::STEM_PART) : (uint32_t)C::SLAB;
                 mbar_expect_tx(BAR(BAR_WFULL + s), bytes);
-                bulk_g2s(wb_s + (uint32_t)(s * C::SLAB), wsrc + (size_t)s * wstride, bytes, BAR(BAR_WFULL + s));
+                bulk_g2s(wb_s + (uint32_t)(s * C::SLAB), wsrc + (size_t)ss * wstride, bytes, BAR(BAR_WFULL + s));
             }
         }
         __syncwarp();
@@ -410,8 +442,8 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     int o_row = 0;
     if (tid < n_obs) {
         const int bl = tid / HW, pos = tid - bl * HW, y = pos / W, xx = pos - y * W;
-        int gb = 2 * (tbase + tstride * (bl >> 1)) + (bl & 1);
-        o_have = gb < B;
+        int gb = b0 + KSTEP * (bl >> 1) + (bl & 1);
+        o_have = gb < blim;
         if (o_have && rows != nullptr) gb = rows[gb];
         o_row = C::PADR + bl * 64 + y * 8 + xx;
 #pragma unroll
@@ -457,8 +489,8 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     if (tid < n_obs) stage_obs(oc, o_row);
     for (int i = tid + C::THREADS; i < n_obs; i += C::THREADS) {          // more positions than threads (7 tiles of 7x7 boards)
         const int bl = i / HW, pos = i - bl * HW, y = pos / W, xx = pos - y * W;
-        int gb = 2 * (tbase + tstride * (bl >> 1)) + (bl & 1);
-        const bool have = gb < B;
+        int gb = b0 + KSTEP * (bl >> 1) + (bl & 1);
+        const bool have = gb < blim;
         if (have && rows != nullptr) gb = rows[gb];
         float2 c[4];
 #pragma unroll
@@ -476,24 +508,24 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     if (warp < 3) {
         // ---- MMA issuers: warp k feeds the tiles g = k, k + nissue, ... (g = layer * tiles + tile) ---------------
         if (warp < nissue && rank == 0 && elect_one_sync()) {
-            int l = warp / tiles, t = warp - l * tiles, seen = 0, turn = 0;
+            int v = 0, l = 0, rs = 0, t = warp, seen = 0, turn = 0;     // v = round * layers + l; rs = round * nslabs (warp < tiles)
             const uint32_t my_turn = BAR(BAR_TURN + warp), next_turn = BAR(BAR_TURN + (warp + 1 == nissue ? 0 : warp + 1));
 #pragma unroll 1
             for (int g = warp; g < total; g += nissue) {
                 const int slot = g % C::NRING, use = g / C::NRING;
                 const uint32_t d_tmem = tmem_base + C::COL_P + (uint32_t)(slot * C::NACC);
                 if (C::PAIR) {
-                    if (l > 0) mbar_wait_cluster(BAR(BAR_READY + t), (uint32_t)((l - 1) & 1));
+                    if (v > 0) mbar_wait_cluster(BAR(BAR_READY + t), (uint32_t)((v - 1) & 1));
                     if (use > 0) mbar_wait_cluster(BAR(BAR_PEMPTY + slot), (uint32_t)((use - 1) & 1));
                 } else {
-                    if (l > 0) mbar_wait(BAR(BAR_READY + t), (uint32_t)((l - 1) & 1));         // my tile's previous epilogue
+                    if (v > 0) mbar_wait(BAR(BAR_READY + t), (uint32_t)((v - 1) & 1));         // my tile's previous epilogue
                     if (use > 0) mbar_wait(BAR(BAR_PEMPTY + slot), (uint32_t)((use - 1) & 1));  // ring slot drained
                 }
                 tc_fence_after();
                 if (nissue > 1) mbar_wait(my_turn, (uint32_t)(turn & 1));          // a single issuer is in order by itself
                 turn++;
                 if (DBG && blockIdx.x == 0 && g < 256) g_trace[4 * g] = clock64();
-                const int s0 = l == 0 ? 0 : 1 + (l - 1) * C::SLABS, ns = l == 0 ? 1 : C::SLABS;
+                const int s0 = rs + (l == 0 ? 0 : 1 + (l - 1) * C::SLABS), ns = l == 0 ? 1 : C::SLABS;
                 const bool my_last = t + nissue >= tiles;          // my last tile of this layer: release its slabs
 #pragma unroll 1
                 for (int j = 0; j < ns; j++) {
@@ -510,13 +542,13 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
                 if (C::PAIR) umma_commit_pair(BAR(BAR_PFULL + slot)); else umma_commit(BAR(BAR_PFULL + slot));
                 if (DBG && blockIdx.x == 0 && g < 256) g_trace[4 * g + 1] = clock64();
                 t += nissue;
-                while (t >= tiles) { t -= tiles; l++; }
+                while (t >= tiles) { t -= tiles; v++; if (++l == layers) { l = 0; rs += nslabs; } }
             }
         }
         // ---- peer CTA of a pair: tell the leader when MY half of a weight slab has landed ------------------------------
         if (C::PAIR && warp == 0 && rank == 1 && elect_one_sync()) {
 #pragma unroll 1
-            for (int s = 0; s < nslabs; s++) {
+            for (int s = 0; s < vslabs; s++) {
                 const int ws = s % C::NSLOT;
                 mbar_wait(BAR(BAR_WFULL + ws), (uint32_t)((s / C::NSLOT) & 1));
                 mbar_arrive_cluster(LBAR(BAR_WFULLP + ws));
@@ -527,12 +559,12 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
         // ---- weight producer (pair mode: each CTA streams its own half of every slab: [slab][rank][...]) --------------
         if (elect_one_sync()) {
 #pragma unroll 1
-            for (int s = early; s < nslabs; s++) {
-                const int ws = s % C::NSLOT, use = s / C::NSLOT;
+            for (int s = early; s < vslabs; s++) {
+                const int ws = s % C::NSLOT, use = s / C::NSLOT, ss = s % nslabs;
                 if (use > 0) mbar_wait(BAR(BAR_WEMPTY + ws), (uint32_t)((use - 1) & 1));
-                const uint32_t bytes = s == 0 ? (uint32_t)(C::PARTS * C::STEM_PART) : (uint32_t)C::SLAB;
+                const uint32_t bytes = ss == 0 ? (uint32_t)(C::PARTS * C::STEM_PART) : (uint32_t)C::SLAB;
                 mbar_expect_tx(BAR(BAR_WFULL + ws), bytes);
-                bulk_g2s(wb_s + (uint32_t)(ws * C::SLAB), wsrc + (size_t)s * wstride, bytes, BAR(BAR_WFULL + ws));
+                bulk_g2s(wb_s + (uint32_t)(ws * C::SLAB), wsrc + (size_t)ss * wstride, bytes, BAR(BAR_WFULL + ws));
             }
         }
         __syncwarp();
@@ -543,15 +575,16 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
         const int r0 = q * 32 + lane, fy = (r0 & 63) >> 3, fx = r0 & 7;
         const bool live_pos = fx < W && fy < H;
         const int pos = fy * W + fx;
-        int l = grp / tiles, t = grp - l * tiles;
+        int l = 0, kb = 0, t = grp;                          // layer, round * tiles, tile of the round
+        while (t >= tiles) { t -= tiles; if (++l == layers) { l = 0; kb += tiles; } }
 #pragma unroll 1
         for (int g = grp; g < total; g += C::NGROUPS) {
             const int slot = g % C::NRING, use = g / C::NRING;
             const bool is_c1 = (l & 1) == 1, last = l + 1 == layers;
             const uint32_t t_p = tmem_base + lane_off + C::COL_P + (uint32_t)(slot * C::NACC + 16 * cg);
             const uint32_t t_x = tmem_base + lane_off + C::COL_X + (uint32_t)(C::CH * t + 16 * cg);
-            const int brd = 2 * (tbase + tstride * t) + (r0 >> 6);       // (compact) board index of this row
-            const bool live = live_pos && brd < B;
+            const int brd = b0 + KSTEP * (kb + t) + (r0 >> 6);          // (compact) board index of this row
+            const bool live = live_pos && brd < blim;
             unsigned char *dst;
             size_t part_stride, chunk_stride;
             if (last) {     // head GEMM A operand: [part][M tile of 128 boards][K chunk = pos * C8 + c][board][16 B]
@@ -564,7 +597,19 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
                 dst = frame + (size_t)(2 * cg) * C::PLANE + (size_t)(C::PADR + 128 * t + r0) * 16;
             }
             float *dmp = nullptr;
-            if (DBG && dump != nullptr && l == dump_layer && brd < B) dmp = dump + ((size_t)brd * 64 + (r0 & 63)) * C::CH + 16 * cg;
+            if (DBG && dump != nullptr && l == dump_layer && brd < blim) dmp = dump + ((size_t)brd * 64 + (r0 & 63)) * C::CH + 16 * cg;
+            // last layer of a round that is not the last: this thread's position of the next round's board goes into the frame
+            // after the epilogue.  Its row index is fetched and its observation lines are requested into L2 now, under the
+            // wait for this tile's MMAs (no registers held across the epilogue: the kernel sits at its register limit)
+            int ngb = -1;
+            if (last && cg == 0 && live_pos && kb + tiles < ktot) {
+                const int nb = brd + KSTEP * tiles;
+                if (nb < blim) {
+                    ngb = rows != nullptr ? rows[nb] : nb;
+                    const float *o = obs + (size_t)ngb * in_ch * HW + pos;
+                    for (int k = 0; k < in_ch; k++) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(o + (size_t)k * HW));
+                }
+            }
             if (within == 0) mbar_wait<32>(BAR(BAR_PFULL + slot), (uint32_t)(use & 1));
             asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "r"(C::GW * 32) : "memory");
             tc_fence_after();
@@ -581,12 +626,23 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
                 epilogue_tile<C, EPI_CONV2, DBG>(t_p, t_x, dst, part_stride, chunk_stride, pv, 0, last ? -1 : nblk * C::CH + ho, live, lane,
                                                  LBAR(BAR_PEMPTY + slot), dmp);
             }
+            // the frame rows of this tile are free (its last MMAs completed before this epilogue started): the stem of round
+            // r + 1 waits for the same READY barrier as any layer
+            if (ngb >= 0) {
+                float2 nc[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    nc[k].x = 2 * k < in_ch ? obs[((size_t)ngb * in_ch + 2 * k) * HW + pos] : 0.0f;
+                    nc[k].y = 2 * k + 1 < in_ch ? obs[((size_t)ngb * in_ch + 2 * k + 1) * HW + pos] : 0.0f;
+                }
+                stage_obs(nc, C::PADR + 128 * t + r0);
+            }
             fence_proxy_async();              // the next layer's MMAs read these rows through the async proxy
             __syncwarp();
             if (lane == 0) { if (C::PAIR) mbar_arrive_cluster(LBAR(BAR_READY + t)); else mbar_arrive(BAR(BAR_READY + t)); }
             if (DBG && blockIdx.x == 0 && within == 0 && lane == 0 && g < 256) g_trace[4 * g + 3] = clock64();
             t += C::NGROUPS;
-            while (t >= tiles) { t -= tiles; l++; }
+            while (t >= tiles) { t -= tiles; if (++l == layers) { l = 0; kb += tiles; } }
         }
     }
     tc_fence_before();
@@ -1101,7 +1157,14 @@ int launch_trunk(const azb_nng_net *n, const float *obs, int batch, const int *r
         sms = 2 * pairs;
     }
     // compact mode: upper bound, surplus CTAs exit at once.  Pair mode: pairs of tiles over pairs of CTAs
-    const int grid = C::PAIR ? 2 * tile_share((batch + 1) / 2, C::TILES, sms / 2).nct : tile_share(batch, C::TILES, sms).nct;
+    // one wave of persistent units, or whole waves of one-round units: the net's flags, else AZB_NNG_PERSIST=0 / 1, else the default
+    static int persist_default = -1;
+    if (persist_default < 0) {
+        const char *e = getenv("AZB_NNG_PERSIST");
+        persist_default = e != nullptr ? (atoi(e) != 0 ? 1 : 0) : 1;
+    }
+    const int persist = (n->flags & AZB_NNG_PERSIST) ? 1 : (n->flags & AZB_NNG_ONE_ROUND) ? 0 : persist_default;
+    const int grid = (C::PAIR ? 2 : 1) * unit_share(batch, C::TILES, sms, C::PAIR, persist != 0, 0).units;
     const int MT = (n->max_boards + 127) / 128;
     const unsigned char *wt = reinterpret_cast<const unsigned char *>(n->wtrunk);
     unsigned char *gact = reinterpret_cast<unsigned char *>(n->gact);
@@ -1113,9 +1176,9 @@ int launch_trunk(const azb_nng_net *n, const float *obs, int batch, const int *r
     memcpy(P.sh, n->h_params + (size_t)(L + D1) * C::CH, sizeof(float) * (size_t)D1 * C::CH);
     if (dump != nullptr)
         return launch_maybe_pair(k_trunk_tc<C, true>, C::PAIR, grid, C::THREADS, C::SMEM, s, obs, batch, (int)n->in_channels, (int)n->board_h,
-                                 (int)n->board_w, (int)n->depth, wt, P, gact, MT, (int)n->head_kc, dump, dump_layer, rows, count, sms);
+                                 (int)n->board_w, (int)n->depth, wt, P, gact, MT, (int)n->head_kc, dump, dump_layer, rows, count, sms, persist);
     return launch_maybe_pair(k_trunk_tc<C, false>, C::PAIR, grid, C::THREADS, C::SMEM, s, obs, batch, (int)n->in_channels, (int)n->board_h,
-                             (int)n->board_w, (int)n->depth, wt, P, gact, MT, (int)n->head_kc, (float *)nullptr, -1, rows, count, sms);
+                             (int)n->board_w, (int)n->depth, wt, P, gact, MT, (int)n->head_kc, (float *)nullptr, -1, rows, count, sms, persist);
 }
 
 template <class C>
@@ -1243,6 +1306,15 @@ extern "C" int azb_nng_layout(int32_t channels, int32_t precision, int32_t *out)
     out[5] = g::MAXD;
     out[6] = 3 / dys;                                       /* weight slabs per trunk layer */
     out[7] = 1;                                             /* weight slabs of the stem */
+    return 0;
+}
+
+/* host-only: how k_trunk_tc deals the tiles of `boards` boards to its units -- see include/azb200_nn.h */
+extern "C" int azb_nng_tile_plan(int32_t channels, int32_t boards, int32_t sms, int32_t pair, int32_t persist, int32_t unit, int32_t *out)
+{
+    if (!out || (channels != 32 && channels != 64) || boards < 0 || sms < 2) return -1;
+    const g::UnitShare u = g::unit_share(boards, channels == 32 ? 7 : 2, sms, pair != 0, persist != 0, unit);
+    out[0] = u.units; out[1] = u.n; out[2] = u.first; out[3] = u.rounds; out[4] = u.tiles;
     return 0;
 }
 

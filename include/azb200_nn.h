@@ -76,8 +76,12 @@ int azb_nn_tc_frame_rows_per_board(void);
 enum { AZB_NN_BF16 = 0, AZB_NN_F16 = 1, AZB_NN_BF16X2 = 2, AZB_NN_F16X2 = 3 };
 
 /* azb_nng_net.flags.  AZB_NNG_PAIR: the 32 / 64-channel trunk runs as clusters of two CTAs whose tiles advance in
- * lockstep as one M = 256 MMA stream (tcgen05 cta_group::2), each CTA staging half of the N rows of every weight chunk. */
-enum { AZB_NNG_PAIR = 1 };
+ * lockstep as one M = 256 MMA stream (tcgen05 cta_group::2), each CTA staging half of the N rows of every weight chunk.
+ * AZB_NNG_PERSIST / AZB_NNG_ONE_ROUND: how the 32 / 64-channel trunk deals its tiles -- ONE wave of resident CTAs (pairs)
+ * that run their share in several rounds (set-up and tail of a CTA paid once), or whole waves of CTAs with one round
+ * each.  Neither flag: the kernel's default (environment AZB_NNG_PERSIST=0 / 1, else persistent).  Same arithmetic:
+ * outputs are bit-identical. */
+enum { AZB_NNG_PAIR = 1, AZB_NNG_PERSIST = 2, AZB_NNG_ONE_ROUND = 4 };
 
 typedef struct azb_nng_net {
     int32_t channels, depth, in_channels, board_h, board_w, action_size;
@@ -86,7 +90,8 @@ typedef struct azb_nng_net {
     int32_t head_nt;        /* head GEMM N tile (multiple of 16, <= 256)                                      */
     int32_t head_ntiles;    /* head_nt * head_ntiles >= action_size + 3                                       */
     int32_t head_kc;        /* head K in 8-element chunks, >= H*W*channels/8, multiple of layout[4]           */
-    int32_t flags;          /* AZB_NNG_PAIR: wtrunk is laid out for CTA pairs (32 / 64 channels), see wtrunk            */
+    int32_t flags;          /* AZB_NNG_PAIR: wtrunk is laid out for CTA pairs (32 / 64 channels), see wtrunk;          */
+                            /*   AZB_NNG_PERSIST / AZB_NNG_ONE_ROUND                                                   */
     const void *wtrunk;     /* device, slab stream: slab s at s * layout[2] bytes.  32 / 64 channels: slab 0 = stem    */
                             /*   [part][4 K chunks: dy=-1,0,+1,zero][3*channels][8 cin], the others, layer by     */
                             /*   layer, [part][dy in slab][cin/8][dx*channels + cout][8 cin]; part = hi, lo.       */
@@ -113,6 +118,11 @@ typedef struct azb_nng_net {
  * channels), slab bytes, boards per CTA, head K-chunk granularity, max depth, weight slabs per trunk layer, weight slabs
  * of the stem.  -1: unsupported channels / precision. */
 int azb_nng_layout(int32_t channels, int32_t precision, int32_t *out);
+/* Host only, no device needed: how the 32 / 64-channel trunk deals the tiles (two boards each; pair: pairs of tiles) of
+ * `boards` boards to its units (CTAs; pair: CTA pairs) on `sms` SMs.  out[0..4] = number of units, then for `unit`: its
+ * number of tiles, its first tile, its rounds, its tiles per round (rounds * tiles per round >= number of tiles; all 0
+ * for a unit beyond the grid).  -1: bad argument. */
+int azb_nng_tile_plan(int32_t channels, int32_t boards, int32_t sms, int32_t pair, int32_t persist, int32_t unit, int32_t *out);
 /* obs f32 [batch, C, H, W] -> policy f32 [batch, A], value f32 [batch, 3] (probabilities).  rows / count (both or
  * neither): compact evaluation of boards rows[0 .. *count) as azb_nn_forward_tc_rows, batch = upper bound.
  * Asynchronous on `stream` (two or three kernel launches).  Status codes as azb_nn_forward. */

@@ -177,13 +177,13 @@ def _tol(precision, m, obs, want):
     return max(2 * err, 1e-4)
 
 
-def _run(geom, batch, precision, sharpen=1.0, depth=None, pair=None):
+def _run(geom, batch, precision, sharpen=1.0, depth=None, pair=None, persist=None):
     dev = torch.device("cuda")
     m = _model(geom, depth=depth, sharpen=sharpen).to(dev)
     obs = _obs(geom, batch).to(dev)
     A = GEOMS[geom]["A"]
     pol = torch.zeros(batch, A, device=dev); val = torch.zeros(batch, 3, device=dev)
-    ev = nn_tc.TensorCoreEvaluator(m, obs, pol, val, precision=precision, pair=pair)
+    ev = nn_tc.TensorCoreEvaluator(m, obs, pol, val, precision=precision, pair=pair, persist=persist)
     ev()
     torch.cuda.synchronize()
     return m, obs, pol, val, ev
@@ -304,3 +304,83 @@ def test_cta_pairs_equal_single_ctas_bit_for_bit(geom, precision, batch):
     m2, obs2, pol2, val2, ev2 = _run(geom, batch, precision, pair=False)
     assert not ev2.pair
     assert torch.equal(pol, pol2) and torch.equal(val, val2)
+
+
+@pytest.mark.parametrize("channels", [32, 64])
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("persist", [0, 1])
+def test_tile_plan_deals_every_tile_exactly_once(channels, pair, persist):
+    """azb_nng_tile_plan (host only): the units' shares are consecutive, disjoint and cover all tiles (pair mode: pairs of
+    tiles); a unit's rounds x tiles-per-round hold its share with fewer than `rounds` empty tiles, tiles per round fit the
+    CTA's tensor memory; persistent plans never exceed one wave of resident units."""
+    import ctypes as C
+    from azb200 import _capi
+    lib = _capi.load()
+    cap = 7 if channels == 32 else 2
+    for sms in (148, 132, 3):
+        resident = sms // 2 if pair else sms
+        if resident < 1:
+            continue
+        for boards in [0, 1, 2, 3, 4, 5, 27, 28, 29, 147, 148, 296, 297, 1000, 2048, 3915, 4133, 6960, 8192, 16384, 65536]:
+            out = (C.c_int32 * 5)()
+            assert lib.azb_nng_tile_plan(channels, boards, sms, pair, persist, 0, out) == 0
+            units = out[0]
+            tiles = (boards + 1) // 2
+            items = (tiles + 1) // 2 if pair else tiles
+            assert units == (0 if boards == 0 else units) and (units > 0) == (boards > 0)
+            if persist:
+                assert units == min(items, resident)
+            nxt = 0
+            for u in range(units):
+                assert lib.azb_nng_tile_plan(channels, boards, sms, pair, persist, u, out) == 0
+                _, n, first, rounds, per = out
+                assert n >= 1 and first == nxt
+                assert 1 <= per <= cap and rounds * per >= n and rounds * per - n < rounds
+                if not persist:
+                    assert rounds == 1
+                nxt += n
+            assert nxt == items
+            assert lib.azb_nng_tile_plan(channels, boards, sms, pair, persist, units, out) == 0 and list(out)[1:] == [0, 0, 0, 0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", ["connect4", "brandubh", "brandubh32", "connect4_64"])
+@pytest.mark.parametrize("precision", ["bf16x2", "fp16"])
+@pytest.mark.parametrize("pair", [True, False])
+@pytest.mark.parametrize("batch", [3, 1000, 4133, 8192])
+def test_persistent_units_equal_one_round_units_bit_for_bit(geom, precision, pair, batch):
+    """AZB_NNG_PERSIST (one wave of CTAs running their share of the tiles in several rounds, the next round's observations
+    staged by the last layer's epilogue) against AZB_NNG_ONE_ROUND (whole waves of CTAs): the same arithmetic per board,
+    so policy and value are bit-identical -- at batch sizes of one round, of several rounds, and with empty tiles."""
+    m, obs, pol, val, ev = _run(geom, batch, precision, pair=pair, persist=True)
+    m2, obs2, pol2, val2, ev2 = _run(geom, batch, precision, pair=pair, persist=False)
+    assert torch.equal(pol, pol2) and torch.equal(val, val2)
+    want = _want(m, obs)
+    tol = _tol(precision, m, obs, want)
+    assert float((pol - want[0]).abs().max()) <= tol and float((val - want[1]).abs().max()) <= tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", ["connect4", "brandubh"])
+def test_persistent_units_compact_rows(geom):
+    """compact evaluation (rows / device-side count) through several rounds of persistent units"""
+    dev = torch.device("cuda")
+    batch = 8192
+    m = _model(geom).to(dev)
+    obs = _obs(geom, batch).to(dev)
+    A = GEOMS[geom]["A"]
+    rng = np.random.RandomState(5)
+    sel = np.sort(rng.choice(batch, size=6960, replace=False)).astype(np.int32)
+    rows = torch.zeros(batch, dtype=torch.int32, device=dev)
+    rows[:len(sel)] = torch.from_numpy(sel).to(dev)
+    count = torch.tensor([len(sel)], dtype=torch.int32, device=dev)
+    outs = []
+    for persist in (True, False):
+        pol = torch.full((batch, A), -1.0, device=dev); val = torch.full((batch, 3), -1.0, device=dev)
+        nn_tc.TensorCoreEvaluator(m, obs, pol, val, precision="bf16x2", rows=rows, count=count, persist=persist)()
+        torch.cuda.synchronize()
+        outs.append((pol, val))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    mask = torch.zeros(batch, dtype=torch.bool, device=dev)
+    mask[torch.from_numpy(sel).long().to(dev)] = True
+    assert bool((outs[0][0][~mask] == -1).all()) and bool((outs[0][0][mask] >= 0).all())
