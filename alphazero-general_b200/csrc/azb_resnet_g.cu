@@ -182,7 +182,9 @@ struct SmemPrm {                               // the three arrays staged in sha
 // channels, xv = the residual stream's 16 values (EPI_CONV2 only; rewritten for stem / conv2).
 // boff: offset of this thread's 16 bias values (stem / conv1); soff: of its 16 BN1 scale / shift values, < 0: no BN + ReLU
 // after the residual update (the last block hands x itself to the heads; depth 0: the stem does)
-template <class C, int EPI, bool DBG, bool WAIT_ST = true, class PV>
+// KEEP_X = false (k_trunk_tc): the LAST layer (soff < 0: its output goes to the heads) does not write x back to tensor
+// memory -- nobody reads it, and in a persistent CTA the next round's stem epilogue of the same tile may already be running
+template <class C, int EPI, bool DBG, bool WAIT_ST = true, bool KEEP_X = true, class PV>
 __device__ __forceinline__ void epilogue_finish(float2 (&r)[8], uint32_t (&xv)[16], uint32_t t_x, unsigned char *dst, size_t part_stride,
                                                 size_t chunk_stride, const PV &pv, int boff, int soff, bool live, float *dump_row)
 {
@@ -200,14 +202,14 @@ __device__ __forceinline__ void epilogue_finish(float2 (&r)[8], uint32_t (&xv)[1
             r[c].x = fmaxf(r[c].x, 0.0f); r[c].y = fmaxf(r[c].y, 0.0f);
             xv[2 * c] = __float_as_uint(r[c].x); xv[2 * c + 1] = __float_as_uint(r[c].y);
         }
-        tmem_st16(t_x, xv);
+        if (KEEP_X || soff >= 0) tmem_st16(t_x, xv);
     } else if (EPI == EPI_CONV2) {
 #pragma unroll
         for (int c = 0; c < 8; c++) {
             r[c] = __fadd2_rn(r[c], f2(xv[2 * c], xv[2 * c + 1]));
             xv[2 * c] = __float_as_uint(r[c].x); xv[2 * c + 1] = __float_as_uint(r[c].y);
         }
-        tmem_st16(t_x, xv);
+        if (KEEP_X || soff >= 0) tmem_st16(t_x, xv);
     }
     if (EPI == EPI_CONV1 || soff >= 0) {
         if (EPI != EPI_CONV1) {
@@ -232,7 +234,8 @@ __device__ __forceinline__ void epilogue_finish(float2 (&r)[8], uint32_t (&xv)[1
 //   conv2: x += D -> TMEM;  a = relu(bn1_next(x))               (last block: a = x, the head input)
 template <class C, int EPI, bool DBG, class PV>
 __device__ __forceinline__ void epilogue_tile(uint32_t t_p, uint32_t t_x, unsigned char *dst, size_t part_stride, size_t chunk_stride,
-                                              const PV &pv, int boff, int soff, bool live, int lane, uint32_t bar_pempty, float *dump_row)
+                                              const PV &pv, int boff, int soff, bool live, int lane, uint32_t bar_pempty, uint32_t bar_ready,
+                                              float *dump_row)
 {
     uint32_t pm[16], p0[16], pp[16], xv[16];
     tmem_ld16(t_p, pm);
@@ -241,8 +244,15 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_p, uint32_t t_x, unsign
     if (EPI == EPI_CONV2) tmem_ld16(t_x, xv);
     tmem_ld_wait();
     tc_fence_before();                    // the accumulator is in registers: hand the ring slot back to the MMA warps
+    // bar_ready != 0 (last layer of a round that is not the last): the tile itself is handed on here, too -- x has been read,
+    // the next round's observations are in the frame (staged by the caller; this fence publishes them to the async proxy),
+    // and what is left of this epilogue touches neither the frame nor tensor memory
+    if (bar_ready != 0u) fence_proxy_async();
     __syncwarp();
-    if (lane == 0) { if (C::PAIR) mbar_arrive_cluster(bar_pempty); else mbar_arrive(bar_pempty); }
+    if (lane == 0) {
+        if (C::PAIR) mbar_arrive_cluster(bar_pempty); else mbar_arrive(bar_pempty);
+        if (bar_ready != 0u) { if (C::PAIR) mbar_arrive_cluster(bar_ready); else mbar_arrive(bar_ready); }
+    }
     const int src_up = (lane + 31) & 31, src_dn = (lane + 1) & 31;
     float2 r[8];
 #pragma unroll
@@ -261,7 +271,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_p, uint32_t t_x, unsign
         }
         r[c] = __fadd2_rn(__fadd2_rn(up, f2(p0[2 * c], p0[2 * c + 1])), dn);
     }
-    epilogue_finish<C, EPI, DBG>(r, xv, t_x, dst, part_stride, chunk_stride, pv, boff, soff, live, dump_row);
+    epilogue_finish<C, EPI, DBG, true, false>(r, xv, t_x, dst, part_stride, chunk_stride, pv, boff, soff, live, dump_row);
 }
 
 // MMAs of one (tile, slab).  Trunk slab: [part][dy in slab][K chunk][NACC][8]; per 16-channel K step the passes
@@ -598,36 +608,26 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
             }
             float *dmp = nullptr;
             if (DBG && dump != nullptr && l == dump_layer && brd < blim) dmp = dump + ((size_t)brd * 64 + (r0 & 63)) * C::CH + 16 * cg;
-            // last layer of a round that is not the last: this thread's position of the next round's board goes into the frame
-            // after the epilogue.  Its row index is fetched and its observation lines are requested into L2 now, under the
-            // wait for this tile's MMAs (no registers held across the epilogue: the kernel sits at its register limit)
+            // Last layer of a round that is not the last (`handoff`): its epilogue writes to global memory only, and the tile's
+            // frame rows are free as soon as its MMAs have completed.  So the next round's observation of this thread's
+            // position is requested into L1 now, under the wait for those MMAs (its row index is the one register held across
+            // the wait: the kernel sits at its register limit, and values parked in local memory would expose the latency of
+            // both loads), converted into the frame right after the wait, and epilogue_tile hands the tile to the next round's
+            // stem together with the accumulator -- the stem's MMAs run under this epilogue's stores.
+            const bool handoff = last && kb + tiles < ktot;
             int ngb = -1;
-            if (last && cg == 0 && live_pos && kb + tiles < ktot) {
+            if (handoff && cg == 0 && live_pos) {
                 const int nb = brd + KSTEP * tiles;
                 if (nb < blim) {
                     ngb = rows != nullptr ? rows[nb] : nb;
                     const float *o = obs + (size_t)ngb * in_ch * HW + pos;
-                    for (int k = 0; k < in_ch; k++) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(o + (size_t)k * HW));
+                    for (int k = 0; k < in_ch; k++) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(o + (size_t)k * HW));
                 }
             }
             if (within == 0) mbar_wait<32>(BAR(BAR_PFULL + slot), (uint32_t)(use & 1));
             asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "r"(C::GW * 32) : "memory");
             tc_fence_after();
             if (DBG && blockIdx.x == 0 && within == 0 && lane == 0 && g < 256) g_trace[4 * g + 2] = clock64();
-            const int ho = 16 * cg;
-            if (l == 0) {
-                epilogue_tile<C, EPI_STEM, DBG>(t_p, t_x, dst, part_stride, chunk_stride, pv, ho, depth > 0 ? ho : -1, live, lane,
-                                                LBAR(BAR_PEMPTY + slot), dmp);
-            } else if (is_c1) {
-                epilogue_tile<C, EPI_CONV1, DBG>(t_p, t_x, dst, part_stride, chunk_stride, pv, l * C::CH + ho, -1, live, lane,
-                                                 LBAR(BAR_PEMPTY + slot), dmp);
-            } else {
-                const int nblk = l >> 1;                      // the block that consumes x next
-                epilogue_tile<C, EPI_CONV2, DBG>(t_p, t_x, dst, part_stride, chunk_stride, pv, 0, last ? -1 : nblk * C::CH + ho, live, lane,
-                                                 LBAR(BAR_PEMPTY + slot), dmp);
-            }
-            // the frame rows of this tile are free (its last MMAs completed before this epilogue started): the stem of round
-            // r + 1 waits for the same READY barrier as any layer
             if (ngb >= 0) {
                 float2 nc[4];
 #pragma unroll
@@ -637,9 +637,24 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
                 }
                 stage_obs(nc, C::PADR + 128 * t + r0);
             }
-            fence_proxy_async();              // the next layer's MMAs read these rows through the async proxy
-            __syncwarp();
-            if (lane == 0) { if (C::PAIR) mbar_arrive_cluster(LBAR(BAR_READY + t)); else mbar_arrive(BAR(BAR_READY + t)); }
+            const uint32_t rdy = handoff ? LBAR(BAR_READY + t) : 0u;
+            const int ho = 16 * cg;
+            if (l == 0) {
+                epilogue_tile<C, EPI_STEM, DBG>(t_p, t_x, dst, part_stride, chunk_stride, pv, ho, depth > 0 ? ho : -1, live, lane,
+                                                LBAR(BAR_PEMPTY + slot), rdy, dmp);
+            } else if (is_c1) {
+                epilogue_tile<C, EPI_CONV1, DBG>(t_p, t_x, dst, part_stride, chunk_stride, pv, l * C::CH + ho, -1, live, lane,
+                                                 LBAR(BAR_PEMPTY + slot), 0u, dmp);
+            } else {
+                const int nblk = l >> 1;                      // the block that consumes x next
+                epilogue_tile<C, EPI_CONV2, DBG>(t_p, t_x, dst, part_stride, chunk_stride, pv, 0, last ? -1 : nblk * C::CH + ho, live, lane,
+                                                 LBAR(BAR_PEMPTY + slot), rdy, dmp);
+            }
+            if (!handoff) {
+                fence_proxy_async();          // the next layer's MMAs read these rows through the async proxy
+                __syncwarp();
+                if (lane == 0) { if (C::PAIR) mbar_arrive_cluster(LBAR(BAR_READY + t)); else mbar_arrive(BAR(BAR_READY + t)); }
+            }
             if (DBG && blockIdx.x == 0 && within == 0 && lane == 0 && g < 256) g_trace[4 * g + 3] = clock64();
             t += C::NGROUPS;
             while (t >= tiles) { t -= tiles; if (++l == layers) { l = 0; kb += tiles; } }

@@ -34,11 +34,37 @@ t0 = buf[0]
 print(f"set-up detail: frame zeroed by thread 0 {buf[1008] - t0}, barriers initialised {buf[1009] - t0}, init fence done {buf[1010] - t0}")
 print(f"set-up detail: alloc starts {buf[1004] - t0}, alloc done {buf[1005] - t0}, frame zeroed {buf[1006] - t0}, after __syncthreads {buf[1007] - t0}")
 print(f"CTA entry {buf[1000] - t0}, set-up done {buf[1001] - t0}, observations staged {buf[1002] - t0}, first issue 0, exit {buf[1003] - t0}")
+plan = (C.c_int32 * 5)()
+sms = torch.cuda.get_device_properties(0).multi_processor_count
+assert ev.lib.azb_nng_tile_plan(ev.net.channels, batch, sms, 1 if ev.pair else 0, int(os.environ.get("AZB_NNG_PERSIST", "1")), 0, plan) == 0
+units, n_tiles, first, rounds, tiles = plan
+print(f"unit 0 of {units}: {n_tiles} tiles in {rounds} rounds of {tiles}; {layers} layers")
+ev_rows = []
 g = 0
-while g < 256 and buf[4 * g] != 0 and g < layers * tiles:
+while g < 256 and buf[4 * g] != 0 and g < rounds * layers * tiles:
     a, b, c, d = (buf[4 * g + i] - t0 for i in range(4))
-    print(f"g {g:3d}: issue {a:8d} commit {b:8d} (+{b - a:5d})  epi start {c:8d} (+{c - b:5d} after commit)  done {d:8d} (epilogue {d - c:5d})")
+    ev_rows.append((g, a, b, c, d))
+    if os.environ.get("NN_TRACE_FULL"):
+        print(f"g {g:3d}: issue {a:8d} commit {b:8d} (+{b - a:5d})  epi start {c:8d} (+{c - b:5d} after commit)  done {d:8d} (epilogue {d - c:5d})")
     g += 1
+# summary: per (round, layer) the span of its tiles' MMAs, and the idle time of the issue stream before each tile
+print("round layer: first issue, last commit, span, issue time (sum of commit - issue), idle before its tiles (sum of issue - previous commit)")
+prev_commit = 0
+for v in range(rounds * layers):
+    rows = ev_rows[v * tiles:(v + 1) * tiles]
+    if not rows:
+        break
+    busy = sum(b - a for _, a, b, _, _ in rows)
+    idle = 0
+    for _, a, b, _, _ in rows:
+        idle += max(0, a - prev_commit)
+        prev_commit = b
+    epi = [d - c for _, _, _, c, d in rows]
+    lag = [c - b for _, _, b, c, _ in rows]
+    print(f"r {v // layers} l {v % layers}: {rows[0][1]:8d} {rows[-1][2]:8d} span {rows[-1][2] - rows[0][1]:6d} issue {busy:6d} idle {idle:6d}  "
+          f"epilogue mean {sum(epi) // len(epi):5d}  commit->epilogue start mean {sum(lag) // len(lag):5d}")
+if ev_rows:
+    print(f"last commit {ev_rows[-1][2]}, last epilogue done {max(r[4] for r in ev_rows)}, exit {buf[1003] - t0}")
 
 # every CTA: life time and the gap to the next CTA on the same SM
 import collections
