@@ -703,7 +703,9 @@ def main():
                                    f"{'tree-only warmup mode' if a.tree_only else 'NN in the loop'}",
                        "games_per_gpu": B, "sims_per_move": sims, "net": a.net, "nn": a.nn, "nn_kernel": nn_kernel, "nn_precision": a.precision,
                        "cohorts": a.cohorts, "round_graph": bool(drv.round_graph),
-                       "nn_rows": "non-terminal leaves only" if compact else "every leaf", "channels_last": not a.nchw, "lanes_per_game": a.lanes or 8, "rng": "philox", "parallelism": f"games x{world} (no data-path collective)",
+                       "nn_rows": "non-terminal leaves only" if compact else "every leaf",
+                       "nn_tile_plan": ("whole waves of one-round CTAs" if os.environ.get("AZB_NNG_PERSIST", "1") == "0"
+                                        else "one wave of persistent CTAs, tiles in rounds") if a.nn == "tc" else None, "channels_last": not a.nchw, "lanes_per_game": a.lanes or 8, "rng": "philox", "parallelism": f"games x{world} (no data-path collective)",
                        "l2": "node pool %.1f GB per GPU > 126 MB L2; no flush" % (st1["pool_bytes"] / 1e9),
                        "preroll_rounds": a.preroll},
             "clocks": clk, "gpu_launches": drv.launches - launches0,
