@@ -384,3 +384,30 @@ def test_persistent_units_compact_rows(geom):
     mask = torch.zeros(batch, dtype=torch.bool, device=dev)
     mask[torch.from_numpy(sel).long().to(dev)] = True
     assert bool((outs[0][0][~mask] == -1).all()) and bool((outs[0][0][mask] >= 0).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", ["connect4", "brandubh"])
+@pytest.mark.parametrize("depth", [0, 1])
+@pytest.mark.parametrize("pair", [True, False])
+def test_persistent_units_shallow_networks(geom, depth, pair):
+    """depth 0 (the stem is the last layer and hands the tile on itself) and depth 1 through several rounds: equal to the
+    one-round plan bit for bit and within 1e-5 of the module; layer activations of a board of the LAST round are the
+    module's (the debug kernel dumps the layer for every round)."""
+    batch = 8192
+    m, obs, pol, val, ev = _run(geom, batch, "bf16x2", depth=depth, pair=pair, persist=True)
+    m2, obs2, pol2, val2, ev2 = _run(geom, batch, "bf16x2", depth=depth, pair=pair, persist=False)
+    assert torch.equal(pol, pol2) and torch.equal(val, val2)
+    want = _want(m, obs)
+    assert float((pol - want[0]).abs().max()) <= 1e-5 and float((val - want[1]).abs().max()) <= 1e-5
+    got = ev.debug_layer(0)                                  # [batch, H, W, channels]: what the stem hands on
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        x = F.relu(m.bn1(m.conv1(obs)))
+        blocks = list(m.resnet)
+        a = F.relu(blocks[0].bn1(x)) if blocks else x
+    torch.backends.cudnn.allow_tf32 = old
+    a = a.permute(0, 2, 3, 1)
+    scale = float(a.abs().max())
+    assert float((got - a).abs().max()) <= 2e-5 * max(scale, 1.0)      # as test_layer_by_layer
