@@ -66,6 +66,8 @@ SYMBOLS = {
     "azb_set_state": (C.c_int, [_vp, _i32, _vp, _i32, _vp]),
     "azb_force_move": (C.c_int, [_vp, _i32, _i32, _vp]),
     "azb_set_root_flags": (C.c_int, [_vp, _i32, _i32]),
+    "azb_set_leaf_dedup": (C.c_int, [_vp, _i32]),
+    "azb_duplicate_leaves": (C.c_int, [_vp, _vp]),
     "azb_set_root_noise": (C.c_int, [_vp, _vp, _i32, _i32]),
     "azb_drain_samples": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _vp]),
     "azb_drain_samples_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), _vp]),

@@ -106,8 +106,9 @@ def run_selfplay_iteration(game_cls, nnet_module, args, device=0, seed=0, warmup
         # leaf evaluator: the hand-written tcgen05 kernels at their default precision ("bf16x2": within 1e-5 of the
         # reference's fp32 module) wherever they cover the network, else cuDNN TF32 (the reference's own arithmetic);
         # a narrower type only when the caller asks for it (args.nn_precision / precision=)
+        # args.leaf_dedup (optional, default on): games whose leaves have the same observation share one evaluation
         drv = DeviceSelfPlay(engine, nnet_module, cohorts=1, precision=precision or g("nn_precision"), channels_last=True,
-                             fused=fused)
+                             fused=fused, dedup=g("leaf_dedup", None))
     rs = np.random.RandomState(seed)
     quota = int(g("gamesPerIteration"))
     rslot, rturns, rwin = [], [], []

@@ -64,6 +64,7 @@ class SelfPlayEngine:
         cfg.lanes_per_game = int(lanes_per_game)
         cfg.arena = int(bool(arena))
         self.arena = bool(arena)
+        self.leaf_dedup = False
         cfg.cpuct, cfg.fpu_reduction = float(cpuct), float(fpu_reduction)
         cfg.root_noise_frac, cfg.root_policy_temp = float(root_noise_frac), float(root_policy_temp)
         if temps is not None:
@@ -186,6 +187,19 @@ class SelfPlayEngine:
 
     def set_root_flags(self, add_root_noise, add_root_temp):
         check(self.lib.azb_set_root_flags(self.h, int(bool(add_root_noise)), int(bool(add_root_temp))))
+
+    def set_leaf_dedup(self, on=True):
+        """Games whose leaves have the same observation share one network evaluation (include/azb200.h:
+        azb_set_leaf_dedup): select lists only the first of them in nn_rows, expand/backup reads its rows for the others.
+        Bit-identical results; engine-owned policy / value rows and compact evaluation only."""
+        check(self.lib.azb_set_leaf_dedup(self.h, int(bool(on))))
+        self.leaf_dedup = bool(on)
+
+    def duplicate_leaves(self):
+        """leaves served by another game's evaluation since creation / reset"""
+        out = C.c_int64(0)
+        check(self.lib.azb_duplicate_leaves(self.h, C.byref(out)))
+        return int(out.value)
 
     def arena_set_player_to_index(self, player_to_index):
         """arena: SelfPlayAgent.player_to_index = [m, 1 - m]; the per-model row lists follow it."""

@@ -334,11 +334,13 @@ class DeviceSelfPlay:
     that tree work of one half overlaps inference of the other."""
 
     def __init__(self, engine, nnet, cohorts=1, precision=None, use_graph=True, channels_last=False, fused=None,
-                 split=None, round_graph=None, skip_terminal=True):
+                 split=None, round_graph=None, skip_terminal=True, dedup=None):
         """precision: operand precision of the leaf evaluator, see azb200.nn_tc.make_evaluator -- "bf16x2" (default:
         hand-written tcgen05 kernels, within 1e-5 of the reference's fp32 module), "fp16", "bf16" (opt-in performance
         modes), "fp32" / "tf32" / "cudnn-bf16" (PyTorch / cuDNN).  fused: None = the hand-written kernels whenever they
-        cover the network and the precision; False = cuDNN; "tc-r1" / "mma" = the round-1 bf16-only kernels."""
+        cover the network and the precision; False = cuDNN; "tc-r1" / "mma" = the round-1 bf16-only kernels.
+        dedup: leaf de-duplication (engine.set_leaf_dedup: games whose leaves have the same observation share one
+        evaluation; bit-identical results) -- None = on whenever the evaluator takes the engine's compact row list."""
         assert cohorts in (1, 2)
         from . import nn_tc
         self.engine = engine
@@ -353,7 +355,11 @@ class DeviceSelfPlay:
             split = B // 2
         bounds = [0, B] if cohorts == 1 else [0, split, B]
         self.ranges = [(bounds[i], bounds[i + 1] - bounds[i]) for i in range(cohorts)]
-        if hand and kernel != "mma" and skip_terminal and cohorts == 1:
+        self.compact = bool(hand and kernel != "mma" and skip_terminal and cohorts == 1)
+        self.dedup = bool(self.compact and not getattr(engine, "arena", False) and (True if dedup is None else dedup))
+        if self.dedup or getattr(engine, "leaf_dedup", False):
+            engine.set_leaf_dedup(self.dedup)
+        if self.compact:
             # compact evaluation: only the leaves that need the network (the reference evaluates terminal leaves
             # too and discards the answers, SelfPlayAgent.pyx:116-123 / MCTS.pyx:234-235)
             self.evals = [nn_tc.make_evaluator(nnet, engine.obs, engine.policy, engine.value, precision=precision, kernel=kernel,

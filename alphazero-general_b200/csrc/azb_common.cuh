@@ -47,6 +47,19 @@ struct __align__(16) GState {
 constexpr int GF_FINISHED = 0x100;   // terminal, waiting for k_finalize / k_emit
 constexpr int GF_DEAD = 0x200;       // finished beyond the games_played quota: no longer stepped
 
+// The words of a game state its observation is a function of (every Game.observation here reads the bitboards and the
+// turn counter, never the flags): the key of leaf de-duplication.  Equal keys <=> bit-equal observation rows is what the
+// engine needs in one direction only (equal keys => equal rows); states that differ in the turn counter but not in the
+// planes derived from it are simply not merged.
+template <class S> struct LeafKey;
+template <> struct LeafKey<GState> {
+    static constexpr int N = 4;
+    __host__ __device__ __forceinline__ static void get(const GState &s, unsigned long long (&k)[N])
+    {
+        k[0] = s.b0; k[1] = s.b1; k[2] = s.b2; k[3] = (unsigned long long)(unsigned)s.turns;
+    }
+};
+
 struct __align__(16) NodeHot { int n; float q; float p; int child0; };
 struct __align__(8) NodeCold { float v; uint32_t meta; };
 
@@ -102,6 +115,14 @@ struct DevView {
     int nn_par;                        // nn_count[2][2]: select adds to [nn_par][model] and clears [nn_par ^ 1][*] for the next one
     int arena_swap;                    // arena: model = env player ^ arena_swap (SelfPlayAgent.player_to_index); rows of model m
                                        // are listed at nn_rows + m * (B / 2)
+    // leaf de-duplication (azb_set_leaf_dedup; off: dd_table == nullptr): games whose leaves have the same observation
+    // share ONE network evaluation.  select publishes a leaf in dd_table (open addressing, entry = epoch:32 | tag:12 |
+    // slot:20, epoch = the select launch, so the table never needs clearing between simulations), the first game with a
+    // given state is the representative and the only one listed in nn_rows; dd_src[g] names the row expand/backup reads
+    unsigned long long *dd_table; unsigned dd_mask, dd_epoch;
+    void *dd_state;                    // G::State[B]: the leaf state of slot g (what its observation is a function of)
+    int *dd_src;                       // [B]
+    unsigned long long *dd_dups;       // leaves that were served by another game's evaluation
     const float *warm_policy; const float *warm_value;
     // fed root noise
     const float *noise; int noise_events, noise_stride;

@@ -81,7 +81,21 @@ struct azb_engine {
     int lanes = 8;                  // threads per game (Connect4: 8 / 16 / 32)
     int *scratch_i32 = nullptr;     // B * A ints for introspection
     int8_t *scratch_i8 = nullptr;
+    // leaf de-duplication (azb_set_leaf_dedup): buffers allocated on first use, d.dd_table != nullptr while it is on
+    unsigned long long *dd_table = nullptr;
+    unsigned dd_slots = 0, dd_epoch = 0;
 };
+
+// leaf de-duplication: the next select launch gets a fresh epoch (entries of older epochs read as free)
+static inline void dd_next_epoch(azb_engine *e) { if (e->d.dd_table) e->d.dd_epoch = ++e->dd_epoch; }
+// ... and the table is cleared whenever the epochs start over (every move-round: a captured round graph replays the
+// same epochs, so the clear is part of azb_play_moves)
+static inline int dd_restart(azb_engine *e, cudaStream_t s)
+{
+    if (!e->dd_table) return 0;
+    e->dd_epoch = 0;
+    return cudaMemsetAsync(e->dd_table, 0, (size_t)e->dd_slots * sizeof(unsigned long long), s) == cudaSuccess ? 0 : 1;
+}
 
 template <class T>
 static int dev_alloc(azb_engine *e, T **p, size_t count, bool zero = true)
@@ -173,6 +187,11 @@ static int init_slots(azb_engine *e, const uint32_t *mt_seeds_host)
     }
     CK(cudaMemset(e->d.counters, 0, sizeof(Counters)));
     CK(cudaMemset(e->d.err, 0, sizeof(uint32_t)));
+    if (e->dd_table) {
+        CK(cudaMemset(e->dd_table, 0, (size_t)e->dd_slots * sizeof(unsigned long long)));
+        CK(cudaMemset(e->d.dd_dups, 0, sizeof(unsigned long long)));
+        e->dd_epoch = 0;
+    }
     DISPATCH(e, l_init, e, seeds_dev, (cudaStream_t)0);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
@@ -385,6 +404,7 @@ extern "C" int azb_select(azb_engine *e, int32_t first, int32_t count, void *str
     TRY(range_ok(e, first, count));
     cudaStream_t s = (cudaStream_t)stream;
     e->d.nn_par ^= 1;
+    dd_next_epoch(e);
     DISPATCH(e, l_select, e, first, count, s);
     CK(cudaGetLastError());
     return AZB_OK;
@@ -410,6 +430,7 @@ extern "C" int azb_expand_backup_select(azb_engine *e, int32_t first, int32_t co
     const float *pol = policy ? policy : e->d.policy;
     const float *val = value ? value : e->d.value;
     e->d.nn_par ^= 1;
+    dd_next_epoch(e);
     DISPATCH(e, l_expand_select, e, first, count, pol, val, s);
     CK(cudaGetLastError());
     return AZB_OK;
@@ -422,6 +443,50 @@ extern "C" int azb_play_moves(azb_engine *e, int32_t fast, void *stream)
     DISPATCH(e, l_play, e, fast, s);
     e->d.nn_par = 1;                    // the next select uses counter 0 (k_finalize cleared both)
     CK(cudaGetLastError());
+    if (dd_restart(e, s) != 0) return fail(AZB_ERR_CUDA, "leaf de-duplication table clear failed");
+    return AZB_OK;
+}
+
+// Leaf de-duplication: games whose leaves have bit-equal observations share one network evaluation -- only the first
+// such game of a select launch is listed in azb_nn_rows_ptr, the others read its policy / value rows in expand/backup.
+extern "C" int azb_set_leaf_dedup(azb_engine *e, int32_t on)
+{
+    if (!e) return fail(AZB_ERR_BAD_ARGUMENT, "null engine");
+    if (!on) { e->d.dd_table = nullptr; return AZB_OK; }
+    if (e->d.arena) return fail(AZB_ERR_BAD_ARGUMENT, "leaf de-duplication: not in arena mode (one row list per model)");
+    if (e->d.B > (1 << 20)) return fail(AZB_ERR_BAD_ARGUMENT, "leaf de-duplication: at most 2^20 games per engine");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaDeviceSynchronize());
+    if (!e->dd_table) {
+        unsigned slots = 1024;
+        while (slots < 2u * (unsigned)e->d.B) slots <<= 1;
+        e->dd_slots = slots;
+        TRY(dev_alloc(e, &e->dd_table, (size_t)slots));
+        unsigned char *st = nullptr;
+        TRY(dev_alloc(e, &st, (size_t)e->d.B * (size_t)e->gd.state_bytes));
+        e->d.dd_state = st;
+        TRY(dev_alloc(e, &e->d.dd_src, (size_t)e->d.B));
+        TRY(dev_alloc(e, &e->d.dd_dups, 1));
+        e->d.dd_mask = slots - 1u;
+    }
+    std::vector<int> ident((size_t)e->d.B);
+    for (int i = 0; i < e->d.B; i++) ident[(size_t)i] = i;
+    CK(cudaMemcpy(e->d.dd_src, ident.data(), ident.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemset(e->dd_table, 0, (size_t)e->dd_slots * sizeof(unsigned long long)));
+    e->dd_epoch = 0;
+    e->d.dd_table = e->dd_table;
+    return AZB_OK;
+}
+
+extern "C" int azb_duplicate_leaves(azb_engine *e, int64_t *out)
+{
+    if (!e || !out) return fail(AZB_ERR_BAD_ARGUMENT, "null argument");
+    *out = 0;
+    if (!e->dd_table) return AZB_OK;
+    CK(cudaSetDevice(e->cfg.device));
+    unsigned long long v = 0;
+    CK(cudaMemcpy(&v, e->d.dd_dups, sizeof(v), cudaMemcpyDeviceToHost));
+    *out = (int64_t)v;
     return AZB_OK;
 }
 

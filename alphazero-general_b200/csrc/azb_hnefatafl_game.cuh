@@ -14,6 +14,14 @@ struct __align__(16) HnefState : TState128 {
     int pad0, pad1;
 };
 static_assert(sizeof(HnefState) == 64, "hnefatafl slot state");
+template <> struct LeafKey<HnefState> {
+    static constexpr int N = 7;
+    __host__ __device__ __forceinline__ static void get(const HnefState &s, unsigned long long (&k)[N])
+    {
+        k[0] = s.b0.lo; k[1] = s.b0.hi; k[2] = s.b1.lo; k[3] = s.b1.hi; k[4] = s.b2.lo; k[5] = s.b2.hi;
+        k[6] = (unsigned long long)(unsigned)s.turns;
+    }
+};
 
 struct HnefataflG {
     using State = HnefState;

@@ -337,6 +337,70 @@ __device__ __forceinline__ float seen_policy(const NodeHot (&kh)[IT], const bool
 }
 
 // ------------------------------------------------------------------------------
+// Leaf de-duplication (DevView::dd_table): one thread of a game whose leaf needs the network publishes the leaf's state
+// and returns the slot whose policy / value rows answer for it -- its own (it is the first game of this select launch with
+// that state: the representative, the only one listed for the evaluator) or the representative's.  The answers are
+// bit-identical either way: the evaluator's arithmetic for a row does not depend on where the row sits in the batch
+// (tests: compact == dense, CTA pairs == single CTAs, persistent == one-round plans).
+//   representative: state -> dd_state[g]; __threadfence; CAS (entry of another epoch -> epoch | tag | g)
+//   duplicate:      sees an entry of this epoch with its tag; __threadfence; reads dd_state[rep] from L2; equal keys
+// Open addressing, linear probing, load factor <= 1/2.  A full table (cannot happen) degrades to "evaluate it".
+// ------------------------------------------------------------------------------
+template <class S>
+__device__ __noinline__ int dedup_leaf(unsigned long long *table, unsigned mask, unsigned epoch32, S *states, int g, const S st)
+{
+    using K = LeafKey<S>;
+    static_assert(sizeof(S) % 16 == 0, "state copied in 16-byte pieces");
+    unsigned long long key[K::N];
+    K::get(st, key);
+    unsigned long long h = 0x9E3779B97F4A7C15ULL;
+#pragma unroll
+    for (int i = 0; i < K::N; i++) {               // splitmix-style mixing of the key words
+        h ^= key[i] + 0x9E3779B97F4A7C15ULL + (h << 6) + (h >> 2);
+        h *= 0xBF58476D1CE4E5B9ULL;
+        h ^= h >> 29;
+    }
+    S *mine = states + g;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(&st);
+        uint4 *dst = reinterpret_cast<uint4 *>(mine);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(S) / 16); i++) __stcg(dst + i, src[i]);
+    }
+    __threadfence();
+    const unsigned long long epoch = (unsigned long long)epoch32 << 32;
+    const unsigned long long tag = ((h >> 44) & 0xFFFULL) << 20;
+    const unsigned long long entry = epoch | tag | (unsigned long long)g;
+    unsigned slot = (unsigned)h & mask;
+    for (unsigned probe = 0; probe <= 2u * mask + 1u; probe++) {
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(table + slot);
+        if ((cur & 0xFFFFFFFF00000000ULL) != epoch) {                     // free in this epoch
+            const unsigned long long old = atomicCAS(table + slot, cur, entry);
+            if (old == cur) return g;                                      // representative
+            cur = old;
+            if ((cur & 0xFFFFFFFF00000000ULL) != epoch) continue;          // (only entries of this epoch are ever written)
+        }
+        if ((cur & (0xFFFULL << 20)) == tag) {
+            const int r = (int)(cur & 0xFFFFFULL);
+            __threadfence();
+            const uint4 *rp = reinterpret_cast<const uint4 *>(states + r);
+            S other;
+            uint4 *op = reinterpret_cast<uint4 *>(&other);
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(S) / 16); i++) op[i] = __ldcg(rp + i);
+            unsigned long long ok[K::N];
+            K::get(other, ok);
+            bool same = true;
+#pragma unroll
+            for (int i = 0; i < K::N; i++) same = same && ok[i] == key[i];
+            if (same) return r;
+        }
+        slot = (slot + 1u) & mask;
+    }
+    return g;
+}
+
+// ------------------------------------------------------------------------------
 // MCTS.find_leaf
 // ------------------------------------------------------------------------------
 template <class G, bool WRITE_OBS>
@@ -477,7 +541,18 @@ __device__ __forceinline__ void select_game(const DevView &d, int g, bool active
         // the leaves the network has to evaluate: a terminal leaf's value is its win state (MCTS.pyx:234-235).  One
         // atomic per warp and model, not per game: 8192 adds to one counter were a quarter of this kernel's stall samples
         // arena: one list per model (the model of env player p is p ^ arena_swap), each at most B / 2 long
-        const bool want = active && in_range && lane == 0 && meta_e(cmeta) == 0;
+        bool want = active && in_range && lane == 0 && meta_e(cmeta) == 0;
+        if (d.dd_table != nullptr) {                  // leaf de-duplication: only the first game with this state is listed
+            int src = g;
+            if (want) {
+                src = dedup_leaf<typename G::State>(d.dd_table, d.dd_mask, d.dd_epoch, reinterpret_cast<typename G::State *>(d.dd_state), g, st);
+                d.dd_src[g] = src;
+            }
+            const bool dup = want && src != g;
+            const unsigned db = __ballot_sync(FULL, dup);
+            if (db != 0u && (threadIdx.x & 31u) == (unsigned)__ffs((int)db) - 1u) atomicAdd(d.dd_dups, (unsigned long long)__popc(db));
+            if (dup) want = false;
+        }
         const int m = d.arena ? ((g & 1) ^ d.arena_swap) : 0;
         const unsigned cap = d.arena ? (unsigned)(d.B / 2) : (unsigned)d.B;
         const unsigned wl = threadIdx.x & 31u;
@@ -986,7 +1061,8 @@ __global__ void __launch_bounds__(G::CTA) k_expand_backup(DevView d, int first, 
     int g, lane, sub, gi; bool active;
     if (!group_setup<G>(first, count, g, active, lane, sub, gi)) return;
     if (G::A > G::LANES) { for (int a = lane; a < G::A; a += G::LANES) sm[gi].vec[a] = 0.0f; __syncwarp(); }
-    expand_backup_game<G>(d, g, active, lane, sub, sm[gi], policy + (size_t)g * G::A, value + (size_t)g * 3);
+    const int src = d.dd_table != nullptr ? d.dd_src[g] : g;       // leaf de-duplication: the representative's rows
+    expand_backup_game<G>(d, g, active, lane, sub, sm[gi], policy + (size_t)src * G::A, value + (size_t)src * 3);
 }
 
 // processBatch of simulation s fused with generateBatch of simulation s+1 for the same slots: one launch instead of
@@ -999,7 +1075,8 @@ __global__ void __launch_bounds__(G::CTA) k_expand_select(DevView d, int first, 
     if (blockIdx.x == 0 && threadIdx.x == 0) { d.nn_count[2 * (d.nn_par ^ 1)] = 0; d.nn_count[2 * (d.nn_par ^ 1) + 1] = 0; }   // consumed
     if (!group_setup<G>(first, count, g, active, lane, sub, gi)) return;
     if (G::A > G::LANES) { for (int a = lane; a < G::A; a += G::LANES) sm[gi].vec[a] = 0.0f; __syncwarp(); }
-    expand_backup_game<G>(d, g, active, lane, sub, sm[gi], policy + (size_t)g * G::A, value + (size_t)g * 3);
+    const int src = d.dd_table != nullptr ? d.dd_src[g] : g;       // leaf de-duplication: the representative's rows
+    expand_backup_game<G>(d, g, active, lane, sub, sm[gi], policy + (size_t)src * G::A, value + (size_t)src * 3);
     __syncwarp();
     select_game<G, true>(d, g, active, lane, sub, sm[gi]);
 }

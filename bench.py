@@ -85,6 +85,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-alt", action="store_true")
+    ap.add_argument("--leaf-dedup", action="store_true",
+                    help="headline with leaf de-duplication on (default: every non-terminal leaf is evaluated; the "
+                         "de-duplicated step is reported as the extra key leaf_dedup)")
     ap.add_argument("--no-select-events", action="store_true")
     ap.add_argument("--roofline-steps", type=int, default=3, help="eager move-rounds timed per select launch for the roofline")
     ap.add_argument("--no-round-graph", action="store_true", help="launch every kernel of a move-round from the host")
@@ -371,7 +374,7 @@ def main():
     drv = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision, channels_last=not a.nchw,
                          fused={"tc": None, "tc-r1": "tc-r1", "mma": "mma", "cudnn": False}[a.nn],
                          round_graph=False if a.no_round_graph else None, split=a.split or None,
-                         skip_terminal=not a.eval_terminal)
+                         skip_terminal=not a.eval_terminal, dedup=a.leaf_dedup)
     compact = a.nn in ("tc", "tc-r1") and not a.eval_terminal and a.cohorts == 1
     nn_kernel = {"tc": ("k_trunk_wide" if netargs["num_channels"] == 128 else "k_trunk_tc") + " + k_head_tc (tcgen05/TMEM, csrc/azb_resnet_g.cu)", "tc-r1": "k_resnet_tc (tcgen05/TMEM, round 1)",
                  "mma": "k_resnet_fused (mma.sync)"}.get(a.nn, "cuDNN " + a.precision)
@@ -640,6 +643,25 @@ def main():
         sustained_leg = {"value": v_sus, "unit": UNIT, "steps": n_sus, "seconds": ms_sus / 1000.0,
                          "clocks": clocks2.stop() if rank == 0 else None}
 
+    # the same step with leaf de-duplication (DeviceSelfPlay's default; the headline above evaluates every non-terminal leaf
+    # unless --leaf-dedup): games whose leaves have the same observation share one evaluation, results bit-identical
+    dedup_leg = None
+    if a.nn == "tc" and compact and not a.tree_only and not a.no_alt and not a.leaf_dedup:
+        d4 = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=a.precision, skip_terminal=True, dedup=True)
+        for _ in range(2):
+            d4.run_round(sims); clear_samples()
+        sd0, dd0 = eng.stats(), eng.duplicate_leaves()
+        v4, ms4 = timed_rounds(d4, 20, warm=0)
+        sd1, dd1 = eng.stats(), eng.duplicate_leaves()
+        need = (sd1["sims"] - sd0["sims"]) - (sd1["terminal_leaves"] - sd0["terminal_leaves"])
+        dedup_leg = {"value": v4, "unit": UNIT, "steps": 20, "ms_per_step": ms4 / 20.0,
+                     "duplicate_fraction_of_non_terminal_leaves": (dd1 - dd0) / max(need, 1),
+                     "note": "same step, same games, bit-identical results: a leaf whose observation equals that of another "
+                             "game's leaf in the same simulation round is not evaluated again (azb_set_leaf_dedup); rank 0's "
+                             "duplicate fraction"}
+        del d4
+        eng.set_leaf_dedup(False)
+
     # secondary legs, same step: the PyTorch/cuDNN TF32 evaluator (the reference's own default arithmetic) and the other
     # operand precisions of the hand-written kernels
     alt, alt_prec = None, None
@@ -649,12 +671,13 @@ def main():
             for prec in ("bf16x2", "fp16x2", "fp16", "bf16"):
                 if prec == a.precision:
                     continue
-                d3 = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=prec, skip_terminal=not a.eval_terminal)
+                d3 = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision=prec, skip_terminal=not a.eval_terminal, dedup=a.leaf_dedup)
                 v3, _ = timed_rounds(d3, 5)
                 alt_prec[prec] = {"value": v3, "unit": UNIT, "steps": 5}
                 del d3
             try:
-                d3 = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision="bf16", fused="tc-r1", skip_terminal=not a.eval_terminal)
+                d3 = DeviceSelfPlay(eng, model, cohorts=a.cohorts, precision="bf16", fused="tc-r1", skip_terminal=not a.eval_terminal,
+                                    dedup=a.leaf_dedup)
                 v3, _ = timed_rounds(d3, 5)
                 alt_prec["bf16 (round-1 kernel k_resnet_tc)"] = {"value": v3, "unit": UNIT, "steps": 5}
                 del d3
@@ -671,20 +694,28 @@ def main():
         e2e = run_e2e(a, eng, model, dev, world)
 
     # e2e_coach: the call a user of the drop-in Coach makes (GpuSelfPlayMixin.processSelfPlayBatches)
-    e2e_coach = None
-    if not a.no_e2e and not a.tree_only and a.game == "connect4" and a.net == "default":
+    e2e_coach, e2e_coach_dedup = None, None
+
+    def coach_leg(dedup):
         # every N: the local part may fail without touching a collective; the reduction below always runs on every rank
         try:
-            e2e_coach = run_e2e_coach(a, model, dev, local, rank, world)
+            r = run_e2e_coach(a, model, dev, local, rank, world, dedup)
         except Exception as ex:          # a secondary number must never take the bench down
-            e2e_coach = {"value": None, "error": repr(ex), "seconds": float("nan"), "sims": 0.0}
+            r = {"value": None, "error": repr(ex), "seconds": float("nan"), "sims": 0.0}
         if world > 1:
-            tq = torch.tensor([e2e_coach["seconds"]], device=dev, dtype=torch.float64)
-            nq = torch.tensor([e2e_coach["sims"]], device=dev, dtype=torch.float64)
+            tq = torch.tensor([r["seconds"]], device=dev, dtype=torch.float64)
+            nq = torch.tensor([r["sims"]], device=dev, dtype=torch.float64)
             dist.all_reduce(tq, op=dist.ReduceOp.MAX); dist.all_reduce(nq, op=dist.ReduceOp.SUM)
-            if "error" not in e2e_coach:
-                e2e_coach.update(value=float(nq.item()) / float(tq.item()), seconds=float(tq.item()), sims=float(nq.item()),
-                                 ranks=world)
+            if "error" not in r:
+                r.update(value=float(nq.item()) / float(tq.item()), seconds=float(tq.item()), sims=float(nq.item()), ranks=world)
+        return r
+
+    if not a.no_e2e and not a.tree_only and a.game == "connect4" and a.net == "default":
+        # e2e_coach keeps every non-terminal leaf evaluated (as `value`); e2e_coach_dedup is the same call with the Coach
+        # path's default, leaf de-duplication -- an iteration starts all its games from the empty board together
+        e2e_coach = coach_leg(a.leaf_dedup)
+        if not a.leaf_dedup and not a.no_alt:
+            e2e_coach_dedup = coach_leg(True)
 
     if world > 1:
         clear_samples()
@@ -703,13 +734,15 @@ def main():
                                    f"{'tree-only warmup mode' if a.tree_only else 'NN in the loop'}",
                        "games_per_gpu": B, "sims_per_move": sims, "net": a.net, "nn": a.nn, "nn_kernel": nn_kernel, "nn_precision": a.precision,
                        "cohorts": a.cohorts, "round_graph": bool(drv.round_graph),
-                       "nn_rows": "non-terminal leaves only" if compact else "every leaf",
+                       "nn_rows": ("distinct non-terminal leaves (leaf de-duplication)" if (compact and a.leaf_dedup) else
+                                   "non-terminal leaves only" if compact else "every leaf"),
                        "nn_tile_plan": ("whole waves of one-round CTAs" if os.environ.get("AZB_NNG_PERSIST", "1") == "0"
                                         else "one wave of persistent CTAs, tiles in rounds") if a.nn == "tc" else None, "channels_last": not a.nchw, "lanes_per_game": a.lanes or 8, "rng": "philox", "parallelism": f"games x{world} (no data-path collective)",
                        "l2": "node pool %.1f GB per GPU > 126 MB L2; no flush" % (st1["pool_bytes"] / 1e9),
                        "preroll_rounds": a.preroll},
             "clocks": clk, "gpu_launches": drv.launches - launches0,
-            "roofline": roof, "roofline_nn": roof_nn, "cpu_baseline": cpu_base, "e2e": e2e, "e2e_coach": e2e_coach, "alt_nn": alt,
+            "roofline": roof, "roofline_nn": roof_nn, "cpu_baseline": cpu_base, "e2e": e2e, "e2e_coach": e2e_coach, "e2e_coach_dedup": e2e_coach_dedup,
+            "leaf_dedup": dedup_leg, "alt_nn": alt,
             "alt_precisions": alt_prec, "nn_error": nn_error, "sustained": sustained_leg,
             "tree_stats": {"sims": dsims, "mean_depth": dD / max(dsims, 1), "mean_children_scanned": dC / max(dsims, 1),
                            "games_finished": st1["results"] - st0["results"], "peak_nodes_per_game": st1["peak_nodes"],
@@ -744,7 +777,7 @@ def model_flops(model, obs_shape):
     return float(total[0])
 
 
-def run_e2e_coach(a, model, dev, local, rank, world):
+def run_e2e_coach(a, model, dev, local, rank, world, dedup=False):
     """Secondary end-to-end number: the self-play phase as a user of the drop-in Coach calls it
     (azb200.coach.GpuSelfPlayMixin.processSelfPlayBatches -> run_selfplay_iteration): per iteration the network's
     weights come from HOST memory (pinned state_dict -> device), the engine plays gamesPerIteration games, and the
@@ -768,7 +801,7 @@ def run_e2e_coach(a, model, dev, local, rank, world):
     B, sims = a.games, a.sims
     args = dict(process_batch_size=B, gamesPerIteration=2 * B, numMCTSSims=sims, numFastSims=sims, probFastSim=0.0,
                 cpuct=1.25, fpu_reduction=0.2, root_noise_frac=0.1, root_policy_temp=1.1, add_root_noise=True,
-                add_root_temp=True, symmetricSamples=True)
+                add_root_temp=True, symmetricSamples=True, leaf_dedup=bool(dedup))
     host_weights = {k: v.detach().cpu().pin_memory() for k, v in model.state_dict().items()}
     net = aznet.ResNet((4, 6, 7), 7, 3, **aznet.DEFAULT_NET_ARGS).to(dev).eval()
     eng = SelfPlayEngine(**engine_kwargs_from_args(Connect4, args, B, device=local, rng="philox", seed=1, game_id_base=rank * B))
@@ -785,7 +818,7 @@ def run_e2e_coach(a, model, dev, local, rank, world):
     h2d = sum(v.numel() * v.element_size() for v in host_weights.values())
     d2h = sum(x.numel() * x.element_size() for x in (res.data, res.policy, res.value)) + res.result_turns.nbytes + res.result_winstates.nbytes
     return {"value": float(res.sims) / dt, "unit": UNIT, "seconds": dt, "sims": float(res.sims), "games": int(len(res.result_turns)),
-            "examples": int(res.data.shape[0]), "h2d_bytes": int(h2d), "d2h_bytes": int(d2h),
+            "examples": int(res.data.shape[0]), "h2d_bytes": int(h2d), "d2h_bytes": int(d2h), "leaf_dedup": bool(dedup),
             "api": "azb200.coach.run_selfplay_iteration (the body of GpuSelfPlayMixin.processSelfPlayBatches): network weights from "
                    "pinned host memory, gamesPerIteration = 2 x games, examples and results returned in host memory; wall clock"}
 

@@ -178,6 +178,17 @@ int azb_play_moves(azb_engine *e, int32_t fast, void *stream);
 int azb_set_state(azb_engine *e, int32_t slot, const int8_t *cells, int32_t turns, void *stream);
 int azb_force_move(azb_engine *e, int32_t slot, int32_t action, void *stream);
 int azb_set_root_flags(azb_engine *e, int32_t add_root_noise, int32_t add_root_temp);
+/* Leaf de-duplication (off by default; no counterpart in the reference, whose NN server evaluates every row of
+ * batch_tensor, Coach.py:337-342).  While it is on, games whose leaves have the same observation (same bitboards and
+ * turn counter) share ONE network evaluation: azb_select lists only the first such game of its launch in
+ * azb_nn_rows_ptr / azb_nn_count_ptr, and azb_expand_backup / azb_expand_backup_select read the other games' policy /
+ * value from that game's rows.  Every observation row is still written.  Results are bit-identical to the engine without
+ * it as long as the evaluator's answer for a row does not depend on the other rows of the batch (true of the evaluators
+ * in azb200_nn.h).  Only with the engine-owned policy / value rows and the compact row list; not in arena mode.
+ * Synchronous (allocates 2 x num_games table entries + one state per game on first use).
+ * azb_duplicate_leaves: leaves served by another game's evaluation since creation / reset (synchronous). */
+int azb_set_leaf_dedup(azb_engine *e, int32_t on);
+int azb_duplicate_leaves(azb_engine *e, int64_t *out);
 /* arena mode: players[slot] = env player whose tree this slot holds if it searches in the current simulation round
  * (the player to move of a live game), -1 for the idle tree of the pair and for finished games.  Device int32 [B],
  * asynchronous on `stream`.  The caller maps players to models (SelfPlayAgent.player_to_index) and evaluates the
