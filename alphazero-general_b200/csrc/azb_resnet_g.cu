@@ -333,10 +333,12 @@ __host__ __device__ inline TileShare tile_share(int boards, int tiles_per_cta, i
 }
 
 // k_trunk_tc: how the tiles (pair mode: pairs of tiles) are dealt to units (CTAs, pair mode: CTA pairs).  persist: ONE wave
-// of resident units with equal shares, a unit running its share in `rounds` rounds of `tiles` tiles (the same for every
-// round: at most rounds - 1 empty tiles per unit).  Otherwise whole waves of units with one round each (tile_share).
-struct UnitShare { int units, n, first, rounds, tiles; };
-__host__ __device__ inline UnitShare unit_share(int boards, int tiles_per_cta, int sms, bool pair, bool persist, int unit)
+// of resident units with equal shares, a unit running its share in `rounds` rounds: the first `big` rounds of `tiles`
+// tiles, the others of tiles - 1 -- exactly its share -- as long as the smaller rounds still give every MMA-issuing
+// thread a tile (tiles - 1 >= issuers); else all rounds of `tiles` tiles with at most rounds - 1 empty ones.  Otherwise
+// whole waves of units with one round each (tile_share).
+struct UnitShare { int units, n, first, rounds, tiles, big; };
+__host__ __device__ inline UnitShare unit_share(int boards, int tiles_per_cta, int sms, bool pair, bool persist, int unit, int issuers)
 {
     UnitShare u;
     const int T2 = (boards + 1) / 2, items = pair ? (T2 + 1) / 2 : T2, resident = pair ? sms / 2 : sms;
@@ -345,13 +347,14 @@ __host__ __device__ inline UnitShare unit_share(int boards, int tiles_per_cta, i
         const int waves = (items + tiles_per_cta * resident - 1) / (tiles_per_cta * resident);
         u.units = waves * resident < items ? waves * resident : items;
     }
-    u.n = 0; u.first = 0; u.rounds = 0; u.tiles = 0;
+    u.n = 0; u.first = 0; u.rounds = 0; u.tiles = 0; u.big = 0;
     if (unit < 0 || unit >= u.units) return u;
     const int base = items / u.units, extra = items % u.units;
     u.n = base + (unit < extra ? 1 : 0);
     u.first = unit * base + (unit < extra ? unit : extra);
     u.rounds = (u.n + tiles_per_cta - 1) / tiles_per_cta;
     u.tiles = (u.n + u.rounds - 1) / u.rounds;
+    u.big = u.tiles - 1 >= issuers ? u.n - u.rounds * (u.tiles - 1) : u.rounds;
     return u;
 }
 
@@ -395,15 +398,17 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
     // of once per 5-7 tiles; otherwise whole waves of units with one round each.
     const uint32_t rank = C::PAIR ? cluster_ctarank() : 0u;
     const int unit = C::PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const UnitShare us = unit_share(B, C::TILES, sms, C::PAIR, persist != 0, unit);
+    const UnitShare us = unit_share(B, C::TILES, sms, C::PAIR, persist != 0, unit, C::NISSUE);
     if (us.n <= 0) return;                               // the whole cluster leaves
-    const int tiles = us.tiles, ktot = us.rounds * us.tiles;
+    // round r has `tiles` tiles for r < big, tiles - 1 after (big == rounds: all alike, the last ones possibly empty)
+    const int tiles = us.tiles, big = us.big, nrounds = us.rounds;
+    const int small = big < nrounds ? tiles - 1 : tiles;      // (>= NISSUE >= 1 when it differs from tiles)
     // (compact) board index of half hb of the unit's tile k: b0 + KSTEP * k + hb; it exists if it is below blim
     constexpr int KSTEP = C::PAIR ? 4 : 2;
     const int b0 = C::PAIR ? 4 * us.first + 2 * (int)rank : 2 * us.first;
     const int blim = B < b0 + KSTEP * us.n ? B : b0 + KSTEP * us.n;
-    const int layers = 1 + 2 * depth, total = us.rounds * layers * tiles;
-    const int nissue = tiles < C::NISSUE ? tiles : C::NISSUE;
+    const int layers = 1 + 2 * depth, total = layers * (big * tiles + (nrounds - big) * small);
+    const int nissue = tiles < C::NISSUE ? tiles : C::NISSUE;          // (smaller rounds exist only if tiles - 1 >= NISSUE)
     const uint32_t bar0 = smem_u32(bars), frame_s = smem_u32(frame), wb_s = smem_u32(wb);
 #define BAR(i) (bar0 + 8u * (uint32_t)(i))
 
@@ -519,6 +524,7 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
         // ---- MMA issuers: warp k feeds the tiles g = k, k + nissue, ... (g = layer * tiles + tile) ---------------
         if (warp < nissue && rank == 0 && elect_one_sync()) {
             int v = 0, l = 0, rs = 0, t = warp, seen = 0, turn = 0;     // v = round * layers + l; rs = round * nslabs (warp < tiles)
+            int r = 0, tc = tiles;                                     // round, tiles of this round
             const uint32_t my_turn = BAR(BAR_TURN + warp), next_turn = BAR(BAR_TURN + (warp + 1 == nissue ? 0 : warp + 1));
 #pragma unroll 1
             for (int g = warp; g < total; g += nissue) {
@@ -536,7 +542,7 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
                 turn++;
                 if (DBG && blockIdx.x == 0 && g < 256) g_trace[4 * g] = clock64();
                 const int s0 = rs + (l == 0 ? 0 : 1 + (l - 1) * C::SLABS), ns = l == 0 ? 1 : C::SLABS;
-                const bool my_last = t + nissue >= tiles;          // my last tile of this layer: release its slabs
+                const bool my_last = t + nissue >= tc;             // my last tile of this layer: release its slabs
 #pragma unroll 1
                 for (int j = 0; j < ns; j++) {
                     const int s = s0 + j, ws = s % C::NSLOT;
@@ -552,7 +558,7 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
                 if (C::PAIR) umma_commit_pair(BAR(BAR_PFULL + slot)); else umma_commit(BAR(BAR_PFULL + slot));
                 if (DBG && blockIdx.x == 0 && g < 256) g_trace[4 * g + 1] = clock64();
                 t += nissue;
-                while (t >= tiles) { t -= tiles; v++; if (++l == layers) { l = 0; rs += nslabs; } }
+                while (t >= tc) { t -= tc; v++; if (++l == layers) { l = 0; rs += nslabs; if (++r == big) tc = small; } }
             }
         }
         // ---- peer CTA of a pair: tell the leader when MY half of a weight slab has landed ------------------------------
@@ -585,8 +591,8 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
         const int r0 = q * 32 + lane, fy = (r0 & 63) >> 3, fx = r0 & 7;
         const bool live_pos = fx < W && fy < H;
         const int pos = fy * W + fx;
-        int l = 0, kb = 0, t = grp;                          // layer, round * tiles, tile of the round
-        while (t >= tiles) { t -= tiles; if (++l == layers) { l = 0; kb += tiles; } }
+        int l = 0, kb = 0, t = grp, r = 0, tc = tiles;       // layer, first tile of the round, tile of the round, round, its tiles
+        while (t >= tc) { t -= tc; if (++l == layers) { l = 0; kb += tc; if (++r == big) tc = small; } }
 #pragma unroll 1
         for (int g = grp; g < total; g += C::NGROUPS) {
             const int slot = g % C::NRING, use = g / C::NRING;
@@ -614,10 +620,11 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
             // the wait: the kernel sits at its register limit, and values parked in local memory would expose the latency of
             // both loads), converted into the frame right after the wait, and epilogue_tile hands the tile to the next round's
             // stem together with the accumulator -- the stem's MMAs run under this epilogue's stores.
-            const bool handoff = last && kb + tiles < ktot;
+            // (the tile slot exists in the next round unless that round is a smaller one and this is the last slot)
+            const bool handoff = last && r + 1 < nrounds && t < (r + 1 < big ? tiles : small);
             int ngb = -1;
             if (handoff && cg == 0 && live_pos) {
-                const int nb = brd + KSTEP * tiles;
+                const int nb = brd + KSTEP * tc;
                 if (nb < blim) {
                     ngb = rows != nullptr ? rows[nb] : nb;
                     const float *o = obs + (size_t)ngb * in_ch * HW + pos;
@@ -657,7 +664,7 @@ k_trunk_tc(const float *__restrict__ obs, int B, int in_ch, int H, int W, int de
             }
             if (DBG && blockIdx.x == 0 && within == 0 && lane == 0 && g < 256) g_trace[4 * g + 3] = clock64();
             t += C::NGROUPS;
-            while (t >= tiles) { t -= tiles; if (++l == layers) { l = 0; kb += tiles; } }
+            while (t >= tc) { t -= tc; if (++l == layers) { l = 0; kb += tc; if (++r == big) tc = small; } }
         }
     }
     tc_fence_before();
@@ -1179,7 +1186,7 @@ int launch_trunk(const azb_nng_net *n, const float *obs, int batch, const int *r
         persist_default = e != nullptr ? (atoi(e) != 0 ? 1 : 0) : 1;
     }
     const int persist = (n->flags & AZB_NNG_PERSIST) ? 1 : (n->flags & AZB_NNG_ONE_ROUND) ? 0 : persist_default;
-    const int grid = (C::PAIR ? 2 : 1) * unit_share(batch, C::TILES, sms, C::PAIR, persist != 0, 0).units;
+    const int grid = (C::PAIR ? 2 : 1) * unit_share(batch, C::TILES, sms, C::PAIR, persist != 0, 0, C::NISSUE).units;
     const int MT = (n->max_boards + 127) / 128;
     const unsigned char *wt = reinterpret_cast<const unsigned char *>(n->wtrunk);
     unsigned char *gact = reinterpret_cast<unsigned char *>(n->gact);
@@ -1328,8 +1335,8 @@ extern "C" int azb_nng_layout(int32_t channels, int32_t precision, int32_t *out)
 extern "C" int azb_nng_tile_plan(int32_t channels, int32_t boards, int32_t sms, int32_t pair, int32_t persist, int32_t unit, int32_t *out)
 {
     if (!out || (channels != 32 && channels != 64) || boards < 0 || sms < 2) return -1;
-    const g::UnitShare u = g::unit_share(boards, channels == 32 ? 7 : 2, sms, pair != 0, persist != 0, unit);
-    out[0] = u.units; out[1] = u.n; out[2] = u.first; out[3] = u.rounds; out[4] = u.tiles;
+    const g::UnitShare u = g::unit_share(boards, channels == 32 ? 7 : 2, sms, pair != 0, persist != 0, unit, channels == 32 ? 3 : 2);
+    out[0] = u.units; out[1] = u.n; out[2] = u.first; out[3] = u.rounds; out[4] = u.tiles; out[5] = u.big;
     return 0;
 }
 

@@ -119,9 +119,11 @@ typedef struct azb_nng_net {
  * of the stem.  -1: unsupported channels / precision. */
 int azb_nng_layout(int32_t channels, int32_t precision, int32_t *out);
 /* Host only, no device needed: how the 32 / 64-channel trunk deals the tiles (two boards each; pair: pairs of tiles) of
- * `boards` boards to its units (CTAs; pair: CTA pairs) on `sms` SMs.  out[0..4] = number of units, then for `unit`: its
- * number of tiles, its first tile, its rounds, its tiles per round (rounds * tiles per round >= number of tiles; all 0
- * for a unit beyond the grid).  -1: bad argument. */
+ * `boards` boards to its units (CTAs; pair: CTA pairs) on `sms` SMs.  out[0..5] = number of units, then for `unit`: its
+ * number of tiles, its first tile, its rounds, the tiles of a big round, the number of big rounds (the other rounds have
+ * one tile less: big * tiles + (rounds - big) * (tiles - 1) == number of tiles; when that would leave an MMA-issuing
+ * thread without a tile, big == rounds and rounds * tiles >= number of tiles, the surplus being empty tiles).  All 0 for
+ * a unit beyond the grid.  -1: bad argument. */
 int azb_nng_tile_plan(int32_t channels, int32_t boards, int32_t sms, int32_t pair, int32_t persist, int32_t unit, int32_t *out);
 /* obs f32 [batch, C, H, W] -> policy f32 [batch, A], value f32 [batch, 3] (probabilities).  rows / count (both or
  * neither): compact evaluation of boards rows[0 .. *count) as azb_nn_forward_tc_rows, batch = upper bound.

@@ -34,14 +34,15 @@ t0 = buf[0]
 print(f"set-up detail: frame zeroed by thread 0 {buf[1008] - t0}, barriers initialised {buf[1009] - t0}, init fence done {buf[1010] - t0}")
 print(f"set-up detail: alloc starts {buf[1004] - t0}, alloc done {buf[1005] - t0}, frame zeroed {buf[1006] - t0}, after __syncthreads {buf[1007] - t0}")
 print(f"CTA entry {buf[1000] - t0}, set-up done {buf[1001] - t0}, observations staged {buf[1002] - t0}, first issue 0, exit {buf[1003] - t0}")
-plan = (C.c_int32 * 5)()
+plan = (C.c_int32 * 6)()
 sms = torch.cuda.get_device_properties(0).multi_processor_count
 assert ev.lib.azb_nng_tile_plan(ev.net.channels, batch, sms, 1 if ev.pair else 0, int(os.environ.get("AZB_NNG_PERSIST", "1")), 0, plan) == 0
-units, n_tiles, first, rounds, tiles = plan
-print(f"unit 0 of {units}: {n_tiles} tiles in {rounds} rounds of {tiles}; {layers} layers")
+units, n_tiles, first, rounds, tiles, big = plan
+print(f"unit 0 of {units}: {n_tiles} tiles in {rounds} rounds ({big} of {tiles}, the others of {tiles - 1}); {layers} layers")
 ev_rows = []
 g = 0
-while g < 256 and buf[4 * g] != 0 and g < rounds * layers * tiles:
+n_entries = layers * (big * tiles + (rounds - big) * (tiles - 1)) if big < rounds else rounds * layers * tiles
+while g < 256 and buf[4 * g] != 0 and g < n_entries:
     a, b, c, d = (buf[4 * g + i] - t0 for i in range(4))
     ev_rows.append((g, a, b, c, d))
     if os.environ.get("NN_TRACE_FULL"):
@@ -50,8 +51,11 @@ while g < 256 and buf[4 * g] != 0 and g < rounds * layers * tiles:
 # summary: per (round, layer) the span of its tiles' MMAs, and the idle time of the issue stream before each tile
 print("round layer: first issue, last commit, span, issue time (sum of commit - issue), idle before its tiles (sum of issue - previous commit)")
 prev_commit = 0
+pos = 0
 for v in range(rounds * layers):
-    rows = ev_rows[v * tiles:(v + 1) * tiles]
+    tc = tiles if (v // layers) < big else tiles - 1
+    rows = ev_rows[pos:pos + tc]
+    pos += tc
     if not rows:
         break
     busy = sum(b - a for _, a, b, _, _ in rows)

@@ -311,36 +311,43 @@ def test_cta_pairs_equal_single_ctas_bit_for_bit(geom, precision, batch):
 @pytest.mark.parametrize("persist", [0, 1])
 def test_tile_plan_deals_every_tile_exactly_once(channels, pair, persist):
     """azb_nng_tile_plan (host only): the units' shares are consecutive, disjoint and cover all tiles (pair mode: pairs of
-    tiles); a unit's rounds x tiles-per-round hold its share with fewer than `rounds` empty tiles, tiles per round fit the
-    CTA's tensor memory; persistent plans never exceed one wave of resident units."""
+    tiles); a unit's rounds hold exactly its share (`big` rounds of `tiles` tiles, the others of tiles - 1, every round
+    giving each of the kernel's MMA-issuing threads a tile) or, where that is impossible, rounds x tiles with fewer than
+    `rounds` empty tiles; tiles per round fit the CTA's tensor memory; persistent plans never exceed one wave."""
     import ctypes as C
     from azb200 import _capi
     lib = _capi.load()
-    cap = 7 if channels == 32 else 2
+    cap, issuers = (7, 3) if channels == 32 else (2, 2)
     for sms in (148, 132, 3):
         resident = sms // 2 if pair else sms
         if resident < 1:
             continue
-        for boards in [0, 1, 2, 3, 4, 5, 27, 28, 29, 147, 148, 296, 297, 1000, 2048, 3915, 4133, 6960, 8192, 16384, 65536]:
-            out = (C.c_int32 * 5)()
+        for boards in [0, 1, 2, 3, 4, 5, 27, 28, 29, 147, 148, 296, 297, 1000, 2048, 3915, 4133, 5255, 5831, 6300, 6960, 8192,
+                       16384, 65536]:
+            out = (C.c_int32 * 6)()
             assert lib.azb_nng_tile_plan(channels, boards, sms, pair, persist, 0, out) == 0
             units = out[0]
             tiles = (boards + 1) // 2
             items = (tiles + 1) // 2 if pair else tiles
-            assert units == (0 if boards == 0 else units) and (units > 0) == (boards > 0)
+            assert (units > 0) == (boards > 0)
             if persist:
                 assert units == min(items, resident)
             nxt = 0
             for u in range(units):
                 assert lib.azb_nng_tile_plan(channels, boards, sms, pair, persist, u, out) == 0
-                _, n, first, rounds, per = out
+                _, n, first, rounds, per, big = out
                 assert n >= 1 and first == nxt
-                assert 1 <= per <= cap and rounds * per >= n and rounds * per - n < rounds
+                assert 1 <= per <= cap and 1 <= big <= rounds
+                if big < rounds:
+                    assert big * per + (rounds - big) * (per - 1) == n and per - 1 >= issuers
+                else:
+                    assert rounds * per >= n and rounds * per - n < rounds
+                    assert rounds * per == n or per - 1 < issuers
                 if not persist:
                     assert rounds == 1
                 nxt += n
             assert nxt == items
-            assert lib.azb_nng_tile_plan(channels, boards, sms, pair, persist, units, out) == 0 and list(out)[1:] == [0, 0, 0, 0]
+            assert lib.azb_nng_tile_plan(channels, boards, sms, pair, persist, units, out) == 0 and list(out)[1:] == [0, 0, 0, 0, 0]
 
 
 @pytest.mark.gpu
